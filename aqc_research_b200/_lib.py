@@ -1,0 +1,122 @@
+"""
+ctypes binding of ``libaqc_b200.so`` (C-ABI declared in ``include/aqc_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C aqc_research_b200/csrc``.  Loading never falls back to anything else: if the
+shared object is missing, ``load()`` raises.
+"""
+
+import ctypes as ct
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaqc_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_lock = threading.Lock()
+_lib = None
+
+c_double_p = ct.POINTER(ct.c_double)
+c_int32_p = ct.POINTER(ct.c_int32)
+c_int64_p = ct.POINTER(ct.c_int64)
+
+# name -> (restype, argtypes); mirrors include/aqc_b200.h one to one
+SIGNATURES = {
+    "aqc_last_error": (ct.c_char_p, []),
+    "aqc_version": (ct.c_int, []),
+    "aqc_device_count": (ct.c_int, []),
+    "aqc_circuit_create": (
+        ct.c_int,
+        [ct.c_int, ct.c_int, c_int32_p, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)],
+    ),
+    "aqc_circuit_destroy": (None, [ct.c_void_p]),
+    "aqc_circuit_num_thetas": (ct.c_int, [ct.c_void_p]),
+    "aqc_sv_create": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)],
+    ),
+    "aqc_sv_destroy": (None, [ct.c_void_p]),
+    "aqc_sv_state_size": (ct.c_int64, [ct.c_void_p]),
+    "aqc_sv_upload": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int64]),
+    "aqc_sv_download": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int64]),
+    "aqc_sv_set_basis": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int64]),
+    "aqc_sv_set_identity": (ct.c_int, [ct.c_void_p, ct.c_int]),
+    "aqc_sv_fill_random": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_uint64]),
+    "aqc_sv_gather": (ct.c_int, [ct.c_void_p, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p]),
+    "aqc_sv_vdot": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]),
+    "aqc_sv_apply": (ct.c_int, [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, ct.c_int]),
+    "aqc_sv_grad": (
+        ct.c_int,
+        [ct.c_void_p, c_double_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p],
+    ),
+    "aqc_sv_objective": (
+        ct.c_int,
+        [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p],
+    ),
+    "aqc_sv_last_kernel_ms": (ct.c_float, [ct.c_void_p]),
+    "aqc_sv_last_num_launches": (ct.c_int, [ct.c_void_p]),
+    "aqc_sv_num_passes": (ct.c_int, [ct.c_void_p, ct.c_int]),
+    "aqc_debug_program": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
+    ),
+    "aqc_sv_slot_ptr": (ct.c_void_p, [ct.c_void_p, ct.c_int]),
+    "aqc_sv_stream": (ct.c_void_p, [ct.c_void_p]),
+}
+
+
+class AqcError(RuntimeError):
+    """Error reported by the CUDA library."""
+
+
+def build(verbose: bool = False) -> str:
+    """Compiles the shared library in-tree with nvcc for sm_100a. Returns its path."""
+    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True, check=False)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0 or not os.path.isfile(LIB_PATH):
+        raise AqcError("building libaqc_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def load() -> ct.CDLL:
+    """Loads the library (once) and declares every signature. Raises if it is missing."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise AqcError(
+                f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C aqc_research_b200/csrc`. There is no CPU fallback."
+            )
+        lib = ct.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    """Raises AqcError with the library's message if ``rc`` is an error code."""
+    if rc != 0:
+        msg = load().aqc_last_error()
+        text = msg.decode("utf-8", "replace") if msg else "unknown error"
+        if rc == -1:
+            raise ValueError(text)
+        raise AqcError(f"[{rc}] {text}")
+
+
+def device_count() -> int:
+    return int(load().aqc_device_count())
+
+
+def require_gpu() -> None:
+    """Raises unless at least one CUDA device is visible."""
+    if device_count() <= 0:
+        raise AqcError("no CUDA device visible: aqc_research_b200 has no CPU fallback")

@@ -1,0 +1,101 @@
+"""
+Argument predicates used by the host-side mirror of the reference API
+(reference: aqc_research/checking.py -- same names where callers rely on them).
+All predicates return bool so they can be used inside ``assert``.
+"""
+
+import numbers
+import numpy as np
+
+_COMPLEX = (np.complex128,)
+_FLOAT = (np.float64,)
+
+
+def is_int(x, cond: bool = True) -> bool:
+    return isinstance(x, (int, np.integer)) and not isinstance(x, bool) and bool(cond)
+
+
+def is_float(x, cond: bool = True) -> bool:
+    return isinstance(x, (float, np.floating)) and bool(cond)
+
+
+def is_bool(x) -> bool:
+    return isinstance(x, (bool, np.bool_))
+
+
+def is_str(x, cond: bool = True) -> bool:
+    return isinstance(x, str) and bool(cond)
+
+
+def is_tuple(x, cond: bool = True) -> bool:
+    return isinstance(x, tuple) and bool(cond)
+
+
+def is_dict(x, cond: bool = True) -> bool:
+    return isinstance(x, dict) and bool(cond)
+
+
+def is_number(x) -> bool:
+    return isinstance(x, numbers.Number)
+
+
+def _arr(x, kinds, ndim, cond) -> bool:
+    return (
+        isinstance(x, np.ndarray)
+        and x.dtype.type in kinds
+        and (ndim is None or x.ndim == ndim)
+        and bool(cond)
+    )
+
+
+def float_1d(x, cond: bool = True) -> bool:
+    return _arr(x, _FLOAT, 1, cond)
+
+
+def float_2d(x, cond: bool = True) -> bool:
+    return _arr(x, _FLOAT, 2, cond)
+
+
+def complex_1d(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX, 1, cond)
+
+
+def complex_2d(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX, 2, cond)
+
+
+def complex_array(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX, None, cond)
+
+
+def complex_2d_square(x, cond: bool = True) -> bool:
+    return complex_2d(x, cond) and x.shape[0] == x.shape[1]
+
+
+def complex_or_float_2d(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX + _FLOAT, 2, cond)
+
+
+def block_structure(num_qubits: int, blocks) -> bool:
+    """True if ``blocks`` is a valid (2, depth) integer unit-block layout."""
+    return (
+        is_int(num_qubits, num_qubits >= 2)
+        and isinstance(blocks, np.ndarray)
+        and np.issubdtype(blocks.dtype, np.integer)
+        and blocks.ndim == 2
+        and blocks.shape[0] == 2
+        and bool(np.all((blocks >= 0) & (blocks < num_qubits)))
+        and bool(np.all(blocks[0] != blocks[1]))
+    )
+
+
+def no_overlap(a: np.ndarray, b: np.ndarray) -> bool:
+    return not np.may_share_memory(a, b)
+
+
+def contiguous_c128(*arrays) -> bool:
+    """All arrays are C-contiguous complex128."""
+    return all(
+        isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags.c_contiguous
+        for a in arrays
+    )

@@ -1,0 +1,80 @@
+"""
+Function-level drop-ins for the reference's matrix numeric core
+(reference: aqc_research/core_op_matrix.py:480-762): the same sweeps applied to the columns of
+a row-major ``(2^n, m)`` matrix.  On the GPU the matrix is a state of ``n + ceil(log2 m)`` index
+bits whose low bits are the column index (columns are zero-padded to a power of two; zero
+columns contribute nothing to the Frobenius inner products).
+"""
+
+from typing import Optional
+import numpy as np
+from . import checking as chk
+from .core_operations import _workspace
+from .parametric_circuit import ParametricCircuit
+
+
+def _pad_cols(mat: np.ndarray, log2_cols: int) -> np.ndarray:
+    cols = 1 << log2_cols
+    if mat.shape[1] == cols:
+        return np.ascontiguousarray(mat)
+    out = np.zeros((mat.shape[0], cols), dtype=np.complex128)
+    out[:, : mat.shape[1]] = mat
+    return out
+
+
+def _log2_cols(m: int) -> int:
+    return max(0, int(m - 1).bit_length())
+
+
+def _check(circ, thetas, *mats):
+    assert isinstance(circ, ParametricCircuit)
+    assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
+    for m in mats:
+        assert chk.complex_2d(m, m.shape[0] == circ.dimension and 1 <= m.shape[1] <= m.shape[0])
+        assert m.flags.c_contiguous
+        assert m.shape == mats[0].shape
+
+
+def _apply(circ, thetas, mat, dagger):
+    k = _log2_cols(mat.shape[1])
+    ws = _workspace(circ, log2_cols=k)
+    ws.upload(0, _pad_cols(mat, k))
+    ws.apply(thetas, 0, 0, dagger=dagger)
+    res = ws.download(0, 0).reshape(mat.shape[0], 1 << k)
+    mat[:, :] = res[:, : mat.shape[1]]
+    return mat
+
+
+def v_mul_mat(circ, thetas: np.ndarray, mat: np.ndarray, workspace: Optional[np.ndarray] = None):
+    """``mat <- V @ mat`` in place (core_op_matrix.py:480-559)."""
+    _check(circ, thetas, mat)
+    return _apply(circ, thetas, mat, False)
+
+
+def v_dagger_mul_mat(circ, thetas: np.ndarray, mat: np.ndarray, workspace: Optional[np.ndarray] = None):
+    """``mat <- V^H @ mat`` in place (core_op_matrix.py:562-642)."""
+    _check(circ, thetas, mat)
+    return _apply(circ, thetas, mat, True)
+
+
+def grad_of_matrix_dot_product(
+    circ,
+    thetas: np.ndarray,
+    x_mat: np.ndarray,
+    vh_y_mat: np.ndarray,
+    workspace: Optional[np.ndarray] = None,
+) -> np.ndarray:
+    """
+    Complex gradient of ``<V X, Y>_F`` given ``vh_y_mat = V^H Y`` (core_op_matrix.py:645-762).
+    Like the reference, ``x_mat`` and ``vh_y_mat`` are overwritten (with ``V X`` and ``V V^H Y``).
+    """
+    _check(circ, thetas, x_mat, vh_y_mat)
+    k = _log2_cols(x_mat.shape[1])
+    ws = _workspace(circ, log2_cols=k)
+    ws.upload(0, _pad_cols(x_mat, k))
+    ws.upload(1, _pad_cols(vh_y_mat, k))
+    grad = ws.grad(thetas, x_slot=0, z0=1, w=0, z=1)[0]
+    for slot, mat in ((0, x_mat), (1, vh_y_mat)):
+        res = ws.download(slot, 0).reshape(mat.shape[0], 1 << k)
+        mat[:, :] = res[:, : mat.shape[1]]
+    return grad

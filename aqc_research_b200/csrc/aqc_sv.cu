@@ -1,0 +1,1305 @@
+// aqc_sv.cu -- state-vector / column-batched objective-and-gradient engine for sm_100a.
+//
+// What this replaces (reference = qiskit-community/aqc-research, paths relative to its root):
+//   v_mul_vec / v_dagger_mul_vec / grad_of_dot_product     aqc_research/core_operations.py:606,713,823
+//   v_mul_mat / v_dagger_mul_mat / grad_of_matrix_dot_product   aqc_research/core_op_matrix.py:480,562,645
+// The reference walks the circuit gate by gate and makes ~40-70 full NumPy passes over the
+// 2^n vector per unit block.  Here the circuit STRUCTURE is compiled once (host side, below)
+// into a short list of *tile passes*; each pass stages a tile of 2^tb amplitudes of w and z in
+// shared memory, runs every gate whose qubits live inside the tile on register-resident
+// amplitude quadruples (including the 0.5j<P w|z> inner products of the gradient sweep,
+// reduced with warp shuffles) and writes the tile back once.  Angles enter only through a
+// small (cos, sin) table built on the device, so a new theta costs one tiny launch.
+//
+// Design notes are in DESIGN.md; the C-ABI is declared in include/aqc_b200.h.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aqc_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(AQC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                \
+  } while (0)
+
+extern "C" const char* aqc_last_error(void) { return g_err.c_str(); }
+extern "C" int aqc_version(void) { return 100; }
+extern "C" int aqc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// compiled program: passes -> stages -> units
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads = 128;  // threads per CTA of the pass kernel
+constexpr int kMaxUnits = 3;   // units fused into one stage (a Trotter triplet)
+constexpr int kMaxTileBits = 12;
+
+enum UnitKind : int32_t {
+  U_NONE = 0,
+  U_FRONT_LO = 1,  // Rz Ry Rz front gate on the low register bit of the quad
+  U_FRONT_HI = 2,
+  U_BLOCK_CHI = 3,  // unit block, control on the high register bit
+  U_BLOCK_CLO = 4,
+};
+enum UnitFlags : int32_t {
+  F_PRE = 1,   // Trotter Rz(-pi/2) on control before the block (i % 3 == 0)
+  F_POST = 2,  // Trotter Rz(+pi/2) on target after the block  (i % 3 == 2)
+};
+
+struct UnitDesc {
+  int32_t kind;
+  int32_t flags;
+  int32_t theta;  // index of the unit's first angle == first gradient slot
+  int32_t pad;
+};
+struct StageDesc {
+  int32_t p, q;  // tile-local bit positions held in registers, p > q
+  int32_t nunits;
+  int32_t pad;
+  UnitDesc u[kMaxUnits];
+};
+static_assert(sizeof(StageDesc) == 64, "StageDesc layout");
+
+struct PassDesc {
+  int32_t tb;       // tile bits
+  int32_t nstages;  // stages in this pass
+  int32_t stage0;   // first stage in the program's stage array
+  int32_t nouter;   // number of index bits outside the tile
+  uint8_t bitpos[16];    // global bit position of tile-local bit k
+  uint8_t outerpos[48];  // global bit positions of the non-tile bits, ascending
+};
+
+struct Program {
+  std::vector<PassDesc> passes;
+  std::vector<StageDesc> stages;
+  StageDesc* d_stages = nullptr;
+};
+
+struct HostUnit {
+  int kind;  // 0 front, 1 block
+  int qa;    // front qubit | control
+  int qb;    // -1 | target
+  int theta;
+  int flags;
+};
+
+struct aqc_circuit {
+  int n = 0;
+  int ent = 0;
+  int trotter = 0;
+  int nb = 0;  // blocks in full layers
+  int half = 0;
+  int tpb = 4;
+  int nthetas = 0;
+  std::vector<int> ctrl, targ;
+};
+
+static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUnit>& out) {
+  out.clear();
+  for (int q = 0; q < c.n; ++q) out.push_back({0, q, -1, 3 * q, 0});
+  const int total = c.nb + c.half;
+  for (int i = 0; i < total; ++i) {
+    const int im = c.nb > 0 ? i % c.nb : 0;
+    int flags = 0;
+    if (c.trotter != AQC_GENERIC) {
+      if (i % 3 == 0) flags |= F_PRE;
+      if (i % 3 == 2) flags |= F_POST;
+    }
+    out.push_back({1, c.ctrl[im], c.targ[im], 3 * c.n + c.tpb * im, flags});
+  }
+  if (reversed) std::reverse(out.begin(), out.end());
+}
+
+// Greedy tile-pass scheduler.  `units` is the gate-unit sequence in execution order; units on
+// disjoint qubits commute, so a unit may run in the current pass iff all its qubits are inside
+// the tile and none of them is touched by an earlier unit that had to be deferred.
+static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max, int lowbits,
+                          bool reversed, Program& prog) {
+  std::vector<HostUnit> units;
+  build_units(c, reversed, units);
+  prog.passes.clear();
+  prog.stages.clear();
+  const int tb = std::min(nbits, tb_max);
+  const int low = std::min(lowbits, tb);
+
+  std::vector<char> done(units.size(), 0);
+  size_t ndone = 0;
+  while (ndone < units.size() || prog.passes.empty()) {
+    std::vector<char> intile(nbits, 0), blocked(nbits, 0);
+    int ntile = 0;
+    for (int b = 0; b < low; ++b) intile[b] = 1, ++ntile;
+    std::vector<int> picked;
+    for (size_t k = 0; k < units.size(); ++k) {
+      if (done[k]) continue;
+      const HostUnit& u = units[k];
+      const int ba = u.qa + qoff, bb = u.kind ? u.qb + qoff : -1;
+      const bool blk = blocked[ba] || (bb >= 0 && blocked[bb]);
+      int need = (intile[ba] ? 0 : 1) + ((bb >= 0 && !intile[bb]) ? 1 : 0);
+      if (!blk && ntile + need <= tb) {
+        if (!intile[ba]) intile[ba] = 1, ++ntile;
+        if (bb >= 0 && !intile[bb]) intile[bb] = 1, ++ntile;
+        picked.push_back((int)k);
+      } else {
+        blocked[ba] = 1;
+        if (bb >= 0) blocked[bb] = 1;
+      }
+    }
+    // pad the tile with the lowest free bits (longer contiguous runs)
+    for (int b = 0; b < nbits && ntile < tb; ++b)
+      if (!intile[b]) intile[b] = 1, ++ntile;
+
+    PassDesc pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.tb = tb;
+    pd.stage0 = (int)prog.stages.size();
+    std::vector<int> local(nbits, -1);
+    int kt = 0, ko = 0;
+    for (int b = 0; b < nbits; ++b) {
+      if (intile[b]) {
+        local[b] = kt;
+        pd.bitpos[kt++] = (uint8_t)b;
+      } else {
+        pd.outerpos[ko++] = (uint8_t)b;
+      }
+    }
+    pd.nouter = ko;
+
+    // group the picked units into stages (register-resident quads on one bit pair)
+    struct Open {
+      int a, b;  // tile-local bits (b == -1: partner still free, front-only stage)
+      bool front;
+      StageDesc sd;
+    };
+    std::vector<Open> open;
+    std::vector<int> last(tb, -1);  // last stage that touched tile-local bit
+    auto put = [&](Open& o, int kind, const HostUnit& u) {
+      UnitDesc& d = o.sd.u[o.sd.nunits++];
+      d.kind = kind;
+      d.flags = u.flags;
+      d.theta = u.theta;
+      d.pad = 0;
+    };
+    // units are stored with *qubit roles*; the LO/HI kind is fixed up when the stage closes
+    struct Pending {
+      int stage;
+      int slot;
+      int la, lb;
+      bool front;
+    };
+    std::vector<Pending> pend;
+    for (int k : picked) {
+      const HostUnit& u = units[k];
+      const int la = local[u.qa + qoff];
+      const int lb = u.kind ? local[u.qb + qoff] : -1;
+      int s = -1;
+      if (u.kind == 0) {
+        // front gate: join an open front stage that has a free partner seat
+        // (legal iff no stage created after it has touched this bit)
+        for (size_t i = 0; i < open.size(); ++i)
+          if (open[i].front && open[i].b < 0 && open[i].a != la && open[i].sd.nunits < 2 &&
+              (int)i > last[la]) {
+            s = (int)i;
+            open[i].b = la;
+            break;
+          }
+        if (s < 0) {
+          Open o;
+          memset(&o.sd, 0, sizeof(o.sd));
+          o.a = la;
+          o.b = -1;
+          o.front = true;
+          open.push_back(o);
+          s = (int)open.size() - 1;
+        }
+        last[la] = s;
+      } else {
+        const int sa = last[la], sb = last[lb];
+        if (sa >= 0 && sa == sb && !open[sa].front && open[sa].sd.nunits < kMaxUnits &&
+            ((open[sa].a == la && open[sa].b == lb) || (open[sa].a == lb && open[sa].b == la))) {
+          s = sa;
+        } else {
+          Open o;
+          memset(&o.sd, 0, sizeof(o.sd));
+          o.a = la;
+          o.b = lb;
+          o.front = false;
+          open.push_back(o);
+          s = (int)open.size() - 1;
+        }
+        last[la] = last[lb] = s;
+      }
+      pend.push_back({s, open[s].sd.nunits, la, lb, u.kind == 0});
+      put(open[s], U_NONE, u);
+    }
+    // A front stage whose partner seat stayed free gets any other tile bit as a passive partner.
+    for (auto& o : open)
+      if (o.b < 0) o.b = (o.a == 0) ? 1 : 0;
+    for (auto& pe : pend) {
+      Open& o = open[pe.stage];
+      const int hi = std::max(o.a, o.b), lo = std::min(o.a, o.b);
+      o.sd.p = hi;
+      o.sd.q = lo;
+      UnitDesc& d = o.sd.u[pe.slot];
+      if (pe.front)
+        d.kind = (pe.la == hi) ? U_FRONT_HI : U_FRONT_LO;
+      else
+        d.kind = (pe.la == hi) ? U_BLOCK_CHI : U_BLOCK_CLO;
+      (void)lo;
+    }
+    for (auto& o : open) prog.stages.push_back(o.sd);
+    pd.nstages = (int)open.size();
+    prog.passes.push_back(pd);
+    for (int k : picked) done[k] = 1;
+    ndone += picked.size();
+    if (picked.empty() && ndone < units.size()) break;  // cannot happen (tb >= 2)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// device code
+// ------------------------------------------------------------------------------------------
+struct cd {
+  double x, y;
+};
+
+__device__ __forceinline__ void mul_mi(cd& a) {  // a *= -i
+  const double t = a.x;
+  a.x = a.y;
+  a.y = -t;
+}
+__device__ __forceinline__ void mul_pi(cd& a) {  // a *= +i
+  const double t = a.x;
+  a.x = -a.y;
+  a.y = t;
+}
+// a *= (c + i s)
+__device__ __forceinline__ void mul_cs(cd& a, double c, double s) {
+  const double x = a.x, y = a.y;
+  a.x = fma(-s, y, c * x);
+  a.y = fma(s, x, c * y);
+}
+__device__ __forceinline__ void ry_pair(cd& a0, cd& a1, double c, double s) {
+  const cd b0 = a0, b1 = a1;
+  a0.x = fma(-s, b1.x, c * b0.x);
+  a0.y = fma(-s, b1.y, c * b0.y);
+  a1.x = fma(s, b0.x, c * b1.x);
+  a1.y = fma(s, b0.y, c * b1.y);
+}
+__device__ __forceinline__ void rx_pair(cd& a0, cd& a1, double c, double s) {
+  const cd b0 = a0, b1 = a1;
+  a0.x = fma(s, b1.y, c * b0.x);
+  a0.y = fma(-s, b1.x, c * b0.y);
+  a1.x = fma(s, b0.y, c * b1.x);
+  a1.y = fma(-s, b0.x, c * b1.y);
+}
+__device__ __forceinline__ void rz_pair(cd& a0, cd& a1, double c, double s) {
+  mul_cs(a0, c, -s);
+  mul_cs(a1, c, s);
+}
+// acc += conj(w) * z
+__device__ __forceinline__ void cdot_add(double* acc, const cd& w, const cd& z) {
+  acc[0] = fma(w.x, z.x, acc[0]);
+  acc[0] = fma(w.y, z.y, acc[0]);
+  acc[1] = fma(w.x, z.y, acc[1]);
+  acc[1] = fma(-w.y, z.x, acc[1]);
+}
+__device__ __forceinline__ void cdot_sub(double* acc, const cd& w, const cd& z) {
+  acc[0] = fma(-w.x, z.x, acc[0]);
+  acc[0] = fma(-w.y, z.y, acc[0]);
+  acc[1] = fma(-w.x, z.y, acc[1]);
+  acc[1] = fma(w.y, z.x, acc[1]);
+}
+
+enum { ROT_Y = 0, ROT_Z = 1, ROT_X = 2 };
+
+// One-qubit rotation on register bit HI/LO of a quad for NVEC vectors, plus (NVEC == 2) the raw
+// inner product <P w|z> / (i for Z, X) accumulated into acc[0..1]:
+//   Y: sum conj(w0) z1 - conj(w1) z0      (dot_y core_operations.py:317-322, factor 0.5)
+//   Z: sum conj(w0) z0 - conj(w1) z1      (dot_z :346-351, factor 0.5j)
+//   X: sum conj(w1) z0 + conj(w0) z1      (dot_x :288-293, factor 0.5j)
+template <int NVEC, bool HI, int ROT>
+__device__ __forceinline__ void rot1q(cd (&a)[NVEC][4], double c, double s, double* acc) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i0 = HI ? r : 2 * r;
+    const int i1 = i0 + (HI ? 2 : 1);
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+      if (ROT == ROT_Y) ry_pair(a[v][i0], a[v][i1], c, s);
+      if (ROT == ROT_Z) rz_pair(a[v][i0], a[v][i1], c, s);
+      if (ROT == ROT_X) rx_pair(a[v][i0], a[v][i1], c, s);
+    }
+    if (NVEC == 2) {
+      if (ROT == ROT_Y) {
+        cdot_add(acc, a[0][i0], a[NVEC - 1][i1]);
+        cdot_sub(acc, a[0][i1], a[NVEC - 1][i0]);
+      }
+      if (ROT == ROT_Z) {
+        cdot_add(acc, a[0][i0], a[NVEC - 1][i0]);
+        cdot_sub(acc, a[0][i1], a[NVEC - 1][i1]);
+      }
+      if (ROT == ROT_X) {
+        cdot_add(acc, a[0][i1], a[NVEC - 1][i0]);
+        cdot_add(acc, a[0][i0], a[NVEC - 1][i1]);
+      }
+    }
+  }
+}
+
+// Front-layer gate of one qubit: forward Rz(t2) Ry(t1) Rz(t0) applied right-to-left
+// (core_operations.py:921-935); dagger Rz(-t0) Ry(-t1) Rz(-t2) (:812-818).
+template <int NVEC, bool HI, bool DAG>
+__device__ __forceinline__ void front_unit(cd (&a)[NVEC][4], const double2* __restrict__ tr,
+                                           double* acc) {
+  const double2 t0 = tr[0], t1 = tr[1], t2 = tr[2];
+  if (!DAG) {
+    rot1q<NVEC, HI, ROT_Z>(a, t2.x, t2.y, acc + 4);
+    rot1q<NVEC, HI, ROT_Y>(a, t1.x, t1.y, acc + 2);
+    rot1q<NVEC, HI, ROT_Z>(a, t0.x, t0.y, acc + 0);
+  } else {
+    rot1q<NVEC, HI, ROT_Z>(a, t0.x, -t0.y, acc);
+    rot1q<NVEC, HI, ROT_Y>(a, t1.x, -t1.y, acc);
+    rot1q<NVEC, HI, ROT_Z>(a, t2.x, -t2.y, acc);
+  }
+}
+
+// Unit block (core_operations.py:686-708 forward, :787-809 dagger, :956-1017 gradient sweep).
+// Trotter Rz(-+pi/2) = e^{+-i pi/4} diag(1, -+i): the scalar phases of the two ends of a
+// triplet cancel exactly, so only the free diag(1, -+i) parts are applied.
+template <int NVEC, int ENT, bool CHI, bool DAG>
+__device__ __forceinline__ void block_unit(cd (&a)[NVEC][4], const double2* __restrict__ tr,
+                                           int flags, double* acc) {
+  constexpr int C1A = CHI ? 2 : 1;  // amplitudes with control bit set: C1A, 3
+  constexpr int T1A = CHI ? 1 : 2;  // amplitudes with target bit set:  T1A, 3
+  constexpr int ROT_S = (ENT == AQC_ENT_CX) ? ROT_X : ROT_Z;
+  const double2 t0 = tr[0], t1 = tr[1], t2 = tr[2], t3 = tr[3];
+  if (!DAG) {
+    if (flags & F_PRE) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_mi(a[v][C1A]), mul_mi(a[v][3]);
+    }
+    if (ENT == AQC_ENT_CX) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        const cd t = a[v][C1A];
+        a[v][C1A] = a[v][3];
+        a[v][3] = t;
+      }
+    } else if (ENT == AQC_ENT_CZ) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) a[v][3].x = -a[v][3].x, a[v][3].y = -a[v][3].y;
+    } else {
+      const double2 t4 = tr[4];  // (cos phi, sin phi)
+      if (NVEC == 2) cdot_add(acc + 8, a[0][3], a[NVEC - 1][3]);  // factor -i, :972-975
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_cs(a[v][3], t4.x, t4.y);
+    }
+    rot1q<NVEC, CHI, ROT_Y>(a, t0.x, t0.y, acc + 0);
+    rot1q<NVEC, CHI, ROT_Z>(a, t1.x, t1.y, acc + 2);
+    rot1q<NVEC, !CHI, ROT_Y>(a, t2.x, t2.y, acc + 4);
+    rot1q<NVEC, !CHI, ROT_S>(a, t3.x, t3.y, acc + 6);
+    if (flags & F_POST) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_pi(a[v][T1A]), mul_pi(a[v][3]);
+    }
+  } else {
+    if (flags & F_POST) {  // Rz_t(-pi/2) first (:793-794)
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_mi(a[v][T1A]), mul_mi(a[v][3]);
+    }
+    rot1q<NVEC, !CHI, ROT_S>(a, t3.x, -t3.y, acc);
+    rot1q<NVEC, !CHI, ROT_Y>(a, t2.x, -t2.y, acc);
+    rot1q<NVEC, CHI, ROT_Z>(a, t1.x, -t1.y, acc);
+    rot1q<NVEC, CHI, ROT_Y>(a, t0.x, -t0.y, acc);
+    if (ENT == AQC_ENT_CX) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        const cd t = a[v][C1A];
+        a[v][C1A] = a[v][3];
+        a[v][3] = t;
+      }
+    } else if (ENT == AQC_ENT_CZ) {
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) a[v][3].x = -a[v][3].x, a[v][3].y = -a[v][3].y;
+    } else {
+      const double2 t4 = tr[4];
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_cs(a[v][3], t4.x, -t4.y);
+    }
+    if (flags & F_PRE) {  // Rz_c(+pi/2) last (:808-809)
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) mul_pi(a[v][C1A]), mul_pi(a[v][3]);
+    }
+  }
+}
+
+// Sum 8 per-lane doubles over the warp with 7 + 2 shuffles: after the three halving steps lane L
+// holds entry ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1) summed over lane bits 4,3,2.
+__device__ __forceinline__ double warp_reduce8(const double* v, int lane, int& which) {
+  double a[4], b[2], c;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double send = up ? v[i] : v[i + 4];
+      const double keep = up ? v[i + 4] : v[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = up ? a[i] : a[i + 2];
+      const double keep = up ? a[i + 2] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const double send = up ? b[0] : b[1];
+    const double keep = up ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  which = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  return c;
+}
+
+struct PassArgs {
+  const double2* src[2];  // [0] = w (NVEC == 2) or the single vector; [1] = z
+  double2* dst[2];
+  long long vec_stride;   // amplitudes between consecutive batch elements
+  long long basis_index;  // >= 0: src[0] is the basis state |basis_index> (no load)
+  const StageDesc* stages;
+  const double2* trig;  // [batch][T]
+  double* gacc;         // [batch][T] complex raw inner products
+  int nthetas;
+  PassDesc pd;
+};
+
+template <int NVEC, int ENT, bool DAG>
+__global__ void __launch_bounds__(kThreads, (NVEC == 2 ? 3 : 4)) pass_kernel(const PassArgs A) {
+  extern __shared__ double2 smem[];
+  __shared__ long long s_hioff[32];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int tb = A.pd.tb;
+  const int tsize = 1 << tb;
+
+  long long base = 0;
+  {
+    const unsigned long long tile = blockIdx.x;
+    for (int k = 0; k < A.pd.nouter; ++k)
+      base |= (long long)((tile >> k) & 1ull) << A.pd.outerpos[k];
+  }
+  // offsets: local index l = tid + 128*j  ->  global offset lo_off(tid) | hi_off(j)
+  long long lo_off = 0;
+  for (int k = 0; k < 7 && k < tb; ++k) lo_off |= (long long)((tid >> k) & 1) << A.pd.bitpos[k];
+  if (tid < 32) {
+    long long h = 0;
+    for (int k = 7; k < tb; ++k) h |= (long long)((tid >> (k - 7)) & 1) << A.pd.bitpos[k];
+    s_hioff[tid] = h;
+  }
+  __syncthreads();
+  const long long boff = (long long)blockIdx.y * A.vec_stride + base;
+
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) {
+    double2* sm = smem + (size_t)v * tsize;
+    if (v == 0 && A.basis_index >= 0) {
+      for (int l = tid; l < tsize; l += kThreads) {
+        const long long g = base | lo_off | s_hioff[l >> 7];
+        sm[l] = make_double2(g == A.basis_index ? 1.0 : 0.0, 0.0);
+      }
+    } else {
+      const double2* __restrict__ src = A.src[v] + boff;
+      for (int l = tid; l < tsize; l += kThreads) sm[l] = src[lo_off | s_hioff[l >> 7]];
+    }
+  }
+  __syncthreads();
+
+  const double2* __restrict__ trig = A.trig + (size_t)blockIdx.y * A.nthetas;
+  double* gacc = A.gacc + (size_t)blockIdx.y * A.nthetas * 2;
+  constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;  // doubles per unit (padded to 8/16)
+  const int nquads = tsize >> 2;
+
+  for (int s = 0; s < A.pd.nstages; ++s) {
+    const StageDesc* __restrict__ sd = A.stages + A.pd.stage0 + s;
+    const int p = sd->p, q = sd->q, nunits = sd->nunits;
+    const int mq = (1 << q) - 1, mp = (1 << p) - 1;
+    double acc[kMaxUnits][NACC];
+    if (NVEC == 2) {
+#pragma unroll
+      for (int u = 0; u < kMaxUnits; ++u)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[u][k] = 0.0;
+    }
+    for (int j = tid; j < nquads; j += kThreads) {
+      int i0 = ((j & ~mq) << 1) | (j & mq);
+      i0 = ((i0 & ~mp) << 1) | (i0 & mp);
+      const int i1 = i0 | (1 << q), i2 = i0 | (1 << p), i3 = i1 | (1 << p);
+      cd a[NVEC][4];
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        const double2* sm = smem + (size_t)v * tsize;
+        const double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+        a[v][0].x = x0.x, a[v][0].y = x0.y;
+        a[v][1].x = x1.x, a[v][1].y = x1.y;
+        a[v][2].x = x2.x, a[v][2].y = x2.y;
+        a[v][3].x = x3.x, a[v][3].y = x3.y;
+      }
+#pragma unroll
+      for (int u = 0; u < kMaxUnits; ++u) {
+        if (u < nunits) {
+          const int kind = sd->u[u].kind, flags = sd->u[u].flags;
+          const double2* tr = trig + sd->u[u].theta;
+          double* ac = (NVEC == 2) ? acc[u] : nullptr;
+          switch (kind) {
+            case U_FRONT_LO: front_unit<NVEC, false, DAG>(a, tr, ac); break;
+            case U_FRONT_HI: front_unit<NVEC, true, DAG>(a, tr, ac); break;
+            case U_BLOCK_CHI: block_unit<NVEC, ENT, true, DAG>(a, tr, flags, ac); break;
+            case U_BLOCK_CLO: block_unit<NVEC, ENT, false, DAG>(a, tr, flags, ac); break;
+            default: break;
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        double2* sm = smem + (size_t)v * tsize;
+        sm[i0] = make_double2(a[v][0].x, a[v][0].y);
+        sm[i1] = make_double2(a[v][1].x, a[v][1].y);
+        sm[i2] = make_double2(a[v][2].x, a[v][2].y);
+        sm[i3] = make_double2(a[v][3].x, a[v][3].y);
+      }
+    }
+    if (NVEC == 2) {
+#pragma unroll
+      for (int u = 0; u < kMaxUnits; ++u) {
+        if (u < nunits) {
+          const int kind = sd->u[u].kind;
+          const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI)
+                               ? 6
+                               : (ENT == AQC_ENT_CP ? 10 : 8);
+          double* g = gacc + 2 * (size_t)sd->u[u].theta;
+#pragma unroll
+          for (int h = 0; h < NACC / 8; ++h) {
+            int which;
+            const double r = warp_reduce8(acc[u] + 8 * h, lane, which);
+            which += 8 * h;
+            if ((lane & 3) == 0 && which < nval) atomicAdd(g + which, r);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) {
+    const double2* sm = smem + (size_t)v * tsize;
+    double2* __restrict__ dst = A.dst[v] + boff;
+    for (int l = tid; l < tsize; l += kThreads) dst[lo_off | s_hioff[l >> 7]] = sm[l];
+  }
+}
+
+// (cos, sin) table: half angles for rotations, full angle for the CPhase parameter.
+__global__ void trig_kernel(const double* __restrict__ thetas, double2* __restrict__ trig,
+                            long long total, int nthetas, int n3, int tpb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % nthetas);
+  const bool full = (tpb == 5) && k >= n3 && ((k - n3) % 5 == 4);
+  double s, c;
+  sincos(full ? thetas[i] : 0.5 * thetas[i], &s, &c);
+  trig[i] = make_double2(c, s);
+}
+
+__global__ void set_basis_kernel(double2* __restrict__ v, long long size, long long stride,
+                                 long long index) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= size) return;
+  v[(long long)blockIdx.y * stride + i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
+}
+
+__global__ void set_identity_kernel(double2* __restrict__ v, long long size, long long stride,
+                                    int log2_cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= size) return;
+  const long long row = i >> log2_cols, col = i & ((1ll << log2_cols) - 1);
+  v[(long long)blockIdx.y * stride + i] = make_double2(row == col ? 1.0 : 0.0, 0.0);
+}
+
+__global__ void gather_kernel(const double2* __restrict__ v, long long stride,
+                              const long long* __restrict__ idx, int count,
+                              double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[(size_t)blockIdx.y * count + i] = v[(long long)blockIdx.y * stride + idx[i]];
+}
+
+// out[b] += <a|b> partial sums (out must be zeroed before launch)
+__global__ void vdot_kernel(const double2* __restrict__ a, const double2* __restrict__ b,
+                            long long size, long long stride, double* __restrict__ out) {
+  const double2* pa = a + (long long)blockIdx.y * stride;
+  const double2* pb = b + (long long)blockIdx.y * stride;
+  double re = 0.0, im = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 x = pa[i], y = pb[i];
+    re = fma(x.x, y.x, re);
+    re = fma(x.y, y.y, re);
+    im = fma(x.x, y.y, im);
+    im = fma(-x.y, y.x, im);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 2 * blockIdx.y, re);
+    atomicAdd(out + 2 * blockIdx.y + 1, im);
+  }
+}
+
+// splitmix64-based counter RNG -> U[0,1)
+__device__ __forceinline__ double u01(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+__global__ void fill_random_kernel(double2* __restrict__ v, long long size, long long stride,
+                                   unsigned long long seed, double* __restrict__ norm2) {
+  double acc = 0.0;
+  double2* p = v + (long long)blockIdx.y * stride;
+  const unsigned long long s = seed + 0x632BE59BD9B4E019ull * blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double re = u01(s, 2ull * i), im = u01(s, 2ull * i + 1);
+    p[i] = make_double2(re, im);
+    acc = fma(re, re, acc);
+    acc = fma(im, im, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(norm2 + blockIdx.y, acc);
+}
+__global__ void scale_kernel(double2* __restrict__ v, long long size, long long stride,
+                             const double* __restrict__ norm2) {
+  double2* p = v + (long long)blockIdx.y * stride;
+  const double f = rsqrt(norm2[blockIdx.y]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size;
+       i += (long long)gridDim.x * blockDim.x) {
+    double2 x = p[i];
+    x.x *= f;
+    x.y *= f;
+    p[i] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+struct aqc_sv {
+  aqc_circuit circ;
+  int device = 0;
+  int log2_cols = 0;
+  int nbits = 0;
+  int batch = 1;
+  int nslots = 0;
+  long long size = 0;  // amplitudes per state
+  std::vector<double2*> slots;
+  double* d_thetas = nullptr;
+  double2* d_trig = nullptr;
+  double* d_gacc = nullptr;
+  double* d_scratch = nullptr;     // small outputs (gather / vdot)
+  long long* d_idx = nullptr;
+  size_t idx_cap = 0, scratch_cap = 0;
+  double* h_pinned = nullptr;  // pinned staging for thetas and small results
+  size_t pinned_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  Program prog_grad, prog_fwd, prog_dag;
+};
+
+static int ensure_pinned(aqc_sv* sv, size_t doubles) {
+  if (doubles <= sv->pinned_cap) return AQC_OK;
+  if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
+  sv->h_pinned = nullptr;
+  sv->pinned_cap = 0;
+  CU(cudaMallocHost(&sv->h_pinned, doubles * sizeof(double)));
+  sv->pinned_cap = doubles;
+  return AQC_OK;
+}
+static int ensure_scratch(aqc_sv* sv, size_t doubles) {
+  if (doubles <= sv->scratch_cap) return AQC_OK;
+  if (sv->d_scratch) cudaFree(sv->d_scratch);
+  sv->d_scratch = nullptr;
+  sv->scratch_cap = 0;
+  CU(cudaMalloc(&sv->d_scratch, doubles * sizeof(double)));
+  sv->scratch_cap = doubles;
+  return AQC_OK;
+}
+static int ensure_idx(aqc_sv* sv, size_t count) {
+  if (count <= sv->idx_cap) return AQC_OK;
+  if (sv->d_idx) cudaFree(sv->d_idx);
+  sv->d_idx = nullptr;
+  sv->idx_cap = 0;
+  CU(cudaMalloc(&sv->d_idx, count * sizeof(long long)));
+  sv->idx_cap = count;
+  return AQC_OK;
+}
+
+template <int NVEC, int ENT, bool DAG>
+static int launch_pass_t(aqc_sv* sv, const PassArgs& args) {
+  const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
+  static bool configured[8] = {false};  // per device
+  if (!configured[sv->device & 7]) {
+    CU(cudaFuncSetAttribute(pass_kernel<NVEC, ENT, DAG>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)NVEC * sizeof(double2) << kMaxTileBits)));
+    configured[sv->device & 7] = true;
+  }
+  dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
+  pass_kernel<NVEC, ENT, DAG><<<grid, kThreads, smem, sv->stream>>>(args);
+  CU(cudaGetLastError());
+  return AQC_OK;
+}
+
+template <int NVEC, bool DAG>
+static int launch_pass_e(aqc_sv* sv, const PassArgs& args) {
+  switch (sv->circ.ent) {
+    case AQC_ENT_CX: return launch_pass_t<NVEC, AQC_ENT_CX, DAG>(sv, args);
+    case AQC_ENT_CZ: return launch_pass_t<NVEC, AQC_ENT_CZ, DAG>(sv, args);
+    default: return launch_pass_t<NVEC, AQC_ENT_CP, DAG>(sv, args);
+  }
+}
+
+// NOTE: callers size the pinned staging buffer (ensure_pinned) BEFORE calling this, so that it
+// is never re-allocated while the asynchronous copy below is in flight.
+static int upload_thetas(aqc_sv* sv, const double* thetas) {
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  if (sv->pinned_cap < tot) return fail(AQC_EINVAL, "internal: pinned buffer too small");
+  memcpy(sv->h_pinned, thetas, tot * sizeof(double));
+  CU(cudaMemcpyAsync(sv->d_thetas, sv->h_pinned, tot * sizeof(double), cudaMemcpyHostToDevice,
+                     sv->stream));
+  const int thr = 128;
+  trig_kernel<<<(unsigned)((tot + thr - 1) / thr), thr, 0, sv->stream>>>(
+      sv->d_thetas, sv->d_trig, (long long)tot, sv->circ.nthetas, 3 * sv->circ.n, sv->circ.tpb);
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+static int check_slot(const aqc_sv* sv, int slot) {
+  if (!sv) return fail(AQC_EINVAL, "null workspace");
+  if (slot < 0 || slot >= sv->nslots) return fail(AQC_EINVAL, "slot %d out of range", slot);
+  return AQC_OK;
+}
+
+// runs one compiled program; NVEC == 1: src0 -> dst0; NVEC == 2: (w, z)
+static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, const double2* src0,
+                       long long basis, const double2* src1, double2* dst0, double2* dst1) {
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.vec_stride = sv->size;
+  a.stages = prog.d_stages;
+  a.trig = sv->d_trig;
+  a.gacc = sv->d_gacc;
+  a.nthetas = sv->circ.nthetas;
+  for (size_t i = 0; i < prog.passes.size(); ++i) {
+    a.pd = prog.passes[i];
+    a.src[0] = (i == 0) ? src0 : dst0;
+    a.src[1] = (i == 0) ? src1 : dst1;
+    a.dst[0] = dst0;
+    a.dst[1] = dst1;
+    a.basis_index = (i == 0) ? basis : -1;
+    int rc;
+    if (grad)
+      rc = launch_pass_e<2, false>(sv, a);
+    else if (dag)
+      rc = launch_pass_e<1, true>(sv, a);
+    else
+      rc = launch_pass_e<1, false>(sv, a);
+    if (rc) return rc;
+    sv->last_launches += 1;
+  }
+  return AQC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int aqc_circuit_create(int num_qubits, int entangler, const int32_t* blocks,
+                                  int num_blocks, int trotter, aqc_circuit** out) {
+  if (!out) return fail(AQC_EINVAL, "out is null");
+  *out = nullptr;
+  if (num_qubits < 2 || num_qubits > 40) return fail(AQC_EINVAL, "num_qubits must be in [2, 40]");
+  if (entangler < 0 || entangler > 2) return fail(AQC_EINVAL, "unknown entangler %d", entangler);
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks)) return fail(AQC_EINVAL, "bad blocks");
+  if (trotter < 0 || trotter > 2) return fail(AQC_EINVAL, "bad trotter flag");
+  if (trotter != AQC_GENERIC && entangler != AQC_ENT_CX)
+    return fail(AQC_EINVAL, "Trotter ansatz requires the cx entangler");
+  aqc_circuit* c = new aqc_circuit();
+  c->n = num_qubits;
+  c->ent = entangler;
+  c->trotter = trotter;
+  c->nb = num_blocks;
+  c->tpb = entangler == AQC_ENT_CP ? 5 : 4;
+  c->nthetas = 3 * num_qubits + c->tpb * num_blocks;
+  c->ctrl.assign(blocks, blocks + num_blocks);
+  c->targ.assign(blocks + num_blocks, blocks + 2 * num_blocks);
+  for (int i = 0; i < num_blocks; ++i) {
+    const int a = c->ctrl[i], b = c->targ[i];
+    if (a < 0 || a >= num_qubits || b < 0 || b >= num_qubits || a == b) {
+      delete c;
+      return fail(AQC_EINVAL, "not a valid structure of unit-blocks (block %d)", i);
+    }
+  }
+  if (trotter != AQC_GENERIC) {
+    // parametric_circuit.py:391-423: layers of triplets on adjacent qubits, middle one flipped
+    bool ok = num_blocks % (3 * (num_qubits - 1)) == 0;
+    for (int t = 0; ok && t < num_blocks / 3; ++t) {
+      const int i = 3 * t;
+      ok = c->ctrl[i] == c->ctrl[i + 2] && c->targ[i] == c->targ[i + 2] &&
+           c->ctrl[i] == c->targ[i + 1] && c->targ[i] == c->ctrl[i + 1] &&
+           c->ctrl[i] == c->targ[i] + 1;
+    }
+    if (ok && trotter == AQC_TROTTER_2ND && num_blocks > 0)
+      for (int i = 0; ok && i < num_qubits / 2; ++i)
+        ok = c->ctrl[3 * i + 1] == 2 * i && c->targ[3 * i + 1] == 2 * i + 1;
+    if (!ok) {
+      delete c;
+      return fail(AQC_EINVAL, "not a valid Trotterized block layout");
+    }
+    c->half = (trotter == AQC_TROTTER_2ND && num_blocks > 0) ? 3 * (num_qubits / 2) : 0;
+  }
+  *out = c;
+  return AQC_OK;
+}
+
+extern "C" void aqc_circuit_destroy(aqc_circuit* c) { delete c; }
+extern "C" int aqc_circuit_num_thetas(const aqc_circuit* c) { return c ? c->nthetas : AQC_EINVAL; }
+
+static int upload_program(Program& p) {
+  if (p.stages.empty()) return AQC_OK;
+  CU(cudaMalloc(&p.d_stages, p.stages.size() * sizeof(StageDesc)));
+  CU(cudaMemcpy(p.d_stages, p.stages.data(), p.stages.size() * sizeof(StageDesc),
+                cudaMemcpyHostToDevice));
+  return AQC_OK;
+}
+
+extern "C" void aqc_sv_destroy(aqc_sv* sv) {
+  if (!sv) return;
+  cudaSetDevice(sv->device);
+  for (auto p : sv->slots)
+    if (p) cudaFree(p);
+  if (sv->d_thetas) cudaFree(sv->d_thetas);
+  if (sv->d_trig) cudaFree(sv->d_trig);
+  if (sv->d_gacc) cudaFree(sv->d_gacc);
+  if (sv->d_scratch) cudaFree(sv->d_scratch);
+  if (sv->d_idx) cudaFree(sv->d_idx);
+  if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
+  for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
+    if (p->d_stages) cudaFree(p->d_stages);
+  if (sv->ev0) cudaEventDestroy(sv->ev0);
+  if (sv->ev1) cudaEventDestroy(sv->ev1);
+  if (sv->stream) cudaStreamDestroy(sv->stream);
+  delete sv;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols, int batch,
+                             int num_slots, aqc_sv** out) {
+  if (!out) return fail(AQC_EINVAL, "out is null");
+  *out = nullptr;
+  if (!circ) return fail(AQC_EINVAL, "circuit is null");
+  if (log2_cols < 0 || log2_cols > circ->n)
+    return fail(AQC_EINVAL, "log2_cols must be in [0, num_qubits]");
+  if (batch < 1 || batch > 65535) return fail(AQC_EINVAL, "batch must be in [1, 65535]");
+  if (num_slots < 1 || num_slots > 64) return fail(AQC_EINVAL, "num_slots must be in [1, 64]");
+  const int ndev = aqc_device_count();
+  if (ndev <= 0) return fail(AQC_ENODEV, "no CUDA device visible: this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(AQC_EINVAL, "device %d out of range", device);
+  if (circ->n + log2_cols > 34) return fail(AQC_EINVAL, "state too large for one GPU");
+  CU(cudaSetDevice(device));
+  aqc_sv* sv = new aqc_sv();
+  sv->circ = *circ;
+  sv->device = device;
+  sv->log2_cols = log2_cols;
+  sv->nbits = circ->n + log2_cols;
+  sv->batch = batch;
+  sv->nslots = num_slots;
+  sv->size = 1ll << sv->nbits;
+  sv->slots.assign(num_slots, nullptr);
+  auto bail = [&](int rc) {
+    std::string keep = g_err;
+    aqc_sv_destroy(sv);
+    g_err = keep;
+    return rc;
+  };
+#define CUB(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      fail(e_ == cudaErrorMemoryAllocation ? AQC_ENOMEM : AQC_ECUDA, "%s failed: %s", #call, \
+           cudaGetErrorString(e_));                                                      \
+      return bail(e_ == cudaErrorMemoryAllocation ? AQC_ENOMEM : AQC_ECUDA);             \
+    }                                                                                    \
+  } while (0)
+  CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
+  CUB(cudaEventCreate(&sv->ev0));
+  CUB(cudaEventCreate(&sv->ev1));
+  const size_t bytes = (size_t)sv->size * batch * sizeof(double2);
+  for (int s = 0; s < num_slots; ++s) CUB(cudaMalloc(&sv->slots[s], bytes));
+  const size_t tot = (size_t)batch * circ->nthetas;
+  CUB(cudaMalloc(&sv->d_thetas, tot * sizeof(double)));
+  CUB(cudaMalloc(&sv->d_trig, tot * sizeof(double2)));
+  CUB(cudaMalloc(&sv->d_gacc, tot * 2 * sizeof(double)));
+#undef CUB
+  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", 11), kMaxTileBits - 1);
+  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", 11), kMaxTileBits);
+  const int low = env_int("AQC_TILE_LOW_BITS", 4);
+  build_program(sv->circ, log2_cols, sv->nbits, tb_grad, low, false, sv->prog_grad);
+  build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, false, sv->prog_fwd);
+  build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, true, sv->prog_dag);
+  for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag}) {
+    int rc = upload_program(*p);
+    if (rc) return bail(rc);
+  }
+  *out = sv;
+  return AQC_OK;
+}
+
+extern "C" int64_t aqc_sv_state_size(const aqc_sv* sv) { return sv ? sv->size : 0; }
+extern "C" float aqc_sv_last_kernel_ms(const aqc_sv* sv) { return sv ? sv->last_ms : 0.f; }
+extern "C" int aqc_sv_last_num_launches(const aqc_sv* sv) { return sv ? sv->last_launches : 0; }
+extern "C" void* aqc_sv_slot_ptr(aqc_sv* sv, int slot) {
+  return (sv && slot >= 0 && slot < sv->nslots) ? (void*)sv->slots[slot] : nullptr;
+}
+extern "C" void* aqc_sv_stream(aqc_sv* sv) { return sv ? (void*)sv->stream : nullptr; }
+extern "C" int aqc_sv_num_passes(const aqc_sv* sv, int mode) {
+  if (!sv) return AQC_EINVAL;
+  const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
+  return (int)p.passes.size();
+}
+
+extern "C" int aqc_sv_upload(aqc_sv* sv, int slot, int batch_index, const double* host,
+                             int64_t count) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!host || count < 0 || count > sv->size) return fail(AQC_EINVAL, "bad host buffer/count");
+  if (batch_index < -1 || batch_index >= sv->batch) return fail(AQC_EINVAL, "bad batch index");
+  CU(cudaSetDevice(sv->device));
+  const int b0 = batch_index < 0 ? 0 : batch_index, b1 = batch_index < 0 ? sv->batch : b0 + 1;
+  for (int b = b0; b < b1; ++b)
+    CU(cudaMemcpyAsync(sv->slots[slot] + (size_t)b * sv->size, host, (size_t)count * 16,
+                       cudaMemcpyHostToDevice, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_download(aqc_sv* sv, int slot, int batch_index, double* host,
+                               int64_t count) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!host || count < 0 || count > sv->size) return fail(AQC_EINVAL, "bad host buffer/count");
+  if (batch_index < 0 || batch_index >= sv->batch) return fail(AQC_EINVAL, "bad batch index");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaMemcpyAsync(host, sv->slots[slot] + (size_t)batch_index * sv->size, (size_t)count * 16,
+                     cudaMemcpyDeviceToHost, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+static dim3 grid1d(long long size, int batch, int thr) {
+  return dim3((unsigned)((size + thr - 1) / thr), (unsigned)batch);
+}
+
+extern "C" int aqc_sv_set_basis(aqc_sv* sv, int slot, int64_t index) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (index < 0 || index >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
+  CU(cudaSetDevice(sv->device));
+  set_basis_kernel<<<grid1d(sv->size, sv->batch, 256), 256, 0, sv->stream>>>(
+      sv->slots[slot], sv->size, sv->size, index);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_set_identity(aqc_sv* sv, int slot) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (sv->log2_cols != sv->circ.n) return fail(AQC_EINVAL, "identity needs log2_cols == n");
+  CU(cudaSetDevice(sv->device));
+  set_identity_kernel<<<grid1d(sv->size, sv->batch, 256), 256, 0, sv->stream>>>(
+      sv->slots[slot], sv->size, sv->size, sv->log2_cols);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_fill_random(aqc_sv* sv, int slot, uint64_t seed) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  CU(cudaSetDevice(sv->device));
+  rc = ensure_scratch(sv, (size_t)sv->batch);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(sv->d_scratch, 0, sv->batch * sizeof(double), sv->stream));
+  const unsigned gx = (unsigned)std::min<long long>((sv->size + 255) / 256, 148 * 16);
+  fill_random_kernel<<<dim3(gx, sv->batch), 256, 0, sv->stream>>>(sv->slots[slot], sv->size,
+                                                                   sv->size, seed, sv->d_scratch);
+  scale_kernel<<<dim3(gx, sv->batch), 256, 0, sv->stream>>>(sv->slots[slot], sv->size, sv->size,
+                                                             sv->d_scratch);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+static int gather_async(aqc_sv* sv, int slot, const int64_t* idx, int count) {
+  int rc = ensure_idx(sv, (size_t)count);
+  if (rc) return rc;
+  rc = ensure_scratch(sv, (size_t)2 * count * sv->batch);
+  if (rc) return rc;
+  for (int i = 0; i < count; ++i)
+    if (idx[i] < 0 || idx[i] >= sv->size) return fail(AQC_EINVAL, "gather index out of range");
+  CU(cudaMemcpyAsync(sv->d_idx, idx, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice,
+                     sv->stream));
+  gather_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
+      sv->slots[slot], sv->size, sv->d_idx, count, (double2*)sv->d_scratch);
+  CU(cudaGetLastError());
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_gather(aqc_sv* sv, int slot, const int64_t* idx, int count, double* out) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!idx || !out || count <= 0) return fail(AQC_EINVAL, "bad gather arguments");
+  CU(cudaSetDevice(sv->device));
+  rc = gather_async(sv, slot, idx, count);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, sv->d_scratch, (size_t)2 * count * sv->batch * sizeof(double),
+                     cudaMemcpyDeviceToHost, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_vdot(aqc_sv* sv, int slot_a, int slot_b, double* out) {
+  int rc = check_slot(sv, slot_a);
+  if (rc) return rc;
+  rc = check_slot(sv, slot_b);
+  if (rc) return rc;
+  if (!out) return fail(AQC_EINVAL, "out is null");
+  CU(cudaSetDevice(sv->device));
+  rc = ensure_scratch(sv, (size_t)2 * sv->batch);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(sv->d_scratch, 0, 2 * sv->batch * sizeof(double), sv->stream));
+  const unsigned gx = (unsigned)std::min<long long>((sv->size + 255) / 256, 148 * 8);
+  vdot_kernel<<<dim3(gx, sv->batch), 256, 0, sv->stream>>>(sv->slots[slot_a], sv->slots[slot_b],
+                                                            sv->size, sv->size, sv->d_scratch);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, sv->d_scratch, 2 * sv->batch * sizeof(double), cudaMemcpyDeviceToHost,
+                     sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+static int apply_async(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int dst_slot) {
+  int rc = ensure_pinned(sv, (size_t)sv->batch * sv->circ.nthetas * 2 + 64);
+  if (rc) return rc;
+  rc = upload_thetas(sv, thetas);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  const Program& prog = dagger ? sv->prog_dag : sv->prog_fwd;
+  rc = run_program(sv, prog, false, dagger != 0, sv->slots[src_slot], -1, nullptr,
+                   sv->slots[dst_slot], nullptr);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_apply(aqc_sv* sv, const double* thetas, int dagger, int src_slot,
+                            int dst_slot) {
+  int rc = check_slot(sv, src_slot);
+  if (rc) return rc;
+  rc = check_slot(sv, dst_slot);
+  if (rc) return rc;
+  if (!thetas) return fail(AQC_EINVAL, "thetas is null");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  rc = apply_async(sv, thetas, dagger, src_slot, dst_slot);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
+                                const int64_t* idx, int count, double* hs_out) {
+  int rc = check_slot(sv, target_slot);
+  if (rc) return rc;
+  rc = check_slot(sv, z0_slot);
+  if (rc) return rc;
+  if (!thetas || !idx || !hs_out || count <= 0) return fail(AQC_EINVAL, "bad arguments");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const size_t nout = (size_t)2 * count * sv->batch;
+  rc = ensure_pinned(sv, nout + (size_t)sv->batch * sv->circ.nthetas * 2 + 64);
+  if (rc) return rc;
+  rc = apply_async(sv, thetas, 1, target_slot, z0_slot);
+  if (rc) return rc;
+  rc = gather_async(sv, z0_slot, idx, count);
+  if (rc) return rc;
+  sv->last_launches += 1;
+  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_scratch, nout * sizeof(double), cudaMemcpyDeviceToHost,
+                     sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  memcpy(hs_out, sv->h_pinned, nout * sizeof(double));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis,
+                           int z0_slot, int w_slot, int z_slot, double* grad_out) {
+  int rc = check_slot(sv, z0_slot);
+  if (rc) return rc;
+  rc = check_slot(sv, w_slot);
+  if (rc) return rc;
+  rc = check_slot(sv, z_slot);
+  if (rc) return rc;
+  if (x_slot >= 0) {
+    rc = check_slot(sv, x_slot);
+    if (rc) return rc;
+  } else if (x_basis < 0 || x_basis >= sv->size) {
+    return fail(AQC_EINVAL, "basis index out of range");
+  }
+  if (w_slot == z_slot || w_slot == z0_slot || (x_slot >= 0 && x_slot == z_slot))
+    return fail(AQC_EINVAL, "slot aliasing: w must differ from z/z0 and x from z");
+  if (!thetas || !grad_out) return fail(AQC_EINVAL, "null pointer argument");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  rc = ensure_pinned(sv, tot * 2 + 64);
+  if (rc) return rc;
+  rc = upload_thetas(sv, thetas);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  rc = run_program(sv, sv->prog_grad, true, false, x_slot >= 0 ? sv->slots[x_slot] : nullptr,
+                   x_slot >= 0 ? -1 : x_basis, sv->slots[z0_slot], sv->slots[w_slot],
+                   sv->slots[z_slot]);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                     sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  // raw sums -> 0.5j <P w|z>: Ry 0.5, Rz/Rx 0.5j, CPhase -i
+  const int n3 = 3 * sv->circ.n, tpb = sv->circ.tpb, T = sv->circ.nthetas;
+  const bool cx = sv->circ.ent == AQC_ENT_CX;
+  (void)cx;
+  for (int b = 0; b < sv->batch; ++b) {
+    const double* raw = sv->h_pinned + (size_t)b * T * 2;
+    double* g = grad_out + (size_t)b * T * 2;
+    for (int k = 0; k < T; ++k) {
+      const double re = raw[2 * k], im = raw[2 * k + 1];
+      int kind;  // 0: Ry (0.5), 1: Rz/Rx (0.5j), 2: cphase (-i)
+      if (k < n3)
+        kind = (k % 3 == 1) ? 0 : 1;
+      else {
+        const int r = (k - n3) % tpb;
+        kind = (r == 4) ? 2 : ((r == 0 || r == 2) ? 0 : 1);
+      }
+      if (kind == 0) {
+        g[2 * k] = 0.5 * re;
+        g[2 * k + 1] = 0.5 * im;
+      } else if (kind == 1) {
+        g[2 * k] = -0.5 * im;
+        g[2 * k + 1] = 0.5 * re;
+      } else {
+        g[2 * k] = im;
+        g[2 * k + 1] = -re;
+      }
+    }
+  }
+  return AQC_OK;
+}
+
+
+// Host-only scheduler introspection (no device needed): serialises the compiled program as
+// int32 words so that the CPU test-suite can replay it gate by gate against the oracle.
+// Layout: npasses, then per pass {tb, nstages, nouter, bitpos[16], outerpos[48],
+// per stage {p, q, nunits, (kind, flags, theta) x 3}}.
+extern "C" int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int tile_bits,
+                                 int low_bits, int reversed, int32_t* out, int64_t cap,
+                                 int64_t* needed) {
+  if (!circ || !needed) return fail(AQC_EINVAL, "null argument");
+  if (tile_bits < 2 || tile_bits > kMaxTileBits) return fail(AQC_EINVAL, "bad tile_bits");
+  Program p;
+  build_program(*circ, log2_cols, circ->n + log2_cols, tile_bits, low_bits, reversed != 0, p);
+  std::vector<int32_t> w;
+  w.push_back((int32_t)p.passes.size());
+  for (const PassDesc& pd : p.passes) {
+    w.push_back(pd.tb);
+    w.push_back(pd.nstages);
+    w.push_back(pd.nouter);
+    for (int k = 0; k < 16; ++k) w.push_back(pd.bitpos[k]);
+    for (int k = 0; k < 48; ++k) w.push_back(pd.outerpos[k]);
+    for (int s = 0; s < pd.nstages; ++s) {
+      const StageDesc& sd = p.stages[pd.stage0 + s];
+      w.push_back(sd.p);
+      w.push_back(sd.q);
+      w.push_back(sd.nunits);
+      for (int u = 0; u < kMaxUnits; ++u) {
+        w.push_back(sd.u[u].kind);
+        w.push_back(sd.u[u].flags);
+        w.push_back(sd.u[u].theta);
+      }
+    }
+  }
+  *needed = (int64_t)w.size();
+  if (out && cap >= (int64_t)w.size()) memcpy(out, w.data(), w.size() * sizeof(int32_t));
+  return AQC_OK;
+}

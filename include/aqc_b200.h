@@ -1,0 +1,149 @@
+/*
+ * aqc_b200.h -- C-ABI of the B200-native objective-and-gradient engine.
+ *
+ * The reference (qiskit-community/aqc-research) is pure Python and has no FFI of
+ * its own; its hot path is entered through duck-typed Python calls
+ *     objv.objective(thetas) / objv.gradient(thetas)       (optimizer.py:561-590)
+ * which bottom out in the NumPy kernels of core_operations.py, core_op_matrix.py
+ * and mps_operations.py / mps_dot_objective.py.  Every entry point below names the
+ * reference function (file:line, relative to the reference root) it replaces.  A
+ * ctypes binding that a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - all functions return 0 on success, a negative AQC_E* code otherwise;
+ *    aqc_last_error() gives a thread-local human-readable message;
+ *  - handles are opaque; host pointers are borrowed for the duration of the call;
+ *  - complex numbers are interleaved (re, im) float64 pairs, i.e. numpy complex128;
+ *  - qubit q <-> bit q (LSB = qubit 0) of the flat amplitude index
+ *    (core_operations.py:34-43,77);
+ *  - all calls are synchronous: outputs are valid on return;
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef AQC_B200_H
+#define AQC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQC_OK 0
+#define AQC_EINVAL (-1)  /* bad argument */
+#define AQC_ECUDA (-2)   /* CUDA runtime error */
+#define AQC_ENODEV (-3)  /* no CUDA device */
+#define AQC_ENOMEM (-4)  /* allocation failed */
+
+#define AQC_ENT_CX 0
+#define AQC_ENT_CZ 1
+#define AQC_ENT_CP 2
+
+#define AQC_GENERIC 0        /* ParametricCircuit                       */
+#define AQC_TROTTER_1ST 1    /* TrotterAnsatz(second_order=False)       */
+#define AQC_TROTTER_2ND 2    /* TrotterAnsatz(second_order=True)        */
+
+typedef struct aqc_circuit aqc_circuit;
+typedef struct aqc_sv aqc_sv;
+typedef struct aqc_mps aqc_mps;
+
+const char* aqc_last_error(void);
+int aqc_version(void);
+/* Number of visible CUDA devices (0 if none / no driver). */
+int aqc_device_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Circuit structure (host only, no angles).
+ * Replaces: ParametricCircuit / TrotterAnsatz (parametric_circuit.py:37-70,300-320).
+ * blocks: int32[2*num_blocks], row 0 = control qubits, row 1 = target qubits.
+ * theta layout: [3n front | num_blocks x tpb], tpb = 5 for cp else 4 (:66,108-112).
+ * For AQC_TROTTER_2ND the trailing half-layer of 3*(n/2) blocks re-using the
+ * angles of the first half-layer is implied (core_operations.py:638-641,686-690).
+ */
+int aqc_circuit_create(int num_qubits, int entangler, const int32_t* blocks, int num_blocks,
+                       int trotter, aqc_circuit** out);
+void aqc_circuit_destroy(aqc_circuit* circ);
+int aqc_circuit_num_thetas(const aqc_circuit* circ);
+
+/* ---------------------------------------------------------------------------
+ * State-vector / column-batched workspace on one GPU.
+ *
+ * A workspace owns `num_slots` device arrays ("slots"), each holding `batch`
+ * independent states of 2^(n + log2_cols) complex128 amplitudes.  log2_cols = 0 is
+ * the vector path (core_operations.py); log2_cols = k is the matrix path
+ * (core_op_matrix.py): a row-major (2^n, 2^k) matrix whose gates act on the ROW
+ * index bits (core_op_matrix.py:56), i.e. on bits k..k+n-1 of the flat index.
+ * `batch` independent angle sets (multistart) are evaluated by one launch sequence.
+ */
+int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols, int batch, int num_slots,
+                  aqc_sv** out);
+void aqc_sv_destroy(aqc_sv* sv);
+/* Amplitudes per state = 2^(n + log2_cols). */
+int64_t aqc_sv_state_size(const aqc_sv* sv);
+
+/* Host -> slot.  `count` complex numbers are copied into state `batch_index`
+ * (batch_index = -1: the same host data is replicated into every batch element). */
+int aqc_sv_upload(aqc_sv* sv, int slot, int batch_index, const double* host, int64_t count);
+/* Slot -> host. */
+int aqc_sv_download(aqc_sv* sv, int slot, int batch_index, double* host, int64_t count);
+/* slot[b] = |index>  for all b (ThinStateHandler states, objective_base.py:42-173). */
+int aqc_sv_set_basis(aqc_sv* sv, int slot, int64_t index);
+/* slot[b] = identity matrix (requires log2_cols == n), FullRangeSketchingVectors
+ * (sk_core.py:317-326). */
+int aqc_sv_set_identity(aqc_sv* sv, int slot);
+/* Fills a slot with the distribution of utils.rand_state (utils.py:71-79): re, im ~ U[0,1)
+ * from a counter-based generator keyed on (seed, amplitude index), then normalised. */
+int aqc_sv_fill_random(aqc_sv* sv, int slot, uint64_t seed);
+/* out[b*count + i] = slot[b][idx[i]]   (ThinStateHandler.state_dot_vector,
+ * objective_base.py:164-173: <e_k|v> = v[k]). */
+int aqc_sv_gather(aqc_sv* sv, int slot, const int64_t* idx, int count, double* out);
+/* out[b] = <slot_a[b] | slot_b[b]>  (np.vdot; GenericStateHandler.state_dot_vector,
+ * objective_base.py:313-316; sk_core.py:192). */
+int aqc_sv_vdot(aqc_sv* sv, int slot_a, int slot_b, double* out);
+
+/* dst = V(thetas) src  (dagger = 0; v_mul_vec core_operations.py:606-710,
+ *                       v_mul_mat core_op_matrix.py:480-559)
+ * dst = V(thetas)^H src (dagger = 1; v_dagger_mul_vec core_operations.py:713-820,
+ *                       v_dagger_mul_mat core_op_matrix.py:562-642).
+ * thetas: float64[batch * num_thetas].  src_slot may equal dst_slot. */
+int aqc_sv_apply(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int dst_slot);
+
+/* Full complex gradient of <V x | y> by all thetas, given z0 = V^H y
+ * (grad_of_dot_product core_operations.py:823-1019; grad_of_matrix_dot_product
+ * core_op_matrix.py:645-762).  x is slot `x_slot`, or the basis state |x_basis>
+ * when x_slot < 0.  w_slot / z_slot are scratch slots that receive V x and V z0
+ * (they may equal x_slot / z0_slot, which are then destroyed like in the matrix
+ * version of the reference).  Second-order Trotter half-layer derivatives are
+ * accumulated into the entries of the leading half-layer (core_operations.py:966-994).
+ * grad_out: complex128[batch * num_thetas]. */
+int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
+                int w_slot, int z_slot, double* grad_out);
+
+/* Fused objective step of the state-preparation objectives
+ * (objective_lhs_sur_max.py:98-106): z0_slot = V^H target_slot; hs_out[b*count+i] =
+ * z0_slot[b][idx[i]]. */
+int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
+                     const int64_t* idx, int count, double* hs_out);
+
+/* Device time (ms, CUDA events on the workspace stream) of the kernels launched by the
+ * most recent aqc_sv_apply / aqc_sv_grad / aqc_sv_objective call, and how many
+ * kernels that call launched.  Used by bench.py for the roofline figure. */
+float aqc_sv_last_kernel_ms(const aqc_sv* sv);
+int aqc_sv_last_num_launches(const aqc_sv* sv);
+/* Scheduler introspection: number of tile passes over the state for one gradient
+ * sweep (mode 0), one V apply (1) or one V^H apply (2). */
+int aqc_sv_num_passes(const aqc_sv* sv, int mode);
+/* Host-only (no device needed): serialises the tile-pass program the scheduler compiles for
+ * `circ` as int32 words (layout documented in csrc/aqc_sv.cu); reversed = 1 gives the V^H
+ * program.  *needed receives the word count; data are written iff cap is large enough. */
+int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
+                      int reversed, int32_t* out, int64_t cap, int64_t* needed);
+/* Device-pointer access for zero-copy callers (torch tensors): address of slot. */
+void* aqc_sv_slot_ptr(aqc_sv* sv, int slot);
+/* CUDA stream handle (cudaStream_t) the workspace launches on. */
+void* aqc_sv_stream(aqc_sv* sv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQC_B200_H */

@@ -1,0 +1,170 @@
+"""
+GPU parity tests (state-vector and matrix paths): CUDA engine through the C-ABI vs the CPU
+oracle on identical seeded inputs.  Tolerance: 1e-10 relative, norm-wise (north star).
+"""
+
+import numpy as np
+import pytest
+
+from aqc_research_b200 import circuit_structures as cs
+from aqc_research_b200 import core_op_matrix as cpm
+from aqc_research_b200 import core_operations as cop
+from aqc_research_b200 import utils
+from aqc_research_b200.engine import SvWorkspace
+from aqc_research_b200.parametric_circuit import ParametricCircuit, TrotterAnsatz
+from oracle import sv_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10  # relative, norm-wise
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+def _circuits(n, layers=2, depth=9):
+    yield "t1", TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), False)
+    yield "t2", TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    for ent in ("cx", "cz", "cp"):
+        yield ent, ParametricCircuit(n, ent, utils.rand_circuit(n, depth))
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 10, 12, 13])
+def test_apply_and_grad_vs_oracle(n):
+    np.random.seed(4242 + n)
+    for name, circ in _circuits(n):
+        th = utils.rand_thetas(circ.num_thetas)
+        x, y = utils.rand_state(n), utils.rand_state(n)
+        out = np.zeros_like(y)
+        ws_unused = np.zeros((3, y.size), dtype=np.complex128)
+        v = cop.v_mul_vec(circ, th, y, out, ws_unused).copy()
+        assert _rel(v, O.apply_v(circ, th, y)) < TOL, (name, "V")
+        z0 = cop.v_dagger_mul_vec(circ, th, y, out, ws_unused).copy()
+        assert _rel(z0, O.apply_v(circ, th, y, dagger=True)) < TOL, (name, "VH")
+        g = cop.grad_of_dot_product(circ, th, x, z0, ws_unused)
+        assert _rel(g, O.grad_sweep(circ, th, x, z0)) < TOL, (name, "grad")
+        if circ.num_blocks > 4:
+            br = (2, circ.num_blocks - 1)
+            g = cop.grad_of_dot_product(circ, th, x, z0, ws_unused, block_range=br, front_layer=False)
+            assert _rel(g, O.grad_sweep(circ, th, x, z0, br, False)) < TOL, (name, "partial grad")
+    cop.clear_workspace_cache()
+
+
+def test_round_trip_and_aliasing():
+    """V V^H v = v (test_core_operations.py:252-281), with out aliasing vec."""
+    np.random.seed(5)
+    n = 9
+    for name, circ in _circuits(n, layers=3):
+        th = utils.rand_thetas(circ.num_thetas)
+        v = utils.rand_state(n)
+        buf = v.copy()
+        cop.v_dagger_mul_vec(circ, th, buf, buf)
+        cop.v_mul_vec(circ, th, buf, buf)
+        assert _rel(buf, v) < TOL, name
+    cop.clear_workspace_cache()
+
+
+@pytest.mark.parametrize("n,m", [(2, 2), (3, 5), (4, 16), (5, 7), (7, 128)])
+def test_matrix_path_vs_oracle(n, m):
+    np.random.seed(99 + n + m)
+    for ent in ("cx", "cz", "cp"):
+        circ = ParametricCircuit(n, ent, utils.rand_circuit(n, 12))
+        th = utils.rand_thetas(circ.num_thetas)
+        X = np.random.rand(2**n, m) + 1j * np.random.rand(2**n, m)
+        Y = np.random.rand(2**n, m) + 1j * np.random.rand(2**n, m)
+        a = cpm.v_mul_mat(circ, th, Y.copy())
+        assert _rel(a, O.apply_v(circ, th, Y.ravel(), False, m).reshape(Y.shape)) < TOL
+        z0 = cpm.v_dagger_mul_mat(circ, th, Y.copy())
+        z0_ref = O.apply_v(circ, th, Y.ravel(), True, m)
+        assert _rel(z0, z0_ref.reshape(Y.shape)) < TOL
+        xw, zw = X.copy(), z0.copy()
+        g = cpm.grad_of_matrix_dot_product(circ, th, xw, zw)
+        assert _rel(g, O.grad_sweep(circ, th, X.ravel(), z0.ravel(), ncols=m)) < TOL
+        assert _rel(zw, Y) < 1e-9  # z ends as V V^H Y = Y
+    cop.clear_workspace_cache()
+
+
+def test_batched_thetas():
+    """batch independent angle sets in one launch sequence == one at a time."""
+    np.random.seed(31)
+    n, batch = 6, 5
+    circ = ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "cyclic_spin", "full", 24))
+    ws = SvWorkspace(circ, num_slots=4, batch=batch)
+    ths = np.stack([utils.rand_thetas(circ.num_thetas) for _ in range(batch)])
+    y, x = utils.rand_state(n), utils.rand_state(n)
+    ws.upload(0, y)
+    ws.upload(3, x)
+    ws.apply(ths, 0, 1, dagger=True)
+    g = ws.grad(ths, x_slot=3, z0=1, w=2, z=0)
+    for b in range(batch):
+        z0 = O.apply_v(circ, ths[b], y, dagger=True)
+        assert _rel(g[b], O.grad_sweep(circ, ths[b], x, z0)) < TOL
+    ws.close()
+
+
+def test_objective_gather_basis_and_vdot():
+    np.random.seed(8)
+    n = 11
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    ws = SvWorkspace(circ, num_slots=4)
+    th = utils.rand_thetas(circ.num_thetas)
+    y = utils.rand_state(n)
+    ws.upload(0, y)
+    idx = O.basis_state_indices(n, init_index=0b10101010101 & (2**n - 1))
+    hs = ws.objective(th, 0, 1, idx)[0]
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    assert _rel(hs, z0[idx]) < TOL
+    g = ws.grad(th, x_basis=int(idx[3]), z0=1, w=2, z=3)[0]
+    e = np.zeros(2**n, dtype=np.complex128)
+    e[idx[3]] = 1
+    assert _rel(g, O.grad_sweep(circ, th, e, z0)) < TOL
+    # slot 1 (z0) must be intact after the sweep that wrote into slots 2, 3
+    assert _rel(ws.download(1), z0) < TOL
+    assert _rel(ws.vdot(0, 3)[0], 1.0) < TOL  # z = V V^H y = y
+    ws.set_basis(2, 5)
+    assert ws.gather(2, [4, 5, 6])[0].tolist() == [0, 1, 0]
+    ws.fill_random(2, 123)
+    r = ws.download(2)
+    assert abs(np.linalg.norm(r) - 1) < 1e-12 and r.real.min() >= 0 and r.imag.min() >= 0
+    ws.close()
+
+
+@pytest.mark.parametrize("n", [16, 20])
+def test_mid_size_vs_oracle(n):
+    """Multi-pass programs with many tiles (sizes the NumPy oracle finishes in seconds)."""
+    np.random.seed(n)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 1), True)
+    th = utils.rand_thetas(circ.num_thetas)
+    y = utils.rand_state(n)
+    ws = SvWorkspace(circ, num_slots=4)
+    ws.upload(0, y)
+    idx = O.basis_state_indices(n)
+    hs = ws.objective(th, 0, 1, idx)[0]
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    assert _rel(hs, z0[idx]) < TOL
+    assert _rel(ws.download(1), z0) < TOL
+    g = ws.grad(th, x_basis=0, z0=1, w=2, z=3)[0]
+    e = np.zeros(2**n, dtype=np.complex128)
+    e[0] = 1
+    assert _rel(g, O.grad_sweep(circ, th, e, z0)) < TOL
+    assert _rel(ws.download(3), y) < 1e-9
+    ws.close()
+
+
+def test_large_properties():
+    """n = 26: size-independent properties (V V^H = I, <w|z> invariance)."""
+    n = 26
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    np.random.seed(26)
+    th = utils.rand_thetas(circ.num_thetas)
+    ws = SvWorkspace(circ, num_slots=4)
+    ws.fill_random(0, 7)
+    idx = O.basis_state_indices(n)
+    hs = ws.objective(th, 0, 1, idx)[0]
+    nrm = ws.vdot(1, 1)[0]
+    assert abs(nrm - 1) < 1e-10  # unitarity
+    ws.grad(th, x_basis=0, z0=1, w=2, z=3)
+    # z = V V^H y = y ; <V e0 | y> = <e0 | V^H y> = hs[0]
+    assert abs(ws.vdot(3, 0)[0] - 1) < 1e-10
+    assert abs(ws.vdot(2, 0)[0] - hs[0]) < 1e-10
+    ws.close()
