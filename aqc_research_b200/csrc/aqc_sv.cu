@@ -754,6 +754,7 @@ struct aqc_sv {
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // user timer (aqc_sv_timer_*)
   float last_ms = 0.f;
   int last_launches = 0;
   Program prog_grad, prog_fwd, prog_dag;
@@ -941,6 +942,8 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
     if (p->d_stages) cudaFree(p->d_stages);
   if (sv->ev0) cudaEventDestroy(sv->ev0);
   if (sv->ev1) cudaEventDestroy(sv->ev1);
+  if (sv->tm0) cudaEventDestroy(sv->tm0);
+  if (sv->tm1) cudaEventDestroy(sv->tm1);
   if (sv->stream) cudaStreamDestroy(sv->stream);
   delete sv;
 }
@@ -991,6 +994,8 @@ extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols,
   CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&sv->ev0));
   CUB(cudaEventCreate(&sv->ev1));
+  CUB(cudaEventCreate(&sv->tm0));
+  CUB(cudaEventCreate(&sv->tm1));
   const size_t bytes = (size_t)sv->size * batch * sizeof(double2);
   for (int s = 0; s < num_slots; ++s) CUB(cudaMalloc(&sv->slots[s], bytes));
   const size_t tot = (size_t)batch * circ->nthetas;
@@ -1301,5 +1306,23 @@ extern "C" int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int til
   }
   *needed = (int64_t)w.size();
   if (out && cap >= (int64_t)w.size()) memcpy(out, w.data(), w.size() * sizeof(int32_t));
+  return AQC_OK;
+}
+
+
+// CUDA-event stopwatch on the workspace stream: brackets any sequence of calls on this
+// workspace (bench.py times one objective + gradient step with it).
+extern "C" int aqc_sv_timer_start(aqc_sv* sv) {
+  if (!sv) return fail(AQC_EINVAL, "null workspace");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaEventRecord(sv->tm0, sv->stream));
+  return AQC_OK;
+}
+extern "C" int aqc_sv_timer_stop(aqc_sv* sv, float* ms) {
+  if (!sv || !ms) return fail(AQC_EINVAL, "null argument");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaEventRecord(sv->tm1, sv->stream));
+  CU(cudaEventSynchronize(sv->tm1));
+  CU(cudaEventElapsedTime(ms, sv->tm0, sv->tm1));
   return AQC_OK;
 }

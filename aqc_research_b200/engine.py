@@ -197,6 +197,15 @@ class SvWorkspace:
     def last_num_launches(self) -> int:
         return int(self._lib.aqc_sv_last_num_launches(self.handle))
 
+    def timer_start(self):
+        _lib.check(self._lib.aqc_sv_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        """Device milliseconds since ``timer_start`` (CUDA events on the workspace stream)."""
+        ms = ct.c_float(0)
+        _lib.check(self._lib.aqc_sv_timer_stop(self.handle, ct.byref(ms)))
+        return float(ms.value)
+
     def num_passes(self, mode: int) -> int:
         return int(self._lib.aqc_sv_num_passes(self.handle, mode))
 

@@ -1,0 +1,96 @@
+"""
+Surrogate state-preparation objective with a max-projection term, GPU edition.
+Reference: aqc_research/model_sp_lhs/objective_lhs_sur_max.py:42-196.
+
+    hs_i   = <state_i | V^H | target>,   i = 0..num_states-1
+    f      = 1 - (1 - w) |hs_0|^2 - w |hs_max|^2            (w = weight, max = leading flip state)
+    grad f = Re(-2 (1-w) conj(hs_0) d<V s_0|t>) + Re(-2 w conj(hs_max) d<V s_max|t>)
+
+The O(num_thetas) scalar logic (hysteresis on ``max_no``, weight smoothing, amplifier, stats,
+stoppers) runs on the host exactly as in the reference; the vector work runs on the GPU.
+"""
+
+from typing import Optional, Tuple
+import numpy as np
+from .. import checking as chk
+from ..core_operations import mask_gradient
+from ..parametric_circuit import ParametricCircuit
+from .objective_base import SpLHSObjectiveBase
+
+
+class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
+    """Drop-in for the reference class of the same name."""
+
+    _gamma = 0.1  # exponential smoothing rate of the weight (:40)
+
+    def __init__(
+        self,
+        *,
+        user_parameters: dict,
+        circ: ParametricCircuit,
+        block_range: Optional[Tuple[int, int]] = None,
+        front_layer: bool = False,
+        verbose: bool = False,
+        grad_scaler=None,
+    ):
+        super().__init__(user_parameters, circ, verbose=verbose)
+        block_range = (0, circ.num_blocks) if block_range is None else block_range
+        assert chk.is_tuple(block_range, len(block_range) == 2)
+        assert 0 <= block_range[0] < block_range[1] <= circ.num_blocks
+        assert chk.is_bool(front_layer)
+        assert grad_scaler is None or hasattr(grad_scaler, "estimate")
+        self._block_range = block_range
+        self._front_layer = front_layer
+        self._fidelity = float(-1)
+        self._grad_scaler = grad_scaler
+        self._hs = np.zeros(self._num_states, dtype=np.complex128)
+        self._max_no = 0
+
+    def objective(self, thetas: np.ndarray) -> float:
+        self._store_latest_thetas(thetas)
+        self._hs[:] = self._hs_products(thetas)
+        np.copyto(self._hs2, np.abs(self._hs) ** 2)
+        # hysteresis: the leader changes only if a state is better by 10% (:110-117)
+        best = self._hs2[self._max_no]
+        for i in range(self._num_states):
+            if 1.1 * best < self._hs2[i]:
+                best = self._hs2[i]
+                self._max_no = i
+        w = self._weight
+        self._fobj = float(1.0 - (1.0 - w) * self._hs2[0] - w * self._hs2[self._max_no])
+        self._fidelity = float(self._hs2[0])
+        self._service.on_end_objective()
+        return self._fobj
+
+    def gradient(self, thetas: np.ndarray) -> np.ndarray:
+        self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)  # may raise: early stop
+        self._calc_objective_before_gradient(thetas)
+        circ = self._circuit
+        front = bool(self._front_layer or self._block_range == (0, circ.num_blocks))
+
+        g0 = mask_gradient(circ, self._raw_gradient(thetas, 0), self._block_range, front)
+        if self._max_no == 0:
+            full = np.real(-2.0 * np.conj(self._hs[0]) * g0)
+        else:
+            w = self._weight
+            full = np.real(-2.0 * (1.0 - w) * np.conj(self._hs[0]) * g0)
+            gm = mask_gradient(circ, self._raw_gradient(thetas, self._max_no), self._block_range, front)
+            full = full + np.real(-2.0 * w * np.conj(self._hs[self._max_no]) * gm)
+        full = np.ascontiguousarray(full, dtype=np.float64)
+        if self._grad_scaler:
+            full *= self._grad_scaler.estimate(self._fobj)
+        self._weight += self._gamma * (float(np.sqrt(abs(self._fobj))) - self._weight)
+        self._service.on_end_gradient(self._fobj, self._fidelity, full, self._hs2, self._weight)
+        return full
+
+    @property
+    def fidelity(self) -> float:
+        return self._fidelity
+
+    @property
+    def max_no(self) -> int:
+        return self._max_no
+
+    @property
+    def weight(self) -> float:
+        return self._weight

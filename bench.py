@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""
+bench.py -- objective + gradient evaluations per second of the state-vector ASP hot path
+(BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sv20|sv24|sv28|sv12]
+                  [--impl b200|reference]
+
+A "step" is one objective(theta) followed by one gradient(theta) at the same theta (one V^H
+sweep + hs gather, then one forward w/z gradient sweep; the leading flip-state is |0>, i.e. the
+single-term gradient of SURVEY.md section 8(d)), on a 2nd-order TrotterAnsatz with a synthetic
+"near" target V(theta*)|0>, theta = theta* + small perturbation.
+
+  value      evals/s with everything resident in HBM, timed with CUDA events on the engine's
+             stream (aqc_sv_timer_*), max over ranks.  N > 1: independent evaluations, one per
+             GPU (multistart / time horizons -- the path shards with no collective), weak scaling.
+  e2e        the same step through the public objective class (host thetas in, f and gradient
+             out), wall clock, copies included.
+  roofline   dominant kernel (gradient tile pass): algorithmic bytes at pair-run granularity
+             (4 * 16 * 2^n * P bytes per sweep) / its measured device time, against
+             the measured HBM peak of MEASURED_PEAKS.json.
+  cpu_baseline  the C/OpenMP oracle port (oracle/sv_oracle.c) on the host cores, rank 0, N = 1.
+  --impl reference  times that CPU port alone (the reference is pure Python and does not travel
+             to the GPU box; BASELINE.md section 2 has its own NumPy timings).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name -> (num_qubits, layers)
+    "sv12": (12, 2),
+    "sv20": (20, 2),
+    "sv24": (24, 4),
+    "sv28": (28, 4),
+    "sv30": (30, 4),
+}
+METRIC = "objective+gradient evals/sec"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path, encoding="utf-8") as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_circuit(n, layers):
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200.parametric_circuit import TrotterAnsatz
+
+    return TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+
+
+def pair_runs(n, layers):
+    return (n - 1) * layers + n // 2  # P for a 2nd-order TrotterAnsatz
+
+
+def gate_units(circ):
+    return circ.num_qubits + circ.num_blocks + circ.half_layer_num_blocks
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+def cpu_port_eval_seconds(n, layers, seed):
+    """One objective + single-term gradient with the C/OpenMP oracle port; returns seconds."""
+    from aqc_research_b200 import utils
+    from oracle import c_oracle as C
+
+    circ = make_circuit(n, layers)
+    rng = np.random.RandomState(seed)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    y = rng.rand(2**n) + 1j * rng.rand(2**n)
+    y /= np.linalg.norm(y)
+    t0 = time.perf_counter()
+    z0 = C.apply_v(circ, th, y, dagger=True)
+    hs = z0[[0] + [1 << q for q in range(n)]]
+    w = np.zeros(2**n, dtype=np.complex128)
+    w[0] = 1
+    C.grad_sweep(circ, th, w, z0, inplace=True)
+    dt = time.perf_counter() - t0
+    del utils, hs
+    return dt, gate_units(circ)
+
+
+def cpu_baseline(n, layers, seed=7):
+    """
+    Bounded CPU sample: the full workload for n <= 21; above that the same circuit depth at
+    n_s = 21 qubits, scaled by 2^(n - n_s) * G(n)/G(n_s) (cost is linear in amplitudes x gate units).
+    """
+    from oracle import c_oracle as C
+
+    n_s = min(n, 21)
+    secs, g_s = cpu_port_eval_seconds(n_s, layers, seed)
+    g_full = gate_units(make_circuit(n, layers))
+    scale = (2.0 ** (n - n_s)) * g_full / g_s
+    est = secs * scale
+    sample = (f"1 full eval at n={n_s}, L={layers} ({secs:.2f} s)" if n_s == n else
+              f"1 eval at n={n_s}, L={layers} ({secs:.2f} s) scaled x{scale:.1f} "
+              f"(2^{n - n_s} amplitudes x gate units {g_full}/{g_s})")
+    return {"value": 1.0 / est, "unit": UNIT, "cores": C.num_threads(), "kind": "port",
+            "sample": sample}
+
+
+def run_reference_arm(args, n, layers):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(n, layers, seed=100 + i)
+        if i >= args.warmup:
+            vals.append(cb)
+    value = float(np.mean([v["value"] for v in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "num_qubits": n, "layers": layers,
+                   "ansatz": "TrotterAnsatz 2nd order",
+                   "note": "CPU port of the reference algorithm (oracle/sv_oracle.c, OpenMP); the "
+                           "reference itself is pure Python/NumPy, see BASELINE.md section 2"},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
+    """Returns dict with per-step device ms list, kernel split, e2e seconds list, launches."""
+    from aqc_research_b200.model_sp_lhs.objective_lhs_sur_max import SpSurrogateObjectiveMax
+    from aqc_research_b200.model_sp_lhs.objective_base import SLOT_TARGET, SLOT_VH_TARGET, SLOT_W, SLOT_Z
+
+    circ = make_circuit(n, layers)
+    rng = np.random.RandomState(1234 + n)
+    th_star = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    params = dict(num_qubits=n, max_flips=1, maxiter=40, verbose=0, enable_optim_stats=False,
+                  num_simulations=1, trunc_thr=1e-6, state_prep_func=None, device=device)
+    objv = SpSurrogateObjectiveMax(user_parameters=params, circ=circ, front_layer=True)
+    ws = objv.workspace
+    # near target: V(theta*)|0>, generated on the device
+    ws.set_basis(SLOT_TARGET, 0)
+    ws.apply(th_star, SLOT_TARGET, SLOT_TARGET, dagger=False)
+    objv._target = "device-near-target"  # resident; nothing to upload
+    delta = 0.02
+    while True:
+        th = th_star + delta * np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+        objv.objective(th)
+        if objv.max_no == 0 or delta < 1e-6:
+            break
+        delta *= 0.5
+    fidelity = objv.fidelity
+    idx = np.array([0] + [1 << q for q in range(n)], dtype=np.int64)
+
+    flush = None
+    if flush_l2:
+        import torch
+        flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
+
+    def do_flush():
+        if flush is not None:
+            import torch
+            flush.fill_(1)
+            torch.cuda.synchronize(device)
+
+    step_ms, obj_ms, grad_ms, launches = [], [], [], 0
+    for it in range(warmup + steps):
+        if it == warmup and sampler:
+            sampler.start()
+        th_i = th + 1e-3 * np.cos(np.arange(th.size) + it)
+        do_flush()
+        ws.timer_start()
+        ws.objective(th_i, SLOT_TARGET, SLOT_VH_TARGET, idx)
+        o_ms, o_l = ws.last_kernel_ms, ws.last_num_launches
+        ws.grad(th_i, x_basis=0, z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
+        g_ms, g_l = ws.last_kernel_ms, ws.last_num_launches
+        ms = ws.timer_stop()
+        if it >= warmup:
+            step_ms.append(ms)
+            obj_ms.append(o_ms)
+            grad_ms.append(g_ms)
+            launches += o_l + g_l
+    # end-to-end through the public objective class (host thetas in, f and gradient out)
+    e2e_s = []
+    for it in range(warmup + steps):
+        th_i = th + 1e-3 * np.sin(np.arange(th.size) + it)
+        do_flush()
+        t0 = time.perf_counter()
+        f = objv.objective(th_i)
+        g = objv.gradient(th_i)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            e2e_s.append(dt)
+    assert objv.max_no == 0 and np.isfinite(f) and np.all(np.isfinite(g))
+    T = circ.num_thetas
+    return {
+        "circ": circ, "step_ms": step_ms, "obj_ms": obj_ms, "grad_ms": grad_ms, "launches": launches,
+        "e2e_s": e2e_s, "fidelity": fidelity, "passes_grad": ws.num_passes(0), "passes_dag": ws.num_passes(2),
+        "h2d": 2 * 8 * T, "d2h": 16 * (n + 1) + 16 * T,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("AQC_BENCH_WORKLOAD", "sv20"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra sv28 measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    n, layers = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, n, layers)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist  # noqa: F811
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    from aqc_research_b200 import _lib
+    _lib.require_gpu()
+
+    flush_l2 = 3 * 16 * 2**n < 4 * L2_BYTES
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+    res = measure_gpu(n, layers, args.steps, args.warmup, local_rank, flush_l2, sampler)
+    clocks = sampler.stop() if sampler else None
+
+    total_ms = float(np.sum(res["step_ms"]))
+    e2e_total = float(np.sum(res["e2e_s"]))
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(t[0]), float(t[1])
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    circ = res["circ"]
+    P = pair_runs(n, layers)
+    V = 16.0 * 2**n
+    value = world * args.steps / (total_ms * 1e-3)
+    e2e_value = world * args.steps / e2e_total
+    peak, peak_src = measured_peaks()
+    grad_s = float(np.mean(res["grad_ms"])) * 1e-3
+    obj_s = float(np.mean(res["obj_ms"])) * 1e-3
+    alg_grad = 4.0 * V * P  # bytes per gradient sweep at pair-run granularity
+    per_launch_alg = alg_grad / res["passes_grad"]
+    per_launch_s = grad_s / res["passes_grad"]
+    achieved = per_launch_alg / per_launch_s / 1e9
+    flops_eval = (104.0 * (circ.num_blocks + circ.half_layer_num_blocks) + 78.0 * n) * 2**n
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+        "config": {
+            "workload": args.workload, "num_qubits": n, "layers": layers,
+            "ansatz": "TrotterAnsatz 2nd order", "num_thetas": circ.num_thetas,
+            "pair_runs": P, "gate_units": gate_units(circ),
+            "target": "near: V(theta*)|0>, fidelity %.4f" % res["fidelity"],
+            "l2": "flushed between timed steps (256 MiB write)" if flush_l2 else "inputs (3 x %.1f GiB) larger than L2" % (V / 2**30),
+            "parallelism": "1 independent evaluation per GPU (no collective)" if world > 1 else "1 GPU",
+            "tile_passes": {"gradient": res["passes_grad"], "vh_apply": res["passes_dag"]},
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "pass_kernel<2,cx,fwd> (gradient tile pass)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": per_launch_alg, "launch_ms": per_launch_s * 1e3,
+            "eval_frac": (6.0 * V * P / (obj_s + grad_s)) / 1e9 / peak,
+            "fp64_tflops": flops_eval / (obj_s + grad_s) / 1e12,
+            "note": "algorithmic bytes at pair-run granularity (SURVEY 8(d)); passes fuse several "
+                    "pair-runs per tile so DRAM traffic is lower and the binding limit is FP64 issue",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
+                "d2h_bytes_per_step": res["d2h"]},
+        "gpu_launches": res["launches"],
+        "kernel_ms": {"vh_apply_sweep": obj_s * 1e3, "gradient_sweep": grad_s * 1e3},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(n, layers)
+    if world == 1 and not args.no_extra and args.workload == "sv20":
+        # the HBM-meaningful size of BASELINE.json configs[4] (vectors >> L2), same step definition
+        n2, l2 = WORKLOADS["sv28"]
+        r2 = measure_gpu(n2, l2, 3, 3, local_rank, False, None)
+        p2, v2 = pair_runs(n2, l2), 16.0 * 2**n2
+        t2 = float(np.mean(r2["step_ms"])) * 1e-3
+        g2 = float(np.mean(r2["grad_ms"])) * 1e-3
+        line["extra_workloads"] = {"sv28": {
+            "num_qubits": n2, "layers": l2, "num_thetas": r2["circ"].num_thetas, "steps": 3, "warmup": 3,
+            "value": 1.0 / t2, "unit": UNIT, "ms_per_step": t2 * 1e3,
+            "e2e_value": 1.0 / float(np.mean(r2["e2e_s"])),
+            "roofline_frac_gradient_kernel": 4.0 * v2 * p2 / g2 / 1e9 / peak,
+            "roofline_frac_eval": 6.0 * v2 * p2 / t2 / 1e9 / peak,
+            "tile_passes": {"gradient": r2["passes_grad"], "vh_apply": r2["passes_dag"]},
+        }}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

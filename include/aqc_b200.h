@@ -130,6 +130,10 @@ int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slot, int z0_s
  * kernels that call launched.  Used by bench.py for the roofline figure. */
 float aqc_sv_last_kernel_ms(const aqc_sv* sv);
 int aqc_sv_last_num_launches(const aqc_sv* sv);
+/* CUDA-event stopwatch on the workspace stream; brackets any sequence of calls made on this
+ * workspace between start and stop (ms = device time between the two events). */
+int aqc_sv_timer_start(aqc_sv* sv);
+int aqc_sv_timer_stop(aqc_sv* sv, float* ms);
 /* Scheduler introspection: number of tile passes over the state for one gradient
  * sweep (mode 0), one V apply (1) or one V^H apply (2). */
 int aqc_sv_num_passes(const aqc_sv* sv, int mode);

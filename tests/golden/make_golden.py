@@ -1,0 +1,146 @@
+"""
+Generates the golden fixtures ``tests/golden/*.npz`` by running the UNMODIFIED reference
+(/root/reference, imported read-only through ref_loader.py) on seeded inputs.
+Build-container only:  python tests/golden/make_golden.py
+The fixtures hold inputs AND reference outputs, so tests need neither the reference nor the
+global NumPy RNG stream to reproduce them.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference  # noqa: E402
+
+R = load_reference()
+
+
+def make_circuit(kind, n, depth_or_layers):
+    if kind in ("trotter1", "trotter2"):
+        blocks = R.cs.make_trotter_like_circuit(n, depth_or_layers)
+        return R.pc.TrotterAnsatz(n, blocks, kind == "trotter2"), blocks
+    blocks = R.utils.rand_circuit(n, depth_or_layers)
+    return R.pc.ParametricCircuit(n, kind, blocks), blocks
+
+
+def sv_cases():
+    """v_mul_vec, v_dagger_mul_vec, grad_of_dot_product (full and partial)."""
+    out = {}
+    case = 0
+    np.random.seed(0x0696969)  # seed used by the reference's own tests
+    for n in (2, 3, 4, 5, 6):
+        for kind in ("cx", "cz", "cp", "trotter1", "trotter2"):
+            size = 2 if kind.startswith("trotter") else 8
+            circ, blocks = make_circuit(kind, n, size)
+            th = R.utils.rand_thetas(circ.num_thetas)
+            x, y = R.utils.rand_state(n), R.utils.rand_state(n)
+            ws = np.zeros((3, 2**n), dtype=np.complex128)
+            buf = np.zeros(2**n, dtype=np.complex128)
+            vy = R.cop.v_mul_vec(circ, th, y, buf, ws).copy()
+            vhy = R.cop.v_dagger_mul_vec(circ, th, y, buf, ws).copy()
+            grad = R.cop.grad_of_dot_product(circ, th, x, vhy, ws)
+            br = (1, circ.num_blocks - 1)
+            gpart = R.cop.grad_of_dot_product(circ, th, x, vhy, ws, block_range=br, front_layer=False)
+            pre = f"c{case}_"
+            out[pre + "meta"] = np.array([n, ["cx", "cz", "cp", "trotter1", "trotter2"].index(kind), br[0], br[1]])
+            out[pre + "blocks"] = blocks
+            out[pre + "thetas"], out[pre + "x"], out[pre + "y"] = th, x, y
+            out[pre + "v_y"], out[pre + "vh_y"], out[pre + "grad"], out[pre + "grad_part"] = vy, vhy, grad, gpart
+            case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "sv_cases.npz"), **out)
+    print("sv_cases:", case)
+
+
+def mat_cases():
+    """v_mul_mat, v_dagger_mul_mat, grad_of_matrix_dot_product on rectangular matrices."""
+    out = {}
+    case = 0
+    np.random.seed(0x696969)
+    for n, m in ((2, 3), (3, 8), (4, 5), (5, 16)):
+        for kind in ("cx", "cz", "cp"):
+            circ, blocks = make_circuit(kind, n, 10)
+            th = R.utils.rand_thetas(circ.num_thetas)
+            X = np.random.rand(2**n, m) + 1j * np.random.rand(2**n, m)
+            Y = np.random.rand(2**n, m) + 1j * np.random.rand(2**n, m)
+            ws = np.zeros_like(X)
+            vy = R.cpm.v_mul_mat(circ, th, Y.copy(), ws).copy()
+            vhy = R.cpm.v_dagger_mul_mat(circ, th, Y.copy(), ws).copy()
+            grad = R.cpm.grad_of_matrix_dot_product(circ, th, X.copy(), vhy.copy(), ws)
+            pre = f"c{case}_"
+            out[pre + "meta"] = np.array([n, ["cx", "cz", "cp"].index(kind), m])
+            out[pre + "blocks"] = blocks
+            out[pre + "thetas"], out[pre + "x"], out[pre + "y"] = th, X, Y
+            out[pre + "v_y"], out[pre + "vh_y"], out[pre + "grad"] = vy, vhy, grad
+            case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "mat_cases.npz"), **out)
+    print("mat_cases:", case)
+
+
+def objective_sequences():
+    """
+    Stateful call sequences of SpSurrogateObjectiveMax (ThinStateHandler) and of
+    SketchingObjectiveEx + FullRangeSketchingVectors: objective(), gradient() at several thetas.
+    Includes the SURVEY section 8(c) sanity configuration (seed 1234, n = 5 and 12).
+    """
+    out = {}
+    case = 0
+    for n, layers, seed, steps in ((5, 2, 1234, 4), (12, 2, 1234, 2), (4, 1, 77, 5), (7, 3, 5, 3)):
+        np.random.seed(seed)
+        target = R.utils.rand_state(n)
+        blocks = R.cs.make_trotter_like_circuit(n, layers)
+        circ = R.pc.TrotterAnsatz(n, blocks, True)
+        th = R.utils.rand_thetas(circ.num_thetas)
+        params = dict(num_qubits=n, max_flips=1, maxiter=10, verbose=0, enable_optim_stats=False,
+                      num_simulations=1, trunc_thr=1e-6, state_prep_func=None)
+        objv = R.sur_max.SpSurrogateObjectiveMax(user_parameters=params, circ=circ, front_layer=True)
+        objv.set_target(target)
+        ths, fs, gs, ws_, mx, hs = [], [], [], [], [], []
+        for s in range(steps):
+            f = objv.objective(th)
+            hs.append(objv._hs.copy())
+            mx.append(objv._max_no)
+            g = objv.gradient(th)
+            ths.append(th.copy()); fs.append(f); gs.append(g.copy()); ws_.append(objv._weight)
+            th = th - 0.3 * g + 0.01 * np.cos(np.arange(th.size) + s)  # deterministic next point
+        pre = f"sp{case}_"
+        out[pre + "meta"] = np.array([n, layers, steps])
+        out[pre + "blocks"], out[pre + "target"] = blocks, target
+        out[pre + "thetas"], out[pre + "f"], out[pre + "grad"] = np.array(ths), np.array(fs), np.array(gs)
+        out[pre + "weight"], out[pre + "max_no"], out[pre + "hs"] = np.array(ws_), np.array(mx), np.array(hs)
+        case += 1
+    out["num_sp"] = np.array(case)
+
+    case = 0
+    from scipy.stats import unitary_group
+    for n, depth, ent, seed in ((3, 12, "cx", 11), (4, 20, "cz", 12), (5, 25, "cp", 13), (5, 30, "cx", 14)):
+        np.random.seed(seed)
+        U = unitary_group.rvs(2**n, random_state=seed).astype(np.complex128)
+        blocks = R.cs.create_ansatz_structure(n, "cyclic_spin", "full", depth)
+        circ = R.pc.ParametricCircuit(n, ent, blocks)
+        objv = R.sk_core.SketchingObjectiveEx(circ, R.sk_core.FullRangeSketchingVectors(U))
+        th = R.utils.rand_thetas(circ.num_thetas)
+        ths, fs, gs = [], [], []
+        for s in range(3):
+            f = objv.objective(th)
+            g = objv.gradient(th)
+            ths.append(th.copy()); fs.append(f); gs.append(g.copy())
+            th = th - 0.5 * g
+        pre = f"sk{case}_"
+        out[pre + "meta"] = np.array([n, ["cx", "cz", "cp"].index(ent)])
+        out[pre + "blocks"], out[pre + "target"] = blocks, U
+        out[pre + "thetas"], out[pre + "f"], out[pre + "grad"] = np.array(ths), np.array(fs), np.array(gs)
+        case += 1
+    out["num_sk"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "objective_sequences.npz"), **out)
+    print("objective sequences written")
+
+
+if __name__ == "__main__":
+    sv_cases()
+    mat_cases()
+    objective_sequences()
