@@ -65,6 +65,28 @@ SIGNATURES = {
         [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
     ),
     "aqc_sv_slot_ptr": (ct.c_void_p, [ct.c_void_p, ct.c_int]),
+    "aqc_mps_create": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_double, ct.c_int, ct.POINTER(ct.c_void_p)],
+    ),
+    "aqc_mps_destroy": (None, [ct.c_void_p]),
+    "aqc_mps_bond_capacity": (ct.c_int, [ct.c_void_p]),
+    "aqc_mps_upload": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p, c_int32_p]),
+    "aqc_mps_download": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p, c_int32_p]),
+    "aqc_mps_set_product": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int64]),
+    "aqc_mps_apply": (ct.c_int, [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, ct.c_int]),
+    "aqc_mps_amplitudes": (ct.c_int, [ct.c_void_p, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p]),
+    "aqc_mps_objective": (
+        ct.c_int,
+        [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p],
+    ),
+    "aqc_mps_dot": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]),
+    "aqc_mps_grad": (
+        ct.c_int,
+        [ct.c_void_p, c_double_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p],
+    ),
+    "aqc_mps_last_kernel_ms": (ct.c_float, [ct.c_void_p]),
+    "aqc_mps_last_num_launches": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_stream": (ct.c_void_p, [ct.c_void_p]),
 }
 

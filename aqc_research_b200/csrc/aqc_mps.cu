@@ -1,0 +1,1461 @@
+// aqc_mps.cu -- matrix-product-state objective-and-gradient engine for sm_100a.
+//
+// What this replaces (reference = qiskit-community/aqc-research, paths relative to its root):
+//   mps_dot                         aqc_research/mps_operations.py:192-213
+//   v_mul_mps / v_dagger_mul_mps    aqc_research/mps_operations.py:326-371 (gate arithmetic inside
+//                                   qiskit-aer's C++ MPS simulator, one simulator run per call)
+//   fast_dot_gradient               aqc_research/mps_dot_objective.py:41-242 (one qiskit-aer run per
+//                                   gate and one FULL-chain mps_dot per parameter)
+//   MpsStateHandler.state_dot_vector aqc_research/model_sp_lhs/objective_base.py:400-403
+//
+// Design.  States live on the device in Vidal form (Gamma tensors padded to
+// the bond capacity C, lambda vectors, bond dimensions -- all device resident, so a whole sweep is
+// enqueued without a single host synchronisation).  Gates of a pair-run (a Trotter triplet) act on
+// the physical indices of one two-site tensor only, therefore
+//   * the two-site tensor is formed ONCE per pair-run, the 4x4 product of the run's gates is
+//     applied, and ONE Jacobi SVD splits it again (the reference does 3 SVDs per triplet);
+//   * all 12 derivatives of the run follow from ONE 4x4 reduced overlap matrix
+//     rho[b', b] = <w-part b' | E_L . E_R | z-part b> built with cached left / right environments
+//     (O(chi^3)), instead of 12 full-chain contractions (O(n chi^3) each);
+//   * pair-runs of a half-layer touch disjoint sites, so every kernel is batched over them, and
+//     the environments at the bonds a half-layer modifies are refreshed by ONE batched single-site
+//     transfer step (unitaries applied to both states leave environments across untouched bonds
+//     invariant).
+// Truncation follows the published qiskit-aer rule (see oracle/mps_oracle.py); truncated results
+// are "parity unpinned" against qiskit-aer, untruncated ones equal the state-vector path.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aqc_b200.h"
+#include "aqc_gates.cuh"
+
+int aqc_fail(int code, const char* fmt, ...);  // aqc_sv.cu
+#define MCU(call)                                                                                \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return aqc_fail(AQC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                      __LINE__);                                                                 \
+  } while (0)
+
+constexpr int kMaxChi = 64;
+constexpr double kChop = 1e-16;  // singular values <= this are exact zeros (qiskit-aer CHOP)
+
+// One pair-run (or one front gate) of the compiled MPS program.
+struct MpsTask {
+  int32_t site;    // left site of the pair (or the site of a front gate)
+  int32_t nunits;  // 1..3 units
+  int32_t kind[3];
+  int32_t flags[3];
+  int32_t theta[3];
+  int32_t pad;
+};
+
+struct MpsStep {
+  int task0, ntasks;  // range in the task array
+};
+
+struct EnvTask {
+  int32_t site;  // site being absorbed
+  int32_t dir;   // 0: L (E at bond site -> bond site+1), 1: R (E at bond site+1 -> bond site)
+};
+
+struct MpsProgram {
+  std::vector<MpsTask> tasks;  // [front tasks | step tasks ...]
+  std::vector<MpsStep> steps;  // two-qubit steps in execution order
+  int nfront = 0;
+  MpsTask* d_tasks = nullptr;
+  // environment refresh lists: [L sweep 0..n-1 | R sweep n-1..0 | per step: (k, L), (k+1, R) ...]
+  std::vector<EnvTask> env;
+  std::vector<int> env_step0;  // offset of every step's list
+  EnvTask* d_env = nullptr;
+};
+
+struct MpsState {
+  double2* gam = nullptr;  // [n][2][C][C]
+  double* lam = nullptr;   // [n+1][C]  bond j sits left of site j; bonds 0 and n have dimension 1
+  int* dims = nullptr;     // [n+1]
+};
+
+struct aqc_circuit;  // defined in aqc_sv.cu
+// accessors implemented in aqc_sv.cu (keeps struct aqc_circuit private to that file)
+int aqc_circ_n(const aqc_circuit* c);
+int aqc_circ_ent(const aqc_circuit* c);
+int aqc_circ_trotter(const aqc_circuit* c);
+int aqc_circ_nb(const aqc_circuit* c);
+int aqc_circ_half(const aqc_circuit* c);
+int aqc_circ_tpb(const aqc_circuit* c);
+int aqc_circ_nthetas(const aqc_circuit* c);
+int aqc_circ_ctrl(const aqc_circuit* c, int i);
+int aqc_circ_targ(const aqc_circuit* c, int i);
+
+struct aqc_mps {
+  int device = 0;
+  int n = 0, C = 0, ent = 0, tpb = 4, nthetas = 0;
+  int chi_max = 0;
+  double trunc_thr = 1e-16;
+  int nslots = 0;
+  int maxtasks = 0;  // max tasks in one step (>= n for the front layer)
+  std::vector<MpsState> st;
+  MpsProgram fwd, dag;
+  // scratch
+  double* d_thetas = nullptr;
+  double2* d_gate = nullptr;    // [maxtasks][16] 4x4 gate of each task of the current step
+  double2* d_theta0 = nullptr;  // [2][maxtasks][4][C][C]  two-site tensors before the gate
+  double2* d_work = nullptr;    // [2][maxtasks][2C][2C]   SVD working matrices (column-major)
+  double2* d_vmat = nullptr;    // [2][maxtasks][2C][2C]   right rotations
+  double2* d_envL = nullptr;    // [n+1][C][C]
+  double2* d_envR = nullptr;    // [n+1][C][C]
+  double2* d_rho = nullptr;     // [maxtasks][16]
+  double* d_gacc = nullptr;     // [nthetas] complex raw sums
+  double2* d_small = nullptr;   // small outputs
+  long long* d_idx = nullptr;
+  double* h_pinned = nullptr;
+  size_t pinned_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// host: program construction
+// ------------------------------------------------------------------------------------------
+static int build_mps_program(const aqc_circuit* c, bool reversed, MpsProgram& prog, std::string& err) {
+  const int n = aqc_circ_n(c), nb = aqc_circ_nb(c), half = aqc_circ_half(c), tpb = aqc_circ_tpb(c);
+  const bool trot = aqc_circ_trotter(c) != AQC_GENERIC;
+  prog.tasks.clear();
+  prog.steps.clear();
+  for (int q = 0; q < n; ++q) {
+    MpsTask t;
+    memset(&t, 0, sizeof(t));
+    t.site = q;
+    t.nunits = 1;
+    t.kind[0] = U_FRONT_LO;
+    t.theta[0] = 3 * q;
+    prog.tasks.push_back(t);
+  }
+  prog.nfront = n;
+  // blocks in circuit order -> steps of pair-runs on disjoint pairs
+  struct Blk {
+    int lo, kind, flags, theta;
+  };
+  std::vector<Blk> blks;
+  for (int i = 0; i < nb + half; ++i) {
+    const int k = nb > 0 ? i % nb : 0;
+    const int cq = aqc_circ_ctrl(c, k), tq = aqc_circ_targ(c, k);
+    if (std::abs(cq - tq) != 1) {
+      err = "the MPS path supports unit-blocks on adjacent qubits only";
+      return AQC_EINVAL;
+    }
+    int flags = 0;
+    if (trot && i % 3 == 0) flags |= F_PRE;
+    if (trot && i % 3 == 2) flags |= F_POST;
+    blks.push_back({std::min(cq, tq), cq > tq ? U_BLOCK_CHI : U_BLOCK_CLO, flags, 3 * n + tpb * k});
+  }
+  // level[s] = index of the last step that touched site s; open task of that site (if the last
+  // thing that touched both sites of a pair is the same task, a block can be chained onto it)
+  std::vector<int> last_step(n, -1), last_task(n, -1);
+  std::vector<std::vector<MpsTask>> steps;
+  for (const Blk& b : blks) {
+    const int s0 = b.lo, s1 = b.lo + 1;
+    int step = -1, task = -1;
+    if (last_step[s0] >= 0 && last_step[s0] == last_step[s1] && last_task[s0] == last_task[s1] &&
+        last_task[s0] >= 0) {
+      MpsTask& t = steps[last_step[s0]][last_task[s0]];
+      if (t.site == b.lo && t.nunits < 3) {
+        step = last_step[s0];
+        task = last_task[s0];
+      }
+    }
+    if (task < 0) {
+      step = std::max(last_step[s0], last_step[s1]) + 1;
+      if ((int)steps.size() <= step) steps.resize(step + 1);
+      MpsTask t;
+      memset(&t, 0, sizeof(t));
+      t.site = b.lo;
+      steps[step].push_back(t);
+      task = (int)steps[step].size() - 1;
+    }
+    MpsTask& t = steps[step][task];
+    t.kind[t.nunits] = b.kind;
+    t.flags[t.nunits] = b.flags;
+    t.theta[t.nunits] = b.theta;
+    t.nunits++;
+    last_step[s0] = last_step[s1] = step;
+    last_task[s0] = last_task[s1] = task;
+  }
+  if (reversed) {
+    std::reverse(steps.begin(), steps.end());
+    for (auto& s : steps)
+      for (auto& t : s) {
+        std::reverse(t.kind, t.kind + t.nunits);
+        std::reverse(t.flags, t.flags + t.nunits);
+        std::reverse(t.theta, t.theta + t.nunits);
+      }
+  }
+  for (auto& s : steps) {
+    prog.steps.push_back({(int)prog.tasks.size(), (int)s.size()});
+    for (auto& t : s) prog.tasks.push_back(t);
+  }
+  prog.env.clear();
+  prog.env_step0.clear();
+  for (int k = 0; k < n; ++k) prog.env.push_back({k, 0});
+  for (int k = n - 1; k >= 0; --k) prog.env.push_back({k, 1});
+  for (auto& st : prog.steps) {
+    prog.env_step0.push_back((int)prog.env.size());
+    for (int i = 0; i < st.ntasks; ++i) {
+      const int k = prog.tasks[st.task0 + i].site;
+      prog.env.push_back({k, 0});      // E_L(k+1) from E_L(k) and the new site k
+      prog.env.push_back({k + 1, 1});  // E_R(k+1) from E_R(k+2) and the new site k+1
+    }
+  }
+  return AQC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
+  return make_double2(fma(-a.y, b.y, a.x * b.x), fma(a.y, b.x, a.x * b.y));
+}
+__device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {  // acc += a * b
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfma_conj(double2& acc, double2 a, double2 b) {  // acc += conj(a) * b
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+
+struct StateView {
+  const double2* gam;
+  const double* lam;
+  const int* dims;
+};
+struct StateMut {
+  double2* gam;
+  double* lam;
+  int* dims;
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel: 4x4 algebra of one task -- gate product, and (gradient) the derivatives from rho
+// ------------------------------------------------------------------------------------------
+// mode 0: write the task's 4x4 gate (forward product)         -> gate[task][16]
+// mode 1: same for the daggered product (units already reversed by the host)
+// mode 2: gradient: derivatives of all units from rho[task] (raw sums, same convention as the
+//         state-vector kernel) are ADDED to gacc; one thread per (task, basis vector j)
+template <int ENT>
+__global__ void mps_algebra_kernel(const MpsTask* __restrict__ tasks, int ntasks,
+                                   const double* __restrict__ thetas, int mode,
+                                   double2* __restrict__ gate, const double2* __restrict__ rho,
+                                   double* __restrict__ gacc) {
+  const int t = blockIdx.x * (blockDim.x / 4) + threadIdx.x / 4;
+  const int j = threadIdx.x & 3;
+  if (t >= ntasks) return;  // the 4 threads of a task leave together
+  const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+  const MpsTask tk = tasks[t];
+  constexpr int NP = (ENT == AQC_ENT_CP) ? 5 : 4;
+  if (mode < 2) {
+    cd a[1][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[0][i].x = (i == j) ? 1.0 : 0.0, a[0][i].y = 0.0;
+    for (int u = 0; u < tk.nunits; ++u) {
+      double2 tr[5];
+      const int kind = tk.kind[u];
+      const int np = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : NP;
+      for (int k = 0; k < np; ++k) {
+        const double th = thetas[tk.theta[u] + k];
+        double s, c;
+        sincos((k == 4) ? th : 0.5 * th, &s, &c);
+        tr[k] = make_double2(c, s);
+      }
+      if (mode == 0) {
+        if (kind == U_FRONT_LO) front_unit<1, false, false>(a, tr, nullptr);
+        if (kind == U_BLOCK_CHI) block_unit<1, ENT, true, false>(a, tr, tk.flags[u], nullptr);
+        if (kind == U_BLOCK_CLO) block_unit<1, ENT, false, false>(a, tr, tk.flags[u], nullptr);
+      } else {
+        if (kind == U_FRONT_LO) front_unit<1, false, true>(a, tr, nullptr);
+        if (kind == U_BLOCK_CHI) block_unit<1, ENT, true, true>(a, tr, tk.flags[u], nullptr);
+        if (kind == U_BLOCK_CLO) block_unit<1, ENT, false, true>(a, tr, tk.flags[u], nullptr);
+      }
+    }
+    // column j of the gate: gate[row i][col j]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gate[(size_t)t * 16 + i * 4 + j] = make_double2(a[0][i].x, a[0][i].y);
+  } else {
+    // rho[b'][b] = <w-part b'|z-part b>  =  sum_j conj(e_j)[b'] (rho row j)[b]:
+    // run the two-vector gradient code on (w, z) = (e_j, rho[j, :]) and add the four partial sums
+    cd a[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[0][i].x = (i == j) ? 1.0 : 0.0;
+      a[0][i].y = 0.0;
+      const double2 r = rho[(size_t)t * 16 + j * 4 + i];
+      a[1][i].x = r.x;
+      a[1][i].y = r.y;
+    }
+    for (int u = 0; u < tk.nunits; ++u) {
+      double2 tr[5];
+      double acc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+      const int kind = tk.kind[u];
+      const bool front = (kind == U_FRONT_LO || kind == U_FRONT_HI);
+      const int np = front ? 3 : NP;
+      for (int k = 0; k < np; ++k) {
+        const double th = thetas[tk.theta[u] + k];
+        double s, c;
+        sincos((k == 4) ? th : 0.5 * th, &s, &c);
+        tr[k] = make_double2(c, s);
+      }
+      if (kind == U_FRONT_LO) front_unit<2, false, false>(a, tr, acc);
+      if (kind == U_BLOCK_CHI) block_unit<2, ENT, true, false>(a, tr, tk.flags[u], acc);
+      if (kind == U_BLOCK_CLO) block_unit<2, ENT, false, false>(a, tr, tk.flags[u], acc);
+      const int nval = 2 * np;
+      for (int k = 0; k < nval; ++k) {
+        double v = acc[k];
+        v += __shfl_xor_sync(gmask, v, 1);
+        v += __shfl_xor_sync(gmask, v, 2);
+        if (j == 0) atomicAdd(gacc + 2 * (size_t)tk.theta[u] + k, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: two-site tensor of a task (+ gate) -> SVD working matrix; optional copy before the gate
+// ------------------------------------------------------------------------------------------
+// grid (ntasks, nstates), 512 threads.  thread: column gamma = tid % 64, rows alpha = 8 per thread.
+struct ThetaArgs {
+  StateView st[2];
+  const MpsTask* tasks;
+  const double2* gate;  // [task][16] or nullptr (identity)
+  double2* theta0;      // [state][maxtasks][4][C][C] or nullptr
+  double2* work;        // [state][maxtasks][2C*2C] or nullptr
+  int C, maxtasks, single_site;
+};
+
+__global__ void __launch_bounds__(512) mps_theta_kernel(const ThetaArgs A) {
+  const int t = blockIdx.x, s = blockIdx.y, C = A.C;
+  const MpsTask tk = A.tasks[t];
+  const StateView S = A.st[s];
+  const int k = tk.site;
+  const int cl = S.dims[k], cm = S.dims[k + 1];
+  const int cr = A.single_site ? cm : S.dims[k + 2];
+  const int g = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const double2* Ga = S.gam + (size_t)k * 2 * C * C;
+  if (A.single_site) {
+    // theta0[b][alpha][gamma] = Gamma_k[b][alpha, gamma] * lambda_{k+1}[gamma]   (b = 0, 1)
+    double2* out = A.theta0 + ((size_t)s * A.maxtasks + t) * 4 * C * C;
+    const double lr = (g < cr) ? S.lam[(size_t)(k + 1) * C + g] : 0.0;
+    for (int r = 0; r < 8; ++r) {
+      const int al = grp * 8 + r;
+      if (al < cl && g < cr) {
+        for (int b = 0; b < 2; ++b) {
+          const double2 v = Ga[((size_t)b * C + al) * C + g];
+          out[((size_t)b * C + al) * C + g] = make_double2(v.x * lr, v.y * lr);
+        }
+      }
+    }
+    return;
+  }
+  const double2* Gb = S.gam + (size_t)(k + 1) * 2 * C * C;
+  const double* lamL = S.lam + (size_t)k * C;
+  const double* lamM = S.lam + (size_t)(k + 1) * C;
+  const double* lamR = S.lam + (size_t)(k + 2) * C;
+  double2 acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = make_double2(0.0, 0.0);
+  const bool colok = g < cr;
+  for (int be = 0; be < cm; ++be) {
+    const double lm = lamM[be];
+    double2 b0 = make_double2(0.0, 0.0), b1 = b0;
+    if (colok) {
+      b0 = Gb[((size_t)0 * C + be) * C + g];
+      b1 = Gb[((size_t)1 * C + be) * C + g];
+      b0.x *= lm, b0.y *= lm, b1.x *= lm, b1.y *= lm;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int al = grp * 8 + r;
+      if (al < cl) {
+        const double2 a0 = Ga[((size_t)0 * C + al) * C + be];
+        const double2 a1 = Ga[((size_t)1 * C + al) * C + be];
+        // quad index = (b2 << 1) | b1   (hi = site k+1, lo = site k)
+        cfma(acc[r][0], a0, b0);
+        cfma(acc[r][1], a1, b0);
+        cfma(acc[r][2], a0, b1);
+        cfma(acc[r][3], a1, b1);
+      }
+    }
+  }
+  if (!colok) return;
+  const double lr = lamR[g];
+  double2 G4[16];
+  if (A.gate) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) G4[i] = A.gate[(size_t)t * 16 + i];
+  }
+  const int M = 2 * cl, N = 2 * cr, LD = 2 * C;
+  const bool transposed = M < N;
+  double2* T0 = A.theta0 ? A.theta0 + ((size_t)s * A.maxtasks + t) * 4 * C * C : nullptr;
+  double2* W = A.work ? A.work + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD : nullptr;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int al = grp * 8 + r;
+    if (al >= cl) continue;
+    const double ll = lamL[al];
+    double2 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = make_double2(acc[r][c].x * lr, acc[r][c].y * lr);
+    if (T0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) T0[((size_t)c * C + al) * C + g] = v[c];
+    }
+    if (W) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // output quad index c = (b2' << 1) | b1'
+        double2 o = make_double2(0.0, 0.0);
+        if (A.gate) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) cfma(o, G4[c * 4 + d], v[d]);
+        } else {
+          o = v[c];
+        }
+        o.x *= ll, o.y *= ll;
+        const int row = (c & 1) * cl + al, col = (c >> 1) * cr + g;
+        if (!transposed)
+          W[row + (size_t)col * LD] = o;
+        else
+          W[col + (size_t)row * LD] = make_double2(o.x, -o.y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: one-sided Jacobi SVD of the working matrix + truncation + split into Gamma, lambda
+// ------------------------------------------------------------------------------------------
+struct SvdArgs {
+  StateMut st[2];
+  const MpsTask* tasks;
+  double2* work;
+  double2* vmat;
+  int C, maxtasks, chi_max;
+  double trunc_thr;
+};
+
+__global__ void __launch_bounds__(512) mps_svd_kernel(const SvdArgs A) {
+  __shared__ double s_sig[2 * kMaxChi];
+  __shared__ int s_order[2 * kMaxChi];
+  __shared__ int s_keep, s_total;
+  __shared__ double s_scale;
+  const int t = blockIdx.x, s = blockIdx.y, C = A.C;
+  const MpsTask tk = A.tasks[t];
+  const StateMut S = A.st[s];
+  const int k = tk.site;
+  const int cl = S.dims[k], cr = S.dims[k + 2];
+  const int M = 2 * cl, N = 2 * cr, LD = 2 * C;
+  const bool transposed = M < N;
+  const int R = transposed ? N : M;   // rows of the working matrix
+  const int Cc = transposed ? M : N;  // columns (<= rows)
+  double2* B = A.work + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
+  double2* V = A.vmat + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  for (int i = tid; i < Cc * Cc; i += blockDim.x) {
+    const int r = i % Cc, c = i / Cc;
+    V[r + (size_t)c * LD] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+
+  const int ne = (Cc + 1) & ~1;  // even number of players (one phantom if Cc is odd)
+  const int npairs = ne / 2;
+  const double tol = 1e-15;
+  for (int sweep = 0; sweep < 40 && ne > 1; ++sweep) {
+    int rotated = 0;
+    for (int round = 0; round < ne - 1; ++round) {
+      for (int pi = warp; pi < npairs; pi += nwarps) {
+        int p, q;
+        if (pi == 0) {
+          p = ne - 1;
+          q = round;
+        } else {
+          p = (round + pi) % (ne - 1);
+          q = (round + ne - 1 - pi) % (ne - 1);
+        }
+        if (p > q) {
+          const int tmp = p;
+          p = q;
+          q = tmp;
+        }
+        if (q >= Cc) continue;  // phantom
+        double2* bp = B + (size_t)p * LD;
+        double2* bq = B + (size_t)q * LD;
+        double2 xp[4], xq[4];
+        double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = lane + 32 * e;
+          xp[e] = (r < R) ? bp[r] : make_double2(0.0, 0.0);
+          xq[e] = (r < R) ? bq[r] : make_double2(0.0, 0.0);
+          al = fma(xp[e].x, xp[e].x, fma(xp[e].y, xp[e].y, al));
+          be = fma(xq[e].x, xq[e].x, fma(xq[e].y, xq[e].y, be));
+          gr = fma(xp[e].x, xq[e].x, fma(xp[e].y, xq[e].y, gr));   // Re conj(p) q
+          gi = fma(xp[e].x, xq[e].y, fma(-xp[e].y, xq[e].x, gi));  // Im conj(p) q
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          gr += __shfl_xor_sync(0xffffffffu, gr, o);
+          gi += __shfl_xor_sync(0xffffffffu, gi, o);
+        }
+        const double gabs = sqrt(gr * gr + gi * gi);
+        if (gabs <= tol * sqrt(al * be) || gabs == 0.0) continue;
+        rotated = 1;
+        const double zeta = (be - al) / (2.0 * gabs);
+        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+        const double er = gr / gabs, ei = gi / gabs;  // e^{i phi}
+        // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q
+        const double2 fm = make_double2(-sn * er, sn * ei);  // -sn e^{-i phi}
+        const double2 fp = make_double2(sn * er, sn * ei);   //  sn e^{+i phi}
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = lane + 32 * e;
+          if (r < R) {
+            double2 np_ = make_double2(cs * xp[e].x, cs * xp[e].y);
+            cfma(np_, fm, xq[e]);
+            double2 nq = make_double2(cs * xq[e].x, cs * xq[e].y);
+            cfma(nq, fp, xp[e]);
+            bp[r] = np_;
+            bq[r] = nq;
+          }
+        }
+        double2* vp = V + (size_t)p * LD;
+        double2* vq = V + (size_t)q * LD;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = lane + 32 * e;
+          if (r < Cc) {
+            const double2 yp = vp[r], yq = vq[r];
+            double2 np_ = make_double2(cs * yp.x, cs * yp.y);
+            cfma(np_, fm, yq);
+            double2 nq = make_double2(cs * yq.x, cs * yq.y);
+            cfma(nq, fp, yp);
+            vp[r] = np_;
+            vq[r] = nq;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (__syncthreads_or(rotated) == 0) break;
+  }
+
+  // singular values = column norms
+  for (int c = warp; c < Cc; c += nwarps) {
+    double acc = 0.0;
+    const double2* bc = B + (size_t)c * LD;
+    for (int r = lane; r < R; r += 32) acc = fma(bc[r].x, bc[r].x, fma(bc[r].y, bc[r].y, acc));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_sig[c] = sqrt(acc);
+  }
+  __syncthreads();
+  if (tid < Cc) {  // descending rank
+    const double me = s_sig[tid];
+    int rank = 0;
+    for (int i = 0; i < Cc; ++i) {
+      const double o = s_sig[i];
+      rank += (o > me || (o == me && i < tid)) ? 1 : 0;
+    }
+    s_order[rank] = tid;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int total = 0;
+    for (int i = 0; i < Cc; ++i) total += (s_sig[s_order[i]] > kChop) ? 1 : 0;
+    int keep = total < 1 ? 1 : total;
+    if (keep > A.chi_max) keep = A.chi_max;
+    double dropped = 0.0;
+    while (keep > 1) {
+      const double v = s_sig[s_order[keep - 1]];
+      if (dropped + v * v < A.trunc_thr) {
+        dropped += v * v;
+        --keep;
+      } else {
+        break;
+      }
+    }
+    double scale = 1.0;
+    if (keep < total) {
+      double nrm = 0.0;
+      for (int i = 0; i < keep; ++i) nrm += s_sig[s_order[i]] * s_sig[s_order[i]];
+      scale = 1.0 / sqrt(nrm);
+    }
+    s_keep = keep;
+    s_total = total;
+    s_scale = scale;
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  const double scale = s_scale;
+  // write lambda (bond k+1), dims, Gamma_k, Gamma_{k+1}
+  double* lamM = S.lam + (size_t)(k + 1) * C;
+  const double* lamL = S.lam + (size_t)k * C;
+  const double* lamR = S.lam + (size_t)(k + 2) * C;
+  for (int r = tid; r < C; r += blockDim.x) lamM[r] = (r < keep) ? s_sig[s_order[r]] * scale : 0.0;
+  if (tid == 0) S.dims[k + 1] = keep;
+  double2* Ga = S.gam + (size_t)k * 2 * C * C;
+  double2* Gb = S.gam + (size_t)(k + 1) * 2 * C * C;
+  // Gamma_k[b1][alpha, r] = Uleft[(b1 cl + alpha), j_r] / lamL[alpha]
+  for (int i = tid; i < M * keep; i += blockDim.x) {
+    const int row = i % M, r = i / M;
+    const int j = s_order[r];
+    const double sg = s_sig[j];
+    double2 u;
+    if (!transposed) {
+      const double2 b = B[row + (size_t)j * LD];
+      const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
+      u = make_double2(b.x * inv, b.y * inv);
+    } else {
+      u = V[row + (size_t)j * LD];
+    }
+    const int b1 = row / cl, al = row % cl;
+    const double il = 1.0 / lamL[al];
+    Ga[((size_t)b1 * C + al) * C + r] = make_double2(u.x * il, u.y * il);
+  }
+  // Gamma_{k+1}[b2][r, gamma] = conj(Vright[(b2 cr + gamma), j_r]) / lamR[gamma]
+  for (int i = tid; i < N * keep; i += blockDim.x) {
+    const int col = i % N, r = i / N;
+    const int j = s_order[r];
+    const double sg = s_sig[j];
+    double2 v;
+    if (!transposed) {
+      v = V[col + (size_t)j * LD];
+    } else {
+      const double2 b = B[col + (size_t)j * LD];
+      const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
+      v = make_double2(b.x * inv, b.y * inv);
+    }
+    const int b2 = col / cr, ga = col % cr;
+    const double ir = 1.0 / lamR[ga];
+    Gb[((size_t)b2 * C + r) * C + ga] = make_double2(v.x * ir, -v.y * ir);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: single-site transfer step of an environment (left-to-right or right-to-left)
+// ------------------------------------------------------------------------------------------
+//   L: E'[i', j'] = sum_b sum_{i,j} conj(Aw[b][i, i']) E[i, j] Az[b][j, j']   (i = left bond)
+//   R: E'[i', j'] = sum_b sum_{i,j} conj(Aw[b][i', i]) E[i, j] Az[b][j', j]   (i = right bond)
+// with A[b] = Gamma[b] diag(lambda_right).   grid (ntasks), 512 threads, 64 KiB dynamic smem (X).
+struct EnvArgs {
+  StateView w, z;
+  const EnvTask* tasks;
+  double2* envL;
+  double2* envR;
+  int C;
+};
+
+template <bool RIGHT>
+__device__ __forceinline__ double2 site_elem(const StateView& S, int k, int b, int i, int ip, int C) {
+  // element A[b](i -> i'): L: row i (left bond), col i' (right bond);  R: row i' (left), col i (right)
+  const int row = RIGHT ? ip : i, col = RIGHT ? i : ip;
+  const double2 v = S.gam[(((size_t)k * 2 + b) * C + row) * C + col];
+  const double l = S.lam[(size_t)(k + 1) * C + col];
+  return make_double2(v.x * l, v.y * l);
+}
+
+template <bool RIGHT>
+__device__ void env_step(const EnvArgs& A, int k, double2* X) {
+  const int C = A.C;
+  const int wl = A.w.dims[k], wr = A.w.dims[k + 1], zl = A.z.dims[k], zr = A.z.dims[k + 1];
+  const int wi = RIGHT ? wr : wl, wo = RIGHT ? wl : wr;  // contracted / new bond of w
+  const int zi = RIGHT ? zr : zl, zo = RIGHT ? zl : zr;
+  const double2* E = RIGHT ? A.envR + (size_t)(k + 1) * C * C : A.envL + (size_t)k * C * C;
+  double2* Eo = RIGHT ? A.envR + (size_t)k * C * C : A.envL + (size_t)(k + 1) * C * C;
+  const int g = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  double2 out[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) out[r] = make_double2(0.0, 0.0);
+  for (int b = 0; b < 2; ++b) {
+    // X[i, j'] = sum_j E[i, j] Az[b](j -> j')
+    double2 acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = make_double2(0.0, 0.0);
+    if (g < zo) {
+      for (int j = 0; j < zi; ++j) {
+        const double2 az = site_elem<RIGHT>(A.z, k, b, j, g, C);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = grp * 8 + r;
+          if (i < wi) cfma(acc[r], E[(size_t)i * C + j], az);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) X[(size_t)(grp * 8 + r) * 64 + g] = acc[r];
+    __syncthreads();
+    // E'[i', j'] += sum_i conj(Aw[b](i -> i')) X[i, j']
+    if (g < zo) {
+      for (int i = 0; i < wi; ++i) {
+        const double2 x = X[(size_t)i * 64 + g];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int ip = grp * 8 + r;
+          if (ip < wo) cfma_conj(out[r], site_elem<RIGHT>(A.w, k, b, i, ip, C), x);
+        }
+      }
+    }
+  }
+  if (g < zo) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int ip = grp * 8 + r;
+      if (ip < wo) Eo[(size_t)ip * C + g] = out[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) mps_env_kernel(const EnvArgs A) {
+  extern __shared__ double2 smem_x[];
+  const EnvTask tk = A.tasks[blockIdx.x];
+  if (tk.dir == 0)
+    env_step<false>(A, tk.site, smem_x);
+  else
+    env_step<true>(A, tk.site, smem_x);
+}
+
+__global__ void mps_env_init_kernel(double2* envL, double2* envR, int n, int C) {
+  // bond 0 and bond n have dimension 1: E = [[1]]
+  if (threadIdx.x == 0) {
+    envL[0] = make_double2(1.0, 0.0);
+    envR[(size_t)n * C * C] = make_double2(1.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: reduced overlap matrix rho[b'][b] = sum conj(Tw[b'][a, c]) EL[a, a'] Tz[b][a', c'] ER[c, c']
+// ------------------------------------------------------------------------------------------
+// grid (ntasks, nphys), 512 threads, 128 KiB dynamic smem (X and ER^T)
+struct RhoArgs {
+  StateView w, z;
+  const MpsTask* tasks;
+  const double2* theta0;  // [2][maxtasks][4][C][C]  (state 0 = w, 1 = z)
+  const double2* envL;
+  const double2* envR;
+  double2* rho;  // [task][16]
+  int C, maxtasks, nphys, span;  // span = sites covered by a task (2 pairs, 1 front)
+};
+
+__global__ void __launch_bounds__(512) mps_rho_kernel(const RhoArgs A) {
+  extern __shared__ double2 smem_r[];
+  __shared__ double s_red[16][2 * 4];
+  double2* X = smem_r;             // [64][64]
+  double2* ERt = smem_r + 64 * 64;  // [c'][c]
+  const int t = blockIdx.x, b = blockIdx.y, C = A.C;
+  const MpsTask tk = A.tasks[t];
+  const int k = tk.site;
+  const int wl = A.w.dims[k], wr = A.w.dims[k + A.span];
+  const int zl = A.z.dims[k], zr = A.z.dims[k + A.span];
+  const double2* EL = A.envL + (size_t)k * C * C;
+  const double2* ER = A.envR + (size_t)(k + A.span) * C * C;
+  const double2* Tz = A.theta0 + (((size_t)1 * A.maxtasks + t) * 4 + b) * C * C;
+  const double2* Tw = A.theta0 + (((size_t)0 * A.maxtasks + t) * 4) * C * C;
+  const int g = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int c = i / 64, cp = i % 64;  // ER[c][cp] -> ERt[cp][c]
+    ERt[(size_t)cp * 64 + c] = (c < wr && cp < zr) ? ER[(size_t)c * C + cp] : make_double2(0.0, 0.0);
+  }
+  // X[a, c'] = sum_a' EL[a, a'] Tz[b][a', c']
+  double2 acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = make_double2(0.0, 0.0);
+  if (g < zr) {
+    for (int ap = 0; ap < zl; ++ap) {
+      const double2 tz = Tz[(size_t)ap * C + g];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int a = grp * 8 + r;
+        if (a < wl) cfma(acc[r], EL[(size_t)a * C + ap], tz);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) X[(size_t)(grp * 8 + r) * 64 + g] = acc[r];
+  __syncthreads();
+  // Mb[a, c] = sum_c' X[a, c'] ER[c, c'] ; rho[b', b] += conj(Tw[b'][a, c]) Mb[a, c]
+  double2 part[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) part[q] = make_double2(0.0, 0.0);
+  if (g < wr) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int cp = 0; cp < zr; ++cp) {
+      const double2 er = ERt[(size_t)cp * 64 + g];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int a = grp * 8 + r;
+        if (a < wl) cfma(acc[r], X[(size_t)a * 64 + cp], er);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int a = grp * 8 + r;
+      if (a < wl) {
+        for (int bp = 0; bp < A.nphys; ++bp)
+          cfma_conj(part[bp], Tw[((size_t)bp * C + a) * C + g], acc[r]);
+      }
+    }
+  }
+  // block reduction of 4 complex numbers
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      part[q].x += __shfl_xor_sync(0xffffffffu, part[q].x, o);
+      part[q].y += __shfl_xor_sync(0xffffffffu, part[q].y, o);
+    }
+    if (lane == 0) {
+      s_red[warp][2 * q] = part[q].x;
+      s_red[warp][2 * q + 1] = part[q].y;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    for (int w = 0; w < 16; ++w) v += s_red[w][threadIdx.x];
+    const int bp = threadIdx.x >> 1;
+    if (bp < A.nphys) {
+      // rho layout [task][b' * 4 + b]; single-site tasks use the lo bit only (b', b in {0, 1})
+      double* out = (double*)(A.rho + (size_t)t * 16 + bp * 4 + b);
+      out[threadIdx.x & 1] = v;
+    }
+  }
+}
+
+__global__ void mps_zero_rho_kernel(double2* rho, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) rho[i] = make_double2(0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: apply the 2x2 gate of single-site tasks (front layer) to Gamma
+// ------------------------------------------------------------------------------------------
+__global__ void mps_apply1q_kernel(StateMut S, const MpsTask* __restrict__ tasks,
+                                   const double2* __restrict__ gate, int C) {
+  const MpsTask tk = tasks[blockIdx.x];
+  const int k = tk.site;
+  const int cl = S.dims[k], cr = S.dims[k + 1];
+  // 2x2 block of the 4x4 gate acting on the lo bit: rows/cols 0, 1
+  const double2 g00 = gate[(size_t)blockIdx.x * 16 + 0], g01 = gate[(size_t)blockIdx.x * 16 + 1];
+  const double2 g10 = gate[(size_t)blockIdx.x * 16 + 4], g11 = gate[(size_t)blockIdx.x * 16 + 5];
+  double2* G0 = S.gam + ((size_t)k * 2 + 0) * C * C;
+  double2* G1 = S.gam + ((size_t)k * 2 + 1) * C * C;
+  for (int i = threadIdx.x; i < cl * cr; i += blockDim.x) {
+    const int a = i / cr, c = i % cr;
+    const double2 x0 = G0[(size_t)a * C + c], x1 = G1[(size_t)a * C + c];
+    double2 y0 = cmul2(g00, x0), y1 = cmul2(g10, x0);
+    cfma(y0, g01, x1);
+    cfma(y1, g11, x1);
+    G0[(size_t)a * C + c] = y0;
+    G1[(size_t)a * C + c] = y1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: amplitudes of basis states  out[i] = <idx_i | state>  (one CTA per index)
+// ------------------------------------------------------------------------------------------
+__global__ void mps_amplitude_kernel(StateView S, const long long* __restrict__ idx, int n, int C,
+                                     double2* __restrict__ out) {
+  __shared__ double2 v[2][kMaxChi];
+  const long long index = idx[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (tid < kMaxChi) v[0][tid] = make_double2(tid == 0 ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+  int cur = 0;
+  for (int k = 0; k < n; ++k) {
+    const int b = (int)((index >> k) & 1);
+    const int cl = S.dims[k], cr = S.dims[k + 1];
+    const double2* G = S.gam + ((size_t)k * 2 + b) * C * C;
+    if (tid < cr) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int a = 0; a < cl; ++a) cfma(acc, v[cur][a], G[(size_t)a * C + tid]);
+      const double l = S.lam[(size_t)(k + 1) * C + tid];
+      v[cur ^ 1][tid] = make_double2(acc.x * l, acc.y * l);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  if (tid == 0) out[blockIdx.x] = v[cur][0];
+}
+
+__global__ void mps_set_product_kernel(StateMut S, long long index, int n, int C) {
+  const int k = blockIdx.x;
+  double2* G = S.gam + (size_t)k * 2 * C * C;
+  for (int i = threadIdx.x; i < 2 * C * C; i += blockDim.x) G[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int b = (int)((index >> k) & 1);
+    G[(size_t)b * C * C] = make_double2(1.0, 0.0);
+    S.dims[k] = 1;
+    if (k == n - 1) S.dims[n] = 1;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    S.lam[(size_t)k * C + i] = (i == 0) ? 1.0 : 0.0;
+    if (k == n - 1) S.lam[(size_t)n * C + i] = (i == 0) ? 1.0 : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static size_t gam_elems(const aqc_mps* m) { return (size_t)m->n * 2 * m->C * m->C; }
+static size_t lam_elems(const aqc_mps* m) { return (size_t)(m->n + 1) * m->C; }
+
+static StateView view(const aqc_mps* m, int slot) {
+  return {m->st[slot].gam, m->st[slot].lam, m->st[slot].dims};
+}
+static StateMut mut(const aqc_mps* m, int slot) {
+  return {m->st[slot].gam, m->st[slot].lam, m->st[slot].dims};
+}
+
+static int mps_check_slot(const aqc_mps* m, int slot) {
+  if (!m) return aqc_fail(AQC_EINVAL, "null MPS workspace");
+  if (slot < 0 || slot >= m->nslots) return aqc_fail(AQC_EINVAL, "MPS slot %d out of range", slot);
+  return AQC_OK;
+}
+
+static int mps_ensure_pinned(aqc_mps* m, size_t doubles) {
+  if (doubles <= m->pinned_cap) return AQC_OK;
+  if (m->h_pinned) cudaFreeHost(m->h_pinned);
+  m->h_pinned = nullptr;
+  m->pinned_cap = 0;
+  MCU(cudaMallocHost(&m->h_pinned, doubles * sizeof(double)));
+  m->pinned_cap = doubles;
+  return AQC_OK;
+}
+
+extern "C" void aqc_mps_destroy(aqc_mps* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (auto& s : m->st) {
+    if (s.gam) cudaFree(s.gam);
+    if (s.lam) cudaFree(s.lam);
+    if (s.dims) cudaFree(s.dims);
+  }
+  for (void* p : {(void*)m->d_thetas, (void*)m->d_gate, (void*)m->d_theta0, (void*)m->d_work,
+                  (void*)m->d_vmat, (void*)m->d_envL, (void*)m->d_envR, (void*)m->d_rho,
+                  (void*)m->d_gacc, (void*)m->d_small, (void*)m->d_idx, (void*)m->fwd.d_tasks,
+                  (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env})
+    if (p) cudaFree(p);
+  if (m->h_pinned) cudaFreeHost(m->h_pinned);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, double trunc_thr,
+                              int num_slots, aqc_mps** out) {
+  if (!out) return aqc_fail(AQC_EINVAL, "out is null");
+  *out = nullptr;
+  if (!circ) return aqc_fail(AQC_EINVAL, "circuit is null");
+  if (chi_max < 1 || chi_max > kMaxChi)
+    return aqc_fail(AQC_EINVAL, "chi_max must be in [1, %d]", kMaxChi);
+  if (!(trunc_thr >= 0.0 && trunc_thr <= 0.1)) return aqc_fail(AQC_EINVAL, "bad trunc_thr");
+  if (num_slots < 1 || num_slots > 64) return aqc_fail(AQC_EINVAL, "num_slots must be in [1, 64]");
+  const int ndev = aqc_device_count();
+  if (ndev <= 0) return aqc_fail(AQC_ENODEV, "no CUDA device visible: this library has no CPU path");
+  if (device < 0 || device >= ndev) return aqc_fail(AQC_EINVAL, "device %d out of range", device);
+  aqc_mps* m = new aqc_mps();
+  m->device = device;
+  m->n = aqc_circ_n(circ);
+  m->C = kMaxChi;
+  m->ent = aqc_circ_ent(circ);
+  m->tpb = aqc_circ_tpb(circ);
+  m->nthetas = aqc_circ_nthetas(circ);
+  m->chi_max = chi_max;
+  m->trunc_thr = trunc_thr;
+  m->nslots = num_slots;
+  std::string err;
+  if (build_mps_program(circ, false, m->fwd, err) || build_mps_program(circ, true, m->dag, err)) {
+    delete m;
+    return aqc_fail(AQC_EINVAL, "%s", err.c_str());
+  }
+  m->maxtasks = m->n;
+  for (auto& s : m->fwd.steps) m->maxtasks = std::max(m->maxtasks, s.ntasks);
+  cudaError_t e = cudaSetDevice(device);
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, 0);
+  };
+  m->st.resize(num_slots);
+  for (auto& s : m->st) {
+    alloc((void**)&s.gam, gam_elems(m) * sizeof(double2));
+    alloc((void**)&s.lam, lam_elems(m) * sizeof(double));
+    alloc((void**)&s.dims, (m->n + 1) * sizeof(int));
+  }
+  const size_t C = m->C, mt = m->maxtasks;
+  alloc((void**)&m->d_thetas, (size_t)m->nthetas * sizeof(double));
+  alloc((void**)&m->d_gate, mt * 16 * sizeof(double2));
+  alloc((void**)&m->d_theta0, 2 * mt * 4 * C * C * sizeof(double2));
+  alloc((void**)&m->d_work, 2 * mt * 4 * C * C * sizeof(double2));
+  alloc((void**)&m->d_vmat, 2 * mt * 4 * C * C * sizeof(double2));
+  alloc((void**)&m->d_envL, (size_t)(m->n + 1) * C * C * sizeof(double2));
+  alloc((void**)&m->d_envR, (size_t)(m->n + 1) * C * C * sizeof(double2));
+  alloc((void**)&m->d_rho, mt * 16 * sizeof(double2));
+  alloc((void**)&m->d_gacc, (size_t)m->nthetas * 2 * sizeof(double));
+  alloc((void**)&m->d_small, 4096 * sizeof(double2));
+  alloc((void**)&m->d_idx, 4096 * sizeof(long long));
+  for (MpsProgram* p : {&m->fwd, &m->dag}) {
+    alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_tasks, p->tasks.data(), p->tasks.size() * sizeof(MpsTask),
+                     cudaMemcpyHostToDevice);
+    alloc((void**)&p->d_env, p->env.size() * sizeof(EnvTask));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_env, p->env.data(), p->env.size() * sizeof(EnvTask), cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mps_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mps_rho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    const int code = (e == cudaErrorMemoryAllocation) ? AQC_ENOMEM : AQC_ECUDA;
+    aqc_fail(code, "MPS workspace setup failed: %s", cudaGetErrorString(e));
+    std::string keep = aqc_last_error();
+    aqc_mps_destroy(m);
+    aqc_fail(code, "%s", keep.c_str());
+    return code;
+  }
+  *out = m;
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_bond_capacity(const aqc_mps* m) { return m ? m->C : AQC_EINVAL; }
+
+// Host layout of a state (all sites padded to the capacity C):
+//   gam: complex128 [n][2][C][C], lam: float64 [n+1][C] (bond j left of site j; bonds 0, n = [1]),
+//   dims: int32 [n+1].
+extern "C" int aqc_mps_upload(aqc_mps* m, int slot, const double* gam, const double* lam,
+                              const int32_t* dims) {
+  int rc = mps_check_slot(m, slot);
+  if (rc) return rc;
+  if (!gam || !lam || !dims) return aqc_fail(AQC_EINVAL, "null argument");
+  for (int j = 0; j <= m->n; ++j)
+    if (dims[j] < 1 || dims[j] > m->C) return aqc_fail(AQC_EINVAL, "bond dimension out of range");
+  if (dims[0] != 1 || dims[m->n] != 1) return aqc_fail(AQC_EINVAL, "outer bonds must have dimension 1");
+  MCU(cudaSetDevice(m->device));
+  MCU(cudaMemcpyAsync(m->st[slot].gam, gam, gam_elems(m) * sizeof(double2), cudaMemcpyHostToDevice, m->stream));
+  MCU(cudaMemcpyAsync(m->st[slot].lam, lam, lam_elems(m) * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  MCU(cudaMemcpyAsync(m->st[slot].dims, dims, (m->n + 1) * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_download(aqc_mps* m, int slot, double* gam, double* lam, int32_t* dims) {
+  int rc = mps_check_slot(m, slot);
+  if (rc) return rc;
+  if (!gam || !lam || !dims) return aqc_fail(AQC_EINVAL, "null argument");
+  MCU(cudaSetDevice(m->device));
+  MCU(cudaMemcpyAsync(gam, m->st[slot].gam, gam_elems(m) * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaMemcpyAsync(lam, m->st[slot].lam, lam_elems(m) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaMemcpyAsync(dims, m->st[slot].dims, (m->n + 1) * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+static int copy_state_async(aqc_mps* m, int src, int dst) {
+  if (src == dst) return AQC_OK;
+  MCU(cudaMemcpyAsync(m->st[dst].gam, m->st[src].gam, gam_elems(m) * sizeof(double2), cudaMemcpyDeviceToDevice, m->stream));
+  MCU(cudaMemcpyAsync(m->st[dst].lam, m->st[src].lam, lam_elems(m) * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  MCU(cudaMemcpyAsync(m->st[dst].dims, m->st[src].dims, (m->n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
+  return AQC_OK;
+}
+
+static int set_product_async(aqc_mps* m, int slot, long long index) {
+  mps_set_product_kernel<<<m->n, 256, 0, m->stream>>>(mut(m, slot), index, m->n, m->C);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_set_product(aqc_mps* m, int slot, int64_t index) {
+  int rc = mps_check_slot(m, slot);
+  if (rc) return rc;
+  if (index < 0 || (m->n < 63 && index >= (1ll << m->n))) return aqc_fail(AQC_EINVAL, "basis index out of range");
+  MCU(cudaSetDevice(m->device));
+  rc = set_product_async(m, slot, index);
+  if (rc) return rc;
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+static int upload_thetas_async(aqc_mps* m, const double* thetas) {
+  int rc = mps_ensure_pinned(m, (size_t)m->nthetas * 2 + 8192);
+  if (rc) return rc;
+  memcpy(m->h_pinned, thetas, (size_t)m->nthetas * sizeof(double));
+  MCU(cudaMemcpyAsync(m->d_thetas, m->h_pinned, (size_t)m->nthetas * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  return AQC_OK;
+}
+
+static int launch_algebra(aqc_mps* m, const MpsTask* tasks, int ntasks, int mode) {
+  const int per = 32;  // tasks per CTA (4 threads each)
+  dim3 grid((ntasks + per - 1) / per);
+  switch (m->ent) {
+    case AQC_ENT_CX:
+      mps_algebra_kernel<AQC_ENT_CX><<<grid, per * 4, 0, m->stream>>>(tasks, ntasks, m->d_thetas, mode, m->d_gate, m->d_rho, m->d_gacc);
+      break;
+    case AQC_ENT_CZ:
+      mps_algebra_kernel<AQC_ENT_CZ><<<grid, per * 4, 0, m->stream>>>(tasks, ntasks, m->d_thetas, mode, m->d_gate, m->d_rho, m->d_gacc);
+      break;
+    default:
+      mps_algebra_kernel<AQC_ENT_CP><<<grid, per * 4, 0, m->stream>>>(tasks, ntasks, m->d_thetas, mode, m->d_gate, m->d_rho, m->d_gacc);
+  }
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+// applies the front layer (single-site tasks) of `prog` to the given states
+static int run_front(aqc_mps* m, const MpsProgram& prog, bool dagger, const int* slots, int nstates) {
+  int rc = launch_algebra(m, prog.d_tasks, prog.nfront, dagger ? 1 : 0);
+  if (rc) return rc;
+  for (int s = 0; s < nstates; ++s) {
+    mps_apply1q_kernel<<<prog.nfront, 256, 0, m->stream>>>(mut(m, slots[s]), prog.d_tasks, m->d_gate, m->C);
+    MCU(cudaGetLastError());
+    m->last_launches++;
+  }
+  return AQC_OK;
+}
+
+// gate + SVD of one two-qubit step for the given states (theta0 saved when keep0)
+static int run_step_theta(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, const int* slots,
+                          int nstates, bool with_gate, bool keep0, bool with_work) {
+  ThetaArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  for (int s = 0; s < nstates; ++s) ta.st[s] = view(m, slots[s]);
+  ta.tasks = prog.d_tasks + st.task0;
+  ta.gate = with_gate ? m->d_gate : nullptr;
+  ta.theta0 = keep0 ? m->d_theta0 : nullptr;
+  ta.work = with_work ? m->d_work : nullptr;
+  ta.C = m->C;
+  ta.maxtasks = m->maxtasks;
+  ta.single_site = 0;
+  mps_theta_kernel<<<dim3(st.ntasks, nstates), 512, 0, m->stream>>>(ta);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, const int* slots, int nstates) {
+  SvdArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  for (int s = 0; s < nstates; ++s) sa.st[s] = mut(m, slots[s]);
+  sa.tasks = prog.d_tasks + st.task0;
+  sa.work = m->d_work;
+  sa.vmat = m->d_vmat;
+  sa.C = m->C;
+  sa.maxtasks = m->maxtasks;
+  sa.chi_max = m->chi_max;
+  sa.trunc_thr = m->trunc_thr;
+  mps_svd_kernel<<<dim3(st.ntasks, nstates), 512, 0, m->stream>>>(sa);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+static int apply_async(aqc_mps* m, const double* thetas, int dagger, int src, int dst) {
+  int rc = upload_thetas_async(m, thetas);
+  if (rc) return rc;
+  rc = copy_state_async(m, src, dst);
+  if (rc) return rc;
+  const MpsProgram& prog = dagger ? m->dag : m->fwd;
+  const int slots[1] = {dst};
+  if (!dagger) {
+    rc = run_front(m, prog, false, slots, 1);
+    if (rc) return rc;
+  }
+  for (const MpsStep& st : prog.steps) {
+    rc = launch_algebra(m, prog.d_tasks + st.task0, st.ntasks, dagger ? 1 : 0);
+    if (rc) return rc;
+    rc = run_step_theta(m, prog, st, slots, 1, true, false, true);
+    if (rc) return rc;
+    rc = run_step_svd(m, prog, st, slots, 1);
+    if (rc) return rc;
+  }
+  if (dagger) {
+    rc = run_front(m, prog, true, slots, 1);
+    if (rc) return rc;
+  }
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_apply(aqc_mps* m, const double* thetas, int dagger, int src_slot, int dst_slot) {
+  int rc = mps_check_slot(m, src_slot);
+  if (rc) return rc;
+  rc = mps_check_slot(m, dst_slot);
+  if (rc) return rc;
+  if (!thetas) return aqc_fail(AQC_EINVAL, "thetas is null");
+  MCU(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  MCU(cudaEventRecord(m->ev0, m->stream));
+  rc = apply_async(m, thetas, dagger, src_slot, dst_slot);
+  if (rc) return rc;
+  MCU(cudaEventRecord(m->ev1, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  MCU(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+  return AQC_OK;
+}
+
+static int amplitudes_async(aqc_mps* m, int slot, const int64_t* idx, int count) {
+  if (count > 4096) return aqc_fail(AQC_EINVAL, "too many indices");
+  MCU(cudaMemcpyAsync(m->d_idx, idx, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice, m->stream));
+  mps_amplitude_kernel<<<count, 64, 0, m->stream>>>(view(m, slot), m->d_idx, m->n, m->C, m->d_small);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+// out[i] = <idx_i | slot>   (MpsStateHandler.state_dot_vector for basis-state handlers)
+extern "C" int aqc_mps_amplitudes(aqc_mps* m, int slot, const int64_t* idx, int count, double* out) {
+  int rc = mps_check_slot(m, slot);
+  if (rc) return rc;
+  if (!idx || !out || count <= 0) return aqc_fail(AQC_EINVAL, "bad arguments");
+  MCU(cudaSetDevice(m->device));
+  rc = amplitudes_async(m, slot, idx, count);
+  if (rc) return rc;
+  MCU(cudaMemcpyAsync(out, m->d_small, (size_t)count * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_objective(aqc_mps* m, const double* thetas, int target_slot, int z0_slot,
+                                 const int64_t* idx, int count, double* hs_out) {
+  int rc = mps_check_slot(m, target_slot);
+  if (rc) return rc;
+  rc = mps_check_slot(m, z0_slot);
+  if (rc) return rc;
+  if (!thetas || !idx || !hs_out || count <= 0) return aqc_fail(AQC_EINVAL, "bad arguments");
+  MCU(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  MCU(cudaEventRecord(m->ev0, m->stream));
+  rc = apply_async(m, thetas, 1, target_slot, z0_slot);
+  if (rc) return rc;
+  rc = amplitudes_async(m, z0_slot, idx, count);
+  if (rc) return rc;
+  MCU(cudaEventRecord(m->ev1, m->stream));
+  MCU(cudaMemcpyAsync(hs_out, m->d_small, (size_t)count * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  MCU(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+  return AQC_OK;
+}
+
+static int env_launch(aqc_mps* m, int wslot, int zslot, int count, const EnvTask* d_tasks) {
+  if (count <= 0) return AQC_OK;
+  EnvArgs ea;
+  ea.w = view(m, wslot);
+  ea.z = view(m, zslot);
+  ea.tasks = d_tasks;
+  ea.envL = m->d_envL;
+  ea.envR = m->d_envR;
+  ea.C = m->C;
+  mps_env_kernel<<<(unsigned)count, 512, 64 * 1024, m->stream>>>(ea);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  return AQC_OK;
+}
+
+// full left-to-right and right-to-left environment sweeps of <w|z>
+static int env_full_sweeps(aqc_mps* m, int wslot, int zslot, bool left_only) {
+  mps_env_init_kernel<<<1, 32, 0, m->stream>>>(m->d_envL, m->d_envR, m->n, m->C);
+  MCU(cudaGetLastError());
+  m->last_launches++;
+  const EnvTask* d = m->fwd.d_env;  // [L 0..n-1 | R n-1..0]
+  for (int i = 0; i < m->n; ++i) {
+    int rc = env_launch(m, wslot, zslot, 1, d + i);
+    if (rc) return rc;
+    if (!left_only) {
+      rc = env_launch(m, wslot, zslot, 1, d + m->n + i);
+      if (rc) return rc;
+    }
+  }
+  return AQC_OK;
+}
+
+// <slot_a | slot_b>  (mps_dot, mps_operations.py:192-213)
+extern "C" int aqc_mps_dot(aqc_mps* m, int slot_a, int slot_b, double* out) {
+  int rc = mps_check_slot(m, slot_a);
+  if (rc) return rc;
+  rc = mps_check_slot(m, slot_b);
+  if (rc) return rc;
+  if (!out) return aqc_fail(AQC_EINVAL, "out is null");
+  MCU(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  rc = env_full_sweeps(m, slot_a, slot_b, true);
+  if (rc) return rc;
+  MCU(cudaMemcpyAsync((void*)out, m->d_envL + (size_t)m->n * m->C * m->C,
+                      sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+// Complex gradient of <V x | y> given z0 = V^H y in MPS form (fast_dot_gradient).
+// x = basis state |x_basis> (x_slot < 0) or the state in x_slot.  w_slot / z_slot receive V x, V z0.
+extern "C" int aqc_mps_grad(aqc_mps* m, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
+                            int w_slot, int z_slot, double* grad_out) {
+  int rc = mps_check_slot(m, z0_slot);
+  if (rc) return rc;
+  rc = mps_check_slot(m, w_slot);
+  if (rc) return rc;
+  rc = mps_check_slot(m, z_slot);
+  if (rc) return rc;
+  if (x_slot >= 0 && (rc = mps_check_slot(m, x_slot))) return rc;
+  if (w_slot == z_slot || w_slot == z0_slot) return aqc_fail(AQC_EINVAL, "slot aliasing");
+  if (!thetas || !grad_out) return aqc_fail(AQC_EINVAL, "null argument");
+  MCU(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  const int n = m->n;
+  auto done = [&](int code) {
+    cudaStreamSynchronize(m->stream);
+    return code;
+  };
+  MCU(cudaEventRecord(m->ev0, m->stream));
+  rc = upload_thetas_async(m, thetas);
+  if (rc) return done(rc);
+  cudaMemsetAsync(m->d_gacc, 0, (size_t)m->nthetas * 2 * sizeof(double), m->stream);
+  if (x_slot >= 0)
+    rc = copy_state_async(m, x_slot, w_slot);
+  else
+    rc = set_product_async(m, w_slot, x_basis);
+  if (rc) return done(rc);
+  rc = copy_state_async(m, z0_slot, z_slot);
+  if (rc) return done(rc);
+  const int slots[2] = {w_slot, z_slot};
+  const MpsProgram& prog = m->fwd;
+
+  // environments of <w|z> at every bond
+  rc = env_full_sweeps(m, w_slot, z_slot, false);
+  if (rc) return done(rc);
+
+  // ---- front layer: rho of every site, derivatives, then the gates
+  {
+    ThetaArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.st[0] = view(m, w_slot);
+    ta.st[1] = view(m, z_slot);
+    ta.tasks = prog.d_tasks;
+    ta.theta0 = m->d_theta0;
+    ta.C = m->C;
+    ta.maxtasks = m->maxtasks;
+    ta.single_site = 1;
+    mps_theta_kernel<<<dim3(n, 2), 512, 0, m->stream>>>(ta);
+    mps_zero_rho_kernel<<<(m->maxtasks * 16 + 255) / 256, 256, 0, m->stream>>>(m->d_rho, m->maxtasks * 16);
+    RhoArgs ra;
+    ra.w = view(m, w_slot);
+    ra.z = view(m, z_slot);
+    ra.tasks = prog.d_tasks;
+    ra.theta0 = m->d_theta0;
+    ra.envL = m->d_envL;
+    ra.envR = m->d_envR;
+    ra.rho = m->d_rho;
+    ra.C = m->C;
+    ra.maxtasks = m->maxtasks;
+    ra.nphys = 2;
+    ra.span = 1;
+    mps_rho_kernel<<<dim3(n, 2), 512, 128 * 1024, m->stream>>>(ra);
+    MCU(cudaGetLastError());
+    m->last_launches += 3;
+    rc = launch_algebra(m, prog.d_tasks, n, 2);
+    if (rc) return done(rc);
+    rc = run_front(m, prog, false, slots, 2);
+    if (rc) return done(rc);
+  }
+
+  // ---- two-qubit steps
+  for (size_t si = 0; si < prog.steps.size(); ++si) {
+    const MpsStep& st = prog.steps[si];
+    const MpsTask* tasks = prog.d_tasks + st.task0;
+    rc = launch_algebra(m, tasks, st.ntasks, 0);  // 4x4 gates of the step
+    if (rc) return done(rc);
+    rc = run_step_theta(m, prog, st, slots, 2, true, true, true);
+    if (rc) return done(rc);
+    RhoArgs ra;
+    ra.w = view(m, w_slot);
+    ra.z = view(m, z_slot);
+    ra.tasks = tasks;
+    ra.theta0 = m->d_theta0;
+    ra.envL = m->d_envL;
+    ra.envR = m->d_envR;
+    ra.rho = m->d_rho;
+    ra.C = m->C;
+    ra.maxtasks = m->maxtasks;
+    ra.nphys = 4;
+    ra.span = 2;
+    mps_rho_kernel<<<dim3(st.ntasks, 4), 512, 128 * 1024, m->stream>>>(ra);
+    MCU(cudaGetLastError());
+    m->last_launches++;
+    rc = launch_algebra(m, tasks, st.ntasks, 2);  // derivatives
+    if (rc) return done(rc);
+    rc = run_step_svd(m, prog, st, slots, 2);
+    if (rc) return done(rc);
+    // refresh the environments at the bonds this step modified: bond k+1 of every pair (k, k+1)
+    rc = env_launch(m, w_slot, z_slot, 2 * st.ntasks, prog.d_env + prog.env_step0[si]);
+    if (rc) return done(rc);
+  }
+  MCU(cudaEventRecord(m->ev1, m->stream));
+  rc = mps_ensure_pinned(m, (size_t)m->nthetas * 2 + 8192);
+  if (rc) return done(rc);
+  MCU(cudaMemcpyAsync(m->h_pinned, m->d_gacc, (size_t)m->nthetas * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  MCU(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+  // raw sums -> 0.5j <P w|z>: same factor map as the state-vector path
+  const int n3 = 3 * n, tpb = m->tpb, T = m->nthetas;
+  for (int k = 0; k < T; ++k) {
+    const double re = m->h_pinned[2 * k], im = m->h_pinned[2 * k + 1];
+    int kind;
+    if (k < n3)
+      kind = (k % 3 == 1) ? 0 : 1;
+    else {
+      const int r = (k - n3) % tpb;
+      kind = (r == 4) ? 2 : ((r == 0 || r == 2) ? 0 : 1);
+    }
+    if (kind == 0)
+      grad_out[2 * k] = 0.5 * re, grad_out[2 * k + 1] = 0.5 * im;
+    else if (kind == 1)
+      grad_out[2 * k] = -0.5 * im, grad_out[2 * k + 1] = 0.5 * re;
+    else
+      grad_out[2 * k] = im, grad_out[2 * k + 1] = -re;
+  }
+  return AQC_OK;
+}
+
+extern "C" float aqc_mps_last_kernel_ms(const aqc_mps* m) { return m ? m->last_ms : 0.f; }
+extern "C" int aqc_mps_last_num_launches(const aqc_mps* m) { return m ? m->last_launches : 0; }

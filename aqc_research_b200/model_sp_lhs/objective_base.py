@@ -248,7 +248,9 @@ class SpLHSObjectiveBase(ABC):
             self._dense = isinstance(self._state_handler, DenseStateHandler)
             self._ws = SvWorkspace(circuit, num_slots=5 if self._dense else 4, device=self._device)
             self._structure = self._ws.circuit.signature()
-        self._init_common()
+            self._init_common()
+        else:
+            self._num_states = num_qubits + 1  # finalised by the MPS subclass
 
     def _init_common(self):
         self._service = SpService(self._params, self._circuit, self._num_states, verbose=self._verbose)

@@ -147,6 +147,47 @@ void* aqc_sv_slot_ptr(aqc_sv* sv, int slot);
 /* CUDA stream handle (cudaStream_t) the workspace launches on. */
 void* aqc_sv_stream(aqc_sv* sv);
 
+/* ---------------------------------------------------------------------------
+ * MPS workspace on one GPU (Vidal form, bond capacity C = aqc_mps_bond_capacity()).
+ * Supports circuits whose unit-blocks act on ADJACENT qubits (TrotterAnsatz, "spin"/"line"
+ * layouts) -- the case of SpSurrogateObjectiveFastMpsTrotter
+ * (objective_lhs_sur_fast_mps_trotter.py:57-99).  Gate arithmetic that the reference delegates to
+ * qiskit-aer (mps_operations.py:248-265) runs here: two-site contraction, one-sided Jacobi SVD,
+ * truncation rule "drop the smallest Schmidt values while the sum of their squares < trunc_thr,
+ * cap at chi_max, renormalise".
+ * Host layout of a state: gam complex128[n][2][C][C] (Gamma_k[b], rows = left bond), lam
+ * float64[n+1][C] (bond j sits LEFT of site j; bonds 0 and n hold [1]), dims int32[n+1].
+ */
+int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, double trunc_thr,
+                   int num_slots, aqc_mps** out);
+void aqc_mps_destroy(aqc_mps* mps);
+int aqc_mps_bond_capacity(const aqc_mps* mps);
+/* QiskitMPS (mps_operations.py:33) -> slot and back. */
+int aqc_mps_upload(aqc_mps* mps, int slot, const double* gam, const double* lam,
+                   const int32_t* dims);
+int aqc_mps_download(aqc_mps* mps, int slot, double* gam, double* lam, int32_t* dims);
+/* slot = |index> as a bond-dimension-1 MPS (MpsStateHandler states for X-type preparations,
+ * objective_base.py:345-398). */
+int aqc_mps_set_product(aqc_mps* mps, int slot, int64_t index);
+/* dst = V src (dagger 0, v_mul_mps mps_operations.py:326-346) or V^H src (dagger 1,
+ * v_dagger_mul_mps :349-371), with truncation. */
+int aqc_mps_apply(aqc_mps* mps, const double* thetas, int dagger, int src_slot, int dst_slot);
+/* out[i] = <idx_i | slot>: MpsStateHandler.state_dot_vector (objective_base.py:400-403) for
+ * basis states. */
+int aqc_mps_amplitudes(aqc_mps* mps, int slot, const int64_t* idx, int count, double* out);
+/* z0_slot = V^H target_slot; hs_out[i] = <idx_i | z0>
+ * (objective_lhs_sur_fast_mps_trotter.py:130-140). */
+int aqc_mps_objective(aqc_mps* mps, const double* thetas, int target_slot, int z0_slot,
+                      const int64_t* idx, int count, double* hs_out);
+/* out = <slot_a | slot_b>  (mps_dot, mps_operations.py:192-213). */
+int aqc_mps_dot(aqc_mps* mps, int slot_a, int slot_b, double* out);
+/* Complex gradient of <V x | y> given z0 = V^H y (fast_dot_gradient,
+ * mps_dot_objective.py:41-242).  x = |x_basis> if x_slot < 0. */
+int aqc_mps_grad(aqc_mps* mps, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
+                 int w_slot, int z_slot, double* grad_out);
+float aqc_mps_last_kernel_ms(const aqc_mps* mps);
+int aqc_mps_last_num_launches(const aqc_mps* mps);
+
 #ifdef __cplusplus
 }
 #endif

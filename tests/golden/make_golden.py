@@ -144,3 +144,36 @@ if __name__ == "__main__":
     sv_cases()
     mat_cases()
     objective_sequences()
+
+
+def mps_cases():
+    """mps_to_vector / mps_dot of the reference (pure NumPy) on fixed MPS tuples (Vidal form)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import mps_oracle as M  # only used to GENERATE input tuples (format), not outputs
+
+    out = {}
+    rng = np.random.RandomState(2718)
+    case = 0
+    for n, chi in ((2, 2), (3, 2), (5, 4), (7, 3), (9, 8)):
+        m1, m2 = M.random_mps(n, chi, rng), M.random_mps(n, chi, rng)
+        assert R.mpsop.check_mps(m1) and R.mpsop.check_mps(m2)
+        pre = f"m{case}_"
+        out[pre + "n"] = np.array(n)
+        for tag, m in (("a", m1), ("b", m2)):
+            for k in range(n):
+                out[pre + f"{tag}_g0_{k}"], out[pre + f"{tag}_g1_{k}"] = m[0][k]
+                if k < n - 1:
+                    out[pre + f"{tag}_l_{k}"] = m[1][k]
+        out[pre + "vec_a"] = R.mpsop.mps_to_vector(m1)
+        out[pre + "vec_b"] = R.mpsop.mps_to_vector(m2)
+        out[pre + "dot_ab"] = np.array(R.mpsop.mps_dot(m1, m2))
+        out[pre + "dot_aa"] = np.array(R.mpsop.mps_dot(m1, m1))
+        case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "mps_cases.npz"), **out)
+    print("mps_cases:", case)
+
+
+if __name__ == "__main__":
+    mps_cases()

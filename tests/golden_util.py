@@ -24,3 +24,11 @@ def rel(a, b) -> float:
     """Norm-wise relative difference (reference: test/utils_for_testing.py:23-44)."""
     a, b = np.ravel(a), np.ravel(b)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def mps_from_golden(g, prefix: str, tag: str):
+    """Rebuilds a QiskitMPS tuple stored by make_golden.mps_cases()."""
+    n = int(g[prefix + "n"])
+    gam = [(g[f"{prefix}{tag}_g0_{k}"], g[f"{prefix}{tag}_g1_{k}"]) for k in range(n)]
+    lam = [g[f"{prefix}{tag}_l_{k}"] for k in range(n - 1)]
+    return gam, lam

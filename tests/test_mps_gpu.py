@@ -1,0 +1,169 @@
+"""
+GPU parity tests of the MPS path against the CPU oracles.
+  * format / dot / amplitudes: vs oracle/mps_oracle.py (pinned to the reference's mps_dot,
+    mps_to_vector);
+  * gate application and gradient WITHOUT truncation (trunc_thr = 1e-16, as in the reference's
+    test_mps.py / test_mps_fast_dot_gradient.py): must equal the state-vector oracle to 1e-10;
+  * with truncation: the result must stay normalised, respect chi_max and approach the exact
+    state as the threshold shrinks (parity with qiskit-aer is unpinned, see oracle header).
+"""
+
+import numpy as np
+import pytest
+
+from aqc_research_b200 import circuit_structures as cs
+from aqc_research_b200.mps_engine import MpsWorkspace
+from aqc_research_b200.parametric_circuit import ParametricCircuit, TrotterAnsatz
+from oracle import mps_oracle as M
+from oracle import sv_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+def _rand_vec(n, rng):
+    v = rng.randn(2**n) + 1j * rng.randn(2**n)
+    return v / np.linalg.norm(v)
+
+
+def _circuits(n, rng):
+    yield "t1", TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), False)
+    yield "t2", TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    for ent in ("cx", "cz", "cp"):
+        blocks = cs.create_ansatz_structure(n, "spin", "full", 2 * (n - 1) + 1)
+        flip = rng.rand(blocks.shape[1]) < 0.5
+        blocks[:, flip] = blocks[::-1, flip]
+        yield ent, ParametricCircuit(n, ent, blocks)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8])
+def test_roundtrip_dot_amplitudes(n):
+    rng = np.random.RandomState(n)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 1), True)
+    ws = MpsWorkspace(circ, num_slots=3)
+    u, v = _rand_vec(n, rng), _rand_vec(n, rng)
+    mu, mv = M.vector_to_mps(u), M.vector_to_mps(v)
+    ws.upload(0, mu)
+    ws.upload(1, mv)
+    assert _rel(M.mps_to_vector(ws.download(0)), u) < TOL
+    assert abs(ws.dot(0, 1) - np.vdot(u, v)) < TOL
+    assert abs(ws.dot(1, 1) - 1) < TOL
+    idx = rng.randint(0, 2**n, size=7)
+    assert _rel(ws.amplitudes(1, idx), v[idx]) < TOL
+    ws.set_product(2, 5 % 2**n)
+    e = np.zeros(2**n, dtype=complex)
+    e[5 % 2**n] = 1
+    assert _rel(M.mps_to_vector(ws.download(2)), e) < TOL
+    assert abs(ws.dot(2, 1) - v[5 % 2**n]) < TOL
+    ws.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 8])
+def test_untruncated_apply_and_gradient_vs_statevector(n):
+    rng = np.random.RandomState(100 + n)
+    for name, circ in _circuits(n, rng):
+        th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+        y = _rand_vec(n, rng)
+        ws = MpsWorkspace(circ, num_slots=5, chi_max=64, trunc_thr=1e-16)
+        ws.upload(0, M.vector_to_mps(y))
+        ws.apply(th, 0, 1, dagger=False)
+        assert _rel(M.mps_to_vector(ws.download(1)), O.apply_v(circ, th, y)) < TOL, (name, "V")
+        idx = O.basis_state_indices(n, 1)
+        hs = ws.objective(th, 0, 1, idx)
+        z0 = O.apply_v(circ, th, y, dagger=True)
+        assert _rel(M.mps_to_vector(ws.download(1)), z0) < TOL, (name, "VH")
+        assert _rel(hs, z0[idx]) < TOL
+        # gradient from a basis state and from a dense (entangled) state
+        g = ws.grad(th, x_basis=int(idx[1]), z0=1, w=2, z=3)
+        e = np.zeros(2**n, dtype=complex)
+        e[idx[1]] = 1
+        assert _rel(g, O.grad_sweep(circ, th, e, z0)) < TOL, (name, "grad basis")
+        x = _rand_vec(n, rng)
+        ws.upload(4, M.vector_to_mps(x))
+        g = ws.grad(th, x_slot=4, z0=1, w=2, z=3)
+        assert _rel(g, O.grad_sweep(circ, th, x, z0)) < TOL, (name, "grad dense")
+        assert _rel(M.mps_to_vector(ws.download(3)), y) < 1e-9  # z ends as V V^H y
+        assert _rel(M.mps_to_vector(ws.download(2)), O.apply_v(circ, th, x)) < 1e-9
+        ws.close()
+
+
+def test_truncation_behaviour():
+    n = 10
+    rng = np.random.RandomState(7)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 3), True)
+    th = 0.3 * (2 * rng.rand(circ.num_thetas) - 1)
+    exact = O.apply_v(circ, th, np.eye(2**n, dtype=complex)[:, 0])
+    errs = []
+    for thr, chi in ((1e-16, 32), (1e-8, 32), (1e-4, 32), (1e-16, 4)):
+        ws = MpsWorkspace(circ, num_slots=2, chi_max=chi, trunc_thr=thr)
+        ws.set_product(0, 0)
+        ws.apply(th, 0, 1)
+        out = ws.download(1)
+        assert max(M.bond_dims(out)) <= chi
+        # simultaneous truncations leave the Vidal form only approximately canonical
+        assert abs(ws.dot(1, 1) - 1) < (1e-10 if (thr < 1e-12 and chi >= 32) else 0.05)
+        errs.append(_rel(M.mps_to_vector(out), exact))
+        # same algorithmic rule on the CPU (gate by gate) stays close
+        ref = M.apply_v(circ, th, M.product_state(n, 0), trunc_thr=thr, chi_max=chi)
+        assert _rel(M.mps_to_vector(out), M.mps_to_vector(ref)) < max(50 * errs[-1], 1e-9)
+        ws.close()
+    assert errs[0] < TOL and errs[0] <= errs[1] * 1.0001 + 1e-12 and errs[1] <= errs[2] + 1e-12
+
+
+def test_non_adjacent_blocks_rejected():
+    circ = ParametricCircuit(4, "cx", np.array([[0, 1], [2, 3]]))
+    with pytest.raises(ValueError, match="adjacent"):
+        MpsWorkspace(circ, num_slots=1)
+
+
+def test_mps_objective_class_reproduces_statevector_golden():
+    """
+    SpSurrogateObjectiveFastMpsTrotter without truncation must reproduce the golden call
+    sequences recorded from the reference's STATE-VECTOR objective (same surrogate, same states).
+    """
+    from golden_util import load, rel
+    from aqc_research_b200.model_sp_lhs.objective_lhs_sur_fast_mps_trotter import (
+        SpSurrogateObjectiveFastMpsTrotter,
+    )
+
+    g = load("objective_sequences.npz")
+    for c in range(int(g["num_sp"])):
+        p = f"sp{c}_"
+        n, layers, steps = [int(v) for v in g[p + "meta"]]
+        if n > 8:
+            continue
+        circ = TrotterAnsatz(n, g[p + "blocks"], True)
+        params = dict(num_qubits=n, max_flips=1, maxiter=10, verbose=0, enable_optim_stats=False,
+                      num_simulations=1, trunc_thr=1e-16, state_prep_func=None)
+        objv = SpSurrogateObjectiveFastMpsTrotter(user_parameters=params, circ=circ)
+        objv.set_target(M.vector_to_mps(g[p + "target"]))
+        for s in range(steps):
+            th = g[p + "thetas"][s]
+            assert abs(objv.objective(th) - g[p + "f"][s]) < TOL
+            assert objv.max_no == int(g[p + "max_no"][s])
+            assert rel(objv.gradient(th), g[p + "grad"][s]) < TOL
+            assert abs(objv.weight - g[p + "weight"][s]) < TOL
+
+
+def test_function_level_shims():
+    from aqc_research_b200 import mps_operations as mpsop
+    from aqc_research_b200.mps_dot_objective import fast_dot_gradient
+
+    rng = np.random.RandomState(12)
+    n = 5
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 1), True)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    x, y = _rand_vec(n, rng), _rand_vec(n, rng)
+    mx, my = M.vector_to_mps(x), M.vector_to_mps(y)
+    assert abs(mpsop.mps_dot(mx, my) - np.vdot(x, y)) < TOL
+    vy = mpsop.v_mul_mps(circ, th, my)
+    assert _rel(mpsop.mps_to_vector(vy), O.apply_v(circ, th, y)) < TOL
+    vhy = mpsop.v_dagger_mul_mps(circ, th, my)
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    assert _rel(mpsop.mps_to_vector(vhy), z0) < TOL
+    g = fast_dot_gradient(circ, th, mx, vhy, block_range=(3, 9), front_layer=False)
+    assert _rel(g, O.grad_sweep(circ, th, x, z0, (3, 9), False)) < TOL
