@@ -24,6 +24,7 @@
 // Truncation follows the published qiskit-aer rule (see oracle/mps_oracle.py); truncated results
 // are "parity unpinned" against qiskit-aer, untruncated ones equal the state-vector path.
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -119,6 +120,9 @@ struct aqc_mps {
   double* d_gacc = nullptr;     // [nthetas] complex raw sums
   double2* d_small = nullptr;   // small outputs
   long long* d_idx = nullptr;
+  int* d_sweeps = nullptr;     // [2][maxtasks]
+  int* d_conv = nullptr;       // [2][maxtasks][32]
+  int num_sms = 148;
   double* h_pinned = nullptr;
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
@@ -460,14 +464,23 @@ struct SvdArgs {
   double2* vmat;
   int C, maxtasks, chi_max;
   double trunc_thr;
+  int* sweeps;  // [state][maxtasks] Jacobi sweeps used (diagnostics)
+  int* conv;    // [state][maxtasks][32] rotations counted per sweep (cluster-wide convergence)
 };
 
-__global__ void __launch_bounds__(512) mps_svd_kernel(const SvdArgs A) {
+__global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
+  __shared__ double s_rot[16 * 28 * 3];
   __shared__ double s_sig[2 * kMaxChi];
   __shared__ int s_order[2 * kMaxChi];
   __shared__ int s_keep, s_total;
   __shared__ double s_scale;
-  const int t = blockIdx.x, s = blockIdx.y, C = A.C;
+  // One SVD is shared by the CTAs of a thread-block cluster: each CTA rotates its share of the
+  // block pairs of a round (the matrix lives in global memory / L2), rounds are separated by
+  // cluster barriers.  Rank 0 finishes (sort, truncate, split).
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int t = blockIdx.x / csize, s = blockIdx.y, C = A.C;
   const MpsTask tk = A.tasks[t];
   const StateMut S = A.st[s];
   const int k = tk.site;
@@ -480,96 +493,222 @@ __global__ void __launch_bounds__(512) mps_svd_kernel(const SvdArgs A) {
   double2* V = A.vmat + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-  for (int i = tid; i < Cc * Cc; i += blockDim.x) {
+  for (int i = tid + crank * blockDim.x; i < Cc * Cc; i += blockDim.x * csize) {
     const int r = i % Cc, c = i / Cc;
     V[r + (size_t)c * LD] = make_double2(r == c ? 1.0 : 0.0, 0.0);
   }
-  __syncthreads();
+  int* conv = A.conv + ((size_t)s * A.maxtasks + t) * 32;
+  if (crank == 0 && tid < 32) conv[tid] = 0;
+  __threadfence();
+  cluster.sync();
 
-  const int ne = (Cc + 1) & ~1;  // even number of players (one phantom if Cc is odd)
+  // Block one-sided Jacobi.  Columns are grouped in fours; a warp takes a PAIR of groups (8 columns,
+  // 4 rows per lane => 32 complex numbers in registers) and orthogonalises all 28 column pairs of
+  // the block in registers (7 inner rounds of 4 independent rotations), so every column is loaded
+  // and stored once per 7 rotations instead of once per rotation: the plain cyclic scheme is bound
+  // by per-SM L2 bandwidth (16 KiB moved per rotation).  The rotations are recorded in shared
+  // memory and replayed on the 8 matching columns of V.
+  const int ng = (Cc + 3) / 4;       // column groups
+  const int ne = (ng + 1) & ~1;      // even number of players (one phantom group if ng is odd)
   const int npairs = ne / 2;
-  const double tol = 1e-15;
-  for (int sweep = 0; sweep < 40 && ne > 1; ++sweep) {
+  // convergence: |<p, q>| <= tol |p| |q| with tol ~ 2 sqrt(R) eps (LAPACK xGESVJ uses sqrt(m) eps);
+  // a tighter value sits below the rounding noise of the inner product and never converges
+  const double tol = 2.0 * sqrt((double)R) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  double* rot = s_rot + warp * (28 * 3);
+  for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
-    for (int round = 0; round < ne - 1; ++round) {
-      for (int pi = warp; pi < npairs; pi += nwarps) {
-        int p, q;
-        if (pi == 0) {
-          p = ne - 1;
-          q = round;
+    const int nrounds = (ne > 1) ? ne - 1 : 1;
+    for (int round = 0; round < nrounds; ++round) {
+      for (int pi = warp * csize + crank; pi < npairs; pi += nwarps * csize) {
+        int gI, gJ;
+        if (ne == 1 || ng == 1) {
+          gI = 0;
+          gJ = 1;  // single group: the second group is empty
+        } else if (pi == 0) {
+          gI = ne - 1;
+          gJ = round;
         } else {
-          p = (round + pi) % (ne - 1);
-          q = (round + ne - 1 - pi) % (ne - 1);
+          gI = (round + pi) % (ne - 1);
+          gJ = (round + ne - 1 - pi) % (ne - 1);
         }
-        if (p > q) {
-          const int tmp = p;
-          p = q;
-          q = tmp;
+        if (gI > gJ) {
+          const int tmp = gI;
+          gI = gJ;
+          gJ = tmp;
         }
-        if (q >= Cc) continue;  // phantom
-        double2* bp = B + (size_t)p * LD;
-        double2* bq = B + (size_t)q * LD;
-        double2 xp[4], xq[4];
-        double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+        if (gI >= ng) continue;
+        int col[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lane + 32 * e;
-          xp[e] = (r < R) ? bp[r] : make_double2(0.0, 0.0);
-          xq[e] = (r < R) ? bq[r] : make_double2(0.0, 0.0);
-          al = fma(xp[e].x, xp[e].x, fma(xp[e].y, xp[e].y, al));
-          be = fma(xq[e].x, xq[e].x, fma(xq[e].y, xq[e].y, be));
-          gr = fma(xp[e].x, xq[e].x, fma(xp[e].y, xq[e].y, gr));   // Re conj(p) q
-          gi = fma(xp[e].x, xq[e].y, fma(-xp[e].y, xq[e].x, gi));  // Im conj(p) q
-        }
+        for (int c = 0; c < 4; ++c) col[c] = 4 * gI + c, col[4 + c] = 4 * gJ + c;
+        double2 x[8][4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          al += __shfl_xor_sync(0xffffffffu, al, o);
-          be += __shfl_xor_sync(0xffffffffu, be, o);
-          gr += __shfl_xor_sync(0xffffffffu, gr, o);
-          gi += __shfl_xor_sync(0xffffffffu, gi, o);
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = lane + 32 * e;
+            x[c][e] = (col[c] < Cc && r < R) ? B[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
+          }
+        bool any = false;
+#pragma unroll
+        for (int ir = 0; ir < 7; ++ir) {
+          // the 4 disjoint pairs of this inner round: partial Gram entries of all four ...
+          double pv[16];
+#pragma unroll
+          for (int ip = 0; ip < 4; ++ip) {
+            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
+            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
+            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
+            double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double2 u = x[pa][e], v = x[pb][e];
+              al = fma(u.x, u.x, fma(u.y, u.y, al));
+              be = fma(v.x, v.x, fma(v.y, v.y, be));
+              gr = fma(u.x, v.x, fma(u.y, v.y, gr));   // Re conj(p) q
+              gi = fma(u.x, v.y, fma(-u.y, v.x, gi));  // Im conj(p) q
+            }
+            pv[ip * 4 + 0] = al, pv[ip * 4 + 1] = be, pv[ip * 4 + 2] = gr, pv[ip * 4 + 3] = gi;
+          }
+          // ... reduced over the warp with a transposing butterfly (16 + 1 shuffles): afterwards
+          // lane L holds entry ((L >> 1) & 15), i.e. the 8 lanes of group ip = L >> 3 hold pair ip
+          double red;
+          {
+            double w8[8], w4[4], w2[2];
+            const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const double send = u16 ? pv[i] : pv[i + 8];
+              const double keep = u16 ? pv[i + 8] : pv[i];
+              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double send = u8 ? w8[i] : w8[i + 4];
+              const double keep = u8 ? w8[i + 4] : w8[i];
+              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double send = u4 ? w4[i] : w4[i + 2];
+              const double keep = u4 ? w4[i + 2] : w4[i];
+              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            const double send = u2 ? w2[0] : w2[1];
+            const double keep = u2 ? w2[1] : w2[0];
+            red = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            red += __shfl_xor_sync(0xffffffffu, red, 1);
+          }
+          const int gbase = lane & 0x18;
+          const double al = __shfl_sync(0xffffffffu, red, gbase | 0);
+          const double be = __shfl_sync(0xffffffffu, red, gbase | 2);
+          const double gr = __shfl_sync(0xffffffffu, red, gbase | 4);
+          const double gi = __shfl_sync(0xffffffffu, red, gbase | 6);
+          // every 8-lane group computes the rotation of ITS pair (4 pairs in parallel):
+          // tan t = 2|g| sign(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = |q|^2 - |p|^2; the phase
+          // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
+          const double g2 = gr * gr + gi * gi;
+          const bool doit = (g2 > tol2 * al * be) && g2 > 0.0;
+          const double d = be - al;
+          const double h = sqrt(fma(d, d, 4.0 * g2));
+          const double kappa = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);
+          const double csl = rsqrt(fma(kappa * kappa, g2, 1.0));
+          const double my_cs = doit ? csl : 1.0;
+          const double my_sr = doit ? csl * kappa * gr : 0.0;
+          const double my_si = doit ? csl * kappa * gi : 0.0;
+          if ((lane & 7) == 0) {
+            double* rr = rot + (ir * 4 + (lane >> 3)) * 3;
+            rr[0] = my_cs, rr[1] = my_sr, rr[2] = my_si;
+          }
+#pragma unroll
+          for (int ip = 0; ip < 4; ++ip) {
+            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
+            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
+            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
+            const double cs = __shfl_sync(0xffffffffu, my_cs, ip << 3);
+            const double sr = __shfl_sync(0xffffffffu, my_sr, ip << 3);
+            const double si = __shfl_sync(0xffffffffu, my_si, ip << 3);
+            any = any || (sr != 0.0) || (si != 0.0);
+            // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q   (identity if not rotated)
+            const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double2 u = x[pa][e], v = x[pb][e];
+              double2 nu = make_double2(cs * u.x, cs * u.y);
+              cfma(nu, fm, v);
+              double2 nv = make_double2(cs * v.x, cs * v.y);
+              cfma(nv, fp, u);
+              x[pa][e] = nu;
+              x[pb][e] = nv;
+            }
+          }
         }
-        const double gabs = sqrt(gr * gr + gi * gi);
-        if (gabs <= tol * sqrt(al * be) || gabs == 0.0) continue;
+        if (!any) continue;  // warp-uniform
         rotated = 1;
-        const double zeta = (be - al) / (2.0 * gabs);
-        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
-        const double er = gr / gabs, ei = gi / gabs;  // e^{i phi}
-        // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q
-        const double2 fm = make_double2(-sn * er, sn * ei);  // -sn e^{-i phi}
-        const double2 fp = make_double2(sn * er, sn * ei);   //  sn e^{+i phi}
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lane + 32 * e;
-          if (r < R) {
-            double2 np_ = make_double2(cs * xp[e].x, cs * xp[e].y);
-            cfma(np_, fm, xq[e]);
-            double2 nq = make_double2(cs * xq[e].x, cs * xq[e].y);
-            cfma(nq, fp, xp[e]);
-            bp[r] = np_;
-            bq[r] = nq;
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = lane + 32 * e;
+            if (col[c] < Cc && r < R) B[r + (size_t)col[c] * LD] = x[c][e];
+          }
+        __syncwarp();
+        // replay on V
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = lane + 32 * e;
+            x[c][e] = (col[c] < Cc && r < Cc) ? V[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+        for (int ir = 0; ir < 7; ++ir) {
+#pragma unroll
+          for (int ip = 0; ip < 4; ++ip) {
+            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
+            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
+            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
+            const double* rr = rot + (ir * 4 + ip) * 3;
+            const double cs = rr[0], sr = rr[1], si = rr[2];
+            if (sr != 0.0 || si != 0.0) {
+              const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const double2 u = x[pa][e], v = x[pb][e];
+                double2 nu = make_double2(cs * u.x, cs * u.y);
+                cfma(nu, fm, v);
+                double2 nv = make_double2(cs * v.x, cs * v.y);
+                cfma(nv, fp, u);
+                x[pa][e] = nu;
+                x[pb][e] = nv;
+              }
+            }
           }
         }
-        double2* vp = V + (size_t)p * LD;
-        double2* vq = V + (size_t)q * LD;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lane + 32 * e;
-          if (r < Cc) {
-            const double2 yp = vp[r], yq = vq[r];
-            double2 np_ = make_double2(cs * yp.x, cs * yp.y);
-            cfma(np_, fm, yq);
-            double2 nq = make_double2(cs * yq.x, cs * yq.y);
-            cfma(nq, fp, yp);
-            vp[r] = np_;
-            vq[r] = nq;
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = lane + 32 * e;
+            if (col[c] < Cc && r < Cc) V[r + (size_t)col[c] * LD] = x[c][e];
           }
-        }
+        __syncwarp();
       }
-      __syncthreads();
+      __threadfence();
+      cluster.sync();
     }
-    if (__syncthreads_or(rotated) == 0) break;
+    if (tid == 0 && A.sweeps && crank == 0) A.sweeps[s * A.maxtasks + t] = sweep + 1;
+    const int mine = __syncthreads_or(rotated);
+    if (csize == 1) {
+      if (mine == 0) break;
+    } else {
+      if (tid == 0 && mine) atomicAdd(conv + sweep, 1);
+      __threadfence();
+      cluster.sync();
+      if (*(volatile int*)(conv + sweep) == 0) break;
+    }
   }
+  if (crank != 0) return;
 
   // singular values = column norms
   for (int c = warp; c < Cc; c += nwarps) {
@@ -969,7 +1108,7 @@ extern "C" void aqc_mps_destroy(aqc_mps* m) {
   for (void* p : {(void*)m->d_thetas, (void*)m->d_gate, (void*)m->d_theta0, (void*)m->d_work,
                   (void*)m->d_vmat, (void*)m->d_envL, (void*)m->d_envR, (void*)m->d_rho,
                   (void*)m->d_gacc, (void*)m->d_small, (void*)m->d_idx, (void*)m->fwd.d_tasks,
-                  (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env})
+                  (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env, (void*)m->d_sweeps, (void*)m->d_conv})
     if (p) cudaFree(p);
   if (m->h_pinned) cudaFreeHost(m->h_pinned);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -1030,6 +1169,9 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   alloc((void**)&m->d_gacc, (size_t)m->nthetas * 2 * sizeof(double));
   alloc((void**)&m->d_small, 4096 * sizeof(double2));
   alloc((void**)&m->d_idx, 4096 * sizeof(long long));
+  alloc((void**)&m->d_sweeps, 2 * mt * sizeof(int));
+  alloc((void**)&m->d_conv, 2 * mt * 32 * sizeof(int));
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
   for (MpsProgram* p : {&m->fwd, &m->dag}) {
     alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
     if (e == cudaSuccess)
@@ -1186,7 +1328,27 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   sa.maxtasks = m->maxtasks;
   sa.chi_max = m->chi_max;
   sa.trunc_thr = m->trunc_thr;
-  mps_svd_kernel<<<dim3(st.ntasks, nstates), 512, 0, m->stream>>>(sa);
+  sa.sweeps = m->d_sweeps;
+  sa.conv = m->d_conv;
+  // as many CTAs per SVD as fit in one wave (cluster of 1, 2 or 4)
+  int csize = 1;
+  const int nsvd = st.ntasks * nstates;
+  if (nsvd * 4 <= m->num_sms) csize = 4;
+  else if (nsvd * 2 <= m->num_sms) csize = 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(st.ntasks * csize, nstates);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = m->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MCU(cudaLaunchKernelEx(&cfg, mps_svd_kernel, sa));
   MCU(cudaGetLastError());
   m->last_launches++;
   return AQC_OK;
@@ -1459,3 +1621,13 @@ extern "C" int aqc_mps_grad(aqc_mps* m, const double* thetas, int x_slot, int64_
 
 extern "C" float aqc_mps_last_kernel_ms(const aqc_mps* m) { return m ? m->last_ms : 0.f; }
 extern "C" int aqc_mps_last_num_launches(const aqc_mps* m) { return m ? m->last_launches : 0; }
+
+// Diagnostics: Jacobi sweeps used by the SVDs of the most recent two-qubit step
+// (out[state * maxtasks + task]); returns the number of ints written.
+extern "C" int aqc_mps_debug_sweeps(aqc_mps* m, int32_t* out, int cap) {
+  if (!m || !out) return aqc_fail(AQC_EINVAL, "null argument");
+  const int cnt = std::min(cap, 2 * m->maxtasks);
+  MCU(cudaSetDevice(m->device));
+  MCU(cudaMemcpy(out, m->d_sweeps, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+  return cnt;
+}

@@ -185,6 +185,8 @@ int aqc_mps_dot(aqc_mps* mps, int slot_a, int slot_b, double* out);
  * mps_dot_objective.py:41-242).  x = |x_basis> if x_slot < 0. */
 int aqc_mps_grad(aqc_mps* mps, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
                  int w_slot, int z_slot, double* grad_out);
+/* Diagnostics: Jacobi sweeps used by the SVDs of the most recent two-qubit step. */
+int aqc_mps_debug_sweeps(aqc_mps* mps, int32_t* out, int cap);
 float aqc_mps_last_kernel_ms(const aqc_mps* mps);
 int aqc_mps_last_num_launches(const aqc_mps* mps);
 
