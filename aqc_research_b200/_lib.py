@@ -65,6 +65,28 @@ SIGNATURES = {
         [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
     ),
     "aqc_sv_slot_ptr": (ct.c_void_p, [ct.c_void_p, ct.c_int]),
+    "aqc_sv_create_sharded": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)],
+    ),
+    "aqc_sv_num_epochs": (ct.c_int, [ct.c_void_p, ct.c_int]),
+    "aqc_sv_epoch_layout": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "aqc_sv_begin": (ct.c_int, [ct.c_void_p, c_double_p, ct.c_int]),
+    "aqc_sv_run_epoch": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int],
+    ),
+    "aqc_sv_grad_finish": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+    "aqc_sv_ipc_export": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p]),
+    "aqc_sv_ipc_import": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]),
+    "aqc_sv_peer_attach": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]),
+    "aqc_sv_exchange": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "aqc_sv_fill_random_logical": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_uint64, c_double_p]),
+    "aqc_sv_scale": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double]),
+    "aqc_debug_program_sharded": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
+    ),
     "aqc_mps_create": (
         ct.c_int,
         [ct.c_void_p, ct.c_int, ct.c_int, ct.c_double, ct.c_int, ct.POINTER(ct.c_void_p)],

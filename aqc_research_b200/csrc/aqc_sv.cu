@@ -106,6 +106,8 @@ struct Program {
   std::vector<PassDesc> passes;
   std::vector<StageDesc> stages;
   StageDesc* d_stages = nullptr;
+  // sharded execution: passes [epoch_pass0[e], epoch_pass0[e+1]) need data layout epoch_layout[e]
+  std::vector<int> epoch_pass0, epoch_layout;
 };
 
 struct HostUnit {
@@ -157,18 +159,17 @@ static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUni
 // Greedy tile-pass scheduler.  `units` is the gate-unit sequence in execution order; units on
 // disjoint qubits commute, so a unit may run in the current pass iff all its qubits are inside
 // the tile and none of them is touched by an earlier unit that had to be deferred.
-static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max, int lowbits,
-                          bool reversed, Program& prog) {
-  std::vector<HostUnit> units;
-  build_units(c, reversed, units);
-  prog.passes.clear();
-  prog.stages.clear();
+// `units` carry PHYSICAL bit positions in qa / qb.  Passes are appended to `prog`.
+static void build_program_units(const std::vector<HostUnit>& units, int nbits, int tb_max,
+                                int lowbits, Program& prog) {
+  const int qoff = 0;
+  const size_t pass_begin = prog.passes.size();
   const int tb = std::min(nbits, tb_max);
   const int low = std::min(lowbits, tb);
 
   std::vector<char> done(units.size(), 0);
   size_t ndone = 0;
-  while (ndone < units.size() || prog.passes.empty()) {
+  while (ndone < units.size() || prog.passes.size() == pass_begin) {
     std::vector<char> intile(nbits, 0), blocked(nbits, 0);
     int ntile = 0;
     for (int b = 0; b < low; ++b) intile[b] = 1, ++ntile;
@@ -297,6 +298,96 @@ static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max,
     ndone += picked.size();
     if (picked.empty() && ndone < units.size()) break;  // cannot happen (tb >= 2)
   }
+}
+
+static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max, int lowbits,
+                          bool reversed, Program& prog) {
+  std::vector<HostUnit> units;
+  build_units(c, reversed, units);
+  for (HostUnit& u : units) {
+    u.qa += qoff;
+    if (u.kind) u.qb += qoff;
+  }
+  prog.passes.clear();
+  prog.stages.clear();
+  prog.epoch_pass0.assign(1, 0);
+  prog.epoch_layout.assign(1, 0);
+  build_program_units(units, nbits, tb_max, lowbits, prog);
+}
+
+// ---- global-qubit sharding (one state over 2^g GPUs) --------------------------------------------
+// The top g index bits select the rank.  Two data layouts alternate:
+//   layout A: qubits n-g..n-1 are global; qubits 0..g-1 sit on the TOP g local bits;
+//   layout B: qubits 0..g-1 are global; qubits n-g..n-1 sit on the top g local bits;
+// the other qubits occupy local bits 0..nl-g-1 (q -> q - g) in both.  Switching layouts is the
+// block transpose new[rank c][chunk r] = old[rank r][chunk c] over chunks of 2^(nl-g) amplitudes
+// (all-to-all over NVLink).  An epoch runs every gate unit that is executable without touching a
+// global qubit (a light-cone trapezoid of the brick-wall circuit); then the layout is switched.
+static int phys_bit(int q, int n, int g, int layout) {
+  const int nl = n - g;
+  if (q < g) return layout == 0 ? nl - g + q : -1;
+  if (q >= n - g) return layout == 0 ? -1 : nl - g + (q - (n - g));
+  return q - g;
+}
+
+static int build_program_sharded(const aqc_circuit& c, int g, int tb_max, int lowbits, bool reversed,
+                                 Program& prog, std::string& err) {
+  const int n = c.n, nl = n - g;
+  if (nl - g < 2 || 2 * g > n - 2) {
+    err = "too few qubits for this number of GPUs";
+    return AQC_EINVAL;
+  }
+  std::vector<HostUnit> units;
+  build_units(c, reversed, units);
+  prog.passes.clear();
+  prog.stages.clear();
+  prog.epoch_pass0.clear();
+  prog.epoch_layout.clear();
+  std::vector<char> done(units.size(), 0);
+  size_t ndone = 0;
+  int layout = 0, idle = 0;
+  while (ndone < units.size()) {
+    std::vector<char> blocked(n, 0);
+    std::vector<HostUnit> now;
+    std::vector<size_t> ids;
+    for (size_t k = 0; k < units.size(); ++k) {
+      if (done[k]) continue;
+      const HostUnit& u = units[k];
+      const int pa = phys_bit(u.qa, n, g, layout);
+      const int pb = u.kind ? phys_bit(u.qb, n, g, layout) : 0;
+      const bool blk = blocked[u.qa] || (u.kind && blocked[u.qb]);
+      if (!blk && pa >= 0 && pb >= 0) {
+        HostUnit v = u;
+        v.qa = pa;
+        if (u.kind) v.qb = pb;
+        now.push_back(v);
+        ids.push_back(k);
+      } else {
+        blocked[u.qa] = 1;
+        if (u.kind) blocked[u.qb] = 1;
+      }
+    }
+    if (now.empty()) {
+      if (++idle > 1) {
+        err = "circuit cannot be scheduled over global qubits (a unit couples the lowest and highest qubits)";
+        return AQC_EINVAL;
+      }
+      layout ^= 1;
+      continue;
+    }
+    idle = 0;
+    prog.epoch_pass0.push_back((int)prog.passes.size());
+    prog.epoch_layout.push_back(layout);
+    build_program_units(now, nl, tb_max, lowbits, prog);
+    for (size_t k : ids) done[k] = 1;
+    ndone += ids.size();
+    layout ^= 1;
+  }
+  if (prog.epoch_pass0.empty()) {  // circuit without units cannot happen (front layer), keep safe
+    prog.epoch_pass0.push_back(0);
+    prog.epoch_layout.push_back(0);
+  }
+  return AQC_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -594,6 +685,9 @@ struct aqc_sv {
   float last_ms = 0.f;
   int last_launches = 0;
   Program prog_grad, prog_fwd, prog_dag;
+  // global-qubit sharding (0 = single GPU)
+  int g = 0, rank = 0;
+  const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
 };
 
 static int ensure_pinned(aqc_sv* sv, size_t doubles) {
@@ -673,7 +767,8 @@ static int check_slot(const aqc_sv* sv, int slot) {
 
 // runs one compiled program; NVEC == 1: src0 -> dst0; NVEC == 2: (w, z)
 static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, const double2* src0,
-                       long long basis, const double2* src1, double2* dst0, double2* dst1) {
+                       long long basis, const double2* src1, double2* dst0, double2* dst1,
+                       int pass_begin = 0, int pass_end = -1) {
   PassArgs a;
   memset(&a, 0, sizeof(a));
   a.vec_stride = sv->size;
@@ -681,13 +776,14 @@ static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, con
   a.trig = sv->d_trig;
   a.gacc = sv->d_gacc;
   a.nthetas = sv->circ.nthetas;
-  for (size_t i = 0; i < prog.passes.size(); ++i) {
+  if (pass_end < 0) pass_end = (int)prog.passes.size();
+  for (int i = pass_begin; i < pass_end; ++i) {
     a.pd = prog.passes[i];
-    a.src[0] = (i == 0) ? src0 : dst0;
-    a.src[1] = (i == 0) ? src1 : dst1;
+    a.src[0] = (i == pass_begin) ? src0 : dst0;
+    a.src[1] = (i == pass_begin) ? src1 : dst1;
     a.dst[0] = dst0;
     a.dst[1] = dst1;
-    a.basis_index = (i == 0) ? basis : -1;
+    a.basis_index = (i == pass_begin) ? basis : -1;
     int rc;
     if (grad)
       rc = launch_pass_e<2, false>(sv, a);
@@ -789,8 +885,8 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols, int batch,
-                             int num_slots, aqc_sv** out) {
+static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, int batch,
+                          int num_slots, int g, int rank, aqc_sv** out) {
   if (!out) return fail(AQC_EINVAL, "out is null");
   *out = nullptr;
   if (!circ) return fail(AQC_EINVAL, "circuit is null");
@@ -801,13 +897,19 @@ extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols,
   const int ndev = aqc_device_count();
   if (ndev <= 0) return fail(AQC_ENODEV, "no CUDA device visible: this library has no CPU path");
   if (device < 0 || device >= ndev) return fail(AQC_EINVAL, "device %d out of range", device);
-  if (circ->n + log2_cols > 34) return fail(AQC_EINVAL, "state too large for one GPU");
+  if (circ->n + log2_cols - g > 34) return fail(AQC_EINVAL, "state too large for one GPU");
+  if (g < 0 || g > 4 || (g > 0 && (log2_cols != 0 || batch != 1)))
+    return fail(AQC_EINVAL, "sharding needs 1 <= log2_world <= 4, a vector state and batch 1");
+  if (rank < 0 || rank >= (1 << g)) return fail(AQC_EINVAL, "rank out of range");
   CU(cudaSetDevice(device));
   aqc_sv* sv = new aqc_sv();
   sv->circ = *circ;
   sv->device = device;
   sv->log2_cols = log2_cols;
-  sv->nbits = circ->n + log2_cols;
+  sv->g = g;
+  sv->rank = rank;
+  memset(sv->peer, 0, sizeof(sv->peer));
+  sv->nbits = circ->n + log2_cols - g;
   sv->batch = batch;
   sv->nslots = num_slots;
   sv->size = 1ll << sv->nbits;
@@ -842,15 +944,36 @@ extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols,
   const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", 11), kMaxTileBits - 1);
   const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", 11), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", 4);
-  build_program(sv->circ, log2_cols, sv->nbits, tb_grad, low, false, sv->prog_grad);
-  build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, false, sv->prog_fwd);
-  build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, true, sv->prog_dag);
+  if (g == 0) {
+    build_program(sv->circ, log2_cols, sv->nbits, tb_grad, low, false, sv->prog_grad);
+    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, false, sv->prog_fwd);
+    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, true, sv->prog_dag);
+  } else {
+    std::string err;
+    if (build_program_sharded(sv->circ, g, tb_grad, low, false, sv->prog_grad, err) ||
+        build_program_sharded(sv->circ, g, tb_apply, low, false, sv->prog_fwd, err) ||
+        build_program_sharded(sv->circ, g, tb_apply, low, true, sv->prog_dag, err)) {
+      fail(AQC_EINVAL, "%s", err.c_str());
+      return bail(AQC_EINVAL);
+    }
+  }
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag}) {
     int rc = upload_program(*p);
     if (rc) return bail(rc);
   }
   *out = sv;
   return AQC_OK;
+}
+
+extern "C" int aqc_sv_create(const aqc_circuit* circ, int device, int log2_cols, int batch,
+                             int num_slots, aqc_sv** out) {
+  return sv_create_impl(circ, device, log2_cols, batch, num_slots, 0, 0, out);
+}
+
+extern "C" int aqc_sv_create_sharded(const aqc_circuit* circ, int device, int log2_world, int rank,
+                                     int num_slots, aqc_sv** out) {
+  if (log2_world < 1) return fail(AQC_EINVAL, "log2_world must be >= 1");
+  return sv_create_impl(circ, device, 0, 1, num_slots, log2_world, rank, out);
 }
 
 extern "C" int64_t aqc_sv_state_size(const aqc_sv* sv) { return sv ? sv->size : 0; }
@@ -901,7 +1024,7 @@ static dim3 grid1d(long long size, int batch, int thr) {
 extern "C" int aqc_sv_set_basis(aqc_sv* sv, int slot, int64_t index) {
   int rc = check_slot(sv, slot);
   if (rc) return rc;
-  if (index < 0 || index >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
+  if (index < -1 || index >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
   CU(cudaSetDevice(sv->device));
   set_basis_kernel<<<grid1d(sv->size, sv->batch, 256), 256, 0, sv->stream>>>(
       sv->slots[slot], sv->size, sv->size, index);
@@ -1160,5 +1283,308 @@ extern "C" int aqc_sv_timer_stop(aqc_sv* sv, float* ms) {
   CU(cudaEventRecord(sv->tm1, sv->stream));
   CU(cudaEventSynchronize(sv->tm1));
   CU(cudaEventElapsedTime(ms, sv->tm0, sv->tm1));
+  return AQC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// epoch-wise execution (global-qubit sharding; a single-GPU workspace has exactly one epoch)
+// ------------------------------------------------------------------------------------------
+static const Program* prog_of(const aqc_sv* sv, int mode) {
+  return mode == 0 ? &sv->prog_grad : (mode == 1 ? &sv->prog_fwd : &sv->prog_dag);
+}
+
+extern "C" int aqc_sv_num_epochs(const aqc_sv* sv, int mode) {
+  if (!sv || mode < 0 || mode > 2) return AQC_EINVAL;
+  return (int)prog_of(sv, mode)->epoch_pass0.size();
+}
+
+extern "C" int aqc_sv_epoch_layout(const aqc_sv* sv, int mode, int epoch) {
+  if (!sv || mode < 0 || mode > 2) return AQC_EINVAL;
+  const Program* p = prog_of(sv, mode);
+  if (epoch < 0 || epoch >= (int)p->epoch_layout.size()) return AQC_EINVAL;
+  return p->epoch_layout[epoch];
+}
+
+// Uploads thetas (cos/sin table) for a following sequence of aqc_sv_run_epoch calls; mode 0
+// (gradient) also clears the raw inner-product accumulators.
+extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
+  if (!sv || !thetas || mode < 0 || mode > 2) return fail(AQC_EINVAL, "bad arguments");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  int rc = ensure_pinned(sv, tot * 2 + 64);
+  if (rc) return rc;
+  rc = upload_thetas(sv, thetas);
+  if (rc) return rc;
+  if (mode == 0) CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+// Runs the tile passes of one epoch.  mode 0: gradient on (vec0, vec1) = (w, z); mode 1 / 2:
+// V / V^H on vec0.  src slots are read by the first pass only (src0 < 0: vec0 is the local part
+// of a basis state: offset `basis_local`, or all zeros if basis_local < 0); dst slots receive the
+// result and are updated in place by the remaining passes.
+extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local,
+                                int src1, int dst0, int dst1) {
+  if (!sv || mode < 0 || mode > 2) return fail(AQC_EINVAL, "bad arguments");
+  const Program* p = prog_of(sv, mode);
+  if (epoch < 0 || epoch >= (int)p->epoch_pass0.size()) return fail(AQC_EINVAL, "bad epoch");
+  int rc = check_slot(sv, dst0);
+  if (rc) return rc;
+  if (src0 >= 0 && (rc = check_slot(sv, src0))) return rc;
+  if (mode == 0) {
+    if ((rc = check_slot(sv, dst1)) || (rc = check_slot(sv, src1))) return rc;
+    if (dst0 == dst1) return fail(AQC_EINVAL, "w and z must be different slots");
+  }
+  if (src0 < 0 && mode != 0) return fail(AQC_EINVAL, "basis source is only valid for the gradient");
+  CU(cudaSetDevice(sv->device));
+  const int p0 = p->epoch_pass0[epoch];
+  const int p1 = epoch + 1 < (int)p->epoch_pass0.size() ? p->epoch_pass0[epoch + 1] : (int)p->passes.size();
+  const long long basis = src0 >= 0 ? -1 : (basis_local >= 0 ? (long long)basis_local : (1ll << 62));
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  rc = run_program(sv, *p, mode == 0, mode == 2, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
+                   mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
+                   mode == 0 ? sv->slots[dst1] : nullptr, p0, p1);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  return AQC_OK;
+}
+
+// Downloads this workspace's (partial) raw inner products and converts them to 0.5j <P w|z>
+// (linear, so partial sums of several ranks may be added afterwards).
+extern "C" int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out) {
+  if (!sv || !grad_out) return fail(AQC_EINVAL, "bad arguments");
+  CU(cudaSetDevice(sv->device));
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  int rc = ensure_pinned(sv, tot * 2 + 64);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                     sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  const int n3 = 3 * sv->circ.n, tpb = sv->circ.tpb, T = sv->circ.nthetas;
+  for (int b = 0; b < sv->batch; ++b) {
+    const double* raw = sv->h_pinned + (size_t)b * T * 2;
+    double* g = grad_out + (size_t)b * T * 2;
+    for (int k = 0; k < T; ++k) {
+      const double re = raw[2 * k], im = raw[2 * k + 1];
+      int kind;
+      if (k < n3)
+        kind = (k % 3 == 1) ? 0 : 1;
+      else {
+        const int r = (k - n3) % tpb;
+        kind = (r == 4) ? 2 : ((r == 0 || r == 2) ? 0 : 1);
+      }
+      if (kind == 0)
+        g[2 * k] = 0.5 * re, g[2 * k + 1] = 0.5 * im;
+      else if (kind == 1)
+        g[2 * k] = -0.5 * im, g[2 * k + 1] = 0.5 * re;
+      else
+        g[2 * k] = im, g[2 * k + 1] = -re;
+    }
+  }
+  return AQC_OK;
+}
+
+// ---- layout switch: block transpose over the ranks through peer memory (NVLink P2P) ----------
+extern "C" int aqc_sv_ipc_export(aqc_sv* sv, int slot, unsigned char* handle64) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!handle64) return fail(AQC_EINVAL, "null handle");
+  CU(cudaSetDevice(sv->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, sv->slots[slot]));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+  memcpy(handle64, &h, 64);
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_ipc_import(aqc_sv* sv, int peer_rank, int slot, const unsigned char* handle64) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!handle64 || peer_rank < 0 || peer_rank >= (1 << sv->g) || peer_rank >= 16)
+    return fail(AQC_EINVAL, "bad peer rank");
+  CU(cudaSetDevice(sv->device));
+  if (peer_rank == sv->rank) {
+    sv->peer[slot][peer_rank] = sv->slots[slot];
+    return AQC_OK;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  sv->peer[slot][peer_rank] = (const double2*)p;
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_peer_attach(aqc_sv* sv, int peer_rank, int slot, aqc_sv* peer) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!peer || peer_rank < 0 || peer_rank >= (1 << sv->g) || peer_rank >= 16 || slot >= peer->nslots)
+    return fail(AQC_EINVAL, "bad peer");
+  CU(cudaSetDevice(sv->device));
+  if (peer->device != sv->device) {
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, sv->device, peer->device));
+    if (!can) return fail(AQC_ECUDA, "device %d cannot access device %d", sv->device, peer->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(AQC_ECUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  sv->peer[slot][peer_rank] = peer->slots[slot];
+  return AQC_OK;
+}
+
+struct ExchangeArgs {
+  const double2* src[16];  // src[r] = rank r's source slot
+  double2* dst;
+  long long chunk;  // amplitudes per chunk
+  int world, rank;
+};
+
+// dst[chunk r] = (rank r).src[chunk my_rank]: every rank pulls its column of the block matrix
+// over NVLink with plain peer loads (coalesced 16-byte accesses) and stores locally.
+__global__ void exchange_kernel(const ExchangeArgs A) {
+  const int r = blockIdx.y;
+  const double2* __restrict__ s = A.src[r] + (long long)A.rank * A.chunk;
+  double2* __restrict__ d = A.dst + (long long)r * A.chunk;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.chunk; i += stride) d[i] = s[i];
+}
+
+extern "C" int aqc_sv_exchange(aqc_sv* sv, int src_slot, int dst_slot) {
+  int rc = check_slot(sv, src_slot);
+  if (rc) return rc;
+  rc = check_slot(sv, dst_slot);
+  if (rc) return rc;
+  if (sv->g <= 0) return fail(AQC_EINVAL, "workspace is not sharded");
+  if (src_slot == dst_slot) return fail(AQC_EINVAL, "exchange is out of place");
+  CU(cudaSetDevice(sv->device));
+  ExchangeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.world = 1 << sv->g;
+  a.rank = sv->rank;
+  a.chunk = sv->size >> sv->g;
+  a.dst = sv->slots[dst_slot];
+  for (int r = 0; r < a.world; ++r) {
+    a.src[r] = (r == sv->rank) ? sv->slots[src_slot] : sv->peer[src_slot][r];
+    if (!a.src[r]) return fail(AQC_EINVAL, "peer %d slot %d was not imported", r, src_slot);
+  }
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  const unsigned gx = (unsigned)std::min<long long>((a.chunk + 255) / 256, 148 * 4);
+  exchange_kernel<<<dim3(gx, a.world), 256, 0, sv->stream>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  sv->last_launches = 1;
+  return AQC_OK;
+}
+
+// Sharded synthetic target: re, im ~ U[0,1) keyed on (seed, LOGICAL amplitude index) in layout A,
+// identical for any number of ranks.  Not normalised: *norm2_out receives the local sum of squares
+// (all-reduce it and call aqc_sv_scale).
+__global__ void fill_random_logical_kernel(double2* __restrict__ v, long long size, int n, int g,
+                                           int rank, unsigned long long seed, double* __restrict__ norm2) {
+  const int nl = n - g, cb = nl - g;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < size;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long lo = (unsigned long long)i & ((1ull << cb) - 1);
+    const unsigned long long top = (unsigned long long)i >> cb;  // qubits 0..g-1
+    const unsigned long long logical = ((unsigned long long)rank << nl) | (lo << g) | top;
+    const double re = u01(seed, 2ull * logical), im = u01(seed, 2ull * logical + 1);
+    v[i] = make_double2(re, im);
+    acc = fma(re, re, acc);
+    acc = fma(im, im, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(norm2, acc);
+}
+
+extern "C" int aqc_sv_fill_random_logical(aqc_sv* sv, int slot, uint64_t seed, double* norm2_out) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!norm2_out || sv->batch != 1 || sv->log2_cols != 0) return fail(AQC_EINVAL, "bad arguments");
+  CU(cudaSetDevice(sv->device));
+  rc = ensure_scratch(sv, 8);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(sv->d_scratch, 0, sizeof(double), sv->stream));
+  const unsigned gx = (unsigned)std::min<long long>((sv->size + 255) / 256, 148 * 16);
+  fill_random_logical_kernel<<<gx, 256, 0, sv->stream>>>(sv->slots[slot], sv->size, sv->circ.n, sv->g,
+                                                        sv->rank, seed, sv->d_scratch);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(norm2_out, sv->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+__global__ void scale_const_kernel(double2* __restrict__ v, long long total, double f) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    double2 x = v[i];
+    x.x *= f;
+    x.y *= f;
+    v[i] = x;
+  }
+}
+
+extern "C" int aqc_sv_scale(aqc_sv* sv, int slot, double factor) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  CU(cudaSetDevice(sv->device));
+  const long long total = sv->size * sv->batch;
+  const unsigned gx = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  scale_const_kernel<<<gx, 256, 0, sv->stream>>>(sv->slots[slot], total, factor);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+// Host-only: epoch plan of the sharded scheduler (no device needed).  Serialises, per epoch, the
+// layout id and the tile-pass program (same word layout as aqc_debug_program) so that the CPU
+// test-suite can replay a sharded run rank by rank.  mode: 0 / 1 forward, 2 reversed (V^H).
+extern "C" int aqc_debug_program_sharded(const aqc_circuit* circ, int log2_world, int tile_bits,
+                                         int low_bits, int reversed, int32_t* out, int64_t cap,
+                                         int64_t* needed) {
+  if (!circ || !needed) return fail(AQC_EINVAL, "null argument");
+  if (tile_bits < 2 || tile_bits > kMaxTileBits) return fail(AQC_EINVAL, "bad tile_bits");
+  Program p;
+  std::string err;
+  if (build_program_sharded(*circ, log2_world, tile_bits, low_bits, reversed != 0, p, err))
+    return fail(AQC_EINVAL, "%s", err.c_str());
+  std::vector<int32_t> w;
+  const int ne = (int)p.epoch_pass0.size();
+  w.push_back(ne);
+  for (int e = 0; e < ne; ++e) {
+    const int p0 = p.epoch_pass0[e], p1 = e + 1 < ne ? p.epoch_pass0[e + 1] : (int)p.passes.size();
+    w.push_back(p.epoch_layout[e]);
+    w.push_back(p1 - p0);
+    for (int i = p0; i < p1; ++i) {
+      const PassDesc& pd = p.passes[i];
+      w.push_back(pd.tb);
+      w.push_back(pd.nstages);
+      w.push_back(pd.nouter);
+      for (int k = 0; k < 16; ++k) w.push_back(pd.bitpos[k]);
+      for (int k = 0; k < 48; ++k) w.push_back(pd.outerpos[k]);
+      for (int s = 0; s < pd.nstages; ++s) {
+        const StageDesc& sd = p.stages[pd.stage0 + s];
+        w.push_back(sd.p);
+        w.push_back(sd.q);
+        w.push_back(sd.nunits);
+        for (int u = 0; u < kMaxUnits; ++u) {
+          w.push_back(sd.u[u].kind);
+          w.push_back(sd.u[u].flags);
+          w.push_back(sd.u[u].theta);
+        }
+      }
+    }
+  }
+  *needed = (int64_t)w.size();
+  if (out && cap >= (int64_t)w.size()) memcpy(out, w.data(), w.size() * sizeof(int32_t));
   return AQC_OK;
 }

@@ -1,0 +1,319 @@
+"""
+One state vector over 2^g GPUs (global-qubit sharding) -- SURVEY.md section 8(e), item 2.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing (barriers, the tiny
+all-reduce of the partial gradient sums and of the gathered amplitudes).  The heavy step, the
+layout switch between epochs, is a block transpose over the ranks done by ``aqc_sv_exchange``
+(every rank pulls its chunks from its peers' HBM with plain peer loads over NVLink; the peers'
+buffers are mapped with CUDA IPC).  If IPC mapping is unavailable the same transpose is done with
+``isend / irecv`` pairs of the process group (NCCL, or gloo in the CPU tests).
+
+Layouts (see ``build_program_sharded`` in csrc/aqc_sv.cu), n qubits, g = log2(world), nl = n - g:
+  A: qubits n-g..n-1 global;  qubits 0..g-1 on local bits nl-g..nl-1;  qubit q -> bit q - g otherwise
+  B: qubits 0..g-1 global;    qubits n-g..n-1 on local bits nl-g..nl-1; the rest as in A
+Data at rest (between calls) are always in layout A.
+
+The numeric backend is pluggable: ``GpuShardBackend`` (the CUDA workspace) in production and a
+NumPy replay of the compiled program in the CPU test-suite (tests/sharded_sim.py).
+"""
+
+import ctypes as ct
+from typing import Dict, List, Optional, Sequence
+import numpy as np
+from . import _lib
+from .engine import CircuitHandle, _dptr, _thetas_ptr
+from .parametric_circuit import ParametricCircuit
+
+MODE_GRAD, MODE_FWD, MODE_DAG = 0, 1, 2
+
+
+def locate(index: int, n: int, g: int):
+    """Logical amplitude index -> (rank, local offset) in layout A."""
+    nl = n - g
+    cb = nl - g
+    rank = index >> nl
+    low = index & ((1 << g) - 1)  # qubits 0..g-1 -> top local bits
+    mid = (index >> g) & ((1 << cb) - 1)
+    return rank, (low << cb) | mid
+
+
+class GpuShardBackend:
+    """Thin wrapper of a sharded ``aqc_sv`` workspace (one rank)."""
+
+    def __init__(self, circ: ParametricCircuit, log2_world: int, rank: int, device: int, num_slots: int):
+        self._lib = _lib.load()
+        self.circuit = CircuitHandle(circ)
+        self.num_thetas = circ.num_thetas
+        self.num_slots = num_slots
+        handle = ct.c_void_p()
+        _lib.check(
+            self._lib.aqc_sv_create_sharded(
+                self.circuit.handle, device, log2_world, rank, num_slots, ct.byref(handle)
+            )
+        )
+        self.handle = handle
+        self.size = int(self._lib.aqc_sv_state_size(handle))
+        self.device = device
+        self.p2p_ready = False
+
+    def num_epochs(self, mode):
+        return int(self._lib.aqc_sv_num_epochs(self.handle, mode))
+
+    def epoch_layout(self, mode, epoch):
+        return int(self._lib.aqc_sv_epoch_layout(self.handle, mode, epoch))
+
+    def begin(self, thetas, mode):
+        _, ptr = _thetas_ptr(thetas, self.num_thetas)
+        _lib.check(self._lib.aqc_sv_begin(self.handle, ptr, mode))
+
+    def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1):
+        _lib.check(
+            self._lib.aqc_sv_run_epoch(self.handle, mode, epoch, src0, int(basis_local), src1, dst0, dst1)
+        )
+
+    def grad_finish(self) -> np.ndarray:
+        out = np.empty(self.num_thetas, dtype=np.complex128)
+        _lib.check(self._lib.aqc_sv_grad_finish(self.handle, _dptr(out)))
+        return out
+
+    def gather(self, slot, local_indices) -> np.ndarray:
+        idx = np.ascontiguousarray(local_indices, dtype=np.int64)
+        out = np.empty(idx.size, dtype=np.complex128)
+        _lib.check(
+            self._lib.aqc_sv_gather(self.handle, slot, idx.ctypes.data_as(_lib.c_int64_p), idx.size, _dptr(out))
+        )
+        return out
+
+    def set_basis(self, slot, local_index):
+        _lib.check(self._lib.aqc_sv_set_basis(self.handle, slot, int(local_index)))
+
+    def fill_random_logical(self, slot, seed) -> float:
+        out = ct.c_double(0.0)
+        _lib.check(self._lib.aqc_sv_fill_random_logical(self.handle, slot, int(seed), ct.byref(out)))
+        return float(out.value)
+
+    def scale(self, slot, factor):
+        _lib.check(self._lib.aqc_sv_scale(self.handle, slot, float(factor)))
+
+    def vdot(self, a, b) -> complex:
+        out = np.empty(1, dtype=np.complex128)
+        _lib.check(self._lib.aqc_sv_vdot(self.handle, a, b, _dptr(out)))
+        return complex(out[0])
+
+    def upload(self, slot, data):
+        arr = np.ascontiguousarray(data, dtype=np.complex128).ravel()
+        _lib.check(self._lib.aqc_sv_upload(self.handle, slot, -1, _dptr(arr), arr.size))
+
+    def download(self, slot) -> np.ndarray:
+        out = np.empty(self.size, dtype=np.complex128)
+        _lib.check(self._lib.aqc_sv_download(self.handle, slot, 0, _dptr(out), out.size))
+        return out
+
+    # -- layout switch ---------------------------------------------------------------------
+    def ipc_export(self, slot) -> bytes:
+        buf = (ct.c_ubyte * 64)()
+        _lib.check(self._lib.aqc_sv_ipc_export(self.handle, slot, buf))
+        return bytes(buf)
+
+    def ipc_import(self, peer_rank, slot, handle: bytes):
+        buf = (ct.c_ubyte * 64).from_buffer_copy(handle)
+        _lib.check(self._lib.aqc_sv_ipc_import(self.handle, peer_rank, slot, buf))
+
+    def exchange_p2p(self, src, dst):
+        _lib.check(self._lib.aqc_sv_exchange(self.handle, src, dst))
+
+    def slot_tensor(self, slot):
+        """torch view (float64, 2 * size) of a slot's device memory (zero copy)."""
+        import torch  # pylint: disable=import-outside-toplevel
+
+        ptr = int(self._lib.aqc_sv_slot_ptr(self.handle, slot))
+
+        class _Iface:  # pylint: disable=too-few-public-methods
+            __cuda_array_interface__ = {
+                "shape": (2 * self.size,), "typestr": "<f8", "data": (ptr, False), "version": 2,
+            }
+
+        return torch.as_tensor(_Iface(), device=f"cuda:{self.device}")
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.aqc_sv_last_kernel_ms(self.handle))
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self._lib.aqc_sv_destroy(h)
+
+    def __del__(self):
+        self.close()
+
+
+class DistComm:
+    """torch.distributed process group (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.backend = dist.get_backend()
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def allreduce_sum(self, arr: np.ndarray, device: Optional[str] = None) -> np.ndarray:
+        import torch  # pylint: disable=import-outside-toplevel
+
+        flat = np.ascontiguousarray(arr).view(np.float64).copy()
+        t = torch.from_numpy(flat)
+        if self.backend == "nccl":
+            t = t.to(device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy().view(arr.dtype).reshape(arr.shape)
+
+    def allgather_bytes(self, blob: bytes) -> List[bytes]:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, blob)
+        return out
+
+    def transpose_chunks(self, send, recv):
+        """recv[chunk r] = (rank r).send[chunk my_rank]; send/recv: 1-D tensors of world equal chunks."""
+        world, rank = self.world, self.rank
+        cs = send.numel() // world
+        ops = []
+        for r in range(world):
+            if r == rank:
+                recv[r * cs : (r + 1) * cs].copy_(send[r * cs : (r + 1) * cs])
+            else:
+                ops.append(self.dist.P2POp(self.dist.irecv, recv[r * cs : (r + 1) * cs], r))
+                ops.append(self.dist.P2POp(self.dist.isend, send[r * cs : (r + 1) * cs], r))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+class ShardedStateVector:
+    """
+    Objective / gradient building blocks on a sharded state.  Vectors are addressed by NAME
+    ("target", "z0", "w", "z"); the driver keeps the name -> slot map because a layout switch
+    writes into the spare slot and swaps the roles.
+    """
+
+    NAMES = ("target", "z0", "w", "z")
+
+    def __init__(self, circ: ParametricCircuit, comm, backend, use_p2p: bool = True):
+        self.circ = circ
+        self.comm = comm
+        self.be = backend
+        self.n = circ.num_qubits
+        self.g = int(comm.world).bit_length() - 1
+        assert 1 << self.g == comm.world, "world size must be a power of two"
+        self.slot: Dict[str, int] = {name: i for i, name in enumerate(self.NAMES)}
+        self.slot["spare"] = len(self.NAMES)
+        self.layout: Dict[str, int] = {name: 0 for name in self.NAMES}
+        self.exchange_ms = 0.0
+        self.compute_ms = 0.0
+        self.p2p = False
+        if use_p2p and hasattr(backend, "ipc_export"):
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Maps every slot of every peer through CUDA IPC; falls back to send/recv on failure."""
+        ok = 1
+        try:
+            mine = [self.be.ipc_export(s) for s in range(self.be.num_slots)]
+            everyone = self.comm.allgather_bytes(b"".join(mine))
+            for r, blob in enumerate(everyone):
+                for s in range(self.be.num_slots):
+                    self.be.ipc_import(r, s, blob[64 * s : 64 * (s + 1)])
+        except Exception:  # noqa: BLE001  (IPC unavailable: use the process group instead)
+            ok = 0
+        total = self.comm.allreduce_sum(np.array([float(ok)]), device=self._dev())
+        self.p2p = bool(total[0] == self.comm.world)
+
+    def _dev(self):
+        return f"cuda:{self.be.device}" if hasattr(self.be, "device") else None
+
+    # -- layout switch ---------------------------------------------------------------------
+    def _switch(self, names: Sequence[str]):
+        import time  # pylint: disable=import-outside-toplevel
+
+        for name in names:
+            src, dst = self.slot[name], self.slot["spare"]
+            self.comm.barrier()  # every rank finished writing its source
+            t0 = time.perf_counter()
+            if self.p2p:
+                self.be.exchange_p2p(src, dst)
+            else:
+                self.comm.transpose_chunks(self.be.slot_tensor(src), self.be.slot_tensor(dst))
+            self.comm.barrier()  # every rank pulled: sources are free again
+            self.exchange_ms += (time.perf_counter() - t0) * 1e3
+            self.slot[name], self.slot["spare"] = dst, src
+            self.layout[name] ^= 1
+
+    def _run(self, mode, first_sources, names):
+        """Runs all epochs of ``mode`` on the named vectors (vec0[, vec1])."""
+        be = self.be
+        for e in range(be.num_epochs(mode)):
+            need = be.epoch_layout(mode, e)
+            if e == 0:
+                src0, basis_local, src1 = first_sources
+                # sources must be in the layout of the first epoch
+                if need != 0:
+                    raise NotImplementedError("first epoch must run in layout A")
+                dst = [self.slot[nm] for nm in names]
+                be.run_epoch(mode, e, src0, basis_local, src1, dst[0], dst[1] if len(dst) > 1 else 0)
+                for nm in names:
+                    self.layout[nm] = 0
+            else:
+                if self.layout[names[0]] != need:
+                    self._switch(names)
+                dst = [self.slot[nm] for nm in names]
+                be.run_epoch(mode, e, dst[0], -1, dst[1] if len(dst) > 1 else 0, dst[0],
+                             dst[1] if len(dst) > 1 else 0)
+            self.compute_ms += getattr(be, "last_kernel_ms", 0.0)
+        if self.layout[names[0]] != 0:
+            self._switch(names)  # data at rest are in layout A
+
+    # -- public operations -------------------------------------------------------------------
+    def set_target_random(self, seed: int):
+        local = self.be.fill_random_logical(self.slot["target"], seed)
+        total = self.comm.allreduce_sum(np.array([local]), device=self._dev())[0]
+        self.be.scale(self.slot["target"], 1.0 / np.sqrt(total))
+
+    def set_basis(self, name: str, index: int):
+        rank, off = locate(index, self.n, self.g)
+        self.be.set_basis(self.slot[name], off if rank == self.comm.rank else -1)
+        self.layout[name] = 0
+
+    def apply(self, thetas, src: str, dst: str, dagger: bool = False):
+        """dst = V src or V^H src (src in layout A; dst may equal src)."""
+        mode = MODE_DAG if dagger else MODE_FWD
+        self.be.begin(thetas, mode)
+        self._run(mode, (self.slot[src], -1, 0), [dst])
+
+    def amplitudes(self, name: str, indices) -> np.ndarray:
+        """<e_idx | vector> for logical basis indices (sum of per-rank gathers)."""
+        vals = np.zeros(len(indices), dtype=np.complex128)
+        mine = [(i, locate(int(ix), self.n, self.g)) for i, ix in enumerate(indices)]
+        pos = [i for i, (r, _) in mine if r == self.comm.rank]
+        if pos:
+            vals[pos] = self.be.gather(self.slot[name], [mine[i][1][1] for i in pos])
+        return self.comm.allreduce_sum(vals, device=self._dev())
+
+    def objective(self, thetas, indices) -> np.ndarray:
+        """z0 = V^H target; returns hs_i = z0[indices] (objective_lhs_sur_max.py:98-106)."""
+        self.apply(thetas, "target", "z0", dagger=True)
+        return self.amplitudes("z0", indices)
+
+    def grad(self, thetas, x_basis: int) -> np.ndarray:
+        """Complex gradient of <V e_x | y> given z0 (grad_of_dot_product)."""
+        rank, off = locate(int(x_basis), self.n, self.g)
+        self.be.begin(thetas, MODE_GRAD)
+        self._run(MODE_GRAD, (-1, off if rank == self.comm.rank else -1, self.slot["z0"]), ["w", "z"])
+        return self.comm.allreduce_sum(self.be.grad_finish(), device=self._dev())
+
+    def vdot(self, a: str, b: str) -> complex:
+        v = self.be.vdot(self.slot[a], self.slot[b])
+        return complex(self.comm.allreduce_sum(np.array([v]), device=self._dev())[0])

@@ -148,6 +148,45 @@ void* aqc_sv_slot_ptr(aqc_sv* sv, int slot);
 void* aqc_sv_stream(aqc_sv* sv);
 
 /* ---------------------------------------------------------------------------
+ * One state vector over 2^log2_world GPUs (global-qubit sharding, n >= 32 qubits; one process or
+ * workspace per GPU).  The reference has no distributed code; this is new.
+ * The top log2_world index bits select the rank; two layouts alternate (A: highest g qubits
+ * global, B: lowest g qubits global); an "epoch" runs every gate unit that does not touch a
+ * global qubit, then the layout is switched by a block transpose over the ranks
+ * (aqc_sv_exchange: NVLink peer loads; or any all-to-all of the caller).  Inner products are
+ * partial per rank: add the outputs of aqc_sv_grad_finish / aqc_sv_gather over the ranks.
+ * A single-GPU workspace behaves as one epoch in layout A.
+ */
+int aqc_sv_create_sharded(const aqc_circuit* circ, int device, int log2_world, int rank,
+                          int num_slots, aqc_sv** out);
+/* mode: 0 gradient sweep, 1 V apply, 2 V^H apply. */
+int aqc_sv_num_epochs(const aqc_sv* sv, int mode);
+int aqc_sv_epoch_layout(const aqc_sv* sv, int mode, int epoch); /* 0 = A, 1 = B */
+int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode);
+/* Tile passes of one epoch (src slots are read by the first pass only; src0 < 0: vec0 = local part
+ * of a basis state at offset basis_local, or zeros if basis_local < 0). */
+int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local, int src1,
+                     int dst0, int dst1);
+/* This rank's partial complex gradient (already scaled like grad_of_dot_product). */
+int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out);
+/* Peer mapping of the other ranks' slots: CUDA IPC between processes ... */
+int aqc_sv_ipc_export(aqc_sv* sv, int slot, unsigned char* handle64);
+int aqc_sv_ipc_import(aqc_sv* sv, int peer_rank, int slot, const unsigned char* handle64);
+/* ... or direct peer access when all workspaces live in one process. */
+int aqc_sv_peer_attach(aqc_sv* sv, int peer_rank, int slot, aqc_sv* peer);
+/* dst_slot[chunk r] = (rank r).src_slot[chunk my_rank] for all r: layout switch A <-> B.
+ * Callers must barrier before (sources complete) and after (sources free again). */
+int aqc_sv_exchange(aqc_sv* sv, int src_slot, int dst_slot);
+/* Synthetic target keyed on the LOGICAL amplitude index (layout A), not normalised; returns the
+ * local sum of squares. */
+int aqc_sv_fill_random_logical(aqc_sv* sv, int slot, uint64_t seed, double* norm2_out);
+int aqc_sv_scale(aqc_sv* sv, int slot, double factor);
+/* Host-only: per-epoch tile-pass programs of the sharded scheduler (for CPU replay tests). */
+int aqc_debug_program_sharded(const aqc_circuit* circ, int log2_world, int tile_bits,
+                              int low_bits, int reversed, int32_t* out, int64_t cap,
+                              int64_t* needed);
+
+/* ---------------------------------------------------------------------------
  * MPS workspace on one GPU (Vidal form, bond capacity C = aqc_mps_bond_capacity()).
  * Supports circuits whose unit-blocks act on ADJACENT qubits (TrotterAnsatz, "spin"/"line"
  * layouts) -- the case of SpSurrogateObjectiveFastMpsTrotter
