@@ -378,17 +378,117 @@ def measure_mat7(batch=64, layers=40, steps=5, warmup=2, device=0, with_cpu=True
     return out
 
 
+def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
+    """
+    BASELINE.json configs[4], second half: ONE state vector over `world` GPUs (global-qubit
+    sharding), weak scaling: n = base_qubits + log2(world) qubits, i.e. a constant 2^base_qubits
+    amplitudes per GPU.  One step = objective + single-term gradient of the whole sharded state;
+    layout switches go through the peer-memory exchange kernel (NVLink).  Wall clock per step
+    (max over ranks via the barriers inside the driver).
+    """
+    import torch.distributed as dist
+    from aqc_research_b200.sharded import DistComm, GpuShardBackend, ShardedStateVector
+
+    g = world.bit_length() - 1
+    n = base_qubits + g
+    circ = make_circuit(n, layers)
+    comm = DistComm()
+    be = GpuShardBackend(circ, g, comm.rank, local_rank, num_slots=5)
+    sv = ShardedStateVector(circ, comm, be)
+    rng = np.random.RandomState(4321)
+    th_star = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    th = th_star + 0.02 * np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    sv.set_basis("w", 0)
+    sv.apply(th_star, "w", "target", dagger=False)  # near target V(theta*)|0>
+    idx = np.array([0] + [1 << q for q in range(n)], dtype=np.int64)
+    times = []
+    for it in range(warmup + steps):
+        sv.exchange_ms = sv.compute_ms = 0.0
+        dist.barrier()
+        t0 = time.perf_counter()
+        hs = sv.objective(th, idx)
+        grad = sv.grad(th, 0)
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append((dt, sv.compute_ms, sv.exchange_ms))
+    assert np.all(np.isfinite(grad))
+    t = np.array(times)
+    res = {"num_qubits": n, "layers": layers, "num_thetas": circ.num_thetas, "p2p_exchange": bool(sv.p2p),
+           "epochs": {"gradient": be.num_epochs(0), "vh_apply": be.num_epochs(2)},
+           "s_per_step": float(t[:, 0].mean()), "compute_ms": float(t[:, 1].mean()),
+           "exchange_ms": float(t[:, 2].mean()), "fidelity": float(abs(hs[0]) ** 2)}
+    be.close()
+    return res
+
+
+def run_sharded_bench(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    base, layers = args.shard_qubits, 4
+    if world == 1:
+        res = measure_gpu(base, layers, args.steps, args.warmup, 0, False, None)
+        out = {"num_qubits": base, "s_per_step": float(np.mean(res["step_ms"])) * 1e-3, "exchange_ms": 0.0,
+               "compute_ms": float(np.mean(res["step_ms"])), "epochs": {"gradient": 1, "vh_apply": 1},
+               "layers": layers, "num_thetas": res["circ"].num_thetas, "p2p_exchange": False}
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        out = measure_sharded(base, layers, args.steps, args.warmup, local_rank, world)
+    if rank == 0:
+        n = out["num_qubits"]
+        P = pair_runs(n, layers)
+        peak, peak_src = measured_peaks()
+        value = 1.0 / out["s_per_step"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": out["s_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "config": {"workload": "svshard", "num_qubits": n, "layers": layers,
+                       "ansatz": "TrotterAnsatz 2nd order", "num_thetas": out["num_thetas"],
+                       "amplitudes_per_gpu": 2**args.shard_qubits, "parallelism": f"one state over {world} GPUs (global-qubit sharding)",
+                       "epochs": out["epochs"], "p2p_exchange": out["p2p_exchange"],
+                       "l2": "inputs larger than L2"},
+            "roofline": {"bound": "hbm", "kernel": "pass_kernel<2,cx,fwd> (gradient tile pass)",
+                         "achieved": 96.0 * 2**n * P * value / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": 96.0 * 2**n * P * value / 1e9 / world / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "whole evaluation (pair-run algorithmic bytes per GPU) incl. exchange time"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 16 * out["num_thetas"],
+                    "d2h_bytes_per_step": 16 * (n + 1) + 16 * out["num_thetas"]},
+            "kernel_ms": {"compute": out["compute_ms"], "exchange": out["exchange_ms"]},
+            "gpu_launches": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("AQC_BENCH_WORKLOAD", "sv20"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("AQC_BENCH_WORKLOAD", "sv20"),
+                    choices=sorted(WORKLOADS) + ["svshard"])
+    ap.add_argument("--shard-qubits", type=int, default=28, help="svshard: qubits per GPU shard (log2 amplitudes)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra sv28 measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "svshard":
+        if args.impl == "reference":
+            args.workload = "sv28"
+        else:
+            args.warmup = min(args.warmup, 1)
+            run_sharded_bench(args)
+            return
     n, layers = WORKLOADS[args.workload]
 
     if args.impl == "reference":
