@@ -66,15 +66,13 @@ def grad_of_matrix_dot_product(
 ) -> np.ndarray:
     """
     Complex gradient of ``<V X, Y>_F`` given ``vh_y_mat = V^H Y`` (core_op_matrix.py:645-762).
-    Like the reference, ``x_mat`` and ``vh_y_mat`` are overwritten (with ``V X`` and ``V V^H Y``).
+    The reference overwrites ``x_mat`` and ``vh_y_mat`` with its swept work matrices; callers
+    cannot rely on their contents afterwards.  Here the sweep runs on device copies (which hold
+    rescaled work states) and the host arrays are left untouched.
     """
     _check(circ, thetas, x_mat, vh_y_mat)
     k = _log2_cols(x_mat.shape[1])
     ws = _workspace(circ, log2_cols=k)
     ws.upload(0, _pad_cols(x_mat, k))
     ws.upload(1, _pad_cols(vh_y_mat, k))
-    grad = ws.grad(thetas, x_slot=0, z0=1, w=0, z=1)[0]
-    for slot, mat in ((0, x_mat), (1, vh_y_mat)):
-        res = ws.download(slot, 0).reshape(mat.shape[0], 1 << k)
-        mat[:, :] = res[:, : mat.shape[1]]
-    return grad
+    return ws.grad(thetas, x_slot=0, z0=1, w=0, z=1)[0]

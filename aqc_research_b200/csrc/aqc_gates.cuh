@@ -195,3 +195,122 @@ __device__ __forceinline__ void block_unit(cd (&a)[NVEC][4], const double2* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Scale-free ("fast Givens") forms used by the gradient sweep.
+//
+// Both swept vectors w and z go through the same gates and only inner products <P w|z> are wanted,
+// so a common complex scalar on w and z matters only through its squared modulus.  Hence
+//   Rz(phi)   = e^{-i phi/2} diag(1, e^{i phi})      -> multiply a1 by e^{i phi}      (no scale)
+//   Ry(theta) = c [[1, -t], [t, 1]],   t = s / c      -> one FMA per component        (scale c)
+//             = s [[r, -1], [1, r]],   r = c / s      (used when |c| is small)        (scale s)
+//   Rx(theta) = c [[1, -i t], [-i t, 1]] = s [[r, -i], [-i, r]]
+// The dropped real scale factors are tracked by the prep kernel (aqc_sv.cu): the raw inner
+// product taken after a rotation is multiplied by the squared cumulative scale afterwards.
+// Parameter encoding (double2 p): Ry / Rx: p.x = t or r, p.y = 0 (c-form) or 1 (s-form);
+// Rz / CPhase: p = (cos phi, sin phi) of the FULL angle.
+// ------------------------------------------------------------------------------------------------
+template <bool HI, int ROT>
+__device__ __forceinline__ void srot1q(cd (&a)[2][4], const double2 p, double* acc) {
+  constexpr int I0a = 0, I0b = HI ? 1 : 2;          // the two pairs (i0, i1 = i0 + step)
+  constexpr int STEP = HI ? 2 : 1;
+  if (ROT == ROT_Z) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) mul_cs(a[v][I0a + STEP], p.x, p.y), mul_cs(a[v][I0b + STEP], p.x, p.y);
+  } else if (p.y == 0.0) {  // c-form
+    const double t = p.x;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
+        const cd b0 = a[v][i0], b1 = a[v][i1];
+        if (ROT == ROT_Y) {
+          a[v][i0].x = fma(-t, b1.x, b0.x), a[v][i0].y = fma(-t, b1.y, b0.y);
+          a[v][i1].x = fma(t, b0.x, b1.x), a[v][i1].y = fma(t, b0.y, b1.y);
+        } else {  // Rx: a0 - i t a1 ; a1 - i t a0
+          a[v][i0].x = fma(t, b1.y, b0.x), a[v][i0].y = fma(-t, b1.x, b0.y);
+          a[v][i1].x = fma(t, b0.y, b1.x), a[v][i1].y = fma(-t, b0.x, b1.y);
+        }
+      }
+  } else {  // s-form
+    const double rr = p.x;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
+        const cd b0 = a[v][i0], b1 = a[v][i1];
+        if (ROT == ROT_Y) {  // r a0 - a1 ; a0 + r a1
+          a[v][i0].x = fma(rr, b0.x, -b1.x), a[v][i0].y = fma(rr, b0.y, -b1.y);
+          a[v][i1].x = fma(rr, b1.x, b0.x), a[v][i1].y = fma(rr, b1.y, b0.y);
+        } else {  // Rx: r a0 - i a1 ; r a1 - i a0
+          a[v][i0].x = fma(rr, b0.x, b1.y), a[v][i0].y = fma(rr, b0.y, -b1.x);
+          a[v][i1].x = fma(rr, b1.x, b0.y), a[v][i1].y = fma(rr, b1.y, -b0.x);
+        }
+      }
+  }
+  // raw inner products after the rotation (same forms as rot1q)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
+    if (ROT == ROT_Y) {
+      cdot_add(acc, a[0][i0], a[1][i1]);
+      cdot_sub(acc, a[0][i1], a[1][i0]);
+    }
+    if (ROT == ROT_Z) {
+      cdot_add(acc, a[0][i0], a[1][i0]);
+      cdot_sub(acc, a[0][i1], a[1][i1]);
+    }
+    if (ROT == ROT_X) {
+      cdot_add(acc, a[0][i1], a[1][i0]);
+      cdot_add(acc, a[0][i0], a[1][i1]);
+    }
+  }
+}
+
+template <bool HI>
+__device__ __forceinline__ void sfront_unit(cd (&a)[2][4], const double2* __restrict__ p, double* acc) {
+  srot1q<HI, ROT_Z>(a, p[2], acc + 4);
+  srot1q<HI, ROT_Y>(a, p[1], acc + 2);
+  srot1q<HI, ROT_Z>(a, p[0], acc + 0);
+}
+
+// Unit block of the gradient sweep with scale-free rotations.  PRE / POST: -1 = runtime flags,
+// 0 / 1 = compile-time (the Trotter triplet specialisation).
+template <int ENT, bool CHI, int PRE, int POST>
+__device__ __forceinline__ void sblock_unit(cd (&a)[2][4], const double2* __restrict__ p, int flags,
+                                            double* acc) {
+  constexpr int C1A = CHI ? 2 : 1;
+  constexpr int T1A = CHI ? 1 : 2;
+  constexpr int ROT_S = (ENT == AQC_ENT_CX) ? ROT_X : ROT_Z;
+  const bool pre = (PRE < 0) ? (flags & F_PRE) != 0 : (PRE != 0);
+  const bool post = (POST < 0) ? (flags & F_POST) != 0 : (POST != 0);
+  if (pre) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) mul_mi(a[v][C1A]), mul_mi(a[v][3]);
+  }
+  if (ENT == AQC_ENT_CX) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const cd t = a[v][C1A];
+      a[v][C1A] = a[v][3];
+      a[v][3] = t;
+    }
+  } else if (ENT == AQC_ENT_CZ) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) a[v][3].x = -a[v][3].x, a[v][3].y = -a[v][3].y;
+  } else {
+    cdot_add(acc + 8, a[0][3], a[1][3]);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) mul_cs(a[v][3], p[4].x, p[4].y);
+  }
+  srot1q<CHI, ROT_Y>(a, p[0], acc + 0);
+  srot1q<CHI, ROT_Z>(a, p[1], acc + 2);
+  srot1q<!CHI, ROT_Y>(a, p[2], acc + 4);
+  srot1q<!CHI, ROT_S>(a, p[3], acc + 6);
+  if (post) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) mul_pi(a[v][T1A]), mul_pi(a[v][3]);
+  }
+}

@@ -82,13 +82,13 @@ constexpr int kMaxTileBits = 12;
 struct UnitDesc {
   int32_t kind;
   int32_t flags;
-  int32_t theta;  // index of the unit's first angle == first gradient slot
-  int32_t pad;
+  int32_t theta;  // index of the unit's first angle
+  int32_t slot;   // first raw-gradient accumulator of this unit OCCURRENCE (5 per unit)
 };
 struct StageDesc {
   int32_t p, q;  // tile-local bit positions held in registers, p > q
   int32_t nunits;
-  int32_t pad;
+  int32_t triplet;  // 1: Trotter triplet (ctrl hi / lo / hi, Rz(-pi/2) first, Rz(+pi/2) last)
   UnitDesc u[kMaxUnits];
 };
 static_assert(sizeof(StageDesc) == 64, "StageDesc layout");
@@ -108,6 +108,10 @@ struct Program {
   StageDesc* d_stages = nullptr;
   // sharded execution: passes [epoch_pass0[e], epoch_pass0[e+1]) need data layout epoch_layout[e]
   std::vector<int> epoch_pass0, epoch_layout;
+  // gradient only: rotations in execution order (scaled-rotation bookkeeping)
+  std::vector<int> sched_theta, sched_occ, sched_pass, pass_start, occ_theta;
+  int *d_sched_theta = nullptr, *d_sched_occ = nullptr, *d_sched_pass = nullptr, *d_pass_start = nullptr,
+      *d_occ_theta = nullptr;
 };
 
 struct HostUnit {
@@ -116,6 +120,7 @@ struct HostUnit {
   int qb;    // -1 | target
   int theta;
   int flags;
+  int seq;  // index of the unit in forward circuit order (names its gradient accumulators)
 };
 
 struct aqc_circuit {
@@ -142,7 +147,7 @@ int aqc_circ_targ(const aqc_circuit* c, int i) { return c->targ[i]; }
 
 static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUnit>& out) {
   out.clear();
-  for (int q = 0; q < c.n; ++q) out.push_back({0, q, -1, 3 * q, 0});
+  for (int q = 0; q < c.n; ++q) out.push_back({0, q, -1, 3 * q, 0, q});
   const int total = c.nb + c.half;
   for (int i = 0; i < total; ++i) {
     const int im = c.nb > 0 ? i % c.nb : 0;
@@ -151,7 +156,7 @@ static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUni
       if (i % 3 == 0) flags |= F_PRE;
       if (i % 3 == 2) flags |= F_POST;
     }
-    out.push_back({1, c.ctrl[im], c.targ[im], 3 * c.n + c.tpb * im, flags});
+    out.push_back({1, c.ctrl[im], c.targ[im], 3 * c.n + c.tpb * im, flags, c.n + i});
   }
   if (reversed) std::reverse(out.begin(), out.end());
 }
@@ -222,7 +227,7 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
       d.kind = kind;
       d.flags = u.flags;
       d.theta = u.theta;
-      d.pad = 0;
+      d.slot = 5 * u.seq;
     };
     // units are stored with *qubit roles*; the LO/HI kind is fixed up when the stage closes
     struct Pending {
@@ -291,7 +296,15 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
         d.kind = (pe.la == hi) ? U_BLOCK_CHI : U_BLOCK_CLO;
       (void)lo;
     }
-    for (auto& o : open) prog.stages.push_back(o.sd);
+    for (auto& o : open) {
+      const StageDesc& d = o.sd;
+      o.sd.triplet = (d.nunits == 3 && d.u[0].kind == U_BLOCK_CHI && d.u[1].kind == U_BLOCK_CLO &&
+                      d.u[2].kind == U_BLOCK_CHI && d.u[0].flags == F_PRE && d.u[1].flags == 0 &&
+                      d.u[2].flags == F_POST)
+                         ? 1
+                         : 0;
+      prog.stages.push_back(o.sd);
+    }
     pd.nstages = (int)open.size();
     prog.passes.push_back(pd);
     for (int k : picked) done[k] = 1;
@@ -564,6 +577,271 @@ __global__ void __launch_bounds__(kThreads, (NVEC == 2 ? 3 : 4)) pass_kernel(con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// gradient sweep with scale-free rotations (see aqc_gates.cuh): prep, pass and finalize kernels
+// ------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const double* thetas;    // [batch][T]
+  double2* par;            // [batch][T]  rotation parameters
+  double* logf;            // [batch][T]  log2 |dropped scale| of each angle's rotation
+  double* lbuf;            // [batch][J]  inclusive prefix of logf in execution order
+  double* ebuf;            // [batch][npasses]  cumulative power-of-two renormalisation exponent
+  double* rescale;         // [batch][npasses]  factor applied to the tile when a pass loads it
+  double* dscale;          // [batch][nocc]  squared cumulative scale of each accumulator
+  const int* sched_theta;  // [J] angle of the j-th rotation in execution order
+  const int* sched_occ;    // [J] its accumulator
+  const int* sched_pass;   // [J] its pass
+  const int* pass_start;   // [npasses] first rotation of each pass
+  int T, J, npasses, nocc, n3, tpb, cx;
+};
+
+// One CTA per angle set.  (1) rotation parameters; (2) prefix sums of log2|scale| along the
+// execution order; (3) per-pass power-of-two renormalisation keeping stored ~ true magnitudes;
+// (4) the squared scale each raw inner product has to be multiplied with.
+__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs A) {
+  __shared__ double s_part[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* th = A.thetas + (size_t)b * A.T;
+  double2* par = A.par + (size_t)b * A.T;
+  double* logf = A.logf + (size_t)b * A.T;
+  for (int k = tid; k < A.T; k += 256) {
+    int kind;  // 0 Ry, 1 Rz, 2 Rx, 3 cphase
+    if (k < A.n3)
+      kind = (k % 3 == 1) ? 0 : 1;
+    else {
+      const int r = (k - A.n3) % A.tpb;
+      kind = (r == 4) ? 3 : ((r == 0 || r == 2) ? 0 : (r == 1 ? 1 : (A.cx ? 2 : 1)));
+    }
+    double sn, cs;
+    if (kind == 1 || kind == 3) {
+      sincos(th[k], &sn, &cs);
+      par[k] = make_double2(cs, sn);
+      logf[k] = 0.0;
+    } else {
+      sincos(0.5 * th[k], &sn, &cs);
+      if (fabs(cs) >= 0.3) {
+        par[k] = make_double2(sn / cs, 0.0);
+        logf[k] = log2(fabs(cs));
+      } else {
+        par[k] = make_double2(cs / sn, 1.0);
+        logf[k] = log2(fabs(sn));
+      }
+    }
+  }
+  __syncthreads();
+  // chunked inclusive scan over the execution order
+  double* L = A.lbuf + (size_t)b * A.J;
+  const int chunk = (A.J + 255) / 256;
+  const int j0 = tid * chunk, j1 = min(A.J, j0 + chunk);
+  double sum = 0.0;
+  for (int j = j0; j < j1; ++j) sum += logf[A.sched_theta[j]];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const double add = (tid >= o) ? s_part[tid - o] : 0.0;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  double run = (tid > 0) ? s_part[tid - 1] : 0.0;
+  for (int j = j0; j < j1; ++j) {
+    run += logf[A.sched_theta[j]];
+    L[j] = run;
+  }
+  __syncthreads();
+  double* E = A.ebuf + (size_t)b * A.npasses;
+  double* rs = A.rescale + (size_t)b * A.npasses;
+  for (int p = tid; p < A.npasses; p += 256) {
+    const int js = A.pass_start[p];
+    E[p] = (js > 0) ? rint(L[js - 1]) : 0.0;
+  }
+  __syncthreads();
+  for (int p = tid; p < A.npasses; p += 256) rs[p] = exp2(E[p] - (p > 0 ? E[p - 1] : 0.0));
+  double* ds = A.dscale + (size_t)b * A.nocc;
+  for (int j = tid; j < A.J; j += 256) {
+    const int occ = A.sched_occ[j];
+    if (occ >= 0) ds[occ] = exp2(2.0 * (L[j] - E[A.sched_pass[j]]));
+  }
+}
+
+// gacc[theta] += dscale[occ] * raw[occ]  (complex raw sums per accumulator -> per angle)
+__global__ void finalize_kernel(const double* __restrict__ raw, const double* __restrict__ dscale,
+                                const int* __restrict__ occ_theta, int nocc, int T,
+                                double* __restrict__ gacc) {
+  const int occ = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (occ >= nocc) return;
+  const int k = occ_theta[occ];
+  if (k < 0) return;
+  const double f = dscale[(size_t)b * nocc + occ];
+  atomicAdd(gacc + ((size_t)b * T + k) * 2, f * raw[((size_t)b * nocc + occ) * 2]);
+  atomicAdd(gacc + ((size_t)b * T + k) * 2 + 1, f * raw[((size_t)b * nocc + occ) * 2 + 1]);
+}
+
+struct GradPassArgs {
+  const double2* src[2];  // w, z
+  double2* dst[2];
+  long long vec_stride;
+  long long basis_index;
+  const StageDesc* stages;
+  const double2* par;     // [batch][T]
+  const double* rescale;  // [batch][npasses]
+  double* gocc;           // [batch][nocc] complex raw sums
+  int nthetas, nocc, npasses, pass_index;
+  PassDesc pd;
+};
+
+constexpr int kParStages = 32;  // stages whose parameters are staged in shared memory
+
+template <int ENT>
+__global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassArgs A) {
+  extern __shared__ double2 smem[];
+  __shared__ long long s_hioff[32];
+  __shared__ double2 s_par[kParStages * kMaxUnits * 5];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int tb = A.pd.tb;
+  const int tsize = 1 << tb;
+
+  long long base = 0;
+  {
+    const unsigned long long tile = blockIdx.x;
+    for (int k = 0; k < A.pd.nouter; ++k)
+      base |= (long long)((tile >> k) & 1ull) << A.pd.outerpos[k];
+  }
+  long long lo_off = 0;
+  for (int k = 0; k < 7 && k < tb; ++k) lo_off |= (long long)((tid >> k) & 1) << A.pd.bitpos[k];
+  if (tid < 32) {
+    long long h = 0;
+    for (int k = 7; k < tb; ++k) h |= (long long)((tid >> (k - 7)) & 1) << A.pd.bitpos[k];
+    s_hioff[tid] = h;
+  }
+  const double2* __restrict__ par = A.par + (size_t)blockIdx.y * A.nthetas;
+  const StageDesc* __restrict__ stages = A.stages + A.pd.stage0;
+  const int nstages = A.pd.nstages;
+  const bool par_in_smem = nstages <= kParStages;
+  if (par_in_smem) {
+    for (int i = tid; i < nstages * kMaxUnits * 5; i += kThreads) {
+      const int s = i / (kMaxUnits * 5), u = (i / 5) % kMaxUnits, k = i % 5;
+      const int kind = stages[s].u[u].kind;
+      const int np = (kind == U_NONE || u >= stages[s].nunits)
+                         ? 0
+                         : ((kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : (ENT == AQC_ENT_CP ? 5 : 4));
+      s_par[i] = (k < np) ? par[stages[s].u[u].theta + k] : make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  const long long boff = (long long)blockIdx.y * A.vec_stride + base;
+  const double rs = A.rescale[(size_t)blockIdx.y * A.npasses + A.pass_index];
+
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    double2* sm = smem + (size_t)v * tsize;
+    if (v == 0 && A.basis_index >= 0) {
+      for (int l = tid; l < tsize; l += kThreads) {
+        const long long g = base | lo_off | s_hioff[l >> 7];
+        sm[l] = make_double2(g == A.basis_index ? rs : 0.0, 0.0);
+      }
+    } else {
+      const double2* __restrict__ src = A.src[v] + boff;
+      for (int l = tid; l < tsize; l += kThreads) {
+        double2 x = src[lo_off | s_hioff[l >> 7]];
+        x.x *= rs;
+        x.y *= rs;
+        sm[l] = x;
+      }
+    }
+  }
+  __syncthreads();
+
+  double* gocc = A.gocc + (size_t)blockIdx.y * A.nocc * 2;
+  constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
+  const int nquads = tsize >> 2;
+
+  for (int s = 0; s < nstages; ++s) {
+    const StageDesc* __restrict__ sd = stages + s;
+    const int p = sd->p, q = sd->q, nunits = sd->nunits;
+    const int mq = (1 << q) - 1, mp = (1 << p) - 1;
+    const bool triplet = sd->triplet != 0;
+    double acc[kMaxUnits][NACC];
+#pragma unroll
+    for (int u = 0; u < kMaxUnits; ++u)
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[u][k] = 0.0;
+    // parameters of this stage: shared-memory copy, or the global table for very long passes
+    const double2* pu[kMaxUnits];
+#pragma unroll
+    for (int u = 0; u < kMaxUnits; ++u)
+      pu[u] = par_in_smem ? s_par + (s * kMaxUnits + u) * 5 : par + sd->u[u].theta;
+    for (int j = tid; j < nquads; j += kThreads) {
+      int i0 = ((j & ~mq) << 1) | (j & mq);
+      i0 = ((i0 & ~mp) << 1) | (i0 & mp);
+      const int i1 = i0 | (1 << q), i2 = i0 | (1 << p), i3 = i1 | (1 << p);
+      cd a[2][4];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const double2* sm = smem + (size_t)v * tsize;
+        const double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+        a[v][0].x = x0.x, a[v][0].y = x0.y;
+        a[v][1].x = x1.x, a[v][1].y = x1.y;
+        a[v][2].x = x2.x, a[v][2].y = x2.y;
+        a[v][3].x = x3.x, a[v][3].y = x3.y;
+      }
+      if (triplet) {
+        // straight-line Trotter triplet (cx): ctrl hi + Rz(-pi/2) | ctrl lo | ctrl hi + Rz(+pi/2)
+        sblock_unit<AQC_ENT_CX, true, 1, 0>(a, pu[0], 0, acc[0]);
+        sblock_unit<AQC_ENT_CX, false, 0, 0>(a, pu[1], 0, acc[1]);
+        sblock_unit<AQC_ENT_CX, true, 0, 1>(a, pu[2], 0, acc[2]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < kMaxUnits; ++u) {
+          if (u < nunits) {
+            const int kind = sd->u[u].kind, flags = sd->u[u].flags;
+            switch (kind) {
+              case U_FRONT_LO: sfront_unit<false>(a, pu[u], acc[u]); break;
+              case U_FRONT_HI: sfront_unit<true>(a, pu[u], acc[u]); break;
+              case U_BLOCK_CHI: sblock_unit<ENT, true, -1, -1>(a, pu[u], flags, acc[u]); break;
+              case U_BLOCK_CLO: sblock_unit<ENT, false, -1, -1>(a, pu[u], flags, acc[u]); break;
+              default: break;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        double2* sm = smem + (size_t)v * tsize;
+        sm[i0] = make_double2(a[v][0].x, a[v][0].y);
+        sm[i1] = make_double2(a[v][1].x, a[v][1].y);
+        sm[i2] = make_double2(a[v][2].x, a[v][2].y);
+        sm[i3] = make_double2(a[v][3].x, a[v][3].y);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kMaxUnits; ++u) {
+      if (u < nunits) {
+        const int kind = sd->u[u].kind;
+        const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : (ENT == AQC_ENT_CP ? 10 : 8);
+        double* g = gocc + 2 * (size_t)sd->u[u].slot;
+#pragma unroll
+        for (int h = 0; h < NACC / 8; ++h) {
+          int which;
+          const double r = warp_reduce8(acc[u] + 8 * h, lane, which);
+          which += 8 * h;
+          if ((lane & 3) == 0 && which < nval) atomicAdd(g + which, r);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const double2* sm = smem + (size_t)v * tsize;
+    double2* __restrict__ dst = A.dst[v] + boff;
+    for (int l = tid; l < tsize; l += kThreads) dst[lo_off | s_hioff[l >> 7]] = sm[l];
+  }
+}
+
 // (cos, sin) table: half angles for rotations, full angle for the CPhase parameter.
 __global__ void trig_kernel(const double* __restrict__ thetas, double2* __restrict__ trig,
                             long long total, int nthetas, int n3, int tpb) {
@@ -685,6 +963,12 @@ struct aqc_sv {
   float last_ms = 0.f;
   int last_launches = 0;
   Program prog_grad, prog_fwd, prog_dag;
+  // scale-free gradient sweep (prep_kernel / grad_pass_kernel / finalize_kernel)
+  bool legacy_grad = false;
+  int nocc = 0, nsched = 0;
+  double2* d_par = nullptr;
+  double *d_logf = nullptr, *d_lbuf = nullptr, *d_ebuf = nullptr, *d_rescale = nullptr,
+         *d_dscale = nullptr, *d_gocc = nullptr;
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
@@ -762,6 +1046,95 @@ static int upload_thetas(aqc_sv* sv, const double* thetas) {
 static int check_slot(const aqc_sv* sv, int slot) {
   if (!sv) return fail(AQC_EINVAL, "null workspace");
   if (slot < 0 || slot >= sv->nslots) return fail(AQC_EINVAL, "slot %d out of range", slot);
+  return AQC_OK;
+}
+
+template <int ENT>
+static int launch_grad_pass_t(aqc_sv* sv, const GradPassArgs& args) {
+  const size_t smem = (size_t)2 * sizeof(double2) << args.pd.tb;
+  static bool configured[8] = {false};
+  if (!configured[sv->device & 7]) {
+    CU(cudaFuncSetAttribute(grad_pass_kernel<ENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)2 * sizeof(double2) << (kMaxTileBits - 1))));
+    configured[sv->device & 7] = true;
+  }
+  dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
+  grad_pass_kernel<ENT><<<grid, kThreads, smem, sv->stream>>>(args);
+  CU(cudaGetLastError());
+  return AQC_OK;
+}
+
+// angle-dependent tables of the scale-free gradient sweep (thetas already uploaded) + zeroed sums
+static int grad_prepare(aqc_sv* sv) {
+  const Program& p = sv->prog_grad;
+  PrepArgs a;
+  a.thetas = sv->d_thetas;
+  a.par = sv->d_par;
+  a.logf = sv->d_logf;
+  a.lbuf = sv->d_lbuf;
+  a.ebuf = sv->d_ebuf;
+  a.rescale = sv->d_rescale;
+  a.dscale = sv->d_dscale;
+  a.sched_theta = p.d_sched_theta;
+  a.sched_occ = p.d_sched_occ;
+  a.sched_pass = p.d_sched_pass;
+  a.pass_start = p.d_pass_start;
+  a.T = sv->circ.nthetas;
+  a.J = sv->nsched;
+  a.npasses = (int)p.passes.size();
+  a.nocc = sv->nocc;
+  a.n3 = 3 * sv->circ.n;
+  a.tpb = sv->circ.tpb;
+  a.cx = sv->circ.ent == AQC_ENT_CX;
+  CU(cudaMemsetAsync(sv->d_gocc, 0, (size_t)sv->batch * sv->nocc * 2 * sizeof(double), sv->stream));
+  prep_kernel<<<sv->batch, 256, 0, sv->stream>>>(a);
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+// per-accumulator raw sums -> per-angle sums in d_gacc
+static int grad_collect(aqc_sv* sv) {
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  finalize_kernel<<<dim3((sv->nocc + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
+      sv->d_gocc, sv->d_dscale, sv->prog_grad.d_occ_theta, sv->nocc, sv->circ.nthetas, sv->d_gacc);
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+static int run_grad_program(aqc_sv* sv, const double2* src0, long long basis, const double2* src1,
+                            double2* dst0, double2* dst1, int pass_begin, int pass_end) {
+  const Program& prog = sv->prog_grad;
+  GradPassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.vec_stride = sv->size;
+  a.stages = prog.d_stages;
+  a.par = sv->d_par;
+  a.rescale = sv->d_rescale;
+  a.gocc = sv->d_gocc;
+  a.nthetas = sv->circ.nthetas;
+  a.nocc = sv->nocc;
+  a.npasses = (int)prog.passes.size();
+  if (pass_end < 0) pass_end = (int)prog.passes.size();
+  for (int i = pass_begin; i < pass_end; ++i) {
+    a.pd = prog.passes[i];
+    a.pass_index = i;
+    a.src[0] = (i == pass_begin) ? src0 : dst0;
+    a.src[1] = (i == pass_begin) ? src1 : dst1;
+    a.dst[0] = dst0;
+    a.dst[1] = dst1;
+    a.basis_index = (i == pass_begin) ? basis : -1;
+    int rc;
+    switch (sv->circ.ent) {
+      case AQC_ENT_CX: rc = launch_grad_pass_t<AQC_ENT_CX>(sv, a); break;
+      case AQC_ENT_CZ: rc = launch_grad_pass_t<AQC_ENT_CZ>(sv, a); break;
+      default: rc = launch_grad_pass_t<AQC_ENT_CP>(sv, a);
+    }
+    if (rc) return rc;
+    sv->last_launches += 1;
+  }
   return AQC_OK;
 }
 
@@ -851,6 +1224,47 @@ extern "C" int aqc_circuit_create(int num_qubits, int entangler, const int32_t* 
 extern "C" void aqc_circuit_destroy(aqc_circuit* c) { delete c; }
 extern "C" int aqc_circuit_num_thetas(const aqc_circuit* c) { return c ? c->nthetas : AQC_EINVAL; }
 
+// Rotations of the gradient program in execution order (pass -> stage -> unit -> rotation), with the
+// accumulator each one feeds: input of prep_kernel.
+static void build_schedule(const aqc_circuit& c, Program& p) {
+  const int units_total = c.n + c.nb + c.half;
+  p.sched_theta.clear();
+  p.sched_occ.clear();
+  p.sched_pass.clear();
+  p.pass_start.clear();
+  p.occ_theta.assign((size_t)units_total * 5, -1);
+  for (size_t ip = 0; ip < p.passes.size(); ++ip) {
+    const PassDesc& pd = p.passes[ip];
+    p.pass_start.push_back((int)p.sched_theta.size());
+    for (int s = 0; s < pd.nstages; ++s) {
+      const StageDesc& sd = p.stages[pd.stage0 + s];
+      for (int u = 0; u < sd.nunits; ++u) {
+        const UnitDesc& ud = sd.u[u];
+        const bool front = ud.kind == U_FRONT_LO || ud.kind == U_FRONT_HI;
+        // execution order inside a unit: front Rz(t2) Ry(t1) Rz(t0); block [cphase] t0 t1 t2 t3
+        const int order_front[3] = {2, 1, 0};
+        const int order_block[5] = {4, 0, 1, 2, 3};
+        const int cnt = front ? 3 : 5;
+        for (int i = 0; i < cnt; ++i) {
+          const int k = front ? order_front[i] : order_block[i];
+          if (!front && k == 4 && c.tpb != 5) continue;
+          p.sched_theta.push_back(ud.theta + k);
+          p.sched_occ.push_back(ud.slot + k);
+          p.sched_pass.push_back((int)ip);
+          p.occ_theta[ud.slot + k] = ud.theta + k;
+        }
+      }
+    }
+  }
+}
+
+static int upload_ints(const std::vector<int>& v, int** d) {
+  if (v.empty()) return AQC_OK;
+  CU(cudaMalloc(d, v.size() * sizeof(int)));
+  CU(cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return AQC_OK;
+}
+
 static int upload_program(Program& p) {
   if (p.stages.empty()) return AQC_OK;
   CU(cudaMalloc(&p.d_stages, p.stages.size() * sizeof(StageDesc)));
@@ -869,6 +1283,11 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   if (sv->d_gacc) cudaFree(sv->d_gacc);
   if (sv->d_scratch) cudaFree(sv->d_scratch);
   if (sv->d_idx) cudaFree(sv->d_idx);
+  for (void* q : {(void*)sv->d_par, (void*)sv->d_logf, (void*)sv->d_lbuf, (void*)sv->d_ebuf, (void*)sv->d_rescale,
+                  (void*)sv->d_dscale, (void*)sv->d_gocc, (void*)sv->prog_grad.d_sched_theta,
+                  (void*)sv->prog_grad.d_sched_occ, (void*)sv->prog_grad.d_sched_pass,
+                  (void*)sv->prog_grad.d_pass_start, (void*)sv->prog_grad.d_occ_theta})
+    if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages);
@@ -960,6 +1379,31 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag}) {
     int rc = upload_program(*p);
     if (rc) return bail(rc);
+  }
+  sv->legacy_grad = env_int("AQC_GRAD_LEGACY", 0) != 0;
+  {
+    Program& p = sv->prog_grad;
+    build_schedule(sv->circ, p);
+    sv->nocc = (int)p.occ_theta.size();
+    sv->nsched = (int)p.sched_theta.size();
+    int rc = upload_ints(p.sched_theta, &p.d_sched_theta);
+    if (!rc) rc = upload_ints(p.sched_occ, &p.d_sched_occ);
+    if (!rc) rc = upload_ints(p.sched_pass, &p.d_sched_pass);
+    if (!rc) rc = upload_ints(p.pass_start, &p.d_pass_start);
+    if (!rc) rc = upload_ints(p.occ_theta, &p.d_occ_theta);
+    if (rc) return bail(rc);
+    const size_t B = batch, np = p.passes.size();
+    cudaError_t e = cudaMalloc(&sv->d_par, B * circ->nthetas * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_logf, B * circ->nthetas * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_lbuf, B * std::max(1, sv->nsched) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_ebuf, B * np * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_rescale, B * np * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_dscale, B * sv->nocc * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_gocc, B * sv->nocc * 2 * sizeof(double));
+    if (e != cudaSuccess) {
+      fail(AQC_ENOMEM, "gradient scratch allocation failed: %s", cudaGetErrorString(e));
+      return bail(AQC_ENOMEM);
+    }
   }
   *out = sv;
   return AQC_OK;
@@ -1191,9 +1635,17 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
   if (rc) return rc;
   CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  rc = run_program(sv, sv->prog_grad, true, false, x_slot >= 0 ? sv->slots[x_slot] : nullptr,
-                   x_slot >= 0 ? -1 : x_basis, sv->slots[z0_slot], sv->slots[w_slot],
-                   sv->slots[z_slot]);
+  if (sv->legacy_grad) {
+    rc = run_program(sv, sv->prog_grad, true, false, x_slot >= 0 ? sv->slots[x_slot] : nullptr,
+                     x_slot >= 0 ? -1 : x_basis, sv->slots[z0_slot], sv->slots[w_slot],
+                     sv->slots[z_slot]);
+  } else {
+    rc = grad_prepare(sv);
+    if (!rc)
+      rc = run_grad_program(sv, x_slot >= 0 ? sv->slots[x_slot] : nullptr, x_slot >= 0 ? -1 : x_basis,
+                            sv->slots[z0_slot], sv->slots[w_slot], sv->slots[z_slot], 0, -1);
+    if (!rc) rc = grad_collect(sv);
+  }
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev1, sv->stream));
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1317,7 +1769,10 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
   if (rc) return rc;
   rc = upload_thetas(sv, thetas);
   if (rc) return rc;
-  if (mode == 0) CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  if (mode == 0) {
+    CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+    if (!sv->legacy_grad && (rc = grad_prepare(sv))) return rc;
+  }
   CU(cudaStreamSynchronize(sv->stream));
   return AQC_OK;
 }
@@ -1344,9 +1799,13 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   const int p1 = epoch + 1 < (int)p->epoch_pass0.size() ? p->epoch_pass0[epoch + 1] : (int)p->passes.size();
   const long long basis = src0 >= 0 ? -1 : (basis_local >= 0 ? (long long)basis_local : (1ll << 62));
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  rc = run_program(sv, *p, mode == 0, mode == 2, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
-                   mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
-                   mode == 0 ? sv->slots[dst1] : nullptr, p0, p1);
+  if (mode == 0 && !sv->legacy_grad)
+    rc = run_grad_program(sv, src0 >= 0 ? sv->slots[src0] : nullptr, basis, sv->slots[src1],
+                          sv->slots[dst0], sv->slots[dst1], p0, p1);
+  else
+    rc = run_program(sv, *p, mode == 0, mode == 2, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
+                     mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
+                     mode == 0 ? sv->slots[dst1] : nullptr, p0, p1);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev1, sv->stream));
   CU(cudaStreamSynchronize(sv->stream));
@@ -1362,6 +1821,7 @@ extern "C" int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   int rc = ensure_pinned(sv, tot * 2 + 64);
   if (rc) return rc;
+  if (!sv->legacy_grad && (rc = grad_collect(sv))) return rc;
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
                      sv->stream));
   CU(cudaStreamSynchronize(sv->stream));

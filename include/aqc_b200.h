@@ -111,9 +111,10 @@ int aqc_sv_apply(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int
 /* Full complex gradient of <V x | y> by all thetas, given z0 = V^H y
  * (grad_of_dot_product core_operations.py:823-1019; grad_of_matrix_dot_product
  * core_op_matrix.py:645-762).  x is slot `x_slot`, or the basis state |x_basis>
- * when x_slot < 0.  w_slot / z_slot are scratch slots that receive V x and V z0
- * (they may equal x_slot / z0_slot, which are then destroyed like in the matrix
- * version of the reference).  Second-order Trotter half-layer derivatives are
+ * when x_slot < 0.  w_slot / z_slot are scratch slots for the swept states (their contents
+ * afterwards are unspecified: the sweep keeps V x and V z0 only up to a common, tracked scale);
+ * they may equal x_slot / z0_slot, which are then destroyed like in the matrix version of the
+ * reference.  Second-order Trotter half-layer derivatives are
  * accumulated into the entries of the leading half-layer (core_operations.py:966-994).
  * grad_out: complex128[batch * num_thetas]. */
 int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
