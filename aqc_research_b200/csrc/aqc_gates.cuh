@@ -210,14 +210,14 @@ __device__ __forceinline__ void block_unit(cd (&a)[NVEC][4], const double2* __re
 // Parameter encoding (double2 p): Ry / Rx: p.x = t or r, p.y = 0 (c-form) or 1 (s-form);
 // Rz / CPhase: p = (cos phi, sin phi) of the FULL angle.
 // ------------------------------------------------------------------------------------------------
-template <bool HI, int ROT>
+template <bool HI, int ROT, bool CFORM = false>
 __device__ __forceinline__ void srot1q(cd (&a)[2][4], const double2 p, double* acc) {
   constexpr int I0a = 0, I0b = HI ? 1 : 2;          // the two pairs (i0, i1 = i0 + step)
   constexpr int STEP = HI ? 2 : 1;
   if (ROT == ROT_Z) {
 #pragma unroll
     for (int v = 0; v < 2; ++v) mul_cs(a[v][I0a + STEP], p.x, p.y), mul_cs(a[v][I0b + STEP], p.x, p.y);
-  } else if (p.y == 0.0) {  // c-form
+  } else if (CFORM || p.y == 0.0) {  // c-form
     const double t = p.x;
 #pragma unroll
     for (int v = 0; v < 2; ++v)
@@ -278,7 +278,7 @@ __device__ __forceinline__ void sfront_unit(cd (&a)[2][4], const double2* __rest
 
 // Unit block of the gradient sweep with scale-free rotations.  PRE / POST: -1 = runtime flags,
 // 0 / 1 = compile-time (the Trotter triplet specialisation).
-template <int ENT, bool CHI, int PRE, int POST>
+template <int ENT, bool CHI, int PRE, int POST, bool CFORM = false>
 __device__ __forceinline__ void sblock_unit(cd (&a)[2][4], const double2* __restrict__ p, int flags,
                                             double* acc) {
   constexpr int C1A = CHI ? 2 : 1;
@@ -305,10 +305,10 @@ __device__ __forceinline__ void sblock_unit(cd (&a)[2][4], const double2* __rest
 #pragma unroll
     for (int v = 0; v < 2; ++v) mul_cs(a[v][3], p[4].x, p[4].y);
   }
-  srot1q<CHI, ROT_Y>(a, p[0], acc + 0);
-  srot1q<CHI, ROT_Z>(a, p[1], acc + 2);
-  srot1q<!CHI, ROT_Y>(a, p[2], acc + 4);
-  srot1q<!CHI, ROT_S>(a, p[3], acc + 6);
+  srot1q<CHI, ROT_Y, CFORM>(a, p[0], acc + 0);
+  srot1q<CHI, ROT_Z, CFORM>(a, p[1], acc + 2);
+  srot1q<!CHI, ROT_Y, CFORM>(a, p[2], acc + 4);
+  srot1q<!CHI, ROT_S, CFORM>(a, p[3], acc + 6);
   if (post) {
 #pragma unroll
     for (int v = 0; v < 2; ++v) mul_pi(a[v][T1A]), mul_pi(a[v][3]);

@@ -619,7 +619,9 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs A) {
       logf[k] = 0.0;
     } else {
       sincos(0.5 * th[k], &sn, &cs);
-      if (fabs(cs) >= 0.3) {
+      // c-form unless cos is tiny: |t| <= 50 keeps the growth within a pass far from overflow and
+      // makes the branch-free all-c-form stage path the common case
+      if (fabs(cs) >= 0.02) {
         par[k] = make_double2(sn / cs, 0.0);
         logf[k] = log2(fabs(cs));
       } else {
@@ -719,17 +721,6 @@ __global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassAr
   const double2* __restrict__ par = A.par + (size_t)blockIdx.y * A.nthetas;
   const StageDesc* __restrict__ stages = A.stages + A.pd.stage0;
   const int nstages = A.pd.nstages;
-  const bool par_in_smem = nstages <= kParStages;
-  if (par_in_smem) {
-    for (int i = tid; i < nstages * kMaxUnits * 5; i += kThreads) {
-      const int s = i / (kMaxUnits * 5), u = (i / 5) % kMaxUnits, k = i % 5;
-      const int kind = stages[s].u[u].kind;
-      const int np = (kind == U_NONE || u >= stages[s].nunits)
-                         ? 0
-                         : ((kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : (ENT == AQC_ENT_CP ? 5 : 4));
-      s_par[i] = (k < np) ? par[stages[s].u[u].theta + k] : make_double2(0.0, 0.0);
-    }
-  }
   __syncthreads();
   const long long boff = (long long)blockIdx.y * A.vec_stride + base;
   const double rs = A.rescale[(size_t)blockIdx.y * A.npasses + A.pass_index];
@@ -760,6 +751,21 @@ __global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassAr
 
   for (int s = 0; s < nstages; ++s) {
     const StageDesc* __restrict__ sd = stages + s;
+    if ((s % kParStages) == 0) {
+      // rotation parameters of the next kParStages stages -> shared memory (the previous chunk is
+      // no longer read: every stage ends with a barrier)
+      const int cnt = min(kParStages, nstages - s);
+      for (int i = tid; i < cnt * kMaxUnits * 5; i += kThreads) {
+        const int ss = s + i / (kMaxUnits * 5), u = (i / 5) % kMaxUnits, k = i % 5;
+        const int kind = stages[ss].u[u].kind;
+        const int np = (kind == U_NONE || u >= stages[ss].nunits)
+                           ? 0
+                           : ((kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : (ENT == AQC_ENT_CP ? 5 : 4));
+        // an absent rotation counts as c-form (flag 0) for the all-c-form test below
+        s_par[i] = (k < np) ? par[stages[ss].u[u].theta + k] : make_double2(0.0, 0.0);
+      }
+      __syncthreads();
+    }
     const int p = sd->p, q = sd->q, nunits = sd->nunits;
     const int mq = (1 << q) - 1, mp = (1 << p) - 1;
     const bool triplet = sd->triplet != 0;
@@ -768,11 +774,16 @@ __global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassAr
     for (int u = 0; u < kMaxUnits; ++u)
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[u][k] = 0.0;
-    // parameters of this stage: shared-memory copy, or the global table for very long passes
     const double2* pu[kMaxUnits];
 #pragma unroll
-    for (int u = 0; u < kMaxUnits; ++u)
-      pu[u] = par_in_smem ? s_par + (s * kMaxUnits + u) * 5 : par + sd->u[u].theta;
+    for (int u = 0; u < kMaxUnits; ++u) pu[u] = s_par + ((s % kParStages) * kMaxUnits + u) * 5;
+    // all scaled rotations of a triplet in c-form (the common case) -> branch-free code
+    bool allc = false;
+    if (triplet) {
+      allc = pu[0][0].y == 0.0 && pu[0][2].y == 0.0 && pu[0][3].y == 0.0 && pu[1][0].y == 0.0 &&
+             pu[1][2].y == 0.0 && pu[1][3].y == 0.0 && pu[2][0].y == 0.0 && pu[2][2].y == 0.0 &&
+             pu[2][3].y == 0.0;
+    }
     for (int j = tid; j < nquads; j += kThreads) {
       int i0 = ((j & ~mq) << 1) | (j & mq);
       i0 = ((i0 & ~mp) << 1) | (i0 & mp);
@@ -787,8 +798,12 @@ __global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassAr
         a[v][2].x = x2.x, a[v][2].y = x2.y;
         a[v][3].x = x3.x, a[v][3].y = x3.y;
       }
-      if (triplet) {
+      if (allc) {
         // straight-line Trotter triplet (cx): ctrl hi + Rz(-pi/2) | ctrl lo | ctrl hi + Rz(+pi/2)
+        sblock_unit<AQC_ENT_CX, true, 1, 0, true>(a, pu[0], 0, acc[0]);
+        sblock_unit<AQC_ENT_CX, false, 0, 0, true>(a, pu[1], 0, acc[1]);
+        sblock_unit<AQC_ENT_CX, true, 0, 1, true>(a, pu[2], 0, acc[2]);
+      } else if (triplet) {
         sblock_unit<AQC_ENT_CX, true, 1, 0>(a, pu[0], 0, acc[0]);
         sblock_unit<AQC_ENT_CX, false, 0, 0>(a, pu[1], 0, acc[1]);
         sblock_unit<AQC_ENT_CX, true, 0, 1>(a, pu[2], 0, acc[2]);
