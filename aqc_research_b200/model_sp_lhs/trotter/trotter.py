@@ -1,0 +1,116 @@
+"""
+Trotter helpers the hot path needs on the host: the "perfect" initial angles that make a
+TrotterAnsatz equal to the Trotter circuit, and target-state generation with the GPU engine.
+Reference: aqc_research/model_sp_lhs/trotter/trotter.py (trotter_alphas :269-283,
+neel_init_state :389-398, half_zero_circuit :401-410, fidelity :413-423, slice2q :432-475,
+init_ansatz_to_trotter :478-537).  The Qiskit circuit builders of that module (trotter_circuit,
+Trotter.as_qcircuit, ...) are callers outside the hot path and are not rebuilt; state-preparation
+"circuits" are represented by the list of qubits that carry an X gate.
+"""
+
+from typing import List, Optional, Tuple, Union
+import numpy as np
+from ... import checking as chk
+from ...parametric_circuit import ParametricCircuit, TrotterAnsatz, first_layer_included
+
+
+def trotter_alphas(dt: float, delta: float) -> np.ndarray:
+    """The three non-trivial angles of one Trotter building block (time step dt)."""
+    assert chk.is_float(dt, dt > 0) and chk.is_float(delta, delta > 0)
+    return np.array([0.5 * np.pi - 0.5 * delta * dt, 0.5 * dt - 0.5 * np.pi, 0.5 * np.pi - 0.5 * dt])
+
+
+def neel_init_state(num_qubits: int) -> List[int]:
+    """X-gate positions preparing the Neel state |..0101> (bits 0, 2, 4, ... set)."""
+    assert chk.is_int(num_qubits, num_qubits >= 2)
+    return list(range(0, num_qubits, 2))
+
+
+def half_zero_circuit(num_qubits: int) -> List[int]:
+    """X-gate positions preparing |1..10..0> (upper half of the qubits set)."""
+    assert chk.is_int(num_qubits, num_qubits >= 2)
+    return list(range(num_qubits // 2, num_qubits))
+
+
+def basis_index(x_positions) -> int:
+    index = 0
+    for q in x_positions:
+        index |= 1 << int(q)
+    return index
+
+
+def fidelity(state1, state2) -> float:
+    """|<state1|state2>|^2 for two vectors or two MPS tuples."""
+    if isinstance(state1, np.ndarray) and isinstance(state2, np.ndarray):
+        assert chk.complex_1d(state1) and chk.complex_1d(state2)
+        return float(np.abs(np.vdot(state1, state2)) ** 2)
+    from ...mps_operations import mps_dot  # pylint: disable=import-outside-toplevel
+
+    return float(np.abs(mps_dot(state1, state2)) ** 2)
+
+
+def state_difference(state1: np.ndarray, state2: np.ndarray) -> float:
+    assert chk.complex_1d(state1) and chk.complex_1d(state2)
+    return float(np.linalg.norm(state1 - state2))
+
+
+def slice2q(circ: ParametricCircuit, vec: np.ndarray, *, layer_range: Optional[Tuple[int, int]] = None):
+    """View (layers, n-1 triplets, 12 angles) of the block part of a theta-sized vector."""
+    if not isinstance(circ, TrotterAnsatz):
+        raise ValueError("expects Trotterized ansatz")
+    assert isinstance(vec, np.ndarray) and vec.shape == (circ.num_thetas,)
+    layers = circ.num_layers
+    layer_range = (0, layers) if layer_range is None else layer_range
+    assert chk.is_tuple(layer_range, len(layer_range) == 2)
+    assert 0 <= layer_range[0] < layer_range[1] <= layers
+    view = circ.subset2q(vec).reshape(layers, circ.num_qubits - 1, 12)[layer_range[0] : layer_range[1]]
+    assert np.shares_memory(view, vec)
+    return view, layer_range
+
+
+def init_ansatz_to_trotter(circ, thetas: np.ndarray, *, evol_time: float, delta: float,
+                           layer_range: Optional[Tuple[int, int]] = None) -> np.ndarray:
+    """
+    Sets (in place) the angles of the layers in ``layer_range`` so that the ansatz reproduces the
+    Trotter circuit over ``evol_time``.  Per triplet only three angles are non-zero: entry 5
+    (Rz of the middle block's control), entry 0 (Ry of the first block's control) and entry 6
+    (Ry of the middle block's target).  For a second-order ansatz the leading half-layer (whose
+    angles the implied trailing half-layer re-uses) gets half the time step.
+    """
+    blocks, layer_range = slice2q(circ, thetas, layer_range=layer_range)
+    dt = evol_time / float(layer_range[1] - layer_range[0])
+    with_first = first_layer_included(circ, layer_range)
+    if with_first:
+        circ.subset1q(thetas)[:] = 0
+    blocks[:] = 0
+    a = trotter_alphas(dt=dt, delta=delta)
+    blocks[:, :, 5], blocks[:, :, 0], blocks[:, :, 6] = a[0], a[1], a[2]
+    if circ.is_second_order and with_first:
+        h = trotter_alphas(dt=0.5 * dt, delta=delta)
+        half = circ.half_layer_num_blocks // 3
+        blocks[0, :half, 5], blocks[0, :half, 0], blocks[0, :half, 6] = h[0], h[1], h[2]
+    return thetas
+
+
+def trotter_state(num_qubits: int, *, evol_time: float, num_steps: int, delta: float,
+                  second_order: bool, ini_state: Union[int, List[int], np.ndarray] = 0) -> np.ndarray:
+    """
+    Trotter-evolved state as a dense vector, computed on the GPU: a TrotterAnsatz with
+    ``num_steps`` layers and the angles of ``init_ansatz_to_trotter`` IS the Trotter circuit
+    (what test_trotter_initial_point.py:90-96 of the reference asserts), so the evolution is one
+    ``v_mul_vec``.  ``ini_state``: basis index, X positions or
+    a dense vector.
+    """
+    from ...circuit_structures import make_trotter_like_circuit  # pylint: disable=import-outside-toplevel
+    from ...core_operations import v_mul_vec  # pylint: disable=import-outside-toplevel
+
+    circ = TrotterAnsatz(num_qubits, make_trotter_like_circuit(num_qubits, num_steps), second_order)
+    thetas = init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=evol_time, delta=delta)
+    if isinstance(ini_state, np.ndarray) and ini_state.ndim == 1 and ini_state.size == 2**num_qubits:
+        vec = ini_state.astype(np.complex128)
+    else:
+        vec = np.zeros(2**num_qubits, dtype=np.complex128)
+        index = int(ini_state) if isinstance(ini_state, (int, np.integer)) else basis_index(ini_state)
+        vec[index] = 1
+    out = np.empty_like(vec)
+    return v_mul_vec(circ, thetas, vec, out)

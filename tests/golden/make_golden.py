@@ -140,12 +140,6 @@ def objective_sequences():
     print("objective sequences written")
 
 
-if __name__ == "__main__":
-    sv_cases()
-    mat_cases()
-    objective_sequences()
-
-
 def mps_cases():
     """mps_to_vector / mps_dot of the reference (pure NumPy) on fixed MPS tuples (Vidal form)."""
     sys.path.insert(0, os.path.dirname(HERE))
@@ -175,5 +169,76 @@ def mps_cases():
     print("mps_cases:", case)
 
 
+def trotter_and_lbfgs():
+    """
+    init_ansatz_to_trotter angles of the reference, and a full SciPy L-BFGS-B run on the
+    reference's SpSurrogateObjectiveMax (config C1 of SURVEY 8(d): n = 5, 2nd-order TrotterAnsatz,
+    Neel initial state, Trotter target with 10x finer steps, theta_0 = init_ansatz_to_trotter).
+    The reference builds its Neel-state handler through Qiskit (absent here); for an X-only
+    preparation the states are basis vectors, so a duck-typed handler with the same indices is
+    swapped in.
+    """
+    from scipy.optimize import minimize
+
+    out = {}
+    case = 0
+    for n, layers, so, t_evol in ((4, 2, True, 0.8), (5, 3, False, 1.0), (6, 2, True, 1.2)):
+        circ = R.pc.TrotterAnsatz(n, R.cs.make_trotter_like_circuit(n, layers), so)
+        th = R.trotter.init_ansatz_to_trotter(circ, np.full(circ.num_thetas, 0.123), evol_time=t_evol, delta=1.0)
+        out[f"ia{case}_meta"] = np.array([n, layers, int(so)])
+        out[f"ia{case}_time"] = np.array(t_evol)
+        out[f"ia{case}_thetas"] = th
+        v = np.zeros(2**n, dtype=np.complex128)
+        v[sum(1 << q for q in range(0, n, 2))] = 1
+        out[f"ia{case}_state"] = R.cop.v_mul_vec(circ, th, v, np.zeros_like(v), np.zeros((2, 2**n), dtype=np.complex128))
+        case += 1
+    out["num_ia"] = np.array(case)
+
+    n, layers, t_evol, delta = 5, 2, 1.2, 1.0
+    neel = sum(1 << q for q in range(0, n, 2))
+    fine = R.pc.TrotterAnsatz(n, R.cs.make_trotter_like_circuit(n, 10 * layers), True)
+    th_f = R.trotter.init_ansatz_to_trotter(fine, np.zeros(fine.num_thetas), evol_time=t_evol, delta=delta)
+    e = np.zeros(2**n, dtype=np.complex128)
+    e[neel] = 1
+    target = R.cop.v_mul_vec(fine, th_f, e, np.zeros_like(e), np.zeros((2, 2**n), dtype=np.complex128)).copy()
+    circ = R.pc.TrotterAnsatz(n, R.cs.make_trotter_like_circuit(n, layers), True)
+    th0 = R.trotter.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=t_evol, delta=delta)
+    params = dict(num_qubits=n, max_flips=1, maxiter=40, verbose=0, enable_optim_stats=False,
+                  num_simulations=1, trunc_thr=1e-6, state_prep_func=None)
+    objv = R.sur_max.SpSurrogateObjectiveMax(user_parameters=params, circ=circ, front_layer=True)
+
+    class NeelHandler:
+        num_states = n + 1
+        idx = [neel] + [neel ^ (1 << q) for q in range(n)]
+
+        def init_state(self, i):
+            v = np.zeros(2**n, dtype=np.complex128)
+            v[self.idx[i]] = 1
+            return v
+
+        @property
+        def state0(self):
+            return self.init_state(0)
+
+        def state_dot_vector(self, i, vec):
+            return vec[self.idx[i]]
+
+    objv._state_handler = NeelHandler()
+    objv.set_target(target)
+    maxiter = 12
+    res = minimize(fun=objv.objective, x0=th0.copy(), jac=objv.gradient, method="L-BFGS-B",
+                   options=dict(maxfun=5 * maxiter, maxiter=maxiter, ftol=10 * np.finfo(float).eps, eps=1e-8))
+    out["lb_meta"] = np.array([n, layers, maxiter, res.nit, res.nfev])
+    out["lb_time"] = np.array(t_evol)
+    out["lb_target"], out["lb_theta0"], out["lb_x"] = target, th0, res.x
+    out["lb_fun"], out["lb_fidelity"] = np.array(res.fun), np.array(objv.fidelity)
+    np.savez_compressed(os.path.join(HERE, "trotter_lbfgs.npz"), **out)
+    print("trotter + lbfgs: nit", res.nit, "nfev", res.nfev, "fun", res.fun, "fidelity", objv.fidelity)
+
+
 if __name__ == "__main__":
+    sv_cases()
+    mat_cases()
+    objective_sequences()
     mps_cases()
+    trotter_and_lbfgs()

@@ -136,3 +136,33 @@ def test_early_stop_exception_propagates():
     objv.objective(g[p + "thetas"][0])
     with pytest.raises(StopIteration):
         objv.gradient(g[p + "thetas"][0])
+
+
+def test_lbfgs_run_matches_reference_trajectory():
+    """
+    Drop-in under SciPy's L-BFGS-B (what optimizer.py:585-590 calls through Qiskit): config C1
+    (n = 5, 2nd-order TrotterAnsatz, Neel state, Trotter target, theta_0 = init_ansatz_to_trotter).
+    The optimiser must follow the trajectory recorded with the unmodified reference objective.
+    """
+    from scipy.optimize import minimize
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trot
+
+    g = load("trotter_lbfgs.npz")
+    n, layers, maxiter, nit, nfev = [int(v) for v in g["lb_meta"]]
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    th0 = trot.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=float(g["lb_time"]), delta=1.0)
+    assert np.array_equal(th0, g["lb_theta0"])
+    # the target itself: GPU Trotter evolution with 10x finer steps == the reference's
+    target = trot.trotter_state(n, evol_time=float(g["lb_time"]), num_steps=10 * layers, delta=1.0,
+                                second_order=True, ini_state=trot.neel_init_state(n))
+    assert rel(target, g["lb_target"]) < TOL
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n, state_prep_func=trot.neel_init_state, maxiter=40),
+                                   circ=circ, front_layer=True)
+    objv.set_target(g["lb_target"])
+    res = minimize(fun=objv.objective, x0=th0.copy(), jac=objv.gradient, method="L-BFGS-B",
+                   options=dict(maxfun=5 * maxiter, maxiter=maxiter, ftol=10 * np.finfo(float).eps, eps=1e-8))
+    assert (res.nit, res.nfev) == (nit, nfev)
+    assert abs(res.fun - float(g["lb_fun"])) < 1e-9
+    assert rel(res.x, g["lb_x"]) < 1e-7
+    assert abs(objv.fidelity - float(g["lb_fidelity"])) < 1e-9
