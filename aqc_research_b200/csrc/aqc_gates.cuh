@@ -314,3 +314,101 @@ __device__ __forceinline__ void sblock_unit(cd (&a)[2][4], const double2* __rest
     for (int v = 0; v < 2; ++v) mul_pi(a[v][T1A]), mul_pi(a[v][3]);
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Scale-free forms for the single-vector sweeps V x / V^H x (no inner products).  The dropped
+// complex scalars (signed cos / sin factors, e^{-i phi/2} of every Rz) are collected by the prep
+// kernel and multiplied back when the last pass stores the tile.  The parameter table is built for
+// the NEGATED angles in the daggered sweep, so DAG only reverses the order of the rotations.
+// ------------------------------------------------------------------------------------------------
+template <bool HI, int ROT>
+__device__ __forceinline__ void arot1q(cd (&a)[4], const double2 p) {
+  constexpr int I0a = 0, I0b = HI ? 1 : 2;
+  constexpr int STEP = HI ? 2 : 1;
+  if (ROT == ROT_Z) {
+    mul_cs(a[I0a + STEP], p.x, p.y);
+    mul_cs(a[I0b + STEP], p.x, p.y);
+    return;
+  }
+  const double t = p.x;
+  if (p.y == 0.0) {  // c-form
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
+      const cd b0 = a[i0], b1 = a[i1];
+      if (ROT == ROT_Y) {
+        a[i0].x = fma(-t, b1.x, b0.x), a[i0].y = fma(-t, b1.y, b0.y);
+        a[i1].x = fma(t, b0.x, b1.x), a[i1].y = fma(t, b0.y, b1.y);
+      } else {
+        a[i0].x = fma(t, b1.y, b0.x), a[i0].y = fma(-t, b1.x, b0.y);
+        a[i1].x = fma(t, b0.y, b1.x), a[i1].y = fma(-t, b0.x, b1.y);
+      }
+    }
+  } else {  // s-form
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
+      const cd b0 = a[i0], b1 = a[i1];
+      if (ROT == ROT_Y) {
+        a[i0].x = fma(t, b0.x, -b1.x), a[i0].y = fma(t, b0.y, -b1.y);
+        a[i1].x = fma(t, b1.x, b0.x), a[i1].y = fma(t, b1.y, b0.y);
+      } else {
+        a[i0].x = fma(t, b0.x, b1.y), a[i0].y = fma(t, b0.y, -b1.x);
+        a[i1].x = fma(t, b1.x, b0.y), a[i1].y = fma(t, b1.y, -b0.x);
+      }
+    }
+  }
+}
+
+template <bool HI, bool DAG>
+__device__ __forceinline__ void afront_unit(cd (&a)[4], const double2* __restrict__ p) {
+  if (!DAG) {
+    arot1q<HI, ROT_Z>(a, p[2]);
+    arot1q<HI, ROT_Y>(a, p[1]);
+    arot1q<HI, ROT_Z>(a, p[0]);
+  } else {
+    arot1q<HI, ROT_Z>(a, p[0]);
+    arot1q<HI, ROT_Y>(a, p[1]);
+    arot1q<HI, ROT_Z>(a, p[2]);
+  }
+}
+
+template <int ENT, bool CHI, bool DAG>
+__device__ __forceinline__ void ablock_unit(cd (&a)[4], const double2* __restrict__ p, int flags) {
+  constexpr int C1A = CHI ? 2 : 1;
+  constexpr int T1A = CHI ? 1 : 2;
+  constexpr int ROT_S = (ENT == AQC_ENT_CX) ? ROT_X : ROT_Z;
+  if (!DAG) {
+    if (flags & F_PRE) mul_mi(a[C1A]), mul_mi(a[3]);
+    if (ENT == AQC_ENT_CX) {
+      const cd t = a[C1A];
+      a[C1A] = a[3];
+      a[3] = t;
+    } else if (ENT == AQC_ENT_CZ) {
+      a[3].x = -a[3].x, a[3].y = -a[3].y;
+    } else {
+      mul_cs(a[3], p[4].x, p[4].y);
+    }
+    arot1q<CHI, ROT_Y>(a, p[0]);
+    arot1q<CHI, ROT_Z>(a, p[1]);
+    arot1q<!CHI, ROT_Y>(a, p[2]);
+    arot1q<!CHI, ROT_S>(a, p[3]);
+    if (flags & F_POST) mul_pi(a[T1A]), mul_pi(a[3]);
+  } else {
+    if (flags & F_POST) mul_mi(a[T1A]), mul_mi(a[3]);
+    arot1q<!CHI, ROT_S>(a, p[3]);
+    arot1q<!CHI, ROT_Y>(a, p[2]);
+    arot1q<CHI, ROT_Z>(a, p[1]);
+    arot1q<CHI, ROT_Y>(a, p[0]);
+    if (ENT == AQC_ENT_CX) {
+      const cd t = a[C1A];
+      a[C1A] = a[3];
+      a[3] = t;
+    } else if (ENT == AQC_ENT_CZ) {
+      a[3].x = -a[3].x, a[3].y = -a[3].y;
+    } else {
+      mul_cs(a[3], p[4].x, p[4].y);  // table holds the negated angle
+    }
+    if (flags & F_PRE) mul_pi(a[C1A]), mul_pi(a[3]);
+  }
+}

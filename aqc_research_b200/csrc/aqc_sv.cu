@@ -857,6 +857,227 @@ __global__ void __launch_bounds__(kThreads, 3) grad_pass_kernel(const GradPassAr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// single-vector sweeps (V x, V^H x) with scale-free rotations
+// ------------------------------------------------------------------------------------------
+struct PrepApplyArgs {
+  const double* thetas;    // [batch][T]
+  double2* par;            // [batch][T]
+  double* logf;            // [batch][T]
+  double2* uph;            // [batch][T] unit-modulus part of each rotation's dropped scalar
+  double* lbuf;            // [batch][J]
+  double* ebuf;            // [batch][npasses]
+  double* rescale;         // [batch][npasses]
+  double2* kappa;          // [batch] scalar restoring the true amplitudes at the last store
+  const int* sched_theta;  // [J]
+  const int* pass_start;   // [npasses]
+  int T, J, npasses, n3, tpb, cx, dagger;
+};
+
+__global__ void __launch_bounds__(256) prep_apply_kernel(const PrepApplyArgs A) {
+  __shared__ double s_part[256];
+  __shared__ double2 s_ph[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* th = A.thetas + (size_t)b * A.T;
+  double2* par = A.par + (size_t)b * A.T;
+  double* logf = A.logf + (size_t)b * A.T;
+  double2* uph = A.uph + (size_t)b * A.T;
+  const double sgn = A.dagger ? -1.0 : 1.0;
+  for (int k = tid; k < A.T; k += 256) {
+    int kind;  // 0 Ry, 1 Rz, 2 Rx, 3 cphase
+    if (k < A.n3)
+      kind = (k % 3 == 1) ? 0 : 1;
+    else {
+      const int r = (k - A.n3) % A.tpb;
+      kind = (r == 4) ? 3 : ((r == 0 || r == 2) ? 0 : (r == 1 ? 1 : (A.cx ? 2 : 1)));
+    }
+    const double phi = sgn * th[k];
+    double sn, cs;
+    if (kind == 3) {
+      sincos(phi, &sn, &cs);
+      par[k] = make_double2(cs, sn);
+      logf[k] = 0.0;
+      uph[k] = make_double2(1.0, 0.0);
+    } else if (kind == 1) {
+      double sh, ch;
+      sincos(0.5 * phi, &sh, &ch);
+      // full-angle phase from the half angle: (ch + i sh)^2; dropped scalar e^{-i phi/2}
+      par[k] = make_double2(fma(ch, ch, -sh * sh), 2.0 * ch * sh);
+      logf[k] = 0.0;
+      uph[k] = make_double2(ch, -sh);
+    } else {
+      sincos(0.5 * phi, &sn, &cs);
+      if (fabs(cs) >= 0.02) {
+        par[k] = make_double2(sn / cs, 0.0);
+        logf[k] = log2(fabs(cs));
+        uph[k] = make_double2(cs < 0.0 ? -1.0 : 1.0, 0.0);
+      } else {
+        par[k] = make_double2(cs / sn, 1.0);
+        logf[k] = log2(fabs(sn));
+        uph[k] = make_double2(sn < 0.0 ? -1.0 : 1.0, 0.0);
+      }
+    }
+  }
+  __syncthreads();
+  double* L = A.lbuf + (size_t)b * A.J;
+  const int chunk = (A.J + 255) / 256;
+  const int j0 = tid * chunk, j1 = min(A.J, j0 + chunk);
+  double sum = 0.0;
+  double2 ph = make_double2(1.0, 0.0);
+  for (int j = j0; j < j1; ++j) {
+    const int k = A.sched_theta[j];
+    sum += logf[k];
+    const double2 u = uph[k];
+    ph = make_double2(fma(-ph.y, u.y, ph.x * u.x), fma(ph.y, u.x, ph.x * u.y));
+  }
+  s_part[tid] = sum;
+  s_ph[tid] = ph;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const double add = (tid >= o) ? s_part[tid - o] : 0.0;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  double run = (tid > 0) ? s_part[tid - 1] : 0.0;
+  for (int j = j0; j < j1; ++j) {
+    run += logf[A.sched_theta[j]];
+    L[j] = run;
+  }
+  // product of the unit-modulus parts (tree)
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const double2 x = s_ph[tid], y = s_ph[tid + o];
+      s_ph[tid] = make_double2(fma(-x.y, y.y, x.x * y.x), fma(x.y, y.x, x.x * y.y));
+    }
+    __syncthreads();
+  }
+  double* E = A.ebuf + (size_t)b * A.npasses;
+  double* rs = A.rescale + (size_t)b * A.npasses;
+  for (int p = tid; p < A.npasses; p += 256) {
+    const int js = A.pass_start[p];
+    E[p] = (js > 0) ? rint(L[js - 1]) : 0.0;
+  }
+  __syncthreads();
+  for (int p = tid; p < A.npasses; p += 256) rs[p] = exp2(E[p] - (p > 0 ? E[p - 1] : 0.0));
+  if (tid == 0) {
+    const double ltot = (A.J > 0) ? L[A.J - 1] : 0.0;
+    const double mag = exp2(ltot - (A.npasses > 0 ? E[A.npasses - 1] : 0.0));
+    A.kappa[b] = make_double2(mag * s_ph[0].x, mag * s_ph[0].y);
+  }
+}
+
+struct ApplyPassArgs {
+  const double2* src;
+  double2* dst;
+  long long vec_stride;
+  const StageDesc* stages;
+  const double2* par;      // [batch][T]
+  const double* rescale;   // [batch][npasses]
+  const double2* kappa;    // [batch]; applied at the store of the LAST pass only
+  int nthetas, npasses, pass_index, last;
+  PassDesc pd;
+};
+
+template <int ENT, bool DAG>
+__global__ void __launch_bounds__(kThreads, 4) apply_pass_kernel(const ApplyPassArgs A) {
+  extern __shared__ double2 smem[];
+  __shared__ long long s_hioff[32];
+  __shared__ double2 s_par[kParStages * kMaxUnits * 5];
+  const int tid = threadIdx.x;
+  const int tb = A.pd.tb;
+  const int tsize = 1 << tb;
+  long long base = 0;
+  {
+    const unsigned long long tile = blockIdx.x;
+    for (int k = 0; k < A.pd.nouter; ++k)
+      base |= (long long)((tile >> k) & 1ull) << A.pd.outerpos[k];
+  }
+  long long lo_off = 0;
+  for (int k = 0; k < 7 && k < tb; ++k) lo_off |= (long long)((tid >> k) & 1) << A.pd.bitpos[k];
+  if (tid < 32) {
+    long long h = 0;
+    for (int k = 7; k < tb; ++k) h |= (long long)((tid >> (k - 7)) & 1) << A.pd.bitpos[k];
+    s_hioff[tid] = h;
+  }
+  const double2* __restrict__ par = A.par + (size_t)blockIdx.y * A.nthetas;
+  const StageDesc* __restrict__ stages = A.stages + A.pd.stage0;
+  const int nstages = A.pd.nstages;
+  __syncthreads();
+  const long long boff = (long long)blockIdx.y * A.vec_stride + base;
+  const double rs = A.rescale[(size_t)blockIdx.y * A.npasses + A.pass_index];
+  {
+    const double2* __restrict__ src = A.src + boff;
+    for (int l = tid; l < tsize; l += kThreads) {
+      double2 x = src[lo_off | s_hioff[l >> 7]];
+      x.x *= rs;
+      x.y *= rs;
+      smem[l] = x;
+    }
+  }
+  __syncthreads();
+  const int nquads = tsize >> 2;
+  for (int s = 0; s < nstages; ++s) {
+    const StageDesc* __restrict__ sd = stages + s;
+    if ((s % kParStages) == 0) {
+      const int cnt = min(kParStages, nstages - s);
+      for (int i = tid; i < cnt * kMaxUnits * 5; i += kThreads) {
+        const int ss = s + i / (kMaxUnits * 5), u = (i / 5) % kMaxUnits, k = i % 5;
+        const int kind = stages[ss].u[u].kind;
+        const int np = (kind == U_NONE || u >= stages[ss].nunits)
+                           ? 0
+                           : ((kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : (ENT == AQC_ENT_CP ? 5 : 4));
+        s_par[i] = (k < np) ? par[stages[ss].u[u].theta + k] : make_double2(0.0, 0.0);
+      }
+      __syncthreads();
+    }
+    const int p = sd->p, q = sd->q, nunits = sd->nunits;
+    const int mq = (1 << q) - 1, mp = (1 << p) - 1;
+    for (int j = tid; j < nquads; j += kThreads) {
+      int i0 = ((j & ~mq) << 1) | (j & mq);
+      i0 = ((i0 & ~mp) << 1) | (i0 & mp);
+      const int i1 = i0 | (1 << q), i2 = i0 | (1 << p), i3 = i1 | (1 << p);
+      cd a[4];
+      {
+        const double2 x0 = smem[i0], x1 = smem[i1], x2 = smem[i2], x3 = smem[i3];
+        a[0].x = x0.x, a[0].y = x0.y;
+        a[1].x = x1.x, a[1].y = x1.y;
+        a[2].x = x2.x, a[2].y = x2.y;
+        a[3].x = x3.x, a[3].y = x3.y;
+      }
+#pragma unroll
+      for (int u = 0; u < kMaxUnits; ++u) {
+        if (u < nunits) {
+          const int kind = sd->u[u].kind, flags = sd->u[u].flags;
+          const double2* pu = s_par + ((s % kParStages) * kMaxUnits + u) * 5;
+          switch (kind) {
+            case U_FRONT_LO: afront_unit<false, DAG>(a, pu); break;
+            case U_FRONT_HI: afront_unit<true, DAG>(a, pu); break;
+            case U_BLOCK_CHI: ablock_unit<ENT, true, DAG>(a, pu, flags); break;
+            case U_BLOCK_CLO: ablock_unit<ENT, false, DAG>(a, pu, flags); break;
+            default: break;
+          }
+        }
+      }
+      smem[i0] = make_double2(a[0].x, a[0].y);
+      smem[i1] = make_double2(a[1].x, a[1].y);
+      smem[i2] = make_double2(a[2].x, a[2].y);
+      smem[i3] = make_double2(a[3].x, a[3].y);
+    }
+    __syncthreads();
+  }
+  double2* __restrict__ dst = A.dst + boff;
+  if (A.last) {
+    const double2 kp = A.kappa[blockIdx.y];
+    for (int l = tid; l < tsize; l += kThreads) {
+      const double2 x = smem[l];
+      dst[lo_off | s_hioff[l >> 7]] = make_double2(fma(-kp.y, x.y, kp.x * x.x), fma(kp.y, x.x, kp.x * x.y));
+    }
+  } else {
+    for (int l = tid; l < tsize; l += kThreads) dst[lo_off | s_hioff[l >> 7]] = smem[l];
+  }
+}
+
 // (cos, sin) table: half angles for rotations, full angle for the CPhase parameter.
 __global__ void trig_kernel(const double* __restrict__ thetas, double2* __restrict__ trig,
                             long long total, int nthetas, int n3, int tpb) {
@@ -984,6 +1205,9 @@ struct aqc_sv {
   double2* d_par = nullptr;
   double *d_logf = nullptr, *d_lbuf = nullptr, *d_ebuf = nullptr, *d_rescale = nullptr,
          *d_dscale = nullptr, *d_gocc = nullptr;
+  // scale-free single-vector sweeps
+  double2 *d_apar = nullptr, *d_uph = nullptr, *d_kappa = nullptr;
+  double *d_albuf = nullptr, *d_aebuf = nullptr, *d_arescale = nullptr;
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
@@ -1153,6 +1377,89 @@ static int run_grad_program(aqc_sv* sv, const double2* src0, long long basis, co
   return AQC_OK;
 }
 
+template <int ENT, bool DAG>
+static int launch_apply_pass_t(aqc_sv* sv, const ApplyPassArgs& args) {
+  const size_t smem = sizeof(double2) << args.pd.tb;
+  static bool configured[8] = {false};
+  if (!configured[sv->device & 7]) {
+    CU(cudaFuncSetAttribute(apply_pass_kernel<ENT, DAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sizeof(double2) << kMaxTileBits)));
+    configured[sv->device & 7] = true;
+  }
+  dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
+  apply_pass_kernel<ENT, DAG><<<grid, kThreads, smem, sv->stream>>>(args);
+  CU(cudaGetLastError());
+  return AQC_OK;
+}
+
+// angle-dependent tables of a single-vector sweep (thetas already uploaded)
+static int apply_prepare(aqc_sv* sv, bool dagger) {
+  const Program& p = dagger ? sv->prog_dag : sv->prog_fwd;
+  PrepApplyArgs a;
+  a.thetas = sv->d_thetas;
+  a.par = sv->d_apar;
+  a.logf = sv->d_logf;
+  a.uph = sv->d_uph;
+  a.lbuf = sv->d_albuf;
+  a.ebuf = sv->d_aebuf;
+  a.rescale = sv->d_arescale;
+  a.kappa = sv->d_kappa;
+  a.sched_theta = p.d_sched_theta;
+  a.pass_start = p.d_pass_start;
+  a.T = sv->circ.nthetas;
+  a.J = (int)p.sched_theta.size();
+  a.npasses = (int)p.passes.size();
+  a.n3 = 3 * sv->circ.n;
+  a.tpb = sv->circ.tpb;
+  a.cx = sv->circ.ent == AQC_ENT_CX;
+  a.dagger = dagger ? 1 : 0;
+  prep_apply_kernel<<<sv->batch, 256, 0, sv->stream>>>(a);
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+// passes [pass_begin, pass_end) of a single-vector program; `final` marks the end of the whole
+// sweep (the stored scalar is multiplied back by the last pass)
+static int run_apply_program(aqc_sv* sv, bool dagger, const double2* src, double2* dst,
+                             int pass_begin, int pass_end) {
+  const Program& prog = dagger ? sv->prog_dag : sv->prog_fwd;
+  ApplyPassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.vec_stride = sv->size;
+  a.stages = prog.d_stages;
+  a.par = sv->d_apar;
+  a.rescale = sv->d_arescale;
+  a.kappa = sv->d_kappa;
+  a.nthetas = sv->circ.nthetas;
+  a.npasses = (int)prog.passes.size();
+  if (pass_end < 0) pass_end = (int)prog.passes.size();
+  for (int i = pass_begin; i < pass_end; ++i) {
+    a.pd = prog.passes[i];
+    a.pass_index = i;
+    a.last = (i + 1 == (int)prog.passes.size()) ? 1 : 0;
+    a.src = (i == pass_begin) ? src : dst;
+    a.dst = dst;
+    int rc;
+    if (dagger) {
+      switch (sv->circ.ent) {
+        case AQC_ENT_CX: rc = launch_apply_pass_t<AQC_ENT_CX, true>(sv, a); break;
+        case AQC_ENT_CZ: rc = launch_apply_pass_t<AQC_ENT_CZ, true>(sv, a); break;
+        default: rc = launch_apply_pass_t<AQC_ENT_CP, true>(sv, a);
+      }
+    } else {
+      switch (sv->circ.ent) {
+        case AQC_ENT_CX: rc = launch_apply_pass_t<AQC_ENT_CX, false>(sv, a); break;
+        case AQC_ENT_CZ: rc = launch_apply_pass_t<AQC_ENT_CZ, false>(sv, a); break;
+        default: rc = launch_apply_pass_t<AQC_ENT_CP, false>(sv, a);
+      }
+    }
+    if (rc) return rc;
+    sv->last_launches += 1;
+  }
+  return AQC_OK;
+}
+
 // runs one compiled program; NVEC == 1: src0 -> dst0; NVEC == 2: (w, z)
 static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, const double2* src0,
                        long long basis, const double2* src1, double2* dst0, double2* dst1,
@@ -1301,7 +1608,11 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   for (void* q : {(void*)sv->d_par, (void*)sv->d_logf, (void*)sv->d_lbuf, (void*)sv->d_ebuf, (void*)sv->d_rescale,
                   (void*)sv->d_dscale, (void*)sv->d_gocc, (void*)sv->prog_grad.d_sched_theta,
                   (void*)sv->prog_grad.d_sched_occ, (void*)sv->prog_grad.d_sched_pass,
-                  (void*)sv->prog_grad.d_pass_start, (void*)sv->prog_grad.d_occ_theta})
+                  (void*)sv->prog_grad.d_pass_start, (void*)sv->prog_grad.d_occ_theta,
+                  (void*)sv->prog_fwd.d_sched_theta, (void*)sv->prog_fwd.d_pass_start,
+                  (void*)sv->prog_dag.d_sched_theta, (void*)sv->prog_dag.d_pass_start, (void*)sv->d_apar,
+                  (void*)sv->d_uph, (void*)sv->d_kappa, (void*)sv->d_albuf, (void*)sv->d_aebuf,
+                  (void*)sv->d_arescale})
     if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
@@ -1417,6 +1728,28 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     if (e == cudaSuccess) e = cudaMalloc(&sv->d_gocc, B * sv->nocc * 2 * sizeof(double));
     if (e != cudaSuccess) {
       fail(AQC_ENOMEM, "gradient scratch allocation failed: %s", cudaGetErrorString(e));
+      return bail(AQC_ENOMEM);
+    }
+  }
+  {
+    size_t jmax = 1, pmax = 1;
+    for (Program* p : {&sv->prog_fwd, &sv->prog_dag}) {
+      build_schedule(sv->circ, *p);
+      int rc = upload_ints(p->sched_theta, &p->d_sched_theta);
+      if (!rc) rc = upload_ints(p->pass_start, &p->d_pass_start);
+      if (rc) return bail(rc);
+      jmax = std::max(jmax, p->sched_theta.size());
+      pmax = std::max(pmax, p->passes.size());
+    }
+    const size_t B = batch;
+    cudaError_t e = cudaMalloc(&sv->d_apar, B * circ->nthetas * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_uph, B * circ->nthetas * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_kappa, B * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_albuf, B * jmax * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_aebuf, B * pmax * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sv->d_arescale, B * pmax * sizeof(double));
+    if (e != cudaSuccess) {
+      fail(AQC_ENOMEM, "apply scratch allocation failed: %s", cudaGetErrorString(e));
       return bail(AQC_ENOMEM);
     }
   }
@@ -1575,9 +1908,14 @@ static int apply_async(aqc_sv* sv, const double* thetas, int dagger, int src_slo
   rc = upload_thetas(sv, thetas);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  const Program& prog = dagger ? sv->prog_dag : sv->prog_fwd;
-  rc = run_program(sv, prog, false, dagger != 0, sv->slots[src_slot], -1, nullptr,
-                   sv->slots[dst_slot], nullptr);
+  if (sv->legacy_grad) {
+    const Program& prog = dagger ? sv->prog_dag : sv->prog_fwd;
+    rc = run_program(sv, prog, false, dagger != 0, sv->slots[src_slot], -1, nullptr,
+                     sv->slots[dst_slot], nullptr);
+  } else {
+    rc = apply_prepare(sv, dagger != 0);
+    if (!rc) rc = run_apply_program(sv, dagger != 0, sv->slots[src_slot], sv->slots[dst_slot], 0, -1);
+  }
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev1, sv->stream));
   return AQC_OK;
@@ -1787,6 +2125,8 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
   if (mode == 0) {
     CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
     if (!sv->legacy_grad && (rc = grad_prepare(sv))) return rc;
+  } else if (!sv->legacy_grad) {
+    if ((rc = apply_prepare(sv, mode == 2))) return rc;
   }
   CU(cudaStreamSynchronize(sv->stream));
   return AQC_OK;
@@ -1817,6 +2157,8 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   if (mode == 0 && !sv->legacy_grad)
     rc = run_grad_program(sv, src0 >= 0 ? sv->slots[src0] : nullptr, basis, sv->slots[src1],
                           sv->slots[dst0], sv->slots[dst1], p0, p1);
+  else if (!sv->legacy_grad)
+    rc = run_apply_program(sv, mode == 2, sv->slots[src0], sv->slots[dst0], p0, p1);
   else
     rc = run_program(sv, *p, mode == 0, mode == 2, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
                      mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
