@@ -1,0 +1,400 @@
+// aqc_dense.cuh -- "dense-stage" sweeps on the FP64 tensor pipe (included by aqc_sv.cu after the
+// program structures).
+//
+// A *stage* is every consecutive gate of the circuit that acts on one pair of tile bits (front
+// gates of the two qubits, the unit blocks of a Trotter triplet, their Rz(-+pi/2)); its action on
+// an amplitude quadruple is ONE 4x4 complex matrix U_s(theta).  The gradient sweep of the reference
+// (core_operations.py:823-1019) records 0.5j <P w|z> after every rotation; with w_k = G_k w_in and
+// z_k = G_k z_in inside the stage (G_k = partial product up to rotation k),
+//     sum_quads <P w_k | z_k> = Tr(G_k^H P G_k  M),      M = sum_quads z_in w_in^H   (4x4 complex),
+// so the sweep over the 2^n amplitudes only has to (1) apply U_s to w and z and (2) accumulate the
+// 4x4 matrix sum_quads z w^H; all per-rotation inner products follow from that matrix in a tiny
+// post-processing kernel (dense_grad_kernel) that re-runs the gate-by-gate recipe of the reference
+// on four "virtual quadruples".  Per quadruple and stage this is 128 + 64 real FMAs instead of
+// ~130 per UNIT, and it is pure small-matrix work, which mma.sync.m8n8k4.f64 (DMMA) executes at
+// the full FP64 rate (37.1 TFLOP/s measured, scripts/ubench_fp64.cu) with ~1/16 of the issue slots
+// and registers of scalar DFMA code.
+//
+// Fragment algebra (PTX m8n8k4.f64: A[l>>2][l&3], B[l&3][l>>2], C[l>>2][2(l&3)+{0,1}]):
+//   apply:  D[c][g] = sum_k UA[c][k] X[k][g],  c = out component (re/im | amp<<1), g = quad slot,
+//           two k-steps: k = re of amplitude (l&3), then im of amplitude (l&3), of quad slot (l>>2)
+//           -> the B fragments are exactly the lane's own (re, im) of one LDS.128;
+//           lane holds D = component c = l>>2 of quad slots 2(l&3), 2(l&3)+1 of the OUTPUT;
+//   M:      R[cz][cw] += sum_g Zout[cz][g] Wout[cw][g]: A = the lane's Zout values, B = its Wout
+//           values, k-steps = the two quad slots a lane holds -> no shuffles, no re-reads.
+//   (the post kernel pulls M_out = U M_in U^H back through the stage).
+//
+// Shared memory holds the tile with an XOR swizzle, slot(i) = i ^ fold3(i >> 3), so that the LDS.128
+// of a quarter warp and the STS.64 of a half warp are bank-conflict free whenever the stage's bits
+// (q, p) and the three quad-slot bits (r0, r1, r2) chosen by the host have suitable residues mod 3
+// (always possible for adjacent-qubit pairs in an 11-bit tile); other pairs only lose bandwidth.
+#pragma once
+
+constexpr int kDThreads = 256;
+constexpr int kDWarps = kDThreads / 32;
+constexpr int kDMinTileBits = 5;  // 8 quads of 4 amplitudes per DMMA
+
+__host__ __device__ __forceinline__ unsigned dense_swz(unsigned i) {
+  return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u);
+}
+
+// Per stage, per (warp, lane): everything the inner loop needs, packed into 8 bytes.
+//   sl : swizzled slot offset (16-byte units) of the lane's amplitude in the load layout
+//   so0, so1 : swizzled offsets (8-byte units) of the lane's two stores
+//   sb : swizzled tile-local base of iteration `warp + kDWarps * lane` (lanes < iterations / warp)
+struct DLane {
+  uint16_t sl, so0, so1, sb;
+};
+static_assert(sizeof(DLane) == 8, "DLane layout");
+
+struct DenseTables {
+  std::vector<DLane> lanes;      // [stage][warp][lane]
+  std::vector<int32_t> rbits;    // [stage][3]  quad-slot bits r0, r1, r2 (introspection)
+  DLane* d_lanes = nullptr;
+};
+
+static int gf2_rank3(unsigned a, unsigned b, unsigned c) {
+  int best = 0;
+  for (unsigned m = 1; m < 8; ++m) {
+    (void)m;
+  }
+  // rank of three 3-bit vectors over GF(2)
+  unsigned v[3] = {a, b, c};
+  int rank = 0;
+  for (int bit = 0; bit < 3; ++bit) {
+    int piv = -1;
+    for (int i = rank; i < 3; ++i)
+      if (v[i] >> bit & 1u) {
+        piv = i;
+        break;
+      }
+    if (piv < 0) continue;
+    std::swap(v[rank], v[piv]);
+    for (int i = 0; i < 3; ++i)
+      if (i != rank && (v[i] >> bit & 1u)) v[i] ^= v[rank];
+    ++rank;
+  }
+  (void)best;
+  return rank;
+}
+
+// Builds the per-stage lane tables of one program (all passes).  Returns false if a pass has a
+// tile of fewer than kDMinTileBits bits.
+static bool build_dense_tables(const Program& prog, DenseTables& T) {
+  T.lanes.assign(prog.stages.size() * kDWarps * 32, DLane{0, 0, 0, 0});
+  T.rbits.assign(prog.stages.size() * 3, 0);
+  for (const PassDesc& pd : prog.passes) {
+    const int tb = pd.tb;
+    if (tb < kDMinTileBits) return false;
+    const int nit = 1 << (tb - 5);
+    for (int s = 0; s < pd.nstages; ++s) {
+      const StageDesc& sd = prog.stages[pd.stage0 + s];
+      const int p = sd.p, q = sd.q;
+      auto h = [](int b) { return 1u << (b % 3); };
+      // quad-slot bits: maximise the GF(2) ranks that make the loads (q, p, r0) and the stores
+      // (q, r1, r2) conflict free; ties -> lowest bits
+      int best = -1, r0 = -1, r1 = -1, r2 = -1;
+      for (int a = 0; a < tb; ++a) {
+        if (a == p || a == q) continue;
+        for (int b = 0; b < tb; ++b) {
+          if (b == p || b == q || b == a) continue;
+          for (int c = b + 1; c < tb; ++c) {
+            if (c == p || c == q || c == a) continue;
+            const int score = 4 * gf2_rank3(h(q), h(p), h(a)) + 4 * gf2_rank3(h(q), h(b), h(c));
+            if (score > best) best = score, r0 = a, r1 = b, r2 = c;
+          }
+        }
+      }
+      T.rbits[(pd.stage0 + s) * 3 + 0] = r0;
+      T.rbits[(pd.stage0 + s) * 3 + 1] = r1;
+      T.rbits[(pd.stage0 + s) * 3 + 2] = r2;
+      std::vector<int> outer;
+      for (int b = 0; b < tb; ++b)
+        if (b != p && b != q && b != r0 && b != r1 && b != r2) outer.push_back(b);
+      auto base_of = [&](int it) {
+        unsigned idx = 0;
+        for (size_t k = 0; k < outer.size(); ++k) idx |= (unsigned)((it >> k) & 1) << outer[k];
+        return idx;
+      };
+      for (int w = 0; w < kDWarps; ++w)
+        for (int l = 0; l < 32; ++l) {
+          DLane& d = T.lanes[((size_t)(pd.stage0 + s) * kDWarps + w) * 32 + l];
+          {  // load layout: quad slot g = l >> 2, amplitude a = l & 3
+            const int g = l >> 2, a = l & 3;
+            const unsigned idx = (unsigned)(a & 1) << q | (unsigned)(a >> 1) << p |
+                                 (unsigned)(g & 1) << r0 | (unsigned)((g >> 1) & 1) << r1 |
+                                 (unsigned)(g >> 2) << r2;
+            d.sl = (uint16_t)dense_swz(idx);
+          }
+          for (int i = 0; i < 2; ++i) {  // store layout: component c = l >> 2, quad slots 2t + i
+            const int c = l >> 2, t = l & 3;
+            const int reim = c & 1, a0 = (c >> 1) & 1, a1 = c >> 2;
+            const unsigned idx = (unsigned)a0 << q | (unsigned)a1 << p | (unsigned)i << r0 |
+                                 (unsigned)(t & 1) << r1 | (unsigned)(t >> 1) << r2;
+            const uint16_t v = (uint16_t)(2u * dense_swz(idx) + (unsigned)reim);
+            if (i == 0)
+              d.so0 = v;
+            else
+              d.so1 = v;
+          }
+          const int it = w + kDWarps * l;
+          d.sb = (uint16_t)(it < nit ? dense_swz(base_of(it)) : 0);
+        }
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage matrices: one thread per (stage, column) applies the stage's gates to a unit vector with
+// the register-level gate functions of aqc_gates.cuh and writes the column in DMMA A-fragment order
+//   umat[(batch * nstages + stage) * 64 + f * 32 + lane],  lane = c * 4 + k,  c = reim | amp << 1:
+//   f = 0: coefficient of re(x_k) in output component c;  f = 1: coefficient of im(x_k).
+// ------------------------------------------------------------------------------------------------
+template <int ENT, bool DAG>
+__device__ __forceinline__ void dense_run_units(const StageDesc& sd, const double2* __restrict__ trig,
+                                                cd (&a)[1][4]) {
+  for (int u = 0; u < sd.nunits; ++u) {
+    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
+    const double2* tr = trig + sd.u[u].theta;
+    switch (kind) {
+      case U_FRONT_LO: front_unit<1, false, DAG>(a, tr, nullptr); break;
+      case U_FRONT_HI: front_unit<1, true, DAG>(a, tr, nullptr); break;
+      case U_BLOCK_CHI: block_unit<1, ENT, true, DAG>(a, tr, flags, nullptr); break;
+      case U_BLOCK_CLO: block_unit<1, ENT, false, DAG>(a, tr, flags, nullptr); break;
+      default: break;
+    }
+  }
+}
+
+template <int ENT, bool DAG>
+__global__ void __launch_bounds__(128) dense_umat_kernel(const StageDesc* __restrict__ stages,
+                                                         int nstages, const double2* __restrict__ trig,
+                                                         int nthetas, double* __restrict__ umat) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nstages * 4) return;
+  const int s = t >> 2, k = t & 3, b = blockIdx.y;
+  const StageDesc sd = stages[s];
+  cd a[1][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
+  dense_run_units<ENT, DAG>(sd, trig + (size_t)b * nthetas, a);
+  double* um = umat + ((size_t)b * nstages + s) * 64;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]
+    um[(2 * i) * 4 + k] = a[0][i].x;
+    um[32 + (2 * i) * 4 + k] = -a[0][i].y;
+    um[(2 * i + 1) * 4 + k] = a[0][i].y;
+    um[32 + (2 * i + 1) * 4 + k] = a[0][i].x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing: raw per-rotation inner products from the stage matrices M_out.
+// One thread per (stage, virtual quadruple r): w' = e_r, z' = M_out[:, r] (sum_r z'_r w'_r^H = M_out);
+// pull both back through the stage (daggered units in reverse order), then run the stage forward
+// with the reference's gate-by-gate accumulation.  Output format = pass_kernel's raw sums.
+// ------------------------------------------------------------------------------------------------
+template <int ENT>
+__global__ void __launch_bounds__(128) dense_grad_kernel(const StageDesc* __restrict__ stages,
+                                                         int nstages, const double2* __restrict__ trig,
+                                                         int nthetas, const double* __restrict__ gm,
+                                                         double* __restrict__ gacc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nstages * 4) return;
+  const int s = t >> 2, r = t & 3, b = blockIdx.y;
+  const StageDesc sd = stages[s];
+  const double2* tg = trig + (size_t)b * nthetas;
+  const double* R = gm + ((size_t)b * nstages + s) * 64;  // R[cz * 8 + cw]
+  cd a[2][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
+    // M[i][r] = sum z_i conj(w_r)
+    a[1][i].x = R[(2 * i) * 8 + 2 * r] + R[(2 * i + 1) * 8 + 2 * r + 1];
+    a[1][i].y = R[(2 * i + 1) * 8 + 2 * r] - R[(2 * i) * 8 + 2 * r + 1];
+  }
+  constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
+  double dummy[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) dummy[k] = 0.0;
+  for (int u = sd.nunits - 1; u >= 0; --u) {
+    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
+    const double2* tr = tg + sd.u[u].theta;
+    switch (kind) {
+      case U_FRONT_LO: front_unit<2, false, true>(a, tr, dummy); break;
+      case U_FRONT_HI: front_unit<2, true, true>(a, tr, dummy); break;
+      case U_BLOCK_CHI: block_unit<2, ENT, true, true>(a, tr, flags, dummy); break;
+      case U_BLOCK_CLO: block_unit<2, ENT, false, true>(a, tr, flags, dummy); break;
+      default: break;
+    }
+  }
+  double* g = gacc + (size_t)b * nthetas * 2;
+  for (int u = 0; u < sd.nunits; ++u) {
+    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
+    const double2* tr = tg + sd.u[u].theta;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int nval = (ENT == AQC_ENT_CP) ? 10 : 8;
+    switch (kind) {
+      case U_FRONT_LO: front_unit<2, false, false>(a, tr, acc); nval = 6; break;
+      case U_FRONT_HI: front_unit<2, true, false>(a, tr, acc); nval = 6; break;
+      case U_BLOCK_CHI: block_unit<2, ENT, true, false>(a, tr, flags, acc); break;
+      case U_BLOCK_CLO: block_unit<2, ENT, false, false>(a, tr, flags, acc); break;
+      default: nval = 0; break;
+    }
+    double* gu = g + 2 * (size_t)sd.u[u].theta;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k)
+      if (k < nval) atomicAdd(gu + k, acc[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+struct DensePassArgs {
+  const double2* src[2];  // [0] = w (NVEC == 2) or the single vector; [1] = z
+  double2* dst[2];
+  long long vec_stride;
+  long long basis_index;  // >= 0: src[0] is the basis state |basis_index> (no load)
+  const DLane* lanes;     // program-wide [stage][warp][lane]
+  const double* umat;     // [batch][nstages_total][64]
+  double* gm;             // [batch][nstages_total][64]   (NVEC == 2)
+  int nstages_total;
+  PassDesc pd;
+};
+
+template <int NVEC>
+__global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePassArgs A) {
+  extern __shared__ double2 smem[];
+  __shared__ long long s_hioff[16];
+  __shared__ double s_mpart[(NVEC == 2) ? 2 * kDWarps * 64 : 2];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int tb = A.pd.tb;
+  const int tsize = 1 << tb;
+
+  long long base = 0;
+  {
+    const unsigned long long tile = blockIdx.x;
+    for (int k = 0; k < A.pd.nouter; ++k)
+      base |= (long long)((tile >> k) & 1ull) << A.pd.outerpos[k];
+  }
+  // local index l = tid + 256 * j  ->  global offset lo_off(tid) | hi_off(j)
+  long long lo_off = 0;
+  for (int k = 0; k < 8 && k < tb; ++k) lo_off |= (long long)((tid >> k) & 1) << A.pd.bitpos[k];
+  if (tid < 16) {
+    long long h = 0;
+    for (int k = 8; k < tb; ++k) h |= (long long)((tid >> (k - 8)) & 1) << A.pd.bitpos[k];
+    s_hioff[tid] = h;
+  }
+  __syncthreads();
+  const long long boff = (long long)blockIdx.y * A.vec_stride + base;
+
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) {
+    double2* sm = smem + (size_t)v * tsize;
+    if (v == 0 && A.basis_index >= 0) {
+      for (int l = tid; l < tsize; l += kDThreads) {
+        const long long g = base | lo_off | s_hioff[l >> 8];
+        sm[dense_swz(l)] = make_double2(g == A.basis_index ? 1.0 : 0.0, 0.0);
+      }
+    } else {
+      const double2* __restrict__ src = A.src[v] + boff;
+#pragma unroll 4
+      for (int l = tid; l < tsize; l += kDThreads) sm[dense_swz(l)] = src[lo_off | s_hioff[l >> 8]];
+    }
+  }
+  __syncthreads();
+
+  const int nstages = A.pd.nstages;
+  const int nit = tsize >> 5;
+  const size_t sbase = (size_t)blockIdx.y * A.nstages_total + A.pd.stage0;
+  const double* __restrict__ um = A.umat + sbase * 64;
+  const DLane* __restrict__ lt = A.lanes + ((size_t)A.pd.stage0 * kDWarps + warp) * 32 + lane;
+  double* smd = reinterpret_cast<double*>(smem);
+
+  // one-stage-ahead prefetch of the per-stage constants
+  double ua0 = 0.0, ua1 = 0.0;
+  DLane dl = {0, 0, 0, 0};
+  if (nstages > 0) {
+    ua0 = um[lane];
+    ua1 = um[32 + lane];
+    dl = lt[0];
+  }
+  for (int s = 0; s < nstages; ++s) {
+    double na0 = 0.0, na1 = 0.0;
+    DLane nl = {0, 0, 0, 0};
+    if (s + 1 < nstages) {
+      na0 = um[(size_t)(s + 1) * 64 + lane];
+      na1 = um[(size_t)(s + 1) * 64 + 32 + lane];
+      nl = lt[(size_t)(s + 1) * kDWarps * 32];
+    }
+    const unsigned sl = dl.sl, so0 = dl.so0, so1 = dl.so1, sbv = dl.sb;
+    double m0 = 0.0, m1 = 0.0;
+    int j = 0;
+#pragma unroll 2
+    for (int it = warp; it < nit; it += kDWarps, ++j) {
+      const unsigned b = __shfl_sync(0xffffffffu, sbv, j);
+      const unsigned slot = b ^ sl;
+      const unsigned d0 = (b << 1) ^ so0, d1 = (b << 1) ^ so1;
+      if (NVEC == 2) {
+        const double2 w = smem[slot];
+        const double2 z = smem[tsize + slot];
+        double w0 = 0.0, w1 = 0.0, z0 = 0.0, z1 = 0.0;
+        dmma884(w0, w1, ua0, w.x);
+        dmma884(z0, z1, ua0, z.x);
+        dmma884(w0, w1, ua1, w.y);
+        dmma884(z0, z1, ua1, z.y);
+        dmma884(m0, m1, z0, w0);
+        dmma884(m0, m1, z1, w1);
+        smd[d0] = w0;
+        smd[d1] = w1;
+        smd[2 * tsize + d0] = z0;
+        smd[2 * tsize + d1] = z1;
+      } else {
+        const double2 x = smem[slot];
+        double x0 = 0.0, x1 = 0.0;
+        dmma884(x0, x1, ua0, x.x);
+        dmma884(x0, x1, ua1, x.y);
+        smd[d0] = x0;
+        smd[d1] = x1;
+      }
+    }
+    if (NVEC == 2) {
+      // R[cz = lane >> 2][cw = 2 (lane & 3) + {0, 1}] partials of this warp
+      double* part = s_mpart + ((s & 1) * kDWarps + warp) * 64;
+      part[2 * lane] = m0;
+      part[2 * lane + 1] = m1;
+      __syncthreads();
+      if (warp == (s & (kDWarps - 1))) {
+        const double* pp = s_mpart + (s & 1) * kDWarps * 64;
+        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 64 + lane], r1 += pp[w * 64 + 32 + lane];
+        double* g = A.gm + (sbase + s) * 64;
+        atomicAdd(g + lane, r0);
+        atomicAdd(g + 32 + lane, r1);
+      }
+    } else {
+      __syncthreads();
+    }
+    ua0 = na0, ua1 = na1, dl = nl;
+  }
+
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) {
+    const double2* sm = smem + (size_t)v * tsize;
+    double2* __restrict__ dst = A.dst[v] + boff;
+#pragma unroll 4
+    for (int l = tid; l < tsize; l += kDThreads) dst[lo_off | s_hioff[l >> 8]] = sm[dense_swz(l)];
+  }
+}

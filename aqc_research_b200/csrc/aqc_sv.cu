@@ -77,6 +77,7 @@ extern "C" int aqc_device_count(void) {
 // ------------------------------------------------------------------------------------------
 constexpr int kThreads = 128;  // threads per CTA of the pass kernel
 constexpr int kMaxUnits = 3;   // units fused into one stage (a Trotter triplet)
+constexpr int kStageUnits = 5; // dense-stage programs: two front gates + a triplet on one bit pair
 constexpr int kMaxTileBits = 12;
 
 struct UnitDesc {
@@ -89,9 +90,9 @@ struct StageDesc {
   int32_t p, q;  // tile-local bit positions held in registers, p > q
   int32_t nunits;
   int32_t triplet;  // 1: Trotter triplet (ctrl hi / lo / hi, Rz(-pi/2) first, Rz(+pi/2) last)
-  UnitDesc u[kMaxUnits];
+  UnitDesc u[kStageUnits];  // legacy / scale-free programs use at most kMaxUnits of them
 };
-static_assert(sizeof(StageDesc) == 64, "StageDesc layout");
+static_assert(sizeof(StageDesc) == 96, "StageDesc layout");
 
 struct PassDesc {
   int32_t tb;       // tile bits
@@ -165,8 +166,11 @@ static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUni
 // disjoint qubits commute, so a unit may run in the current pass iff all its qubits are inside
 // the tile and none of them is touched by an earlier unit that had to be deferred.
 // `units` carry PHYSICAL bit positions in qa / qb.  Passes are appended to `prog`.
+// `max_units` caps the units of a stage; `merge_fronts` (dense-stage programs) lets a block unit
+// join the front-gate stage that holds its qubits, so the front layer costs no stages of its own.
 static void build_program_units(const std::vector<HostUnit>& units, int nbits, int tb_max,
-                                int lowbits, Program& prog) {
+                                int lowbits, Program& prog, int max_units = kMaxUnits,
+                                bool merge_fronts = false) {
   const int qoff = 0;
   const size_t pass_begin = prog.passes.size();
   const int tb = std::min(nbits, tb_max);
@@ -245,7 +249,10 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
       if (u.kind == 0) {
         // front gate: join an open front stage that has a free partner seat
         // (legal iff no stage created after it has touched this bit)
-        for (size_t i = 0; i < open.size(); ++i)
+        if (merge_fronts && last[la] >= 0 && !open[last[la]].front &&
+            open[last[la]].sd.nunits < max_units)
+          s = last[la];  // reversed sweeps: the front gate follows the last stage on its qubit
+        for (size_t i = 0; s < 0 && i < open.size(); ++i)
           if (open[i].front && open[i].b < 0 && open[i].a != la && open[i].sd.nunits < 2 &&
               (int)i > last[la]) {
             s = (int)i;
@@ -264,9 +271,21 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
         last[la] = s;
       } else {
         const int sa = last[la], sb = last[lb];
-        if (sa >= 0 && sa == sb && !open[sa].front && open[sa].sd.nunits < kMaxUnits &&
+        if (sa >= 0 && sa == sb && (merge_fronts || !open[sa].front) && open[sa].sd.nunits < max_units &&
             ((open[sa].a == la && open[sa].b == lb) || (open[sa].a == lb && open[sa].b == la))) {
           s = sa;
+          open[sa].front = false;  // no further front gate may take a seat here
+        } else if (merge_fronts && sa >= 0 && sa > sb && open[sa].front && open[sa].b < 0 &&
+                   open[sa].a == la && open[sa].sd.nunits < max_units) {
+          // single front gate on la with a free partner seat; everything on lb happened earlier
+          s = sa;
+          open[sa].b = lb;
+          open[sa].front = false;
+        } else if (merge_fronts && sb >= 0 && sb > sa && open[sb].front && open[sb].b < 0 &&
+                   open[sb].a == lb && open[sb].sd.nunits < max_units) {
+          s = sb;
+          open[sb].b = la;
+          open[sb].front = false;
         } else {
           Open o;
           memset(&o.sd, 0, sizeof(o.sd));
@@ -314,7 +333,8 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
 }
 
 static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max, int lowbits,
-                          bool reversed, Program& prog) {
+                          bool reversed, Program& prog, int max_units = kMaxUnits,
+                          bool merge_fronts = false) {
   std::vector<HostUnit> units;
   build_units(c, reversed, units);
   for (HostUnit& u : units) {
@@ -325,7 +345,7 @@ static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max,
   prog.stages.clear();
   prog.epoch_pass0.assign(1, 0);
   prog.epoch_layout.assign(1, 0);
-  build_program_units(units, nbits, tb_max, lowbits, prog);
+  build_program_units(units, nbits, tb_max, lowbits, prog, max_units, merge_fronts);
 }
 
 // ---- global-qubit sharding (one state over 2^g GPUs) --------------------------------------------
@@ -344,7 +364,8 @@ static int phys_bit(int q, int n, int g, int layout) {
 }
 
 static int build_program_sharded(const aqc_circuit& c, int g, int tb_max, int lowbits, bool reversed,
-                                 Program& prog, std::string& err) {
+                                 Program& prog, std::string& err, int max_units = kMaxUnits,
+                                 bool merge_fronts = false) {
   const int n = c.n, nl = n - g;
   if (nl - g < 2 || 2 * g > n - 2) {
     err = "too few qubits for this number of GPUs";
@@ -391,7 +412,7 @@ static int build_program_sharded(const aqc_circuit& c, int g, int tb_max, int lo
     idle = 0;
     prog.epoch_pass0.push_back((int)prog.passes.size());
     prog.epoch_layout.push_back(layout);
-    build_program_units(now, nl, tb_max, lowbits, prog);
+    build_program_units(now, nl, tb_max, lowbits, prog, max_units, merge_fronts);
     for (size_t k : ids) done[k] = 1;
     ndone += ids.size();
     layout ^= 1;
@@ -439,6 +460,8 @@ __device__ __forceinline__ double warp_reduce8(const double* v, int lane, int& w
   which = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   return c;
 }
+
+#include "aqc_dense.cuh"
 
 struct PassArgs {
   const double2* src[2];  // [0] = w (NVEC == 2) or the single vector; [1] = z
@@ -1208,6 +1231,10 @@ struct aqc_sv {
   // scale-free single-vector sweeps
   double2 *d_apar = nullptr, *d_uph = nullptr, *d_kappa = nullptr;
   double *d_albuf = nullptr, *d_aebuf = nullptr, *d_arescale = nullptr;
+  // dense-stage engine (aqc_dense.cuh): DMMA sweeps; the default whenever the tile has >= 5 bits
+  bool dense = false;
+  DenseTables dt_grad, dt_fwd, dt_dag;
+  double *d_umat = nullptr, *d_gm = nullptr;
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
@@ -1492,6 +1519,105 @@ static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, con
   return AQC_OK;
 }
 
+// ---- dense-stage engine: host side ----------------------------------------------------------------
+template <int NVEC>
+static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
+  const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
+  static bool configured[8] = {false};
+  if (!configured[sv->device & 7]) {
+    CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)NVEC * sizeof(double2) << (NVEC == 2 ? kMaxTileBits - 1 : kMaxTileBits))));
+    configured[sv->device & 7] = true;
+  }
+  dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
+  dense_pass_kernel<NVEC><<<grid, kDThreads, smem, sv->stream>>>(args);
+  CU(cudaGetLastError());
+  return AQC_OK;
+}
+
+// stage matrices of one program for the uploaded angles (mode 0 gradient, 1 V, 2 V^H)
+static int dense_prepare(aqc_sv* sv, int mode) {
+  const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
+  const int ns = (int)p.stages.size();
+  if (ns == 0) return AQC_OK;
+  const dim3 grid((unsigned)((ns * 4 + 127) / 128), (unsigned)sv->batch);
+  const bool dag = mode == 2;
+#define AQC_UMAT(E)                                                                                  \
+  do {                                                                                               \
+    if (dag)                                                                                         \
+      dense_umat_kernel<E, true><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,          \
+                                                               sv->circ.nthetas, sv->d_umat);       \
+    else                                                                                             \
+      dense_umat_kernel<E, false><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,         \
+                                                                sv->circ.nthetas, sv->d_umat);      \
+  } while (0)
+  switch (sv->circ.ent) {
+    case AQC_ENT_CX: AQC_UMAT(AQC_ENT_CX); break;
+    case AQC_ENT_CZ: AQC_UMAT(AQC_ENT_CZ); break;
+    default: AQC_UMAT(AQC_ENT_CP);
+  }
+#undef AQC_UMAT
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  if (mode == 0)
+    CU(cudaMemsetAsync(sv->d_gm, 0, (size_t)sv->batch * ns * 64 * sizeof(double), sv->stream));
+  return AQC_OK;
+}
+
+// raw per-rotation sums (the format of pass_kernel) from the accumulated stage matrices
+static int dense_collect(aqc_sv* sv) {
+  const Program& p = sv->prog_grad;
+  const int ns = (int)p.stages.size();
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  if (ns == 0) return AQC_OK;
+  const dim3 grid((unsigned)((ns * 4 + 127) / 128), (unsigned)sv->batch);
+  switch (sv->circ.ent) {
+    case AQC_ENT_CX:
+      dense_grad_kernel<AQC_ENT_CX><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
+                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
+      break;
+    case AQC_ENT_CZ:
+      dense_grad_kernel<AQC_ENT_CZ><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
+                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
+      break;
+    default:
+      dense_grad_kernel<AQC_ENT_CP><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
+                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
+  }
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+// passes [pass_begin, pass_end) of a program on the dense engine; mode 0: (w, z), else one vector
+static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long long basis,
+                             const double2* src1, double2* dst0, double2* dst1, int pass_begin,
+                             int pass_end) {
+  const Program& prog = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
+  const DenseTables& dt = mode == 0 ? sv->dt_grad : (mode == 1 ? sv->dt_fwd : sv->dt_dag);
+  DensePassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.vec_stride = sv->size;
+  a.lanes = dt.d_lanes;
+  a.umat = sv->d_umat;
+  a.gm = sv->d_gm;
+  a.nstages_total = (int)prog.stages.size();
+  if (pass_end < 0) pass_end = (int)prog.passes.size();
+  for (int i = pass_begin; i < pass_end; ++i) {
+    a.pd = prog.passes[i];
+    a.src[0] = (i == pass_begin) ? src0 : dst0;
+    a.src[1] = (i == pass_begin) ? src1 : dst1;
+    a.dst[0] = dst0;
+    a.dst[1] = dst1;
+    a.basis_index = (i == pass_begin) ? basis : -1;
+    const int rc = mode == 0 ? launch_dense_pass<2>(sv, a) : launch_dense_pass<1>(sv, a);
+    if (rc) return rc;
+    sv->last_launches += 1;
+  }
+  return AQC_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
@@ -1614,6 +1740,9 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
                   (void*)sv->d_uph, (void*)sv->d_kappa, (void*)sv->d_albuf, (void*)sv->d_aebuf,
                   (void*)sv->d_arescale})
     if (q) cudaFree(q);
+  for (void* q : {(void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
+                  (void*)sv->dt_dag.d_lanes})
+    if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages);
@@ -1689,15 +1818,28 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", 11), kMaxTileBits - 1);
   const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", 11), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", 4);
+  // engine: dense-stage DMMA sweeps (default), "scaled" (scale-free rotations) or "legacy"
+  {
+    const char* eng = getenv("AQC_ENGINE");
+    const std::string e = eng ? eng : "dense";
+    sv->legacy_grad = env_int("AQC_GRAD_LEGACY", 0) != 0 || e == "legacy";
+    sv->dense = !sv->legacy_grad && e != "scaled";
+    if (sv->nbits < kDMinTileBits || tb_grad < kDMinTileBits || tb_apply < kDMinTileBits) {
+      // fewer than 8 amplitude quadruples: nothing for a DMMA to do
+      sv->dense = false;
+      sv->legacy_grad = true;
+    }
+  }
+  const int max_units = sv->dense ? kStageUnits : kMaxUnits;
   if (g == 0) {
-    build_program(sv->circ, log2_cols, sv->nbits, tb_grad, low, false, sv->prog_grad);
-    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, false, sv->prog_fwd);
-    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, true, sv->prog_dag);
+    build_program(sv->circ, log2_cols, sv->nbits, tb_grad, low, false, sv->prog_grad, max_units, sv->dense);
+    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, false, sv->prog_fwd, max_units, sv->dense);
+    build_program(sv->circ, log2_cols, sv->nbits, tb_apply, low, true, sv->prog_dag, max_units, sv->dense);
   } else {
     std::string err;
-    if (build_program_sharded(sv->circ, g, tb_grad, low, false, sv->prog_grad, err) ||
-        build_program_sharded(sv->circ, g, tb_apply, low, false, sv->prog_fwd, err) ||
-        build_program_sharded(sv->circ, g, tb_apply, low, true, sv->prog_dag, err)) {
+    if (build_program_sharded(sv->circ, g, tb_grad, low, false, sv->prog_grad, err, max_units, sv->dense) ||
+        build_program_sharded(sv->circ, g, tb_apply, low, false, sv->prog_fwd, err, max_units, sv->dense) ||
+        build_program_sharded(sv->circ, g, tb_apply, low, true, sv->prog_dag, err, max_units, sv->dense)) {
       fail(AQC_EINVAL, "%s", err.c_str());
       return bail(AQC_EINVAL);
     }
@@ -1706,7 +1848,35 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     int rc = upload_program(*p);
     if (rc) return bail(rc);
   }
-  sv->legacy_grad = env_int("AQC_GRAD_LEGACY", 0) != 0;
+  if (sv->dense) {
+    size_t smax = 1;
+    Program* progs[3] = {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag};
+    DenseTables* tabs[3] = {&sv->dt_grad, &sv->dt_fwd, &sv->dt_dag};
+    for (int i = 0; i < 3; ++i) {
+      if (!build_dense_tables(*progs[i], *tabs[i])) {
+        fail(AQC_EINVAL, "internal: dense engine needs tiles of >= %d bits", kDMinTileBits);
+        return bail(AQC_EINVAL);
+      }
+      smax = std::max(smax, progs[i]->stages.size());
+      if (tabs[i]->lanes.empty()) continue;
+      cudaError_t e = cudaMalloc(&tabs[i]->d_lanes, tabs[i]->lanes.size() * sizeof(DLane));
+      if (e == cudaSuccess)
+        e = cudaMemcpy(tabs[i]->d_lanes, tabs[i]->lanes.data(), tabs[i]->lanes.size() * sizeof(DLane),
+                       cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        fail(AQC_ENOMEM, "dense table upload failed: %s", cudaGetErrorString(e));
+        return bail(AQC_ENOMEM);
+      }
+    }
+    const size_t B = batch;
+    cudaError_t e = cudaMalloc(&sv->d_umat, B * smax * 64 * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&sv->d_gm, B * std::max<size_t>(1, sv->prog_grad.stages.size()) * 64 * sizeof(double));
+    if (e != cudaSuccess) {
+      fail(AQC_ENOMEM, "dense scratch allocation failed: %s", cudaGetErrorString(e));
+      return bail(AQC_ENOMEM);
+    }
+  } else {
   {
     Program& p = sv->prog_grad;
     build_schedule(sv->circ, p);
@@ -1752,6 +1922,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
       fail(AQC_ENOMEM, "apply scratch allocation failed: %s", cudaGetErrorString(e));
       return bail(AQC_ENOMEM);
     }
+  }
   }
   *out = sv;
   return AQC_OK;
@@ -1908,7 +2079,12 @@ static int apply_async(aqc_sv* sv, const double* thetas, int dagger, int src_slo
   rc = upload_thetas(sv, thetas);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  if (sv->legacy_grad) {
+  if (sv->dense) {
+    rc = dense_prepare(sv, dagger ? 2 : 1);
+    if (!rc)
+      rc = run_dense_program(sv, dagger ? 2 : 1, sv->slots[src_slot], -1, nullptr, sv->slots[dst_slot],
+                             nullptr, 0, -1);
+  } else if (sv->legacy_grad) {
     const Program& prog = dagger ? sv->prog_dag : sv->prog_fwd;
     rc = run_program(sv, prog, false, dagger != 0, sv->slots[src_slot], -1, nullptr,
                      sv->slots[dst_slot], nullptr);
@@ -1988,7 +2164,13 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
   if (rc) return rc;
   CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  if (sv->legacy_grad) {
+  if (sv->dense) {
+    rc = dense_prepare(sv, 0);
+    if (!rc)
+      rc = run_dense_program(sv, 0, x_slot >= 0 ? sv->slots[x_slot] : nullptr, x_slot >= 0 ? -1 : x_basis,
+                             sv->slots[z0_slot], sv->slots[w_slot], sv->slots[z_slot], 0, -1);
+    if (!rc) rc = dense_collect(sv);
+  } else if (sv->legacy_grad) {
     rc = run_program(sv, sv->prog_grad, true, false, x_slot >= 0 ? sv->slots[x_slot] : nullptr,
                      x_slot >= 0 ? -1 : x_basis, sv->slots[z0_slot], sv->slots[w_slot],
                      sv->slots[z_slot]);
@@ -2074,6 +2256,54 @@ extern "C" int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int til
 }
 
 
+// Same for the dense-stage engine (up to kStageUnits units per stage, front gates merged), plus the
+// shared-memory lane tables, so that the CPU test-suite can emulate the DMMA data flow.
+// Layout: npasses, then per pass {tb, nstages, nouter, bitpos[16], outerpos[48], per stage
+// {p, q, nunits, (kind, flags, theta) x kStageUnits, r0, r1, r2, (sl, so0, so1, sb) x 8 warps x 32}}.
+extern "C" int aqc_debug_dense_program(const aqc_circuit* circ, int log2_cols, int tile_bits,
+                                       int low_bits, int reversed, int32_t* out, int64_t cap,
+                                       int64_t* needed) {
+  if (!circ || !needed) return fail(AQC_EINVAL, "null argument");
+  if (tile_bits < kDMinTileBits || tile_bits > kMaxTileBits) return fail(AQC_EINVAL, "bad tile_bits");
+  if (circ->n + log2_cols < kDMinTileBits) return fail(AQC_EINVAL, "state too small for the dense engine");
+  Program p;
+  build_program(*circ, log2_cols, circ->n + log2_cols, tile_bits, low_bits, reversed != 0, p,
+                kStageUnits, true);
+  DenseTables dt;
+  if (!build_dense_tables(p, dt)) return fail(AQC_EINVAL, "tile too small for the dense engine");
+  std::vector<int32_t> w;
+  w.push_back((int32_t)p.passes.size());
+  for (const PassDesc& pd : p.passes) {
+    w.push_back(pd.tb);
+    w.push_back(pd.nstages);
+    w.push_back(pd.nouter);
+    for (int k = 0; k < 16; ++k) w.push_back(pd.bitpos[k]);
+    for (int k = 0; k < 48; ++k) w.push_back(pd.outerpos[k]);
+    for (int s = 0; s < pd.nstages; ++s) {
+      const StageDesc& sd = p.stages[pd.stage0 + s];
+      w.push_back(sd.p);
+      w.push_back(sd.q);
+      w.push_back(sd.nunits);
+      for (int u = 0; u < kStageUnits; ++u) {
+        w.push_back(sd.u[u].kind);
+        w.push_back(sd.u[u].flags);
+        w.push_back(sd.u[u].theta);
+      }
+      for (int k = 0; k < 3; ++k) w.push_back(dt.rbits[(pd.stage0 + s) * 3 + k]);
+      for (int i = 0; i < kDWarps * 32; ++i) {
+        const DLane& d = dt.lanes[(size_t)(pd.stage0 + s) * kDWarps * 32 + i];
+        w.push_back(d.sl);
+        w.push_back(d.so0);
+        w.push_back(d.so1);
+        w.push_back(d.sb);
+      }
+    }
+  }
+  *needed = (int64_t)w.size();
+  if (out && cap >= (int64_t)w.size()) memcpy(out, w.data(), w.size() * sizeof(int32_t));
+  return AQC_OK;
+}
+
 // CUDA-event stopwatch on the workspace stream: brackets any sequence of calls on this
 // workspace (bench.py times one objective + gradient step with it).
 extern "C" int aqc_sv_timer_start(aqc_sv* sv) {
@@ -2122,7 +2352,10 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
   if (rc) return rc;
   rc = upload_thetas(sv, thetas);
   if (rc) return rc;
-  if (mode == 0) {
+  if (sv->dense) {
+    if (mode == 0) CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+    if ((rc = dense_prepare(sv, mode))) return rc;
+  } else if (mode == 0) {
     CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
     if (!sv->legacy_grad && (rc = grad_prepare(sv))) return rc;
   } else if (!sv->legacy_grad) {
@@ -2154,7 +2387,11 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   const int p1 = epoch + 1 < (int)p->epoch_pass0.size() ? p->epoch_pass0[epoch + 1] : (int)p->passes.size();
   const long long basis = src0 >= 0 ? -1 : (basis_local >= 0 ? (long long)basis_local : (1ll << 62));
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  if (mode == 0 && !sv->legacy_grad)
+  if (sv->dense)
+    rc = run_dense_program(sv, mode, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
+                           mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
+                           mode == 0 ? sv->slots[dst1] : nullptr, p0, p1);
+  else if (mode == 0 && !sv->legacy_grad)
     rc = run_grad_program(sv, src0 >= 0 ? sv->slots[src0] : nullptr, basis, sv->slots[src1],
                           sv->slots[dst0], sv->slots[dst1], p0, p1);
   else if (!sv->legacy_grad)
@@ -2178,7 +2415,11 @@ extern "C" int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   int rc = ensure_pinned(sv, tot * 2 + 64);
   if (rc) return rc;
-  if (!sv->legacy_grad && (rc = grad_collect(sv))) return rc;
+  if (sv->dense) {
+    if ((rc = dense_collect(sv))) return rc;
+  } else if (!sv->legacy_grad && (rc = grad_collect(sv))) {
+    return rc;
+  }
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
                      sv->stream));
   CU(cudaStreamSynchronize(sv->stream));

@@ -55,17 +55,19 @@ class CircuitHandle:
         """Hashable description of the structure (used to detect structural changes)."""
         return (self.num_qubits, self.entangler, self.trotter, self.blocks.tobytes())
 
-    def debug_program(self, log2_cols: int, tile_bits: int, low_bits: int, reversed_: bool):
-        """Serialised tile-pass program (host-only; see aqc_debug_program)."""
+    def debug_program(self, log2_cols: int, tile_bits: int, low_bits: int, reversed_: bool,
+                      dense: bool = False):
+        """Serialised tile-pass program (host-only; see aqc_debug_program / aqc_debug_dense_program)."""
+        fn = self._lib.aqc_debug_dense_program if dense else self._lib.aqc_debug_program
         need = ct.c_int64(0)
         _lib.check(
-            self._lib.aqc_debug_program(
+            fn(
                 self.handle, log2_cols, tile_bits, low_bits, int(reversed_), None, 0, ct.byref(need)
             )
         )
         buf = np.zeros(need.value, dtype=np.int32)
         _lib.check(
-            self._lib.aqc_debug_program(
+            fn(
                 self.handle,
                 log2_cols,
                 tile_bits,

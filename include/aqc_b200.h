@@ -143,6 +143,11 @@ int aqc_sv_num_passes(const aqc_sv* sv, int mode);
  * program.  *needed receives the word count; data are written iff cap is large enough. */
 int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
                       int reversed, int32_t* out, int64_t cap, int64_t* needed);
+/* Same for the dense-stage (DMMA) engine: stages hold up to 5 units (front gates merged into
+ * the first stage on their qubit pair) and carry the shared-memory lane tables of the sweep
+ * kernel (layout documented in csrc/aqc_sv.cu), so CPU tests can emulate its data flow. */
+int aqc_debug_dense_program(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
+                            int reversed, int32_t* out, int64_t cap, int64_t* needed);
 /* Device-pointer access for zero-copy callers (torch tensors): address of slot. */
 void* aqc_sv_slot_ptr(aqc_sv* sv, int slot);
 /* CUDA stream handle (cudaStream_t) the workspace launches on. */

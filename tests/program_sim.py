@@ -13,8 +13,10 @@ U_FRONT_LO, U_FRONT_HI, U_BLOCK_CHI, U_BLOCK_CLO = 1, 2, 3, 4
 F_PRE, F_POST = 1, 2
 
 
-def parse_program(words: np.ndarray):
+def parse_program(words: np.ndarray, dense: bool = False):
+    """``dense``: format of aqc_debug_dense_program (5 units per stage + lane tables)."""
     w = [int(x) for x in words]
+    per_stage = 5 if dense else 3
     pos = 0
     npasses = w[pos]
     pos += 1
@@ -31,12 +33,19 @@ def parse_program(words: np.ndarray):
             p, q, nunits = w[pos : pos + 3]
             pos += 3
             units = []
-            for u in range(3):
+            for u in range(per_stage):
                 kind, flags, theta = w[pos : pos + 3]
                 pos += 3
                 if u < nunits:
                     units.append((kind, flags, theta))
-            stages.append((p, q, units))
+            if dense:
+                rbits = w[pos : pos + 3]
+                pos += 3
+                lanes = np.array(w[pos : pos + 8 * 32 * 4], dtype=np.int64).reshape(8, 32, 4)
+                pos += 8 * 32 * 4
+                stages.append((p, q, units, rbits, lanes))
+            else:
+                stages.append((p, q, units))
         passes.append(dict(tb=tb, nouter=nouter, bitpos=bitpos[:tb], outer=outer[:nouter], stages=stages))
     assert pos == len(w)
     return passes
@@ -48,9 +57,10 @@ def check_structure(passes, nbits):
         bits = sorted(list(ps["bitpos"]) + list(ps["outer"]))
         assert bits == list(range(nbits)), (bits, nbits)
         assert list(ps["bitpos"]) == sorted(ps["bitpos"])
-        for p, q, units in ps["stages"]:
+        for st in ps["stages"]:
+            p, q, units = st[:3]
             assert 0 <= q < p < ps["tb"]
-            assert 1 <= len(units) <= 3
+            assert 1 <= len(units) <= (5 if len(st) > 3 else 3)
 
 
 def replay(passes, entangler: str, thetas: np.ndarray, vecs, dagger: bool, grad: bool):
@@ -85,7 +95,8 @@ def replay(passes, entangler: str, thetas: np.ndarray, vecs, dagger: bool, grad:
 
     for ps in passes:
         bp = ps["bitpos"]
-        for p, q, units in ps["stages"]:
+        for st in ps["stages"]:
+            p, q, units = st[:3]
             hi, lo = bp[p], bp[q]
             for kind, flags, theta in units:
                 if kind in (U_FRONT_LO, U_FRONT_HI):
@@ -127,4 +138,135 @@ def replay(passes, entangler: str, thetas: np.ndarray, vecs, dagger: bool, grad:
                         ent(c, t, th)
                         if flags & F_PRE:
                             all1(c, O.rz(np.pi / 2))
+    return vecs, g
+
+
+# ------------------------------------------------------------------------------------------------
+# Emulation of the dense-stage (DMMA) sweep kernel of csrc/aqc_dense.cuh: same lane tables, same
+# fragment algebra (PTX mma.m8n8k4.f64: A[l>>2][l&3], B[l&3][l>>2], C[l>>2][2(l&3)+{0,1}]), same
+# post-processing of the accumulated stage matrices.
+# ------------------------------------------------------------------------------------------------
+def _swz(i):
+    return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7)
+
+
+def _mini_pass(units):
+    """The units of one stage as a program on bits (0 = lo, 1 = hi) of a small state."""
+    return [dict(tb=2, nouter=0, bitpos=[0, 1, 2, 3], outer=[], stages=[(1, 0, units)])]
+
+
+def stage_unitary(units, entangler, thetas, dagger):
+    cols = []
+    for k in range(4):
+        e = np.zeros(4, dtype=np.complex128)
+        e[k] = 1.0
+        (v,), _ = replay(_mini_pass(units), entangler, thetas, [e], dagger=dagger, grad=False)
+        cols.append(v)
+    return np.stack(cols, axis=1)  # U[i][k]
+
+
+def dense_check_tables(passes):
+    """Every stage's load and store tables address each tile element exactly once."""
+    for ps in passes:
+        tb = ps["tb"]
+        nit = 1 << (tb - 5)
+        for p, q, units, rbits, lanes in ps["stages"]:
+            assert len({p, q, *rbits}) == 5 and all(0 <= r < tb for r in rbits)
+            slots, dslots = [], []
+            for it in range(nit):
+                w, j = it % 8, it // 8
+                b = lanes[w, j, 3]
+                slots += list(b ^ lanes[w, :, 0])
+                dslots += list((b << 1) ^ lanes[w, :, 1]) + list((b << 1) ^ lanes[w, :, 2])
+            assert sorted(slots) == list(range(1 << tb))
+            assert sorted(dslots) == list(range(2 << tb))
+
+
+def dense_bank_conflicts(passes):
+    """Worst-case shared-memory conflict degree over all stages: (loads, stores)."""
+    worst_l = worst_s = 1
+    for ps in passes:
+        for p, q, units, rbits, lanes in ps["stages"]:
+            sl = lanes[0, :, 0]
+            for qw in range(4):  # LDS.128: quarter warps, 8 bank groups of 16 bytes
+                groups = [int(x) & 7 for x in sl[8 * qw : 8 * qw + 8]]
+                worst_l = max(worst_l, max(groups.count(g) for g in set(groups)))
+            for i in (1, 2):  # STS.64: half warps, 16 bank pairs of 8 bytes
+                so = lanes[0, :, i]
+                for hw in range(2):
+                    banks = [int(x) & 15 for x in so[16 * hw : 16 * hw + 16]]
+                    worst_s = max(worst_s, max(banks.count(g) for g in set(banks)))
+    return worst_l, worst_s
+
+
+def dense_emulate(passes, entangler, thetas, vecs, dagger, grad):
+    """
+    Runs the dense program the way dense_pass_kernel does.  Returns (vecs, complex grad | None);
+    grad is the sum the post kernel (dense_grad_kernel) derives from the stage matrices.
+    """
+    vecs = [np.array(v, dtype=np.complex128).ravel().copy() for v in vecs]
+    nv = len(vecs)
+    g = np.zeros(thetas.size, dtype=np.complex128) if grad else None
+    for ps in passes:
+        tb, bp, outer = ps["tb"], ps["bitpos"], ps["outer"]
+        tsize, nit = 1 << tb, 1 << (tb - 5)
+        loc = np.zeros(tsize, dtype=np.int64)
+        for k in range(tb):
+            loc |= ((np.arange(tsize) >> k) & 1) << bp[k]
+        swz = np.array([_swz(l) for l in range(tsize)])
+        rmats = [np.zeros((8, 8)) for _ in ps["stages"]]
+        for tile in range(1 << len(outer)):
+            base = 0
+            for k, b in enumerate(outer):
+                base |= ((tile >> k) & 1) << b
+            idx = base | loc
+            sm = [np.zeros(2 * tsize) for _ in range(nv)]  # doubles, swizzled slots
+            for v in range(nv):
+                sm[v][2 * swz] = vecs[v][idx].real
+                sm[v][2 * swz + 1] = vecs[v][idx].imag
+            for si, (p, q, units, rbits, lanes) in enumerate(ps["stages"]):
+                U = stage_unitary(units, entangler, thetas, dagger)
+                ua0, ua1 = np.zeros((8, 4)), np.zeros((8, 4))
+                for i in range(4):
+                    ua0[2 * i], ua1[2 * i] = U[i].real, -U[i].imag
+                    ua0[2 * i + 1], ua1[2 * i + 1] = U[i].imag, U[i].real
+                for it in range(nit):
+                    w, j = it % 8, it // 8
+                    b = int(lanes[w, j, 3])
+                    lane = np.arange(32)
+                    slot = b ^ lanes[w, :, 0]
+                    outs = []
+                    for v in range(nv):
+                        b0 = np.zeros((4, 8))
+                        b1 = np.zeros((4, 8))
+                        b0[lane & 3, lane >> 2] = sm[v][2 * slot]
+                        b1[lane & 3, lane >> 2] = sm[v][2 * slot + 1]
+                        outs.append(ua0 @ b0 + ua1 @ b1)  # D[c][g]
+                    for v in range(nv):
+                        d = outs[v]
+                        sm[v][(b << 1) ^ lanes[w, :, 1]] = d[lane >> 2, 2 * (lane & 3)]
+                        sm[v][(b << 1) ^ lanes[w, :, 2]] = d[lane >> 2, 2 * (lane & 3) + 1]
+                    if grad:
+                        rmats[si] += outs[1] @ outs[0].T  # R[cz][cw] = sum_g Z[cz][g] W[cw][g]
+            for v in range(nv):
+                vecs[v][idx] = sm[v][2 * swz] + 1j * sm[v][2 * swz + 1]
+        if grad:
+            for si, (p, q, units, rbits, lanes) in enumerate(ps["stages"]):
+                R = rmats[si]
+                M = np.zeros((4, 4), dtype=np.complex128)
+                for i in range(4):
+                    for r in range(4):
+                        M[i, r] = (R[2 * i, 2 * r] + R[2 * i + 1, 2 * r + 1]) + 1j * (
+                            R[2 * i + 1, 2 * r] - R[2 * i, 2 * r + 1]
+                        )
+                # virtual quadruples on bits (0, 1); bits (2, 3) number them
+                wv = np.zeros(16, dtype=np.complex128)
+                zv = np.zeros(16, dtype=np.complex128)
+                for r in range(4):
+                    wv[4 * r + r] = 1.0
+                    zv[4 * r : 4 * r + 4] = M[:, r]
+                back = [(k, f, t) for (k, f, t) in reversed(units)]
+                (wv, zv), _ = replay(_mini_pass(back), entangler, thetas, [wv, zv], dagger=True, grad=False)
+                _, gs = replay(_mini_pass(units), entangler, thetas, [wv, zv], dagger=False, grad=True)
+                g += gs
     return vecs, g
