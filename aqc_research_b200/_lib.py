@@ -60,6 +60,7 @@ SIGNATURES = {
     "aqc_sv_timer_start": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_timer_stop": (ct.c_int, [ct.c_void_p, ct.POINTER(ct.c_float)]),
     "aqc_sv_num_passes": (ct.c_int, [ct.c_void_p, ct.c_int]),
+    "aqc_sv_num_stages": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_debug_program": (
         ct.c_int,
         [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],

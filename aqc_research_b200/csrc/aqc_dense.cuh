@@ -272,6 +272,13 @@ struct DensePassArgs {
   PassDesc pd;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int NVEC>
 __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePassArgs A) {
   extern __shared__ double2 smem[];
@@ -308,11 +315,15 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
         sm[dense_swz(l)] = make_double2(g == A.basis_index ? 1.0 : 0.0, 0.0);
       }
     } else {
+      // the whole tile goes in flight at once (16-byte LDGSTS straight into the swizzled slots):
+      // the load phase costs one memory round trip instead of one per unrolled batch of LDGs
       const double2* __restrict__ src = A.src[v] + boff;
 #pragma unroll 4
-      for (int l = tid; l < tsize; l += kDThreads) sm[dense_swz(l)] = src[lo_off | s_hioff[l >> 8]];
+      for (int l = tid; l < tsize; l += kDThreads) cp_async16(sm + dense_swz(l), src + (lo_off | s_hioff[l >> 8]));
     }
   }
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
 
   const int nstages = A.pd.nstages;

@@ -1952,6 +1952,12 @@ extern "C" int aqc_sv_num_passes(const aqc_sv* sv, int mode) {
   return (int)p.passes.size();
 }
 
+extern "C" int aqc_sv_num_stages(const aqc_sv* sv, int mode) {
+  if (!sv) return AQC_EINVAL;
+  const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
+  return (int)p.stages.size();
+}
+
 extern "C" int aqc_sv_upload(aqc_sv* sv, int slot, int batch_index, const double* host,
                              int64_t count) {
   int rc = check_slot(sv, slot);

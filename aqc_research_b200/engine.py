@@ -211,6 +211,9 @@ class SvWorkspace:
     def num_passes(self, mode: int) -> int:
         return int(self._lib.aqc_sv_num_passes(self.handle, mode))
 
+    def num_stages(self, mode: int) -> int:
+        return int(self._lib.aqc_sv_num_stages(self.handle, mode))
+
     def slot_ptr(self, slot: int) -> int:
         return int(self._lib.aqc_sv_slot_ptr(self.handle, slot) or 0)
 

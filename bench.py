@@ -59,6 +59,53 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# DRAM bytes per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum +
+# dram__bytes_write.sum; summaries under profiles/): workload -> bytes
+NCU_TRAFFIC = {
+    "sv28": 17.12e9,  # profiles/r01_ncu_dense_grad_sv28.md: one read + one write of w and z (4 x 4.29 GB)
+}
+FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (scripts/ubench_fp64.cu, profiles/r01_ubench_fp64.txt);
+#                          DMMA (mma.sync.m8n8k4.f64) and DFMA share this one FP64 pipe
+
+
+def roofline_block(workload, n, P, passes_grad, passes_dag, stages_grad, stages_dag, grad_s, obj_s):
+    """
+    Roofline of the dominant kernel, dense_pass_kernel<2> (the gradient tile pass).
+      achieved / peak / frac : SURVEY 8(d) contract -- ALGORITHMIC bytes at pair-run granularity
+          (4 * 16 * 2^n * P per gradient sweep, spread over its launches) / measured launch time,
+          against the measured HBM copy peak.  Because a tile pass fuses several pair-runs, the
+          kernel moves fewer DRAM bytes than that, so this fraction exceeds 1 and the binding roofs
+          are the two below:
+      dram   : bytes the launch really moves (one read + one write of w and z) / launch time;
+      fp64   : DMMA flops the launch really issues (6 m8n8k4 per 8 quadruples and stage) against
+               the measured FP64 pipe peak.
+    """
+    peak, peak_src = measured_peaks()
+    V = 16.0 * 2**n
+    per_launch_s = grad_s / passes_grad
+    per_launch_alg = 4.0 * V * P / passes_grad
+    achieved = per_launch_alg / per_launch_s / 1e9
+    dram_per_launch = 4.0 * V
+    dmma_grad = stages_grad * (2**n / 32.0) * 6 * 512.0
+    dmma_apply = stages_dag * (2**n / 32.0) * 2 * 512.0
+    return {
+        "bound": "hbm", "kernel": "dense_pass_kernel<2> (gradient tile pass: cp.async tile load, DMMA stages)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": NCU_TRAFFIC.get(workload), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": per_launch_alg, "launch_ms": per_launch_s * 1e3,
+        "eval_frac": (6.0 * V * P / (obj_s + grad_s)) / 1e9 / peak,
+        "dram": {"bytes_per_launch": dram_per_launch, "achieved_gbs": dram_per_launch / per_launch_s / 1e9,
+                 "frac_of_measured_peak": dram_per_launch / per_launch_s / 1e9 / peak},
+        "fp64": {"dmma_tflops_gradient_kernel": dmma_grad / grad_s / 1e12,
+                 "dmma_tflops_eval": (dmma_grad + dmma_apply) / (grad_s + obj_s) / 1e12,
+                 "peak_tflops": FP64_PEAK_TFLOPS,
+                 "frac_gradient_kernel": dmma_grad / grad_s / 1e12 / FP64_PEAK_TFLOPS,
+                 "frac_eval": (dmma_grad + dmma_apply) / (grad_s + obj_s) / 1e12 / FP64_PEAK_TFLOPS},
+        "note": "frac > 1: tile passes fuse several pair-runs per DRAM round trip; the kernel is bound by "
+                "the FP64 (DMMA) pipe first and DRAM second -- see the dram / fp64 sub-objects",
+    }
+
+
 def make_circuit(n, layers):
     from aqc_research_b200 import circuit_structures as cs
     from aqc_research_b200.parametric_circuit import TrotterAnsatz
@@ -75,60 +122,104 @@ def gate_units(circ):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    """
+    Samples SM clocks / clock-event reasons of one GPU DURING the timed region: NVML in-process
+    (5 ms period, so even a few-millisecond region gets samples), nvidia-smi as the fallback.
+    """
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []  # (sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
         self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and self.index < len(ids) and ids[self.index].isdigit():
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            masks = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                     (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                     (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                     (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append((sm, smax, [n for m, n in masks if bits & m]))
+                    except nv.NVMLError:
+                        pass
+                    self.stop_flag.wait(0.005)
+
+            self.source = "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # NVML missing: fall back to the CLI
+            pass
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.source = "nvidia-smi"
+        self.thread = threading.Thread(target=self._read_cli, daemon=True)
         self.thread.start()
 
-    def _read(self):
+    def _read_cli(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 6:
                 continue
             try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
+                self.rows.append((float(r[0]), float(r[1]),
+                                  [n for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, r[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+    def stop(self):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML / nvidia-smi)"],
+                    "samples": 0}
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        smax = [r[1] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[2]})
         return {
             "sm_mhz": float(np.median(sm)) if sm else None,
             "sm_max_mhz": float(max(smax)) if smax else None,
-            "reasons": sorted(reasons),
+            "reasons": reasons,
             "samples": len(sm),
+            "source": self.source,
         }
 
 
@@ -270,6 +361,7 @@ def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
     return {
         "circ": circ, "step_ms": step_ms, "obj_ms": obj_ms, "grad_ms": grad_ms, "launches": launches,
         "e2e_s": e2e_s, "fidelity": fidelity, "passes_grad": ws.num_passes(0), "passes_dag": ws.num_passes(2),
+        "stages_grad": ws.num_stages(0), "stages_dag": ws.num_stages(2),
         "h2d": 2 * 8 * T, "d2h": 16 * (n + 1) + 16 * T,
     }
 
@@ -533,14 +625,8 @@ def main():
     V = 16.0 * 2**n
     value = world * args.steps / (total_ms * 1e-3)
     e2e_value = world * args.steps / e2e_total
-    peak, peak_src = measured_peaks()
     grad_s = float(np.mean(res["grad_ms"])) * 1e-3
     obj_s = float(np.mean(res["obj_ms"])) * 1e-3
-    alg_grad = 4.0 * V * P  # bytes per gradient sweep at pair-run granularity
-    per_launch_alg = alg_grad / res["passes_grad"]
-    per_launch_s = grad_s / res["passes_grad"]
-    achieved = per_launch_alg / per_launch_s / 1e9
-    flops_eval = (104.0 * (circ.num_blocks + circ.half_layer_num_blocks) + 78.0 * n) * 2**n
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -553,17 +639,10 @@ def main():
             "l2": "flushed between timed steps (256 MiB write)" if flush_l2 else "inputs (3 x %.1f GiB) larger than L2" % (V / 2**30),
             "parallelism": "1 independent evaluation per GPU (no collective)" if world > 1 else "1 GPU",
             "tile_passes": {"gradient": res["passes_grad"], "vh_apply": res["passes_dag"]},
+            "stages": {"gradient": res["stages_grad"], "vh_apply": res["stages_dag"]},
         },
-        "roofline": {
-            "bound": "hbm", "kernel": "pass_kernel<2,cx,fwd> (gradient tile pass)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": per_launch_alg, "launch_ms": per_launch_s * 1e3,
-            "eval_frac": (6.0 * V * P / (obj_s + grad_s)) / 1e9 / peak,
-            "fp64_tflops": flops_eval / (obj_s + grad_s) / 1e12,
-            "note": "algorithmic bytes at pair-run granularity (SURVEY 8(d)); passes fuse several "
-                    "pair-runs per tile so DRAM traffic is lower and the binding limit is FP64 issue",
-        },
+        "roofline": roofline_block(args.workload, n, P, res["passes_grad"], res["passes_dag"],
+                                   res["stages_grad"], res["stages_dag"], grad_s, obj_s),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
                 "d2h_bytes_per_step": res["d2h"]},
         "gpu_launches": res["launches"],
@@ -576,16 +655,19 @@ def main():
         # the HBM-meaningful size of BASELINE.json configs[4] (vectors >> L2), same step definition
         n2, l2 = WORKLOADS["sv28"]
         r2 = measure_gpu(n2, l2, 3, 3, local_rank, False, None)
-        p2, v2 = pair_runs(n2, l2), 16.0 * 2**n2
+        p2 = pair_runs(n2, l2)
         t2 = float(np.mean(r2["step_ms"])) * 1e-3
         g2 = float(np.mean(r2["grad_ms"])) * 1e-3
+        o2 = float(np.mean(r2["obj_ms"])) * 1e-3
         line["extra_workloads"] = {"sv28": {
             "num_qubits": n2, "layers": l2, "num_thetas": r2["circ"].num_thetas, "steps": 3, "warmup": 3,
             "value": 1.0 / t2, "unit": UNIT, "ms_per_step": t2 * 1e3,
             "e2e_value": 1.0 / float(np.mean(r2["e2e_s"])),
-            "roofline_frac_gradient_kernel": 4.0 * v2 * p2 / g2 / 1e9 / peak,
-            "roofline_frac_eval": 6.0 * v2 * p2 / t2 / 1e9 / peak,
+            "kernel_ms": {"vh_apply_sweep": o2 * 1e3, "gradient_sweep": g2 * 1e3},
             "tile_passes": {"gradient": r2["passes_grad"], "vh_apply": r2["passes_dag"]},
+            "stages": {"gradient": r2["stages_grad"], "vh_apply": r2["stages_dag"]},
+            "roofline": roofline_block("sv28", n2, p2, r2["passes_grad"], r2["passes_dag"],
+                                       r2["stages_grad"], r2["stages_dag"], g2, o2),
         }}
         try:
             line["extra_workloads"]["mps50"] = measure_mps(device=local_rank, with_cpu=not args.no_cpu_baseline)

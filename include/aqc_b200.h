@@ -138,6 +138,9 @@ int aqc_sv_timer_stop(aqc_sv* sv, float* ms);
 /* Scheduler introspection: number of tile passes over the state for one gradient
  * sweep (mode 0), one V apply (1) or one V^H apply (2). */
 int aqc_sv_num_passes(const aqc_sv* sv, int mode);
+/* ... and the number of stages (one 4x4 stage matrix applied to every amplitude quadruple of the
+ * state) summed over those passes: the FP64 work of a sweep is proportional to it. */
+int aqc_sv_num_stages(const aqc_sv* sv, int mode);
 /* Host-only (no device needed): serialises the tile-pass program the scheduler compiles for
  * `circ` as int32 words (layout documented in csrc/aqc_sv.cu); reversed = 1 gives the V^H
  * program.  *needed receives the word count; data are written iff cap is large enough. */

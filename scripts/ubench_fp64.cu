@@ -196,6 +196,16 @@ int main() {
            (2.0 * 256 * 4 * warps + 2.0 * 8 * threads) * iters * blocks / ms / 1e9,
            2.0 * 256 * 4 * warps * iters * (double)blocks / ms / 1e9,
            2.0 * 8 * threads * iters * (double)blocks / ms / 1e9);
+    ms = time_it([&] { k_mix<2, 16><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    printf("warps/SM %2d  mix 2 DMMA + 16 DFMA  : %7.2f TFLOP/s (dmma %.2f + dfma %.2f)\n", warps,
+           (2.0 * 256 * 2 * warps + 2.0 * 16 * threads) * iters * blocks / ms / 1e9,
+           2.0 * 256 * 2 * warps * iters * (double)blocks / ms / 1e9,
+           2.0 * 16 * threads * iters * (double)blocks / ms / 1e9);
+    ms = time_it([&] { k_mix<4, 16><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    printf("warps/SM %2d  mix 4 DMMA + 16 DFMA  : %7.2f TFLOP/s (dmma %.2f + dfma %.2f)\n", warps,
+           (2.0 * 256 * 4 * warps + 2.0 * 16 * threads) * iters * blocks / ms / 1e9,
+           2.0 * 256 * 4 * warps * iters * (double)blocks / ms / 1e9,
+           2.0 * 16 * threads * iters * (double)blocks / ms / 1e9);
     ms = time_it([&] { k_lds<<<blocks, threads>>>(out, iters); });
     printf("warps/SM %2d  LDS.128               : %7.2f B/clk/SM at max clock\n", warps,
            16.0 * 8 * iters * (double)threads / (ms * 1e-3 * clk_khz * 1e3));
