@@ -42,7 +42,7 @@ __host__ __device__ __forceinline__ unsigned dense_swz(unsigned i) {
 //   sl : swizzled slot offset (16-byte units) of the lane's amplitude in the load layout
 //   so0, so1 : swizzled offsets (8-byte units) of the lane's two stores
 //   sb : swizzled tile-local base of iteration `warp + kDWarps * lane` (lanes < iterations / warp)
-struct DLane {
+struct alignas(8) DLane {
   uint16_t sl, so0, so1, sb;
 };
 static_assert(sizeof(DLane) == 8, "DLane layout");
@@ -279,8 +279,44 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// shared-memory accesses with explicit 32-bit shared-window addresses (no generic-address
+// arithmetic inside the stage loop)
+__device__ __forceinline__ double2 lds128(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+
+// Tile <-> global memory with the addresses of element l = tid + 256 j built from per-thread
+// constants: swizzled slot = ((tid ^ m(tid)) ^ c_j) + 256 j, c_j = ((j & 1) << 2) ^ (j >> 1), and
+// global offset = lo_off + sum of the strides of the set bits of j (compile-time j).
+template <int NJ, bool LOAD>
+__device__ __forceinline__ void tile_copy(unsigned sbase, unsigned s0x16, const double2* g0,
+                                          double2* gd0, const long long (&hs)[4]) {
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const unsigned cj = (unsigned)((((j & 1) << 2) ^ (j >> 1)) & 7);
+    const unsigned sa = sbase + (s0x16 ^ (cj << 4)) + (unsigned)j * 4096u;
+    long long off = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((j >> k) & 1) off += hs[k];
+    if (LOAD) {
+      cp_async16_s(sa, g0 + off);
+    } else {
+      gd0[off] = lds128(sa);
+    }
+  }
+}
+
 template <int NVEC>
-__global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePassArgs A) {
+__global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_kernel(const DensePassArgs A) {
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * kDWarps * 64 : 2];
@@ -288,6 +324,8 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
   const int lane = tid & 31, warp = tid >> 5;
   const int tb = A.pd.tb;
   const int tsize = 1 << tb;
+  const unsigned sm_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned vbytes = (unsigned)tsize * 16u;  // bytes of one vector's tile
 
   long long base = 0;
   {
@@ -298,28 +336,45 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
   // local index l = tid + 256 * j  ->  global offset lo_off(tid) | hi_off(j)
   long long lo_off = 0;
   for (int k = 0; k < 8 && k < tb; ++k) lo_off |= (long long)((tid >> k) & 1) << A.pd.bitpos[k];
-  if (tid < 16) {
-    long long h = 0;
-    for (int k = 8; k < tb; ++k) h |= (long long)((tid >> (k - 8)) & 1) << A.pd.bitpos[k];
-    s_hioff[tid] = h;
+  long long hs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) hs[k] = (8 + k < tb) ? (1ll << A.pd.bitpos[8 + k]) : 0ll;
+  const bool fast = (tb == 11) || (NVEC == 1 && tb == 12);
+  if (!fast) {
+    if (tid < 16) {
+      long long h = 0;
+      for (int k = 8; k < tb; ++k) h |= (long long)((tid >> (k - 8)) & 1) << A.pd.bitpos[k];
+      s_hioff[tid] = h;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const long long boff = (long long)blockIdx.y * A.vec_stride + base;
+  const unsigned s0x16 = (unsigned)(tid ^ (((tid >> 3) ^ (tid >> 6)) & 7)) << 4;
 
 #pragma unroll
   for (int v = 0; v < NVEC; ++v) {
     double2* sm = smem + (size_t)v * tsize;
     if (v == 0 && A.basis_index >= 0) {
       for (int l = tid; l < tsize; l += kDThreads) {
-        const long long g = base | lo_off | s_hioff[l >> 8];
+        long long h = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (((l >> 8) >> k) & 1) h |= hs[k];
+        const long long g = base | lo_off | h;
         sm[dense_swz(l)] = make_double2(g == A.basis_index ? 1.0 : 0.0, 0.0);
       }
     } else {
       // the whole tile goes in flight at once (16-byte LDGSTS straight into the swizzled slots):
       // the load phase costs one memory round trip instead of one per unrolled batch of LDGs
       const double2* __restrict__ src = A.src[v] + boff;
-#pragma unroll 4
-      for (int l = tid; l < tsize; l += kDThreads) cp_async16(sm + dense_swz(l), src + (lo_off | s_hioff[l >> 8]));
+      if (tb == 11) {
+        tile_copy<8, true>(sm_u32 + v * vbytes, s0x16, src + lo_off, nullptr, hs);
+      } else if (NVEC == 1 && tb == 12) {
+        tile_copy<16, true>(sm_u32 + v * vbytes, s0x16, src + lo_off, nullptr, hs);
+      } else {
+        for (int l = tid; l < tsize; l += kDThreads)
+          cp_async16(sm + dense_swz(l), src + (lo_off | s_hioff[l >> 8]));
+      }
     }
   }
   cp_async_commit();
@@ -329,37 +384,40 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
   const int nstages = A.pd.nstages;
   const int nit = tsize >> 5;
   const size_t sbase = (size_t)blockIdx.y * A.nstages_total + A.pd.stage0;
-  const double* __restrict__ um = A.umat + sbase * 64;
-  const DLane* __restrict__ lt = A.lanes + ((size_t)A.pd.stage0 * kDWarps + warp) * 32 + lane;
-  double* smd = reinterpret_cast<double*>(smem);
+  const double* __restrict__ um = A.umat + sbase * 64 + lane;
+  const uint2* __restrict__ lt =
+      reinterpret_cast<const uint2*>(A.lanes + ((size_t)A.pd.stage0 * kDWarps + warp) * 32 + lane);
+  double* __restrict__ gmp = A.gm + sbase * 64 + lane;
 
   // one-stage-ahead prefetch of the per-stage constants
   double ua0 = 0.0, ua1 = 0.0;
-  DLane dl = {0, 0, 0, 0};
+  uint2 dl = make_uint2(0u, 0u);
   if (nstages > 0) {
-    ua0 = um[lane];
-    ua1 = um[32 + lane];
+    ua0 = um[0];
+    ua1 = um[32];
     dl = lt[0];
   }
   for (int s = 0; s < nstages; ++s) {
     double na0 = 0.0, na1 = 0.0;
-    DLane nl = {0, 0, 0, 0};
+    uint2 nl = make_uint2(0u, 0u);
     if (s + 1 < nstages) {
-      na0 = um[(size_t)(s + 1) * 64 + lane];
-      na1 = um[(size_t)(s + 1) * 64 + 32 + lane];
+      na0 = um[(size_t)(s + 1) * 64];
+      na1 = um[(size_t)(s + 1) * 64 + 32];
       nl = lt[(size_t)(s + 1) * kDWarps * 32];
     }
-    const unsigned sl = dl.sl, so0 = dl.so0, so1 = dl.so1, sbv = dl.sb;
+    // byte offsets inside one vector's tile: load slot (16-byte units), store slots (8-byte units)
+    const unsigned sl16 = (dl.x & 0xffffu) << 4, so0 = (dl.x >> 16) << 3, so1 = (dl.y & 0xffffu) << 3;
+    const unsigned sb16 = (dl.y >> 16) << 4;
     double m0 = 0.0, m1 = 0.0;
     int j = 0;
 #pragma unroll 2
     for (int it = warp; it < nit; it += kDWarps, ++j) {
-      const unsigned b = __shfl_sync(0xffffffffu, sbv, j);
-      const unsigned slot = b ^ sl;
-      const unsigned d0 = (b << 1) ^ so0, d1 = (b << 1) ^ so1;
+      const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
+      const unsigned la = sm_u32 + (b16 ^ sl16);
+      const unsigned d0 = sm_u32 + (b16 ^ so0), d1 = sm_u32 + (b16 ^ so1);
       if (NVEC == 2) {
-        const double2 w = smem[slot];
-        const double2 z = smem[tsize + slot];
+        const double2 w = lds128(la);
+        const double2 z = lds128(la + vbytes);
         double w0 = 0.0, w1 = 0.0, z0 = 0.0, z1 = 0.0;
         dmma884(w0, w1, ua0, w.x);
         dmma884(z0, z1, ua0, z.x);
@@ -367,33 +425,31 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
         dmma884(z0, z1, ua1, z.y);
         dmma884(m0, m1, z0, w0);
         dmma884(m0, m1, z1, w1);
-        smd[d0] = w0;
-        smd[d1] = w1;
-        smd[2 * tsize + d0] = z0;
-        smd[2 * tsize + d1] = z1;
+        sts64(d0, w0);
+        sts64(d1, w1);
+        sts64(d0 + vbytes, z0);
+        sts64(d1 + vbytes, z1);
       } else {
-        const double2 x = smem[slot];
+        const double2 x = lds128(la);
         double x0 = 0.0, x1 = 0.0;
         dmma884(x0, x1, ua0, x.x);
         dmma884(x0, x1, ua1, x.y);
-        smd[d0] = x0;
-        smd[d1] = x1;
+        sts64(d0, x0);
+        sts64(d1, x1);
       }
     }
     if (NVEC == 2) {
       // R[cz = lane >> 2][cw = 2 (lane & 3) + {0, 1}] partials of this warp
       double* part = s_mpart + ((s & 1) * kDWarps + warp) * 64;
-      part[2 * lane] = m0;
-      part[2 * lane + 1] = m1;
+      *reinterpret_cast<double2*>(part + 2 * lane) = make_double2(m0, m1);
       __syncthreads();
       if (warp == (s & (kDWarps - 1))) {
         const double* pp = s_mpart + (s & 1) * kDWarps * 64;
         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
         for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 64 + lane], r1 += pp[w * 64 + 32 + lane];
-        double* g = A.gm + (sbase + s) * 64;
-        atomicAdd(g + lane, r0);
-        atomicAdd(g + 32 + lane, r1);
+        atomicAdd(gmp + (size_t)s * 64, r0);
+        atomicAdd(gmp + (size_t)s * 64 + 32, r1);
       }
     } else {
       __syncthreads();
@@ -405,7 +461,12 @@ __global__ void __launch_bounds__(kDThreads, 3) dense_pass_kernel(const DensePas
   for (int v = 0; v < NVEC; ++v) {
     const double2* sm = smem + (size_t)v * tsize;
     double2* __restrict__ dst = A.dst[v] + boff;
-#pragma unroll 4
-    for (int l = tid; l < tsize; l += kDThreads) dst[lo_off | s_hioff[l >> 8]] = sm[dense_swz(l)];
+    if (tb == 11) {
+      tile_copy<8, false>(sm_u32 + v * vbytes, s0x16, nullptr, dst + lo_off, hs);
+    } else if (NVEC == 1 && tb == 12) {
+      tile_copy<16, false>(sm_u32 + v * vbytes, s0x16, nullptr, dst + lo_off, hs);
+    } else {
+      for (int l = tid; l < tsize; l += kDThreads) dst[lo_off | s_hioff[l >> 8]] = sm[dense_swz(l)];
+    }
   }
 }
