@@ -59,6 +59,10 @@ SIGNATURES = {
     "aqc_sv_last_num_launches": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_timer_start": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_timer_stop": (ct.c_int, [ct.c_void_p, ct.POINTER(ct.c_float)]),
+    "aqc_sv_coord_descent": (
+        ct.c_int,
+        [ct.c_void_p, ct.POINTER(ct.c_double), ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_double)],
+    ),
     "aqc_sv_num_passes": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_sv_num_stages": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_debug_program": (

@@ -76,3 +76,23 @@ def grad_of_matrix_dot_product(
     ws.upload(0, _pad_cols(x_mat, k))
     ws.upload(1, _pad_cols(vh_y_mat, k))
     return ws.grad(thetas, x_slot=0, z0=1, w=0, z=1)[0]
+
+
+def coord_descent_single_sweep(
+    circ, thetas: np.ndarray, target: np.ndarray, workspace: Optional[np.ndarray] = None
+) -> float:
+    """
+    One coordinate-descent sweep over all angles for ``fobj = 1 - |<V, U>|^2 / dim^2``
+    (core_op_matrix.py:765-917): ``thetas`` is modified IN PLACE, the objective at the end of the
+    sweep is returned.  cx / cz entanglers only, as in the reference (:818-819).
+    """
+    assert isinstance(circ, ParametricCircuit)
+    assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
+    assert chk.complex_2d(target, target.shape[0] == target.shape[1] == circ.dimension)
+    if circ.entangler == "cp":
+        raise NotImplementedError("CPhase entangler is not supported yet")
+    ws = _workspace(circ, log2_cols=circ.num_qubits)
+    ws.upload(0, np.ascontiguousarray(target))
+    fobj, new_thetas = ws.coord_descent(thetas, target=0, w=1, z=2, num_sweeps=1)
+    thetas[:] = new_thetas[0]
+    return float(fobj[0, 0])

@@ -462,6 +462,7 @@ __device__ __forceinline__ double warp_reduce8(const double* v, int lane, int& w
 }
 
 #include "aqc_dense.cuh"
+#include "aqc_cd.cuh"
 
 struct PassArgs {
   const double2* src[2];  // [0] = w (NVEC == 2) or the single vector; [1] = z
@@ -1235,6 +1236,10 @@ struct aqc_sv {
   bool dense = false;
   DenseTables dt_grad, dt_fwd, dt_dag;
   double *d_umat = nullptr, *d_gm = nullptr;
+  // coordinate descent (aqc_cd.cuh)
+  CdUnit* d_cd_units = nullptr;
+  int cd_nunits = 0;
+  double* d_cd_fobj = nullptr;
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
@@ -1740,6 +1745,8 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
                   (void*)sv->d_uph, (void*)sv->d_kappa, (void*)sv->d_albuf, (void*)sv->d_aebuf,
                   (void*)sv->d_arescale})
     if (q) cudaFree(q);
+  for (void* q : {(void*)sv->d_cd_units, (void*)sv->d_cd_fobj})
+    if (q) cudaFree(q);
   for (void* q : {(void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
                   (void*)sv->dt_dag.d_lanes})
     if (q) cudaFree(q);
@@ -2116,6 +2123,77 @@ extern "C" int aqc_sv_apply(aqc_sv* sv, const double* thetas, int dagger, int sr
   if (rc) return rc;
   CU(cudaStreamSynchronize(sv->stream));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  return AQC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// coordinate descent (unitary AQC)
+// ------------------------------------------------------------------------------------------
+extern "C" int aqc_sv_coord_descent(aqc_sv* sv, double* thetas, int target_slot, int w_slot, int z_slot,
+                                    int num_sweeps, double* fobj_out) {
+  int rc = check_slot(sv, target_slot);
+  if (!rc) rc = check_slot(sv, w_slot);
+  if (!rc) rc = check_slot(sv, z_slot);
+  if (rc) return rc;
+  if (!thetas || !fobj_out || num_sweeps < 1) return fail(AQC_EINVAL, "bad arguments");
+  if (w_slot == z_slot || w_slot == target_slot || z_slot == target_slot)
+    return fail(AQC_EINVAL, "target, w and z must be three different slots");
+  if (sv->log2_cols != sv->circ.n) return fail(AQC_EINVAL, "coordinate descent needs a square (2^n x 2^n) target");
+  if (sv->g != 0) return fail(AQC_EINVAL, "coordinate descent is not sharded");
+  if (sv->circ.ent == AQC_ENT_CP) return fail(AQC_EINVAL, "CPhase entangler is not supported yet");
+  if (sv->circ.trotter != AQC_GENERIC) return fail(AQC_EINVAL, "coordinate descent needs a ParametricCircuit");
+  CU(cudaSetDevice(sv->device));
+  const int n = sv->circ.n, T = sv->circ.nthetas;
+  if (!sv->d_cd_units) {
+    std::vector<CdUnit> units;
+    for (int q = 0; q < n; ++q) units.push_back({0, q, (q + 1) % n, 3 * q});
+    for (int i = 0; i < sv->circ.nb; ++i)
+      units.push_back({1, sv->circ.ctrl[i], sv->circ.targ[i], 3 * n + sv->circ.tpb * i});
+    sv->cd_nunits = (int)units.size();
+    CU(cudaMalloc(&sv->d_cd_units, units.size() * sizeof(CdUnit)));
+    CU(cudaMemcpy(sv->d_cd_units, units.data(), units.size() * sizeof(CdUnit), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sv->d_cd_fobj, sv->batch * sizeof(double)));
+  }
+  const size_t tot = (size_t)sv->batch * T;
+  rc = ensure_pinned(sv, tot * 2 + 64 + sv->batch);
+  if (rc) return rc;
+  sv->last_launches = 0;
+  float total_ms = 0.f;
+  CdArgs a;
+  a.w = sv->slots[w_slot];
+  a.z = sv->slots[z_slot];
+  a.vec_stride = sv->size;
+  a.thetas = sv->d_thetas;
+  a.units = sv->d_cd_units;
+  a.nunits = sv->cd_nunits;
+  a.n = n;
+  a.T = T;
+  a.fobj = sv->d_cd_fobj;
+  for (int sweep = 0; sweep < num_sweeps; ++sweep) {
+    // z = V(thetas)^H target (thetas uploaded to d_thetas on the way), w = I
+    rc = apply_async(sv, thetas, 1, target_slot, z_slot);
+    if (rc) return rc;
+    set_identity_kernel<<<grid1d(sv->size, sv->batch, 256), 256, 0, sv->stream>>>(
+        sv->slots[w_slot], sv->size, sv->size, sv->log2_cols);
+    if (sv->circ.ent == AQC_ENT_CX)
+      cd_sweep_kernel<AQC_ENT_CX><<<sv->batch, kCdThreads, 0, sv->stream>>>(a);
+    else
+      cd_sweep_kernel<AQC_ENT_CZ><<<sv->batch, kCdThreads, 0, sv->stream>>>(a);
+    CU(cudaGetLastError());
+    sv->last_launches += 2;
+    CU(cudaEventRecord(sv->ev1, sv->stream));
+    // the pinned buffer holds the angles the apply above has consumed already (stream order)
+    CU(cudaMemcpyAsync(sv->h_pinned, sv->d_thetas, tot * sizeof(double), cudaMemcpyDeviceToHost, sv->stream));
+    CU(cudaMemcpyAsync(sv->h_pinned + tot, sv->d_cd_fobj, sv->batch * sizeof(double), cudaMemcpyDeviceToHost,
+                       sv->stream));
+    CU(cudaStreamSynchronize(sv->stream));
+    memcpy(thetas, sv->h_pinned, tot * sizeof(double));
+    memcpy(fobj_out + (size_t)sweep * sv->batch, sv->h_pinned + tot, sv->batch * sizeof(double));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, sv->ev0, sv->ev1));
+    total_ms += ms;
+  }
+  sv->last_ms = total_ms;
   return AQC_OK;
 }
 

@@ -190,6 +190,24 @@ class SvWorkspace:
         )
         return out
 
+    def coord_descent(self, thetas: np.ndarray, *, target: int, w: int, z: int, num_sweeps: int = 1):
+        """
+        ``num_sweeps`` coordinate-descent sweeps (coord_descent_single_sweep,
+        core_op_matrix.py:765-917) for every start of the batch.  Returns
+        (fobj[num_sweeps, batch], new thetas[batch, num_thetas]); ``thetas`` is not modified.
+        """
+        th = np.array(thetas, dtype=np.float64).reshape(-1).copy()
+        if th.size != self.batch * self.num_thetas:
+            raise ValueError(f"expects {self.batch * self.num_thetas} angular parameters, got {th.size}")
+        fobj = np.empty((int(num_sweeps), self.batch), dtype=np.float64)
+        _lib.check(
+            self._lib.aqc_sv_coord_descent(
+                self.handle, th.ctypes.data_as(_lib.c_double_p), target, w, z, int(num_sweeps),
+                fobj.ctypes.data_as(_lib.c_double_p),
+            )
+        )
+        return fobj, th.reshape(self.batch, self.num_thetas)
+
     # -- introspection -----------------------------------------------------------------------
     @property
     def last_kernel_ms(self) -> float:

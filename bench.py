@@ -470,6 +470,46 @@ def measure_mat7(batch=64, layers=40, steps=5, warmup=2, device=0, with_cpu=True
     return out
 
 
+def measure_cd7(batch=64, layers=40, sweeps=3, device=0, with_cpu=True):
+    """
+    SURVEY 8(f) row 2: coordinate descent for unitary AQC (coord_descent_single_sweep), 7 qubits,
+    cyclic_spin ansatz with 7*layers blocks, `batch` starts per call; value = sweeps of one start
+    per second (every sweep updates all T angles once).
+    """
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200.model_sketching.aqc_coord_descent import BatchedCoordinateDescent
+    from aqc_research_b200.parametric_circuit import ParametricCircuit
+
+    n = 7
+    circ = ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "cyclic_spin", "full", n * layers))
+    rng = np.random.RandomState(11)
+    q, r = np.linalg.qr(rng.randn(2**n, 2**n) + 1j * rng.randn(2**n, 2**n))
+    target = np.ascontiguousarray(q * (np.diag(r) / np.abs(np.diag(r))))
+    ths = np.pi * np.clip(rng.randn(batch, circ.num_thetas), -1, 1)
+    opt = BatchedCoordinateDescent(circ, target, batch=batch, device=device)
+    opt.sweep(ths, num_sweeps=1)  # warm-up
+    t0 = time.perf_counter()
+    fobj, _ = opt.sweep(ths, num_sweeps=sweeps)
+    dt = time.perf_counter() - t0
+    dev_ms = opt.workspace.last_kernel_ms
+    opt.close()
+    out = {
+        "workload": f"coordinate descent n={n}, cyclic_spin {layers} layers ({circ.num_blocks} blocks, "
+                    f"{circ.num_thetas} angles), {batch} starts per call",
+        "value": batch * sweeps / dt, "unit": "sweeps/s", "ms_per_sweep_batch": dt * 1e3 / sweeps,
+        "device_ms_per_sweep_batch": dev_ms / sweeps, "fobj_first_last": [float(fobj[0, 0]), float(fobj[-1, 0])],
+    }
+    if with_cpu:
+        from oracle import sv_oracle as O
+
+        t0 = time.perf_counter()
+        O.coord_descent_sweep(circ, ths[0], target)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                               "sample": f"1 sweep of one start with the NumPy restatement ({dt:.2f} s)"}
+    return out
+
+
 def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
     """
     BASELINE.json configs[4], second half: ONE state vector over `world` GPUs (global-qubit
@@ -672,6 +712,7 @@ def main():
         try:
             line["extra_workloads"]["mps50"] = measure_mps(device=local_rank, with_cpu=not args.no_cpu_baseline)
             line["extra_workloads"]["mat7"] = measure_mat7(device=local_rank, with_cpu=not args.no_cpu_baseline)
+            line["extra_workloads"]["cd7"] = measure_cd7(device=local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as ex:  # extras must never break the headline line
             line["extra_workloads"]["error"] = repr(ex)
     print(json.dumps(line), flush=True)

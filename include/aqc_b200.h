@@ -135,6 +135,16 @@ int aqc_sv_last_num_launches(const aqc_sv* sv);
  * workspace between start and stop (ms = device time between the two events). */
 int aqc_sv_timer_start(aqc_sv* sv);
 int aqc_sv_timer_stop(aqc_sv* sv, float* ms);
+/* Coordinate descent for unitary AQC.
+ * Replaces: coord_descent_single_sweep (core_op_matrix.py:765-917), called num_sweeps times.
+ * The workspace must be a matrix workspace with log2_cols == num_qubits (target 2^n x 2^n in
+ * target_slot, row-major); cx and cz ParametricCircuits only (the reference raises
+ * NotImplementedError for cp).  Every sweep: z = V(thetas)^H target, w = I, then every angle
+ * gets one Newton / clipped-gradient update in circuit order (z rotated with the old angle, w with
+ * the new one).  thetas: float64[batch * T], updated IN PLACE; fobj_out: float64[num_sweeps * batch],
+ * fobj = 1 - |<w|z>_F / 2^n|^2 at the end of each sweep (as returned by the reference). */
+int aqc_sv_coord_descent(aqc_sv* sv, double* thetas, int target_slot, int w_slot, int z_slot,
+                         int num_sweeps, double* fobj_out);
 /* Scheduler introspection: number of tile passes over the state for one gradient
  * sweep (mode 0), one V apply (1) or one V^H apply (2). */
 int aqc_sv_num_passes(const aqc_sv* sv, int mode);

@@ -356,3 +356,66 @@ def sketch_full_value_and_grad(circ, thetas, target_matrix):
     f = 1.0 - np.real(np.trace(vh_y)) / d
     g = grad_sweep(circ, thetas, np.eye(d, dtype=C128).ravel(), vh_y.ravel(), ncols=d)
     return f, -np.real(g) / d
+
+
+# ------------------------------------------------------------------------------------------------
+# coordinate descent for unitary AQC
+# ------------------------------------------------------------------------------------------------
+CD_LEARN_RATE = np.pi / 16
+CD_MAX_DELTA = np.pi / 4
+
+
+def cd_delta_theta(prod: complex, grad: complex, dim: int) -> float:
+    """Angle increment of one coordinate (``_delta_theta``, core_op_matrix.py:833-850)."""
+    tol = float(np.sqrt(np.finfo(np.float64).eps))
+    derv1 = (-2.0 * np.real(np.conj(prod) * grad)) / (dim**2)
+    derv2 = (-2.0 * abs(grad) ** 2 + 0.5 * abs(prod) ** 2) / (dim**2)
+    if derv2 < tol:
+        derv1 /= max(abs(derv1), 1.0)
+        dt = -CD_LEARN_RATE * derv1
+    else:
+        dt = -derv1 / derv2
+    a = abs(dt / CD_MAX_DELTA)
+    return float(dt if a <= 1 else dt / a)
+
+
+def coord_descent_sweep(circ, thetas: np.ndarray, target: np.ndarray):
+    """
+    One coordinate-descent sweep over all angles (coord_descent_single_sweep,
+    core_op_matrix.py:765-917): w = I, z = V^H U; before every rotation R_P(theta_k) the product
+    <w|z>_F and 0.5j<P w|z>_F give a Newton / clipped gradient step for theta_k; z is rotated
+    with the OLD angle, w with the NEW one.  Returns (fobj, new_thetas); cx and cz only.
+    """
+    if circ.entangler == "cp":
+        raise NotImplementedError("CPhase entangler is not supported yet")
+    n, nb = circ.num_qubits, circ.num_blocks
+    dim = 1 << n
+    th = np.array(thetas, dtype=np.float64).copy()
+    th1 = th[: 3 * n].reshape(n, 3)
+    th2 = th[3 * n :].reshape(nb, 4)
+    make_rs, pauli_s = _swappable(circ)
+    w = np.eye(dim, dtype=C128).ravel()
+    z = apply_v(circ, th, np.array(target, dtype=C128).ravel(), dagger=True, ncols=dim)
+
+    def step(q, make_gate, pauli, tht, k):
+        nonlocal w, z
+        grad = pauli_dot(w, z, q, pauli, dim)
+        prod = np.vdot(w, z)
+        z = op1(z, q, make_gate(tht[k]), dim)
+        tht[k] += cd_delta_theta(prod, grad, dim)
+        w = op1(w, q, make_gate(tht[k]), dim)
+
+    for q in range(n):
+        step(q, rz, PAULI_Z, th1[q], 2)
+        step(q, ry, PAULI_Y, th1[q], 1)
+        step(q, rz, PAULI_Z, th1[q], 0)
+    e = PAULI_X if circ.entangler == "cx" else PAULI_Z
+    for i in range(nb):
+        c, t = int(circ.blocks[0, i]), int(circ.blocks[1, i])
+        z = ctrl_op(z, c, t, e, dim)
+        w = ctrl_op(w, c, t, e, dim)
+        step(c, ry, PAULI_Y, th2[i], 0)
+        step(c, rz, PAULI_Z, th2[i], 1)
+        step(t, ry, PAULI_Y, th2[i], 2)
+        step(t, make_rs, pauli_s, th2[i], 3)
+    return float(1 - np.abs(np.vdot(w, z) / dim) ** 2), th

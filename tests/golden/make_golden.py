@@ -236,9 +236,40 @@ def trotter_and_lbfgs():
     print("trotter + lbfgs: nit", res.nit, "nfev", res.nfev, "fun", res.fun, "fidelity", objv.fidelity)
 
 
+def cd_cases():
+    """coord_descent_single_sweep (core_op_matrix.py:765-917): several consecutive sweeps."""
+    from scipy.stats import unitary_group
+
+    out = {}
+    case = 0
+    np.random.seed(0x0C0D)
+    for n, nblocks in ((2, 3), (3, 7), (4, 12), (5, 20)):
+        for kind in ("cx", "cz"):
+            circ, blocks = make_circuit(kind, n, nblocks)
+            target = unitary_group.rvs(2**n, random_state=100 * n + len(kind) + case).astype(np.complex128)
+            th = R.utils.rand_thetas(circ.num_thetas)
+            ws = np.zeros((3, 2**n, 2**n), dtype=np.complex128)
+            ths, fs = [th.copy()], []
+            for _ in range(4):
+                f = R.cpm.coord_descent_single_sweep(circ, th, target, ws)
+                ths.append(th.copy())
+                fs.append(f)
+            pre = f"c{case}_"
+            out[pre + "meta"] = np.array([n, ["cx", "cz"].index(kind)])
+            out[pre + "blocks"] = blocks
+            out[pre + "target"] = target
+            out[pre + "thetas"] = np.array(ths)  # [5][T]: start + after each sweep
+            out[pre + "fobj"] = np.array(fs)
+            case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "cd_cases.npz"), **out)
+    print("cd_cases:", case)
+
+
 if __name__ == "__main__":
     sv_cases()
     mat_cases()
     objective_sequences()
     mps_cases()
     trotter_and_lbfgs()
+    cd_cases()

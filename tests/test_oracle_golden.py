@@ -161,3 +161,17 @@ def test_c_oracle_golden():
     z0 = C.apply_v(circ, th, y, dagger=True)
     assert rel(z0, O.apply_v(circ, th, y, dagger=True)) < TOL
     assert rel(C.grad_sweep(circ, th, x, z0)[0], O.grad_sweep(circ, th, x, z0)) < TOL
+
+
+def test_coord_descent_golden():
+    """oracle coord_descent_sweep == reference coord_descent_single_sweep over 4 consecutive sweeps."""
+    g = load("cd_cases.npz")
+    for c in range(int(g["num_cases"])):
+        p = f"c{c}_"
+        n, kind = [int(v) for v in g[p + "meta"]]
+        circ = circuit_from(KINDS[kind], n, g[p + "blocks"])
+        ths, fs = g[p + "thetas"], g[p + "fobj"]
+        for s in range(len(fs)):
+            f, th_new = O.coord_descent_sweep(circ, ths[s], g[p + "target"])
+            assert abs(f - fs[s]) < 1e-11, (c, s, f, fs[s])
+            assert rel(th_new, ths[s + 1]) < 1e-11, (c, s)
