@@ -63,6 +63,11 @@ SIGNATURES = {
         ct.c_int,
         [ct.c_void_p, ct.POINTER(ct.c_double), ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_double)],
     ),
+    "aqc_sv_set_dense_target": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+    "aqc_sv_target_matmul": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int]),
+    "aqc_sv_orthonormalize": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "aqc_sv_sub": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "aqc_sv_gather_target_columns": (ct.c_int, [ct.c_void_p, c_int64_p, ct.c_int, ct.c_int, ct.c_int]),
     "aqc_sv_num_passes": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_sv_num_stages": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_debug_program": (

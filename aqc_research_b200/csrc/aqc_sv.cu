@@ -463,6 +463,7 @@ __device__ __forceinline__ double warp_reduce8(const double* v, int lane, int& w
 
 #include "aqc_dense.cuh"
 #include "aqc_cd.cuh"
+#include "aqc_sketch.cuh"
 
 struct PassArgs {
   const double2* src[2];  // [0] = w (NVEC == 2) or the single vector; [1] = z
@@ -1234,12 +1235,17 @@ struct aqc_sv {
   double *d_albuf = nullptr, *d_aebuf = nullptr, *d_arescale = nullptr;
   // dense-stage engine (aqc_dense.cuh): DMMA sweeps; the default whenever the tile has >= 5 bits
   bool dense = false;
+  int num_sms = 148;
   DenseTables dt_grad, dt_fwd, dt_dag;
   double *d_umat = nullptr, *d_gm = nullptr;
   // coordinate descent (aqc_cd.cuh)
   CdUnit* d_cd_units = nullptr;
   int cd_nunits = 0;
   double* d_cd_fobj = nullptr;
+  // sketching generators (aqc_sketch.cuh): dense target U (d x d) and m x m factorisation scratch
+  double2* d_target = nullptr;
+  double2 *d_gram = nullptr, *d_rinv = nullptr;
+  int* d_info = nullptr;
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
@@ -1745,7 +1751,8 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
                   (void*)sv->d_uph, (void*)sv->d_kappa, (void*)sv->d_albuf, (void*)sv->d_aebuf,
                   (void*)sv->d_arescale})
     if (q) cudaFree(q);
-  for (void* q : {(void*)sv->d_cd_units, (void*)sv->d_cd_fobj})
+  for (void* q : {(void*)sv->d_cd_units, (void*)sv->d_cd_fobj, (void*)sv->d_target, (void*)sv->d_gram,
+                  (void*)sv->d_rinv, (void*)sv->d_info})
     if (q) cudaFree(q);
   for (void* q : {(void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
                   (void*)sv->dt_dag.d_lanes})
@@ -1810,6 +1817,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
       return bail(e_ == cudaErrorMemoryAllocation ? AQC_ENOMEM : AQC_ECUDA);             \
     }                                                                                    \
   } while (0)
+  CUB(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&sv->ev0));
   CUB(cudaEventCreate(&sv->ev1));
@@ -2194,6 +2202,158 @@ extern "C" int aqc_sv_coord_descent(aqc_sv* sv, double* thetas, int target_slot,
     total_ms += ms;
   }
   sv->last_ms = total_ms;
+  return AQC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sketching-vector generators (dense target, GEMMs, thin QR)
+// ------------------------------------------------------------------------------------------
+static int sketch_check(aqc_sv* sv) {
+  if (!sv) return fail(AQC_EINVAL, "null workspace");
+  if (sv->g != 0 || sv->batch != 1) return fail(AQC_EINVAL, "sketching needs an unsharded workspace with batch 1");
+  return AQC_OK;
+}
+
+static int launch_zgemm(aqc_sv* sv, bool trans, const double2* A, long long lda, const double2* B, long long ldb,
+                        double2* C, long long ldc, int M, int N, int K) {
+  GemmArgs g;
+  g.A = A, g.B = B, g.C = C;
+  g.M = M, g.N = N, g.K = K;
+  g.lda = lda, g.ldb = ldb, g.ldc = ldc;
+  const int tiles = ((M + kGemmTileM - 1) / kGemmTileM) * ((N + kGemmTileN - 1) / kGemmTileN);
+  int ksplit = 1;
+  if (tiles < sv->num_sms) ksplit = std::max(1, std::min((K + 255) / 256, (2 * sv->num_sms) / std::max(1, tiles)));
+  g.ksplit = ksplit;
+  if (ksplit > 1) CU(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(double2), sv->stream));
+  const dim3 grid((M + kGemmTileM - 1) / kGemmTileM, (N + kGemmTileN - 1) / kGemmTileN, ksplit);
+  if (trans)
+    zgemm_kernel<1><<<grid, kGemmThreads, 0, sv->stream>>>(g);
+  else
+    zgemm_kernel<0><<<grid, kGemmThreads, 0, sv->stream>>>(g);
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_set_dense_target(aqc_sv* sv, const double* target) {
+  int rc = sketch_check(sv);
+  if (rc) return rc;
+  if (!target) return fail(AQC_EINVAL, "target is null");
+  CU(cudaSetDevice(sv->device));
+  const size_t d = (size_t)1 << sv->circ.n;
+  if (!sv->d_target) {
+    cudaError_t e = cudaMalloc(&sv->d_target, d * d * sizeof(double2));
+    if (e != cudaSuccess) return fail(AQC_ENOMEM, "dense target allocation failed: %s", cudaGetErrorString(e));
+  }
+  CU(cudaMemcpyAsync(sv->d_target, target, d * d * sizeof(double2), cudaMemcpyHostToDevice, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_target_matmul(aqc_sv* sv, int conj_transpose, int src_slot, int dst_slot) {
+  int rc = sketch_check(sv);
+  if (!rc) rc = check_slot(sv, src_slot);
+  if (!rc) rc = check_slot(sv, dst_slot);
+  if (rc) return rc;
+  if (src_slot == dst_slot) return fail(AQC_EINVAL, "matmul is out of place");
+  if (!sv->d_target) return fail(AQC_EINVAL, "no dense target (aqc_sv_set_dense_target)");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const int d = 1 << sv->circ.n, m = 1 << sv->log2_cols;
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  rc = launch_zgemm(sv, conj_transpose != 0, sv->d_target, d, sv->slots[src_slot], m, sv->slots[dst_slot], m, d, m, d);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_orthonormalize(aqc_sv* sv, int slot, int tmp_slot) {
+  int rc = sketch_check(sv);
+  if (!rc) rc = check_slot(sv, slot);
+  if (!rc) rc = check_slot(sv, tmp_slot);
+  if (rc) return rc;
+  if (slot == tmp_slot) return fail(AQC_EINVAL, "tmp_slot must differ from slot");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const int d = 1 << sv->circ.n, m = 1 << sv->log2_cols;
+  if (!sv->d_gram) {
+    CU(cudaMalloc(&sv->d_gram, (size_t)m * m * sizeof(double2)));
+    CU(cudaMalloc(&sv->d_rinv, (size_t)m * m * sizeof(double2)));
+    CU(cudaMalloc(&sv->d_info, sizeof(int)));
+  }
+  rc = ensure_scratch(sv, 4);
+  if (rc) return rc;
+  rc = ensure_pinned(sv, 64);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  CU(cudaMemsetAsync(sv->d_info, 0, sizeof(int), sv->stream));
+  // shift of the first pass: 11 (d m + m (m + 1)) u ||A||_F^2 (shifted Cholesky-QR3)
+  CU(cudaMemsetAsync(sv->d_scratch, 0, sizeof(double), sv->stream));
+  norm2_kernel<<<std::min(1024, (int)(((long long)d * m + 255) / 256)), 256, 0, sv->stream>>>(
+      sv->slots[slot], (long long)d * m, sv->d_scratch);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  const double norm2 = sv->h_pinned[0];
+  if (!(norm2 > 0.0)) return fail(AQC_EINVAL, "cannot orthonormalise a zero matrix");
+  const double shift0 = 11.0 * ((double)d * m + (double)m * (m + 1)) * 1.1102230246251565e-16 * norm2;
+  double2 *cur = sv->slots[slot], *nxt = sv->slots[tmp_slot];
+  for (int pass = 0; pass < 3; ++pass) {
+    rc = launch_zgemm(sv, true, cur, m, cur, m, sv->d_gram, m, m, m, d);  // G = A^H A
+    if (rc) return rc;
+    chol_inv_kernel<<<1, 256, 0, sv->stream>>>(sv->d_gram, sv->d_rinv, m, pass == 0 ? shift0 : 0.0, sv->d_info);
+    CU(cudaGetLastError());
+    rc = launch_zgemm(sv, false, cur, m, sv->d_rinv, m, nxt, m, d, m, m);  // A <- A R^-1
+    if (rc) return rc;
+    sv->last_launches += 1;
+    std::swap(cur, nxt);
+  }
+  // three passes: the result sits in tmp_slot
+  CU(cudaMemcpyAsync(sv->slots[slot], cur, (size_t)d * m * sizeof(double2), cudaMemcpyDeviceToDevice, sv->stream));
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  int* h_info = reinterpret_cast<int*>(sv->h_pinned);
+  CU(cudaMemcpyAsync(h_info, sv->d_info, sizeof(int), cudaMemcpyDeviceToHost, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
+  if (*h_info != 0) return fail(AQC_EINVAL, "sketching matrix is numerically rank deficient (column %d)", *h_info - 1);
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_sub(aqc_sv* sv, int dst_slot, int src_slot) {
+  int rc = check_slot(sv, dst_slot);
+  if (!rc) rc = check_slot(sv, src_slot);
+  if (rc) return rc;
+  CU(cudaSetDevice(sv->device));
+  const long long count = sv->size * sv->batch;
+  sub_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 148 * 16), 256, 0, sv->stream>>>(
+      sv->slots[dst_slot], sv->slots[src_slot], count);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_gather_target_columns(aqc_sv* sv, const int64_t* idx, int count, int x_slot, int y_slot) {
+  int rc = sketch_check(sv);
+  if (!rc) rc = check_slot(sv, x_slot);
+  if (!rc) rc = check_slot(sv, y_slot);
+  if (rc) return rc;
+  const int d = 1 << sv->circ.n, m = 1 << sv->log2_cols;
+  if (!idx || count != m) return fail(AQC_EINVAL, "expects exactly %d column indices", m);
+  if (x_slot == y_slot) return fail(AQC_EINVAL, "x and y must be different slots");
+  if (!sv->d_target) return fail(AQC_EINVAL, "no dense target (aqc_sv_set_dense_target)");
+  for (int i = 0; i < count; ++i)
+    if (idx[i] < 0 || idx[i] >= d) return fail(AQC_EINVAL, "column index out of range");
+  CU(cudaSetDevice(sv->device));
+  rc = ensure_idx(sv, (size_t)count);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(sv->d_idx, idx, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice, sv->stream));
+  const long long tot = (long long)d * m;
+  gather_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, sv->stream>>>(sv->d_target, sv->d_idx, d, m,
+                                                                           sv->slots[x_slot], sv->slots[y_slot]);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sv->stream));
   return AQC_OK;
 }
 

@@ -208,6 +208,33 @@ class SvWorkspace:
         )
         return fobj, th.reshape(self.batch, self.num_thetas)
 
+    # -- sketching generators (dense target, DMMA GEMM, thin QR) --------------------------------
+    def set_dense_target(self, target: np.ndarray):
+        dim = 1 << self.circuit.num_qubits
+        arr = np.ascontiguousarray(target, dtype=np.complex128)
+        if arr.shape != (dim, dim):
+            raise ValueError(f"expects a {dim} x {dim} target matrix")
+        _lib.check(self._lib.aqc_sv_set_dense_target(self.handle, _dptr(arr)))
+
+    def target_matmul(self, src: int, dst: int, conj_transpose: bool = False):
+        """dst = U @ src or U^H @ src (U: the dense target)."""
+        _lib.check(self._lib.aqc_sv_target_matmul(self.handle, int(conj_transpose), src, dst))
+
+    def orthonormalize(self, slot: int, tmp: int):
+        """slot <- orthonormal basis of its column space (thin QR up to a unitary factor)."""
+        _lib.check(self._lib.aqc_sv_orthonormalize(self.handle, slot, tmp))
+
+    def sub(self, dst: int, src: int):
+        _lib.check(self._lib.aqc_sv_sub(self.handle, dst, src))
+
+    def gather_target_columns(self, indices, x: int, y: int):
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        _lib.check(
+            self._lib.aqc_sv_gather_target_columns(
+                self.handle, idx.ctypes.data_as(_lib.c_int64_p), idx.size, x, y
+            )
+        )
+
     # -- introspection -----------------------------------------------------------------------
     @property
     def last_kernel_ms(self) -> float:

@@ -18,7 +18,7 @@ from .. import checking as chk
 from ..engine import SvWorkspace
 from ..parametric_circuit import ParametricCircuit
 
-_SLOT_Y, _SLOT_Z, _SLOT_X = 0, 1, 2
+_SLOT_Y, _SLOT_Z, _SLOT_X, _SLOT_TMP = 0, 1, 2, 3
 
 
 class SketchingVectorsBase(ABC):
@@ -42,6 +42,27 @@ class SketchingVectorsBase(ABC):
 
     #: True if generate() always returns X = I and Y = U (lets the objective keep them on the GPU)
     is_full_range = False
+    #: True if generate_device() is implemented (X and Y are produced in GPU slots, no host round trip)
+    on_device = False
+
+    def generate_device(self, ws: SvWorkspace, x: int, y: int, tmp: int, circ=None, thetas=None) -> None:
+        """Writes X into slot ``x`` and Y = U X into slot ``y`` of ``ws`` (``tmp``: scratch slot)."""
+        raise NotImplementedError("this generator has no device path")
+
+    def _own_workspace(self) -> SvWorkspace:
+        """Workspace for stand-alone generate() calls (the objective class passes its own)."""
+        ws = getattr(self, "_ws_own", None)
+        if ws is None:
+            n = _log2(self._target_mat.shape[0])
+            dummy = ParametricCircuit(n, "cx", np.array([[0], [1]], dtype=np.int64))
+            ws = SvWorkspace(dummy, num_slots=4, log2_cols=_log2(self._num_skvecs), as_generic=True)
+            ws.set_dense_target(self._target_mat)
+            self._ws_own = ws
+        return ws
+
+    def _download_xy(self, ws: SvWorkspace, x: int, y: int):
+        shape = (self._target_mat.shape[0], self._num_skvecs)
+        return ws.download(x).reshape(shape), ws.download(y).reshape(shape)
 
     @abstractmethod
     def generate(self, circ=None, thetas=None) -> Tuple[np.ndarray, np.ndarray]:
@@ -59,6 +80,114 @@ class FullRangeSketchingVectors(SketchingVectorsBase):
     def generate(self, circ=None, thetas=None) -> Tuple[np.ndarray, np.ndarray]:
         dim = self._target_mat.shape[0]
         return np.eye(dim, dtype=np.complex128), np.array(self._target_mat, dtype=np.complex128)
+
+
+class RandomSketchingVectors(SketchingVectorsBase):
+    """
+    New random sketching vectors upon every request (sk_core.py:329-359):
+    ``X = qr(rand + 1j rand)``, ``Y = U X``.  The random matrix comes from the global NumPy RNG in
+    the reference's call order; QR and the GEMM run on the GPU.  X equals the reference's up to a
+    unitary m x m factor (column space identical), which the objective and gradient do not see.
+    """
+
+    on_device = True
+
+    def __init__(self, num_skvecs: int, target_mat: np.ndarray):
+        super().__init__(num_skvecs, target_mat)
+        assert target_mat.shape[0] % self.num_skvecs == 0
+
+    def generate_device(self, ws, x, y, tmp, circ=None, thetas=None) -> None:
+        dim, m = self._target_mat.shape[0], self.num_skvecs
+        ws.upload(x, np.random.rand(dim, m) + 1j * np.random.rand(dim, m))
+        ws.orthonormalize(x, tmp)
+        ws.target_matmul(x, y)
+
+    def generate(self, circ=None, thetas=None):
+        ws = self._own_workspace()
+        self.generate_device(ws, 0, 1, 2)
+        return self._download_xy(ws, 0, 1)
+
+
+class AlternatingSketchingVectors(SketchingVectorsBase):
+    """A random subset of the target's columns per request, cycling through a permutation (sk_core.py:362-407)."""
+
+    on_device = True
+
+    def __init__(self, num_skvecs: int, target_mat: np.ndarray):
+        super().__init__(num_skvecs, target_mat)
+        dim = target_mat.shape[0]
+        assert dim % self.num_skvecs == 0
+        self._offset = 0
+        self._indices = np.random.permutation(dim)
+
+    def generate_device(self, ws, x, y, tmp, circ=None, thetas=None) -> None:
+        dim = self._target_mat.shape[0]
+        if self._offset >= dim:
+            self._offset = 0
+            self._indices = np.random.permutation(dim)
+        idx = self._indices[self._offset : self._offset + self.num_skvecs]
+        ws.gather_target_columns(idx, x, y)
+        self._offset += self.num_skvecs
+
+    def generate(self, circ=None, thetas=None):
+        ws = self._own_workspace()
+        self.generate_device(ws, 0, 1, 2)
+        return self._download_xy(ws, 0, 1)
+
+
+class EigenSketchingVectors(SketchingVectorsBase):
+    """
+    Sketching vectors spanning the dominant range of ``V^H - U^H`` (randomised range finder,
+    sk_core.py:410-462): ``X = qr((V^H - U^H) Omega)``, ``Omega`` complex normal, ``Y = U X``.
+    """
+
+    on_device = True
+
+    def generate_device(self, ws, x, y, tmp, circ=None, thetas=None) -> None:
+        assert isinstance(circ, ParametricCircuit)
+        assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
+        assert circ.dimension == self._target_mat.shape[0]
+        dim, m = circ.dimension, self.num_skvecs
+        omega = 1j * np.random.randn(dim, m)  # same draw order as the reference (:435-438)
+        omega += np.random.randn(dim, m)
+        ws.upload(x, omega)
+        ws.target_matmul(x, tmp, conj_transpose=True)  # U^H Omega
+        ws.apply(thetas, x, x, dagger=True)  # V^H Omega
+        ws.sub(x, tmp)
+        ws.orthonormalize(x, tmp)
+        ws.target_matmul(x, y)
+
+    def generate(self, circ=None, thetas=None):
+        ws = getattr(self, "_ws_own", None)
+        if ws is None or ws.circuit.signature() != _signature(circ):
+            ws = SvWorkspace(circ, num_slots=4, log2_cols=_log2(self.num_skvecs), as_generic=True)
+            ws.set_dense_target(self._target_mat)
+            self._ws_own = ws
+        self.generate_device(ws, 0, 1, 2, circ, thetas)
+        return self._download_xy(ws, 0, 1)
+
+
+def skvecs_generator(skvecs_type: str, num_skvecs: int, target_mat: np.ndarray) -> SketchingVectorsBase:
+    """Factory of the reference (sk_core.py:465-497): one of 'full', 'rand', 'alt', 'eigen'."""
+    assert isinstance(skvecs_type, str)
+    if skvecs_type == "full" or num_skvecs == target_mat.shape[0]:
+        return FullRangeSketchingVectors(target_mat)
+    if skvecs_type == "rand":
+        return RandomSketchingVectors(num_skvecs, target_mat)
+    if skvecs_type == "alt":
+        return AlternatingSketchingVectors(num_skvecs, target_mat)
+    if skvecs_type == "eigen":
+        return EigenSketchingVectors(num_skvecs, target_mat)
+    raise ValueError(
+        f"unknown type of sketching vectors generator, expects one of: "
+        f"['full', 'rand', 'alt', 'eigen'], got {skvecs_type}"
+    )
+
+
+def _signature(circ):
+    from ..engine import CircuitHandle
+
+    return CircuitHandle(circ, as_generic=True).signature()
 
 
 def _log2(m: int) -> int:
@@ -94,10 +223,13 @@ class SketchingObjectiveEx:
         self._stop_small_fobj = stop_small_fobj
         self._logger = logger
         self._ws = SvWorkspace(
-            circ, num_slots=3, device=device, log2_cols=_log2(skvecs.num_skvecs), as_generic=True
+            circ, num_slots=4 if skvecs.on_device else 3, device=device,
+            log2_cols=_log2(skvecs.num_skvecs), as_generic=True
         )
         if skvecs.is_full_range:
             self._ws.upload(_SLOT_Y, np.ascontiguousarray(self._target, dtype=np.complex128))
+        elif skvecs.on_device:
+            self._ws.set_dense_target(self._target)
         self._fobj_best = float(np.inf)
         self._thetas_best = np.zeros(circ.num_thetas)
         self._nit = 0
@@ -116,6 +248,8 @@ class SketchingObjectiveEx:
         ws, m = self._ws, self._skvecs.num_skvecs
         if self._skvecs.is_full_range:
             ws.set_identity(_SLOT_X)
+        elif self._skvecs.on_device:
+            self._skvecs.generate_device(ws, _SLOT_X, _SLOT_Y, _SLOT_TMP, self._circ, thetas)
         else:
             x, y = self._skvecs.generate(self._circ, thetas)
             ws.upload(_SLOT_X, x)

@@ -510,6 +510,57 @@ def measure_cd7(batch=64, layers=40, sweeps=3, device=0, with_cpu=True):
     return out
 
 
+def measure_sketch(n=12, m=64, layers=4, steps=3, device=0, with_cpu=True):
+    """
+    SURVEY 8(f) row 3: sketched unitary AQC with the 'eigen' generator (sk_core.py:410-462) at
+    n qubits, m sketching vectors: per evaluation U^H Omega and U X (d x d . d x m complex GEMMs on
+    the FP64 tensor pipe), thin QR, V^H apply and the gradient sweep on (d, m) matrices.
+    """
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200.model_sketching import sk_core
+    from aqc_research_b200.parametric_circuit import ParametricCircuit
+
+    d = 1 << n
+    circ = ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "spin", "full", (n - 1) * layers))
+    rng = np.random.RandomState(3)
+    q, r = np.linalg.qr(rng.randn(d, d) + 1j * rng.randn(d, d))
+    target = np.ascontiguousarray(q * (np.diag(r) / np.abs(np.diag(r))))
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    np.random.seed(17)
+    gen = sk_core.EigenSketchingVectors(m, target)
+    objv = sk_core.SketchingObjectiveEx(circ, gen, device=device)
+    ws = objv.workspace
+    objv.objective_and_gradient(th)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f, g = objv.objective_and_gradient(th)
+    dt = (time.perf_counter() - t0) / steps
+    ws.target_matmul(2, 3)
+    gemm_ms = ws.last_kernel_ms
+    ws.upload(2, rng.rand(d, m) + 1j * rng.rand(d, m))
+    ws.orthonormalize(2, 3)
+    qr_ms = ws.last_kernel_ms
+    flops = 8.0 * d * d * m
+    out = {
+        "workload": f"sketched AQC n={n}, {m} 'eigen' sketching vectors, spin ansatz {circ.num_blocks} blocks",
+        "value": 1.0 / dt, "unit": UNIT, "ms_per_eval": dt * 1e3,
+        "zgemm_ms": gemm_ms, "zgemm_dmma_tflops": flops / (gemm_ms * 1e-3) / 1e12,
+        "zgemm_frac_of_fp64_peak": flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "qr_ms": qr_ms,
+        "fobj": float(f),
+    }
+    if with_cpu:
+        x = rng.rand(d, m) + 1j * rng.rand(d, m)
+        t0 = time.perf_counter()
+        y = target @ x
+        qq, _ = np.linalg.qr(x)
+        dtc = time.perf_counter() - t0
+        del y, qq
+        out["cpu_baseline"] = {"value": dtc * 1e3, "unit": "ms for one U @ X + one thin QR (NumPy/LAPACK)",
+                               "cores": os.cpu_count(), "kind": "port",
+                               "sample": "generator linear algebra only (the reference adds a V^H sweep and the gradient)"}
+    return out
+
+
 def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
     """
     BASELINE.json configs[4], second half: ONE state vector over `world` GPUs (global-qubit
@@ -713,6 +764,7 @@ def main():
             line["extra_workloads"]["mps50"] = measure_mps(device=local_rank, with_cpu=not args.no_cpu_baseline)
             line["extra_workloads"]["mat7"] = measure_mat7(device=local_rank, with_cpu=not args.no_cpu_baseline)
             line["extra_workloads"]["cd7"] = measure_cd7(device=local_rank, with_cpu=not args.no_cpu_baseline)
+            line["extra_workloads"]["sketch12"] = measure_sketch(device=local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as ex:  # extras must never break the headline line
             line["extra_workloads"]["error"] = repr(ex)
     print(json.dumps(line), flush=True)

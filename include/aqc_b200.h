@@ -135,6 +135,22 @@ int aqc_sv_last_num_launches(const aqc_sv* sv);
  * workspace between start and stop (ms = device time between the two events). */
 int aqc_sv_timer_start(aqc_sv* sv);
 int aqc_sv_timer_stop(aqc_sv* sv, float* ms);
+/* Sketching-vector generators (sk_core.py:329-464) on a matrix workspace (d = 2^n rows,
+ * m = 2^log2_cols columns per slot, batch 1).  The dense target U (d x d, row-major complex128)
+ * lives in its own device buffer. */
+int aqc_sv_set_dense_target(aqc_sv* sv, const double* target);
+/* dst = U @ src (conj_transpose == 0) or U^H @ src: replaces np.dot(target, x_vecs) (sk_core.py:358,
+ * 461) and the U^H Omega product (:446-448); FP64 tensor-core (DMMA) GEMM. */
+int aqc_sv_target_matmul(aqc_sv* sv, int conj_transpose, int src_slot, int dst_slot);
+/* slot <- an orthonormal basis of its column space: replaces `x_vecs, _ = np.linalg.qr(...)`
+ * (sk_core.py:355-357, 458).  Shifted Cholesky-QR3 (three Gram / Cholesky / triangular-solve
+ * rounds, all GEMM shaped); the basis differs from LAPACK's by a unitary m x m factor, which the
+ * sketched objective and gradient are invariant to.  Fails for numerically rank-deficient input. */
+int aqc_sv_orthonormalize(aqc_sv* sv, int slot, int tmp_slot);
+/* dst -= src (sk_core.py:453). */
+int aqc_sv_sub(aqc_sv* sv, int dst_slot, int src_slot);
+/* X[:, i] = e_idx[i], Y[:, i] = U[:, idx[i]] (AlternatingSketchingVectors, sk_core.py:398-404). */
+int aqc_sv_gather_target_columns(aqc_sv* sv, const int64_t* idx, int count, int x_slot, int y_slot);
 /* Coordinate descent for unitary AQC.
  * Replaces: coord_descent_single_sweep (core_op_matrix.py:765-917), called num_sweeps times.
  * The workspace must be a matrix workspace with log2_cols == num_qubits (target 2^n x 2^n in

@@ -419,3 +419,50 @@ def coord_descent_sweep(circ, thetas: np.ndarray, target: np.ndarray):
         step(t, ry, PAULI_Y, th2[i], 2)
         step(t, make_rs, pauli_s, th2[i], 3)
     return float(1 - np.abs(np.vdot(w, z) / dim) ** 2), th
+
+
+# ------------------------------------------------------------------------------------------------
+# sketching-vector generators: sk_core.py:329-464, same global-RNG call order
+# ------------------------------------------------------------------------------------------------
+class SketchOracle:
+    """
+    NumPy restatement of Random / Alternating / Eigen SketchingVectors.generate followed by
+    SketchingObjectiveEx.objective_and_gradient (sk_core.py:167-222).  Draws from the GLOBAL NumPy
+    RNG in the reference's order, so after ``np.random.seed(s)`` it sees the same random numbers.
+    """
+
+    def __init__(self, kind: str, num_skvecs: int, target: np.ndarray):
+        self.kind, self.m, self.target = kind, int(num_skvecs), np.asarray(target, dtype=C128)
+        self.dim = self.target.shape[0]
+        if kind == "alt":  # sk_core.py:375-379
+            self.offset = 0
+            self.indices = np.random.permutation(self.dim)
+
+    def generate(self, circ=None, thetas=None):
+        d, m, u = self.dim, self.m, self.target
+        if self.kind == "rand":  # :347-359
+            x, _ = np.linalg.qr(np.random.rand(d, m) + 1j * np.random.rand(d, m))
+        elif self.kind == "alt":  # :381-407
+            if self.offset >= d:
+                self.offset = 0
+                self.indices = np.random.permutation(d)
+            idx = self.indices[self.offset : self.offset + m]
+            x = np.zeros((d, m), dtype=C128)
+            x[idx, np.arange(idx.size)] = 1
+            self.offset += m
+        elif self.kind == "eigen":  # :424-462
+            omega = 1j * np.random.randn(d, m)
+            omega = omega + np.random.randn(d, m)
+            vh_om = apply_v(circ, thetas, omega.ravel(), dagger=True, ncols=m).reshape(d, m)
+            x, _ = np.linalg.qr(vh_om - u.conj().T @ omega)
+        else:
+            raise ValueError(self.kind)
+        return x, u @ x
+
+    def value_and_grad(self, circ, thetas):
+        x, y = self.generate(circ, thetas)
+        m = self.m
+        vh_y = apply_v(circ, thetas, y.ravel(), dagger=True, ncols=m)
+        f = 1.0 - np.real(np.vdot(x.ravel(), vh_y)) / m
+        g = grad_sweep(circ, thetas, x.ravel(), vh_y, ncols=m)
+        return float(f), -np.real(g) / m

@@ -266,6 +266,40 @@ def cd_cases():
     print("cd_cases:", case)
 
 
+def sketch_cases():
+    """rand / alt / eigen sketching generators + SketchingObjectiveEx (sk_core.py:167-222, 329-464)."""
+    from scipy.stats import unitary_group
+
+    out = {}
+    case = 0
+    for n, m, kind, ent in ((3, 2, "rand", "cx"), (4, 4, "alt", "cz"), (4, 8, "eigen", "cx"), (5, 4, "rand", "cp"),
+                            (5, 8, "alt", "cx"), (5, 16, "eigen", "cz"), (6, 8, "eigen", "cx")):
+        seed = 4242 + case
+        np.random.seed(seed)
+        circ, blocks = make_circuit(ent, n, 3 * n)
+        target = unitary_group.rvs(2**n, random_state=seed).astype(np.complex128)
+        ths = [R.utils.rand_thetas(circ.num_thetas) for _ in range(3)]
+        np.random.seed(seed + 1)  # the stream the generator sees (the test re-seeds the same way)
+        gen = R.sk_core.skvecs_generator(kind, m, target)
+        objv = R.sk_core.SketchingObjectiveEx(circ, gen)
+        fs, gs = [], []
+        for th in ths:
+            f, g = objv.objective_and_gradient(th)
+            fs.append(f)
+            gs.append(g.copy())
+        pre = f"c{case}_"
+        out[pre + "meta"] = np.array([n, m, ["rand", "alt", "eigen"].index(kind), ["cx", "cz", "cp"].index(ent), seed + 1])
+        out[pre + "blocks"] = blocks
+        out[pre + "target"] = target
+        out[pre + "thetas"] = np.array(ths)
+        out[pre + "f"] = np.array(fs)
+        out[pre + "grad"] = np.array(gs)
+        case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "sketch_cases.npz"), **out)
+    print("sketch_cases:", case)
+
+
 if __name__ == "__main__":
     sv_cases()
     mat_cases()
@@ -273,3 +307,4 @@ if __name__ == "__main__":
     mps_cases()
     trotter_and_lbfgs()
     cd_cases()
+    sketch_cases()

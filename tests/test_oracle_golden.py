@@ -175,3 +175,18 @@ def test_coord_descent_golden():
             f, th_new = O.coord_descent_sweep(circ, ths[s], g[p + "target"])
             assert abs(f - fs[s]) < 1e-11, (c, s, f, fs[s])
             assert rel(th_new, ths[s + 1]) < 1e-11, (c, s)
+
+
+def test_sketching_generators_golden():
+    """SketchOracle (same global-RNG call order) == reference generators + SketchingObjectiveEx."""
+    g = load("sketch_cases.npz")
+    for c in range(int(g["num_cases"])):
+        p = f"c{c}_"
+        n, m, kind, ent, seed = [int(v) for v in g[p + "meta"]]
+        circ = ParametricCircuit(n, ["cx", "cz", "cp"][ent], g[p + "blocks"])
+        np.random.seed(seed)
+        orc = O.SketchOracle(["rand", "alt", "eigen"][kind], m, g[p + "target"])
+        for s, th in enumerate(g[p + "thetas"]):
+            f, grad = orc.value_and_grad(circ, th)
+            assert abs(f - g[p + "f"][s]) < 1e-12, (c, s)
+            assert rel(grad, g[p + "grad"][s]) < 1e-11, (c, s)
