@@ -113,7 +113,8 @@ struct aqc_mps {
   double2* d_gate = nullptr;    // [maxtasks][16] 4x4 gate of each task of the current step
   double2* d_theta0 = nullptr;  // [2][maxtasks][4][C][C]  two-site tensors before the gate
   double2* d_work = nullptr;    // [2][maxtasks][2C][2C]   SVD working matrices (column-major)
-  double2* d_vmat = nullptr;    // [2][maxtasks][2C][2C]   right rotations
+  double2* d_vmat = nullptr;    // [2][maxtasks][2C][2C]   right singular vectors of the kept columns
+  double2* d_work0 = nullptr;   // [2][maxtasks][2C][2C]   working matrices before the rotations
   double2* d_envL = nullptr;    // [n+1][C][C]
   double2* d_envR = nullptr;    // [n+1][C][C]
   double2* d_rho = nullptr;     // [maxtasks][16]
@@ -351,6 +352,7 @@ struct ThetaArgs {
   const double2* gate;  // [task][16] or nullptr (identity)
   double2* theta0;      // [state][maxtasks][4][C][C] or nullptr
   double2* work;        // [state][maxtasks][2C*2C] or nullptr
+  double2* work0;       // same layout: untouched copy of the working matrix (V is recovered from it)
   int C, maxtasks, single_site;
 };
 
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(512) mps_theta_kernel(const ThetaArgs A) {
   const bool transposed = M < N;
   double2* T0 = A.theta0 ? A.theta0 + ((size_t)s * A.maxtasks + t) * 4 * C * C : nullptr;
   double2* W = A.work ? A.work + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD : nullptr;
+  double2* W0 = A.work ? A.work0 + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD : nullptr;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int al = grp * 8 + r;
@@ -445,10 +448,13 @@ __global__ void __launch_bounds__(512) mps_theta_kernel(const ThetaArgs A) {
         }
         o.x *= ll, o.y *= ll;
         const int row = (c & 1) * cl + al, col = (c >> 1) * cr + g;
-        if (!transposed)
+        if (!transposed) {
           W[row + (size_t)col * LD] = o;
-        else
+          W0[row + (size_t)col * LD] = o;
+        } else {
           W[col + (size_t)row * LD] = make_double2(o.x, -o.y);
+          W0[col + (size_t)row * LD] = make_double2(o.x, -o.y);
+        }
       }
     }
   }
@@ -461,7 +467,8 @@ struct SvdArgs {
   StateMut st[2];
   const MpsTask* tasks;
   double2* work;
-  double2* vmat;
+  const double2* work0;  // the working matrix before the rotations
+  double2* vmat;         // right singular vectors of the KEPT columns (compacted by rank)
   int C, maxtasks, chi_max;
   double trunc_thr;
   int* sweeps;  // [state][maxtasks] Jacobi sweeps used (diagnostics)
@@ -469,7 +476,7 @@ struct SvdArgs {
 };
 
 __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
-  __shared__ double s_rot[16 * 28 * 3];
+  __shared__ double2 s_ga[8 * 2 * kMaxChi], s_gb[8 * kMaxChi];  // k-slices of B0 and of the kept columns of B
   __shared__ double s_sig[2 * kMaxChi];
   __shared__ int s_order[2 * kMaxChi];
   __shared__ int s_keep, s_total;
@@ -491,12 +498,9 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   const int Cc = transposed ? M : N;  // columns (<= rows)
   double2* B = A.work + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
   double2* V = A.vmat + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
+  const double2* B0 = A.work0 + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-  for (int i = tid + crank * blockDim.x; i < Cc * Cc; i += blockDim.x * csize) {
-    const int r = i % Cc, c = i / Cc;
-    V[r + (size_t)c * LD] = make_double2(r == c ? 1.0 : 0.0, 0.0);
-  }
   int* conv = A.conv + ((size_t)s * A.maxtasks + t) * 32;
   if (crank == 0 && tid < 32) conv[tid] = 0;
   __threadfence();
@@ -515,7 +519,6 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   // a tighter value sits below the rounding noise of the inner product and never converges
   const double tol = 2.0 * sqrt((double)R) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
-  double* rot = s_rot + warp * (28 * 3);
   for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
     const int nrounds = (ne > 1) ? ne - 1 : 1;
@@ -616,10 +619,6 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
           const double my_cs = doit ? csl : 1.0;
           const double my_sr = doit ? csl * kappa * gr : 0.0;
           const double my_si = doit ? csl * kappa * gi : 0.0;
-          if ((lane & 7) == 0) {
-            double* rr = rot + (ir * 4 + (lane >> 3)) * 3;
-            rr[0] = my_cs, rr[1] = my_sr, rr[2] = my_si;
-          }
 #pragma unroll
           for (int ip = 0; ip < 4; ++ip) {
             const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
@@ -651,46 +650,6 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
           for (int e = 0; e < 4; ++e) {
             const int r = lane + 32 * e;
             if (col[c] < Cc && r < R) B[r + (size_t)col[c] * LD] = x[c][e];
-          }
-        __syncwarp();
-        // replay on V
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = lane + 32 * e;
-            x[c][e] = (col[c] < Cc && r < Cc) ? V[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
-          }
-#pragma unroll
-        for (int ir = 0; ir < 7; ++ir) {
-#pragma unroll
-          for (int ip = 0; ip < 4; ++ip) {
-            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
-            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
-            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
-            const double* rr = rot + (ir * 4 + ip) * 3;
-            const double cs = rr[0], sr = rr[1], si = rr[2];
-            if (sr != 0.0 || si != 0.0) {
-              const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const double2 u = x[pa][e], v = x[pb][e];
-                double2 nu = make_double2(cs * u.x, cs * u.y);
-                cfma(nu, fm, v);
-                double2 nv = make_double2(cs * v.x, cs * v.y);
-                cfma(nv, fp, u);
-                x[pa][e] = nu;
-                x[pb][e] = nv;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = lane + 32 * e;
-            if (col[c] < Cc && r < Cc) V[r + (size_t)col[c] * LD] = x[c][e];
           }
         __syncwarp();
       }
@@ -758,6 +717,56 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   __syncthreads();
   const int keep = s_keep;
   const double scale = s_scale;
+  // Right singular vectors of the KEPT columns, compacted by rank: after convergence B = U Sigma, so
+  // V[:, r] = B0^H B[:, j_r] / sigma_{j_r}^2 -- one (Cc x R) x (R x keep) product instead of
+  // replaying every rotation on an accumulated V (37 % of the Jacobi flops and half of its traffic).
+  {
+    const int tr = tid & 31, tc = tid >> 5;  // rows 4 tr .. 4 tr + 3, columns 8 tc .. 8 tc + 7
+    double2 acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[i][c] = make_double2(0.0, 0.0);
+    for (int k0 = 0; k0 < R; k0 += 8) {
+      for (int e = tid; e < 8 * 2 * kMaxChi; e += 256) {
+        const int kk = e & 7, r = e >> 3;
+        s_ga[kk * 2 * kMaxChi + r] =
+            (r < Cc && k0 + kk < R) ? B0[(k0 + kk) + (size_t)r * LD] : make_double2(0.0, 0.0);
+      }
+      for (int e = tid; e < 8 * kMaxChi; e += 256) {
+        const int kk = e & 7, jj = e >> 3;
+        s_gb[kk * kMaxChi + jj] =
+            (jj < keep && k0 + kk < R) ? B[(k0 + kk) + (size_t)s_order[jj] * LD] : make_double2(0.0, 0.0);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        double2 a[4], b[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = s_ga[kk * 2 * kMaxChi + 4 * tr + i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) b[c] = s_gb[kk * kMaxChi + 8 * tc + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) cfma_conj(acc[i][c], a[i], b[c]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int jj = 8 * tc + c;
+      if (jj >= keep) continue;
+      const double sg = s_sig[s_order[jj]];
+      const double inv = sg > 0.0 ? 1.0 / (sg * sg) : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * tr + i;
+        if (r < Cc) V[r + (size_t)jj * LD] = make_double2(acc[i][c].x * inv, acc[i][c].y * inv);
+      }
+    }
+  }
+  __syncthreads();
   // write lambda (bond k+1), dims, Gamma_k, Gamma_{k+1}
   double* lamM = S.lam + (size_t)(k + 1) * C;
   const double* lamL = S.lam + (size_t)k * C;
@@ -777,7 +786,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
       const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
       u = make_double2(b.x * inv, b.y * inv);
     } else {
-      u = V[row + (size_t)j * LD];
+      u = V[row + (size_t)r * LD];
     }
     const int b1 = row / cl, al = row % cl;
     const double il = 1.0 / lamL[al];
@@ -790,7 +799,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     const double sg = s_sig[j];
     double2 v;
     if (!transposed) {
-      v = V[col + (size_t)j * LD];
+      v = V[col + (size_t)r * LD];
     } else {
       const double2 b = B[col + (size_t)j * LD];
       const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
@@ -1106,7 +1115,7 @@ extern "C" void aqc_mps_destroy(aqc_mps* m) {
     if (s.dims) cudaFree(s.dims);
   }
   for (void* p : {(void*)m->d_thetas, (void*)m->d_gate, (void*)m->d_theta0, (void*)m->d_work,
-                  (void*)m->d_vmat, (void*)m->d_envL, (void*)m->d_envR, (void*)m->d_rho,
+                  (void*)m->d_vmat, (void*)m->d_work0, (void*)m->d_envL, (void*)m->d_envR, (void*)m->d_rho,
                   (void*)m->d_gacc, (void*)m->d_small, (void*)m->d_idx, (void*)m->fwd.d_tasks,
                   (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env, (void*)m->d_sweeps, (void*)m->d_conv})
     if (p) cudaFree(p);
@@ -1163,6 +1172,7 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   alloc((void**)&m->d_theta0, 2 * mt * 4 * C * C * sizeof(double2));
   alloc((void**)&m->d_work, 2 * mt * 4 * C * C * sizeof(double2));
   alloc((void**)&m->d_vmat, 2 * mt * 4 * C * C * sizeof(double2));
+  alloc((void**)&m->d_work0, 2 * mt * 4 * C * C * sizeof(double2));
   alloc((void**)&m->d_envL, (size_t)(m->n + 1) * C * C * sizeof(double2));
   alloc((void**)&m->d_envR, (size_t)(m->n + 1) * C * C * sizeof(double2));
   alloc((void**)&m->d_rho, mt * 16 * sizeof(double2));
@@ -1308,6 +1318,7 @@ static int run_step_theta(aqc_mps* m, const MpsProgram& prog, const MpsStep& st,
   ta.gate = with_gate ? m->d_gate : nullptr;
   ta.theta0 = keep0 ? m->d_theta0 : nullptr;
   ta.work = with_work ? m->d_work : nullptr;
+  ta.work0 = with_work ? m->d_work0 : nullptr;
   ta.C = m->C;
   ta.maxtasks = m->maxtasks;
   ta.single_site = 0;
@@ -1323,6 +1334,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   for (int s = 0; s < nstates; ++s) sa.st[s] = mut(m, slots[s]);
   sa.tasks = prog.d_tasks + st.task0;
   sa.work = m->d_work;
+  sa.work0 = m->d_work0;
   sa.vmat = m->d_vmat;
   sa.C = m->C;
   sa.maxtasks = m->maxtasks;

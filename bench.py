@@ -636,7 +636,7 @@ def run_sharded_bench(args):
                        "amplitudes_per_gpu": 2**args.shard_qubits, "parallelism": f"one state over {world} GPUs (global-qubit sharding)",
                        "epochs": out["epochs"], "p2p_exchange": out["p2p_exchange"],
                        "l2": "inputs larger than L2"},
-            "roofline": {"bound": "hbm", "kernel": "pass_kernel<2,cx,fwd> (gradient tile pass)",
+            "roofline": {"bound": "hbm", "kernel": "dense_pass_kernel<2> (gradient tile pass) + exchange_kernel (NVLink block transpose)",
                          "achieved": 96.0 * 2**n * P * value / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": 96.0 * 2**n * P * value / 1e9 / world / peak, "traffic": None,
                          "peak_source": peak_src,
