@@ -31,6 +31,10 @@ def is_tuple(x, cond: bool = True) -> bool:
     return isinstance(x, tuple) and bool(cond)
 
 
+def is_list(x, cond: bool = True) -> bool:
+    return isinstance(x, list) and bool(cond)
+
+
 def is_dict(x, cond: bool = True) -> bool:
     return isinstance(x, dict) and bool(cond)
 
