@@ -552,61 +552,91 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
             const int r = lane + 32 * e;
             x[c][e] = (col[c] < Cc && r < R) ? B[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
           }
+        // squared column norms of the block: computed once per visit, then tracked through the
+        // rotations (|p'|^2 = |p|^2 - t|g|, |q'|^2 = |q|^2 + t|g| with t|g| = kappa |g|^2), so the inner
+        // rounds only need the cross products <p|q>
+        double nrm[8];
+        {
+          double pn[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc = fma(x[c][e].x, x[c][e].x, fma(x[c][e].y, x[c][e].y, acc));
+            pn[c] = acc;
+          }
+          double w4[4], w2[2];
+          const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = u16 ? pn[i] : pn[i + 4];
+            const double keep = u16 ? pn[i + 4] : pn[i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = u8 ? w4[i] : w4[i + 2];
+            const double keep = u8 ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          const double send = u4 ? w2[0] : w2[1];
+          const double keep = u4 ? w2[1] : w2[0];
+          double red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          red += __shfl_xor_sync(0xffffffffu, red, 2);
+          red += __shfl_xor_sync(0xffffffffu, red, 1);
+          // lane L holds column ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            nrm[c] = __shfl_sync(0xffffffffu, red, ((c >> 2) & 1) * 16 + ((c >> 1) & 1) * 8 + (c & 1) * 4);
+        }
         bool any = false;
 #pragma unroll
         for (int ir = 0; ir < 7; ++ir) {
-          // the 4 disjoint pairs of this inner round: partial Gram entries of all four ...
-          double pv[16];
+          // the 4 disjoint pairs of this inner round: partial cross products of all four ...
+          double pv[8];
+          double al = 0.0, be = 0.0;
 #pragma unroll
           for (int ip = 0; ip < 4; ++ip) {
             const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
             const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
             const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
-            double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+            double gr = 0.0, gi = 0.0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const double2 u = x[pa][e], v = x[pb][e];
-              al = fma(u.x, u.x, fma(u.y, u.y, al));
-              be = fma(v.x, v.x, fma(v.y, v.y, be));
               gr = fma(u.x, v.x, fma(u.y, v.y, gr));   // Re conj(p) q
               gi = fma(u.x, v.y, fma(-u.y, v.x, gi));  // Im conj(p) q
             }
-            pv[ip * 4 + 0] = al, pv[ip * 4 + 1] = be, pv[ip * 4 + 2] = gr, pv[ip * 4 + 3] = gi;
+            pv[ip * 2 + 0] = gr, pv[ip * 2 + 1] = gi;
+            if ((lane >> 3) == ip) al = nrm[pa], be = nrm[pb];
           }
-          // ... reduced over the warp with a transposing butterfly (16 + 1 shuffles): afterwards
-          // lane L holds entry ((L >> 1) & 15), i.e. the 8 lanes of group ip = L >> 3 hold pair ip
+          // ... reduced over the warp with a transposing butterfly (7 + 2 shuffles): afterwards
+          // lane L holds entry (L >> 2) & 7, i.e. the 8 lanes of group ip = L >> 3 hold pair ip
           double red;
           {
-            double w8[8], w4[4], w2[2];
-            const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const double send = u16 ? pv[i] : pv[i + 8];
-              const double keep = u16 ? pv[i + 8] : pv[i];
-              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+            double w4[4], w2[2];
+            const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const double send = u8 ? w8[i] : w8[i + 4];
-              const double keep = u8 ? w8[i + 4] : w8[i];
-              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              const double send = u16 ? pv[i] : pv[i + 4];
+              const double keep = u16 ? pv[i + 4] : pv[i];
+              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const double send = u4 ? w4[i] : w4[i + 2];
-              const double keep = u4 ? w4[i + 2] : w4[i];
-              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              const double send = u8 ? w4[i] : w4[i + 2];
+              const double keep = u8 ? w4[i + 2] : w4[i];
+              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
-            const double send = u2 ? w2[0] : w2[1];
-            const double keep = u2 ? w2[1] : w2[0];
-            red = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            const double send = u4 ? w2[0] : w2[1];
+            const double keep = u4 ? w2[1] : w2[0];
+            red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            red += __shfl_xor_sync(0xffffffffu, red, 2);
             red += __shfl_xor_sync(0xffffffffu, red, 1);
           }
           const int gbase = lane & 0x18;
-          const double al = __shfl_sync(0xffffffffu, red, gbase | 0);
-          const double be = __shfl_sync(0xffffffffu, red, gbase | 2);
-          const double gr = __shfl_sync(0xffffffffu, red, gbase | 4);
-          const double gi = __shfl_sync(0xffffffffu, red, gbase | 6);
+          const double gr = __shfl_sync(0xffffffffu, red, gbase | 0);
+          const double gi = __shfl_sync(0xffffffffu, red, gbase | 4);
           // every 8-lane group computes the rotation of ITS pair (4 pairs in parallel):
           // tan t = 2|g| sign(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = |q|^2 - |p|^2; the phase
           // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
@@ -616,6 +646,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
           const double h = sqrt(fma(d, d, 4.0 * g2));
           const double kappa = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);
           const double csl = rsqrt(fma(kappa * kappa, g2, 1.0));
+          const double my_dn = doit ? kappa * g2 : 0.0;
           const double my_cs = doit ? csl : 1.0;
           const double my_sr = doit ? csl * kappa * gr : 0.0;
           const double my_si = doit ? csl * kappa * gi : 0.0;
@@ -627,6 +658,9 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
             const double cs = __shfl_sync(0xffffffffu, my_cs, ip << 3);
             const double sr = __shfl_sync(0xffffffffu, my_sr, ip << 3);
             const double si = __shfl_sync(0xffffffffu, my_si, ip << 3);
+            const double dn = __shfl_sync(0xffffffffu, my_dn, ip << 3);
+            nrm[pa] -= dn;
+            nrm[pb] += dn;
             any = any || (sr != 0.0) || (si != 0.0);
             // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q   (identity if not rotated)
             const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
