@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
   long long hs[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) hs[k] = (8 + k < tb) ? (1ll << A.pd.bitpos[8 + k]) : 0ll;
-  const bool fast = (tb == 11) || (NVEC == 1 && tb == 12);
+  const bool fast = (tb == 10) || (tb == 11) || (NVEC == 1 && tb == 12);
   if (!fast) {
     if (tid < 16) {
       long long h = 0;
@@ -369,6 +369,8 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
       const double2* __restrict__ src = A.src[v] + boff;
       if (tb == 11) {
         tile_copy<8, true>(sm_u32 + v * vbytes, s0x16, src + lo_off, nullptr, hs);
+      } else if (tb == 10) {
+        tile_copy<4, true>(sm_u32 + v * vbytes, s0x16, src + lo_off, nullptr, hs);
       } else if (NVEC == 1 && tb == 12) {
         tile_copy<16, true>(sm_u32 + v * vbytes, s0x16, src + lo_off, nullptr, hs);
       } else {
@@ -463,6 +465,8 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
     double2* __restrict__ dst = A.dst[v] + boff;
     if (tb == 11) {
       tile_copy<8, false>(sm_u32 + v * vbytes, s0x16, nullptr, dst + lo_off, hs);
+    } else if (tb == 10) {
+      tile_copy<4, false>(sm_u32 + v * vbytes, s0x16, nullptr, dst + lo_off, hs);
     } else if (NVEC == 1 && tb == 12) {
       tile_copy<16, false>(sm_u32 + v * vbytes, s0x16, nullptr, dst + lo_off, hs);
     } else {

@@ -31,4 +31,9 @@ for n, chi, L in cases:
     print(f"n={n} chi={chi} L={L} T={circ.num_thetas} target bonds max {max(dims)} (build {t_target*1e3:.1f} ms) "
           f"w bonds max {max(wd)} | obj {ms_o:.2f} ms ({l_o} launches) grad {ms_g:.2f} ms ({l_g} launches) "
           f"wall {wall*1e3:.1f} ms -> {1/wall:.3f} evals/s; |g|={np.linalg.norm(g):.3e} norm z0={abs(ws.dot(1,1)):.6f}", flush=True)
+    import ctypes as ct
+    from aqc_research_b200 import _lib
+    buf = np.zeros(256, dtype=np.int32)
+    cnt = _lib.load().aqc_mps_debug_sweeps(ws.handle, buf.ctypes.data_as(_lib.c_int32_p), buf.size)
+    print('   Jacobi sweeps of the last step:', sorted(set(buf[:cnt].tolist())), flush=True)
     ws.close()
