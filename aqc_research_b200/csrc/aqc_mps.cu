@@ -124,6 +124,7 @@ struct aqc_mps {
   int* d_sweeps = nullptr;     // [2][maxtasks]
   int* d_conv = nullptr;       // [2][maxtasks][32]
   int num_sms = 148;
+  bool theta_scalar = false;  // AQC_MPS_THETA=scalar: thread-per-column contraction instead of the DMMA GEMM
   double* h_pinned = nullptr;
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
@@ -458,6 +459,145 @@ __global__ void __launch_bounds__(512) mps_theta_kernel(const ThetaArgs A) {
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel: the same two-site tensor as a tensor-core GEMM (chi >= 32 makes it a genuine dense
+// complex contraction):  theta[(b1, alpha), (b2, gamma)] = sum_beta GammaA[b1][alpha, beta]
+// lambda_m[beta] GammaB[b2][beta, gamma], real form on mma.sync.m8n8k4.f64 (DMMA).
+// CTA tile: 32 alpha x 32 gamma x the four (b1, b2) combinations = 64 x 64 outputs; warp w owns
+// alpha0 + 4w .. 4w + 3 for BOTH b1 (fragment rows 0-3 / 4-7), so the 4x4 gate on (b1, b2) needs one
+// shuffle (lane ^ 16) and no staging.  grid (ntasks * 4, nstates), 256 threads.
+// ------------------------------------------------------------------------------------------
+constexpr int kThLdA = 20, kThLdB = 68;
+
+__device__ __forceinline__ void mps_dmma884(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) mps_theta_dmma_kernel(const ThetaArgs A) {
+  __shared__ double sAr[64 * kThLdA], sAi[64 * kThLdA];
+  __shared__ double sBr[16 * kThLdB], sBi[16 * kThLdB];
+  const int t = blockIdx.x >> 2, tile = blockIdx.x & 3, s = blockIdx.y, C = A.C;
+  const MpsTask tk = A.tasks[t];
+  const StateView S = A.st[s];
+  const int k = tk.site;
+  const int cl = S.dims[k], cm = S.dims[k + 1], cr = S.dims[k + 2];
+  const int al0 = (tile & 1) * 32, ga0 = (tile >> 1) * 32;
+  if (al0 >= cl || ga0 >= cr) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double2* Ga = S.gam + (size_t)k * 2 * C * C;
+  const double2* Gb = S.gam + (size_t)(k + 1) * 2 * C * C;
+  const double* lamL = S.lam + (size_t)k * C;
+  const double* lamM = S.lam + (size_t)(k + 1) * C;
+  const double* lamR = S.lam + (size_t)(k + 2) * C;
+  double cre[8][2], cim[8][2];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) cre[q][0] = cre[q][1] = cim[q][0] = cim[q][1] = 0.0;
+
+  for (int be0 = 0; be0 < cm; be0 += 16) {
+    // A planes: smem row i = 8 w + ri  <->  b1 = ri >> 2, alpha = al0 + 4 w + (ri & 3)
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int kk = e & 15, i = e >> 4;
+      const int b1 = (i & 7) >> 2, al = al0 + 4 * (i >> 3) + (i & 3);
+      double2 v = make_double2(0.0, 0.0);
+      if (al < cl && be0 + kk < cm) v = Ga[((size_t)b1 * C + al) * C + be0 + kk];
+      sAr[i * kThLdA + kk] = v.x;
+      sAi[i * kThLdA + kk] = v.y;
+    }
+    // B planes: column j  <->  b2 = j >> 5, gamma = ga0 + (j & 31); lambda_m folded in
+    for (int e = tid; e < 16 * 64; e += 256) {
+      const int j = e & 63, kk = e >> 6;
+      const int b2 = j >> 5, ga = ga0 + (j & 31);
+      double2 v = make_double2(0.0, 0.0);
+      if (ga < cr && be0 + kk < cm) {
+        v = Gb[((size_t)b2 * C + be0 + kk) * C + ga];
+        const double lm = lamM[be0 + kk];
+        v.x *= lm, v.y *= lm;
+      }
+      sBr[kk * kThLdB + j] = v.x;
+      sBi[kk * kThLdB + j] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 16; ks += 4) {
+      const int ai = (8 * warp + (lane >> 2)) * kThLdA + ks + (lane & 3);
+      const double ar = sAr[ai], aim = sAi[ai], nai = -aim;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int bi = (ks + (lane & 3)) * kThLdB + 8 * q + (lane >> 2);
+        const double br = sBr[bi], bim = sBi[bi];
+        mps_dmma884(cre[q][0], cre[q][1], ar, br);
+        mps_dmma884(cre[q][0], cre[q][1], nai, bim);
+        mps_dmma884(cim[q][0], cim[q][1], ar, bim);
+        mps_dmma884(cim[q][0], cim[q][1], aim, br);
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: lane holds theta for (b1 = ri >> 2, alpha) and, per n-tile q, (b2 = q >> 2, two gammas)
+  const int ri = lane >> 2, b1 = ri >> 2, al = al0 + 4 * warp + (ri & 3);
+  const int M = 2 * cl, N = 2 * cr, LD = 2 * C;
+  const bool transposed = M < N;
+  double2* T0 = A.theta0 ? A.theta0 + ((size_t)s * A.maxtasks + t) * 4 * C * C : nullptr;
+  double2* W = A.work ? A.work + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD : nullptr;
+  double2* W0 = A.work ? A.work0 + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD : nullptr;
+  // gate rows of the two output combinations this lane produces: c' = (b2' << 1) | b1
+  double2 Grow[2][4];
+#pragma unroll
+  for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      Grow[b2][d] = A.gate ? A.gate[(size_t)t * 16 + ((b2 << 1) | b1) * 4 + d]
+                           : make_double2((d == ((b2 << 1) | b1)) ? 1.0 : 0.0, 0.0);
+  const double ll = (al < cl) ? lamL[al] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ga = ga0 + 8 * q + 2 * (lane & 3) + h;
+      const double lr = (ga < cr) ? lamR[ga] : 0.0;
+      double2 mine[2], other[2];  // index: b2
+      mine[0] = make_double2(cre[q][h] * lr, cim[q][h] * lr);
+      mine[1] = make_double2(cre[q + 4][h] * lr, cim[q + 4][h] * lr);
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2) {
+        other[b2].x = __shfl_xor_sync(0xffffffffu, mine[b2].x, 16);
+        other[b2].y = __shfl_xor_sync(0xffffffffu, mine[b2].y, 16);
+      }
+      if (al >= cl || ga >= cr) continue;
+      double2 v[4];  // quad index c = (b2 << 1) | b1
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2) {
+        v[(b2 << 1) | 0] = b1 ? other[b2] : mine[b2];
+        v[(b2 << 1) | 1] = b1 ? mine[b2] : other[b2];
+      }
+      if (T0) {
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) T0[((size_t)((b2 << 1) | b1) * C + al) * C + ga] = mine[b2];
+      }
+      if (W) {
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const int c = (b2 << 1) | b1;  // the two output combinations with b1' = this lane's b1
+          double2 o = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) cfma(o, Grow[b2][d], v[d]);
+          o.x *= ll, o.y *= ll;
+          const int row = (c & 1) * cl + al, col = (c >> 1) * cr + ga;
+          if (!transposed) {
+            W[row + (size_t)col * LD] = o;
+            W0[row + (size_t)col * LD] = o;
+          } else {
+            W[col + (size_t)row * LD] = make_double2(o.x, -o.y);
+            W0[col + (size_t)row * LD] = make_double2(o.x, -o.y);
+          }
+        }
+      }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1216,6 +1356,10 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   alloc((void**)&m->d_sweeps, 2 * mt * sizeof(int));
   alloc((void**)&m->d_conv, 2 * mt * 32 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
+  {
+    const char* th = getenv("AQC_MPS_THETA");
+    m->theta_scalar = th && std::string(th) == "scalar";
+  }
   for (MpsProgram* p : {&m->fwd, &m->dag}) {
     alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
     if (e == cudaSuccess)
@@ -1356,7 +1500,10 @@ static int run_step_theta(aqc_mps* m, const MpsProgram& prog, const MpsStep& st,
   ta.C = m->C;
   ta.maxtasks = m->maxtasks;
   ta.single_site = 0;
-  mps_theta_kernel<<<dim3(st.ntasks, nstates), 512, 0, m->stream>>>(ta);
+  if (m->C >= 32 && !m->theta_scalar)
+    mps_theta_dmma_kernel<<<dim3(st.ntasks * 4, nstates), 256, 0, m->stream>>>(ta);
+  else
+    mps_theta_kernel<<<dim3(st.ntasks, nstates), 512, 0, m->stream>>>(ta);
   MCU(cudaGetLastError());
   m->last_launches++;
   return AQC_OK;
