@@ -62,7 +62,8 @@ def measured_peaks():
 # DRAM bytes per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum; summaries under profiles/): workload -> bytes
 NCU_TRAFFIC = {
-    "sv28": 17.12e9,  # profiles/r01_ncu_dense_grad_sv28.md: one read + one write of w and z (4 x 4.29 GB)
+    "sv28": 17.12e9,  # profiles/r01_ncu_dense_sv28.md: one read + one write of w and z (8.59 + 8.53 GB)
+    "sv20": 33.6e6,   # same file, n = 20 paragraph: one read of w and z; the L2 absorbs the write-back
 }
 FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (scripts/ubench_fp64.cu, profiles/r01_ubench_fp64.txt);
 #                          DMMA (mma.sync.m8n8k4.f64) and DFMA share this one FP64 pipe
