@@ -124,6 +124,7 @@ struct aqc_mps {
   int* d_sweeps = nullptr;     // [2][maxtasks]
   int* d_conv = nullptr;       // [2][maxtasks][32]
   int num_sms = 148;
+  bool svd_precond = true;    // AQC_MPS_SVD=plain: Jacobi directly on the working matrix
   bool theta_scalar = false;  // AQC_MPS_THETA=scalar: thread-per-column contraction instead of the DMMA GEMM
   double* h_pinned = nullptr;
   size_t pinned_cap = 0;
@@ -613,6 +614,7 @@ struct SvdArgs {
   double trunc_thr;
   int* sweeps;  // [state][maxtasks] Jacobi sweeps used (diagnostics)
   int* conv;    // [state][maxtasks][32] rotations counted per sweep (cluster-wide convergence)
+  int precond;  // 1: Householder QR first, Jacobi on R^H (Drmac-Veselic preconditioning)
 };
 
 __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
@@ -621,6 +623,8 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   __shared__ int s_order[2 * kMaxChi];
   __shared__ int s_keep, s_total;
   __shared__ double s_scale;
+  __shared__ double s_beta;
+  __shared__ double2 s_alpha;
   // One SVD is shared by the CTAs of a thread-block cluster: each CTA rotates its share of the
   // block pairs of a round (the matrix lives in global memory / L2), rounds are separated by
   // cluster barriers.  Rank 0 finishes (sort, truncate, split).
@@ -643,6 +647,82 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 
   int* conv = A.conv + ((size_t)s * A.maxtasks + t) * 32;
   if (crank == 0 && tid < 32) conv[tid] = 0;
+
+  // Preconditioning (Drmac-Veselic): W = Q R by Householder reflections, then the one-sided Jacobi
+  // runs on X = R^H (Cc x Cc, lower triangular), whose columns are far closer to orthogonal than
+  // those of W: 6-8 sweeps instead of 10-20 on graded spectra.  X V' = U' Sigma gives the RIGHT
+  // singular vectors of W directly (U' = normalised columns of the converged X), the left ones are
+  // recovered from W U' Sigma^-1 below; Q is never formed.
+  const bool pre = A.precond != 0 && Cc >= 8;
+  const int Rj = pre ? Cc : R;  // rows of the matrix the Jacobi sweeps work on
+  if (pre && crank == 0) {
+    double2* s_v = s_ga;  // Householder vector of the current column
+    for (int j = 0; j < Cc; ++j) {
+      if (warp == 0) {
+        double acc = 0.0;
+        for (int r = j + lane; r < R; r += 32) {
+          const double2 b = B[r + (size_t)j * LD];
+          acc = fma(b.x, b.x, fma(b.y, b.y, acc));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double nx = sqrt(acc);
+        const double2 x0 = B[j + (size_t)j * LD];
+        const double ax0 = hypot(x0.x, x0.y);
+        const double2 sph = ax0 > 0.0 ? make_double2(x0.x / ax0, x0.y / ax0) : make_double2(1.0, 0.0);
+        // H x = alpha e_0, alpha = -sph |x|;  v = x - alpha e_0;  H = I - beta v v^H, beta = 2 / v^H v
+        for (int r = j + lane; r < R; r += 32)
+          s_v[r - j] = (r == j) ? make_double2(sph.x * (ax0 + nx), sph.y * (ax0 + nx)) : B[r + (size_t)j * LD];
+        if (lane == 0) {
+          s_beta = nx > 0.0 ? 1.0 / (nx * (nx + ax0)) : 0.0;
+          s_alpha = make_double2(-sph.x * nx, -sph.y * nx);
+        }
+      }
+      __syncthreads();
+      const double beta = s_beta;
+      if (beta != 0.0) {
+        for (int c = j + 1 + warp; c < Cc; c += nwarps) {
+          double2 a[4];
+          double2 dot = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = j + lane + 32 * e;
+            a[e] = (r < R) ? B[r + (size_t)c * LD] : make_double2(0.0, 0.0);
+            if (r < R) cfma_conj(dot, s_v[r - j], a[e]);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o);
+            dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
+          }
+          const double2 f = make_double2(-beta * dot.x, -beta * dot.y);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = j + lane + 32 * e;
+            if (r < R) {
+              cfma(a[e], s_v[r - j], f);
+              B[r + (size_t)c * LD] = a[e];
+            }
+          }
+        }
+      }
+      if (tid == 0) B[j + (size_t)j * LD] = s_alpha;
+      __syncthreads();
+    }
+    // X = R^H in place (the strict lower triangle held reflector leftovers)
+    for (int e = tid; e < Cc * Cc; e += blockDim.x) {
+      const int i = e % Cc, jc = e / Cc;
+      if (i > jc) {
+        const double2 r = B[jc + (size_t)i * LD];
+        B[i + (size_t)jc * LD] = make_double2(r.x, -r.y);
+        B[jc + (size_t)i * LD] = make_double2(0.0, 0.0);
+      } else if (i == jc) {
+        const double2 r = B[i + (size_t)i * LD];
+        B[i + (size_t)i * LD] = make_double2(r.x, -r.y);
+      }
+    }
+    __syncthreads();
+  }
   __threadfence();
   cluster.sync();
 
@@ -657,7 +737,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   const int npairs = ne / 2;
   // convergence: |<p, q>| <= tol |p| |q| with tol ~ 2 sqrt(R) eps (LAPACK xGESVJ uses sqrt(m) eps);
   // a tighter value sits below the rounding noise of the inner product and never converges
-  const double tol = 2.0 * sqrt((double)R) * 2.220446049250313e-16;
+  const double tol = 2.0 * sqrt((double)Rj) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
   for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
@@ -690,7 +770,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = lane + 32 * e;
-            x[c][e] = (col[c] < Cc && r < R) ? B[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
+            x[c][e] = (col[c] < Cc && r < Rj) ? B[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
           }
         // squared column norms of the block: computed once per visit, then tracked through the
         // rotations (|p'|^2 = |p|^2 - t|g|, |q'|^2 = |q|^2 + t|g| with t|g| = kappa |g|^2), so the inner
@@ -823,7 +903,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = lane + 32 * e;
-            if (col[c] < Cc && r < R) B[r + (size_t)col[c] * LD] = x[c][e];
+            if (col[c] < Cc && r < Rj) B[r + (size_t)col[c] * LD] = x[c][e];
           }
         __syncwarp();
       }
@@ -847,7 +927,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   for (int c = warp; c < Cc; c += nwarps) {
     double acc = 0.0;
     const double2* bc = B + (size_t)c * LD;
-    for (int r = lane; r < R; r += 32) acc = fma(bc[r].x, bc[r].x, fma(bc[r].y, bc[r].y, acc));
+    for (int r = lane; r < Rj; r += 32) acc = fma(bc[r].x, bc[r].x, fma(bc[r].y, bc[r].y, acc));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s_sig[c] = sqrt(acc);
@@ -891,26 +971,35 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   __syncthreads();
   const int keep = s_keep;
   const double scale = s_scale;
-  // Right singular vectors of the KEPT columns, compacted by rank: after convergence B = U Sigma, so
-  // V[:, r] = B0^H B[:, j_r] / sigma_{j_r}^2 -- one (Cc x R) x (R x keep) product instead of
-  // replaying every rotation on an accumulated V (37 % of the Jacobi flops and half of its traffic).
+  // The other set of singular vectors for the KEPT columns, compacted by rank, from one product with
+  // the untouched working matrix B0 (instead of replaying every rotation on an accumulated V):
+  //   plain:          B = U Sigma  ->  V[:, r] = B0^H B[:, j_r] / sigma^2   (Cc x R) . (R x keep)
+  //   preconditioned: B = V Sigma  ->  U[:, r] = B0   B[:, j_r] / sigma^2   (R x Cc) . (Cc x keep)
   {
     const int tr = tid & 31, tc = tid >> 5;  // rows 4 tr .. 4 tr + 3, columns 8 tc .. 8 tc + 7
+    const int orows = pre ? R : Cc, kdim = pre ? Cc : R;
     double2 acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[i][c] = make_double2(0.0, 0.0);
-    for (int k0 = 0; k0 < R; k0 += 8) {
+    for (int k0 = 0; k0 < kdim; k0 += 8) {
       for (int e = tid; e < 8 * 2 * kMaxChi; e += 256) {
-        const int kk = e & 7, r = e >> 3;
-        s_ga[kk * 2 * kMaxChi + r] =
-            (r < Cc && k0 + kk < R) ? B0[(k0 + kk) + (size_t)r * LD] : make_double2(0.0, 0.0);
+        double2 v = make_double2(0.0, 0.0);
+        if (!pre) {
+          const int kk = e & 7, r = e >> 3;  // consecutive threads walk along k (contiguous)
+          if (r < orows && k0 + kk < kdim) v = B0[(k0 + kk) + (size_t)r * LD];
+          s_ga[kk * 2 * kMaxChi + r] = make_double2(v.x, -v.y);
+        } else {
+          const int r = e & (2 * kMaxChi - 1), kk = e >> 7;  // ... along the rows
+          if (r < orows && k0 + kk < kdim) v = B0[r + (size_t)(k0 + kk) * LD];
+          s_ga[kk * 2 * kMaxChi + r] = v;
+        }
       }
       for (int e = tid; e < 8 * kMaxChi; e += 256) {
         const int kk = e & 7, jj = e >> 3;
         s_gb[kk * kMaxChi + jj] =
-            (jj < keep && k0 + kk < R) ? B[(k0 + kk) + (size_t)s_order[jj] * LD] : make_double2(0.0, 0.0);
+            (jj < keep && k0 + kk < kdim) ? B[(k0 + kk) + (size_t)s_order[jj] * LD] : make_double2(0.0, 0.0);
       }
       __syncthreads();
 #pragma unroll
@@ -923,7 +1012,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cfma_conj(acc[i][c], a[i], b[c]);
+          for (int c = 0; c < 8; ++c) cfma(acc[i][c], a[i], b[c]);
       }
       __syncthreads();
     }
@@ -936,7 +1025,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 4 * tr + i;
-        if (r < Cc) V[r + (size_t)jj * LD] = make_double2(acc[i][c].x * inv, acc[i][c].y * inv);
+        if (r < orows) V[r + (size_t)jj * LD] = make_double2(acc[i][c].x * inv, acc[i][c].y * inv);
       }
     }
   }
@@ -955,11 +1044,11 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     const int j = s_order[r];
     const double sg = s_sig[j];
     double2 u;
-    if (!transposed) {
+    if (transposed == pre) {  // the vectors held by the converged B (scaled by sigma)
       const double2 b = B[row + (size_t)j * LD];
       const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
       u = make_double2(b.x * inv, b.y * inv);
-    } else {
+    } else {  // the recovered set
       u = V[row + (size_t)r * LD];
     }
     const int b1 = row / cl, al = row % cl;
@@ -972,7 +1061,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     const int j = s_order[r];
     const double sg = s_sig[j];
     double2 v;
-    if (!transposed) {
+    if (transposed == pre) {
       v = V[col + (size_t)r * LD];
     } else {
       const double2 b = B[col + (size_t)j * LD];
@@ -1359,6 +1448,8 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   {
     const char* th = getenv("AQC_MPS_THETA");
     m->theta_scalar = th && std::string(th) == "scalar";
+    const char* sv = getenv("AQC_MPS_SVD");
+    m->svd_precond = !(sv && std::string(sv) == "plain");
   }
   for (MpsProgram* p : {&m->fwd, &m->dag}) {
     alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
@@ -1523,6 +1614,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   sa.trunc_thr = m->trunc_thr;
   sa.sweeps = m->d_sweeps;
   sa.conv = m->d_conv;
+  sa.precond = m->svd_precond ? 1 : 0;
   // as many CTAs per SVD as fit in one wave (cluster of 1, 2 or 4)
   int csize = 1;
   const int nsvd = st.ntasks * nstates;
