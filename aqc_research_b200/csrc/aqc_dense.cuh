@@ -205,14 +205,14 @@ __global__ void __launch_bounds__(128) dense_grad_kernel(const StageDesc* __rest
   const int s = t >> 2, r = t & 3, b = blockIdx.y;
   const StageDesc sd = stages[s];
   const double2* tg = trig + (size_t)b * nthetas;
-  const double* R = gm + ((size_t)b * nstages + s) * 64;  // R[cz * 8 + cw]
+  // M[i][r] = sum z_i conj(w_r): entry (i, r) at [(i << 3) | r] (real part) and [(i << 3) | 4 | r]
+  const double* Mq = gm + ((size_t)b * nstages + s) * 64;
   cd a[2][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
-    // M[i][r] = sum z_i conj(w_r)
-    a[1][i].x = R[(2 * i) * 8 + 2 * r] + R[(2 * i + 1) * 8 + 2 * r + 1];
-    a[1][i].y = R[(2 * i + 1) * 8 + 2 * r] - R[(2 * i) * 8 + 2 * r + 1];
+    a[1][i].x = Mq[(i << 3) | r];
+    a[1][i].y = Mq[(i << 3) | 4 | r];
   }
   constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
   double dummy[NACC];
@@ -267,7 +267,7 @@ struct DensePassArgs {
   long long basis_index;  // >= 0: src[0] is the basis state |basis_index> (no load)
   const DLane* lanes;     // program-wide [stage][warp][lane]
   const double* umat;     // [batch][nstages_total][64]
-  double* gm;             // [batch][nstages_total][64]   (NVEC == 2)
+  double* gm;             // [batch][nstages_total][64]: 32 used, (az << 3 | reim << 2 | aw)  (NVEC == 2)
   int nstages_total;
   PassDesc pd;
 };
@@ -319,7 +319,7 @@ template <int NVEC>
 __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_kernel(const DensePassArgs A) {
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
-  __shared__ double s_mpart[(NVEC == 2) ? 2 * kDWarps * 64 : 2];
+  __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int tb = A.pd.tb;
@@ -441,17 +441,19 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
       }
     }
     if (NVEC == 2) {
-      // R[cz = lane >> 2][cw = 2 (lane & 3) + {0, 1}] partials of this warp
-      double* part = s_mpart + ((s & 1) * kDWarps + warp) * 64;
-      *reinterpret_cast<double2*>(part + 2 * lane) = make_double2(m0, m1);
+      // The warp's partial R[cz = lane >> 2][cw = 2 (lane & 3) + {0, 1}] (8x8 real cross products)
+      // folds into the 4x4 complex M = sum z w^H with one exchange between the lanes holding Re z
+      // and Im z (lane ^ 4): lane (az, 0, aw) ends with Re M[az][aw], lane (az, 1, aw) with Im.
+      const double recv = __shfl_xor_sync(0xffffffffu, m1, 4);
+      const double mc = (lane & 4) ? (m0 - recv) : (m0 + recv);
+      s_mpart[((s & 1) * kDWarps + warp) * 32 + lane] = mc;
       __syncthreads();
       if (warp == (s & (kDWarps - 1))) {
-        const double* pp = s_mpart + (s & 1) * kDWarps * 64;
-        double r0 = 0.0, r1 = 0.0;
+        const double* pp = s_mpart + (s & 1) * kDWarps * 32;
+        double r0 = 0.0;
 #pragma unroll
-        for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 64 + lane], r1 += pp[w * 64 + 32 + lane];
+        for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 32 + lane];
         atomicAdd(gmp + (size_t)s * 64, r0);
-        atomicAdd(gmp + (size_t)s * 64 + 32, r1);
       }
     } else {
       __syncthreads();
