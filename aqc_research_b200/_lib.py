@@ -78,6 +78,10 @@ SIGNATURES = {
         ct.c_int,
         [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
     ),
+    "aqc_debug_dense_program_fused": (
+        ct.c_int,
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_int32_p, ct.c_int64, c_int64_p],
+    ),
     "aqc_sv_slot_ptr": (ct.c_void_p, [ct.c_void_p, ct.c_int]),
     "aqc_sv_create_sharded": (
         ct.c_int,

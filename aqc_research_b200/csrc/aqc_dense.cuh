@@ -80,7 +80,13 @@ static int gf2_rank3(unsigned a, unsigned b, unsigned c) {
 
 // Builds the per-stage lane tables of one program (all passes).  Returns false if a pass has a
 // tile of fewer than kDMinTileBits bits.
-static bool build_dense_tables(const Program& prog, DenseTables& T) {
+// Flags packed into DLane::sl (slot offsets need 12 bits):
+//   kPairFirst: this stage and the next one act on DISJOINT bit pairs and run as one fused step --
+//               one LDS.128 and two STS.64 per vector for both stages (see dense_pass_kernel);
+//   kPairSwap : the fused step runs the NEXT stage first (the two commute; chosen for bank conflicts).
+constexpr uint16_t kPairFirst = 0x8000, kPairSwap = 0x4000;
+
+static bool build_dense_tables(const Program& prog, DenseTables& T, int fuse_pairs = 0) {
   T.lanes.assign(prog.stages.size() * kDWarps * 32, DLane{0, 0, 0, 0});
   T.rbits.assign(prog.stages.size() * 3, 0);
   for (const PassDesc& pd : prog.passes) {
@@ -140,6 +146,64 @@ static bool build_dense_tables(const Program& prog, DenseTables& T) {
           const int it = w + kDWarps * l;
           d.sb = (uint16_t)(it < nit ? dense_swz(base_of(it)) : 0);
         }
+    }
+    if (!fuse_pairs) continue;
+    // fused steps: consecutive stages on disjoint bit pairs (p1, q1), (p2, q2).  The first stage
+    // loads with quad-slot bits (r0, q2, p2); after its DMMAs a lane holds one real component of
+    // the slots (i = r0 bit, t = (q2, p2) bits).  One exchange with lane ^ 4 trades the re/im lane
+    // bit for the r0 register bit, which turns the data into the B fragment of the second stage
+    // (k = lane & 3 <-> (q2, p2), n = lane >> 2 <-> (r0, q1, p1)) without touching shared memory.
+    for (int s = 0; s + 1 < pd.nstages; ++s) {
+      const StageDesc& s1 = prog.stages[pd.stage0 + s];
+      const StageDesc& s2 = prog.stages[pd.stage0 + s + 1];
+      if (s1.p == s2.p || s1.p == s2.q || s1.q == s2.p || s1.q == s2.q) continue;
+      auto h = [](int b) { return 1u << (b % 3); };
+      // order: stores of the fused step are indexed by (second.q, first.q, first.p)
+      const int sc_fwd = gf2_rank3(h(s2.q), h(s1.q), h(s1.p)), sc_rev = gf2_rank3(h(s1.q), h(s2.q), h(s2.p));
+      const bool swap = sc_rev > sc_fwd;
+      if (fuse_pairs == 2 && std::max(sc_fwd, sc_rev) < 3) continue;  // only bank-conflict-free fusions
+      const StageDesc& fa = swap ? s2 : s1;  // runs first
+      const StageDesc& fb = swap ? s1 : s2;
+      const int q1 = fa.q, p1 = fa.p, q2 = fb.q, p2 = fb.p;
+      int best = -1, r0 = -1;
+      for (int a = 0; a < tb; ++a) {
+        if (a == p1 || a == q1 || a == p2 || a == q2) continue;
+        const int score = gf2_rank3(h(q1), h(p1), h(a));
+        if (score > best) best = score, r0 = a;
+      }
+      if (r0 < 0) continue;  // tb == 4 cannot happen (kDMinTileBits = 5)
+      std::vector<int> outer;
+      for (int b = 0; b < tb; ++b)
+        if (b != p1 && b != q1 && b != p2 && b != q2 && b != r0) outer.push_back(b);
+      auto base_of = [&](int it) {
+        unsigned idx = 0;
+        for (size_t k = 0; k < outer.size(); ++k) idx |= (unsigned)((it >> k) & 1) << outer[k];
+        return idx;
+      };
+      for (int w = 0; w < kDWarps; ++w)
+        for (int l = 0; l < 32; ++l) {
+          DLane& d = T.lanes[((size_t)(pd.stage0 + s) * kDWarps + w) * 32 + l];
+          {
+            const int g = l >> 2, a = l & 3;
+            const unsigned idx = (unsigned)(a & 1) << q1 | (unsigned)(a >> 1) << p1 | (unsigned)(g & 1) << r0 |
+                                 (unsigned)((g >> 1) & 1) << q2 | (unsigned)(g >> 2) << p2;
+            d.sl = (uint16_t)(dense_swz(idx) | kPairFirst | (swap ? kPairSwap : 0));
+          }
+          for (int i = 0; i < 2; ++i) {  // output of the second stage: component c = l >> 2, slots n = 2t + i
+            const int c = l >> 2, t = l & 3;
+            const int reim = c & 1, a0 = (c >> 1) & 1, a1 = c >> 2;
+            const unsigned idx = (unsigned)a0 << q2 | (unsigned)a1 << p2 | (unsigned)i << r0 |
+                                 (unsigned)(t & 1) << q1 | (unsigned)(t >> 1) << p1;
+            const uint16_t v = (uint16_t)(2u * dense_swz(idx) + (unsigned)reim);
+            if (i == 0)
+              d.so0 = v;
+            else
+              d.so1 = v;
+          }
+          const int it = w + kDWarps * l;
+          d.sb = (uint16_t)(it < nit ? dense_swz(base_of(it)) : 0);
+        }
+      ++s;  // the partner stage is consumed by this step
     }
   }
   return true;
@@ -348,6 +412,29 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
     }
     __syncthreads();
   }
+  // (the first step's constants are requested before the tile load so that their latency hides behind it)
+  const int nstages = A.pd.nstages;
+  const int nit = tsize >> 5;
+  const size_t sbase = (size_t)blockIdx.y * A.nstages_total + A.pd.stage0;
+  const double* __restrict__ um = A.umat + sbase * 64 + lane;
+  const uint2* __restrict__ lt =
+      reinterpret_cast<const uint2*>(A.lanes + ((size_t)A.pd.stage0 * kDWarps + warp) * 32 + lane);
+  double* __restrict__ gmp = A.gm + sbase * 64 + lane;
+
+  // one-step-ahead prefetch of the per-stage constants: the lane-table entry of the next step and the
+  // stage matrices of its (up to) two stages; which of the two runs first is decided by the entry's
+  // kPairSwap flag once it has arrived, so no load waits for another one
+  double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // stage matrices of stages s and s + 1
+  uint2 dl = make_uint2(0u, 0u);
+  if (nstages > 0) {
+    dl = lt[0];
+    c0 = um[0];
+    c1 = um[32];
+    if (nstages > 1) {
+      e0 = um[64];
+      e1 = um[96];
+    }
+  }
   const long long boff = (long long)blockIdx.y * A.vec_stride + base;
   const unsigned s0x16 = (unsigned)(tid ^ (((tid >> 3) ^ (tid >> 6)) & 7)) << 4;
 
@@ -383,82 +470,138 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
   cp_async_wait_all();
   __syncthreads();
 
-  const int nstages = A.pd.nstages;
-  const int nit = tsize >> 5;
-  const size_t sbase = (size_t)blockIdx.y * A.nstages_total + A.pd.stage0;
-  const double* __restrict__ um = A.umat + sbase * 64 + lane;
-  const uint2* __restrict__ lt =
-      reinterpret_cast<const uint2*>(A.lanes + ((size_t)A.pd.stage0 * kDWarps + warp) * 32 + lane);
-  double* __restrict__ gmp = A.gm + sbase * 64 + lane;
-
-  // one-stage-ahead prefetch of the per-stage constants
-  double ua0 = 0.0, ua1 = 0.0;
-  uint2 dl = make_uint2(0u, 0u);
-  if (nstages > 0) {
-    ua0 = um[0];
-    ua1 = um[32];
-    dl = lt[0];
-  }
-  for (int s = 0; s < nstages; ++s) {
-    double na0 = 0.0, na1 = 0.0;
+  int step = 0;
+  for (int s = 0; s < nstages; ++step) {
+    const bool paired = (dl.x & kPairFirst) != 0;
+    const bool swapped = (dl.x & kPairSwap) != 0;
+    const int sA = s + (swapped ? 1 : 0);  // stage that runs first
+    const int sB = 2 * s + 1 - sA;         // its partner (paired steps only)
+    const int snext = s + (paired ? 2 : 1);
+    const double ua0 = swapped ? e0 : c0, ua1 = swapped ? e1 : c1;
+    const double ub0 = swapped ? c0 : e0, ub1 = swapped ? c1 : e1;
+    double nc0 = 0.0, nc1 = 0.0, ne0 = 0.0, ne1 = 0.0;
     uint2 nl = make_uint2(0u, 0u);
-    if (s + 1 < nstages) {
-      na0 = um[(size_t)(s + 1) * 64];
-      na1 = um[(size_t)(s + 1) * 64 + 32];
-      nl = lt[(size_t)(s + 1) * kDWarps * 32];
+    if (snext < nstages) {
+      nl = lt[(size_t)snext * kDWarps * 32];
+      if (paired) {  // an unpaired step already holds the next stage's matrix in (e0, e1)
+        nc0 = um[(size_t)snext * 64];
+        nc1 = um[(size_t)snext * 64 + 32];
+      } else {
+        nc0 = e0, nc1 = e1;
+      }
+      if (snext + 1 < nstages) {
+        ne0 = um[(size_t)(snext + 1) * 64];
+        ne1 = um[(size_t)(snext + 1) * 64 + 32];
+      }
     }
     // byte offsets inside one vector's tile: load slot (16-byte units), store slots (8-byte units)
-    const unsigned sl16 = (dl.x & 0xffffu) << 4, so0 = (dl.x >> 16) << 3, so1 = (dl.y & 0xffffu) << 3;
+    const unsigned sl16 = (dl.x & 0x0fffu) << 4, so0 = (dl.x >> 16) << 3, so1 = (dl.y & 0xffffu) << 3;
     const unsigned sb16 = (dl.y >> 16) << 4;
-    double m0 = 0.0, m1 = 0.0;
+    const bool hi = (lane & 4) != 0;  // lane holds Im (first-stage output) / r0 = 1 (second-stage input)
+    double m0 = 0.0, m1 = 0.0, n0 = 0.0, n1 = 0.0;
     int j = 0;
+    if (!paired) {
 #pragma unroll 2
-    for (int it = warp; it < nit; it += kDWarps, ++j) {
-      const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
-      const unsigned la = sm_u32 + (b16 ^ sl16);
-      const unsigned d0 = sm_u32 + (b16 ^ so0), d1 = sm_u32 + (b16 ^ so1);
-      if (NVEC == 2) {
-        const double2 w = lds128(la);
-        const double2 z = lds128(la + vbytes);
-        double w0 = 0.0, w1 = 0.0, z0 = 0.0, z1 = 0.0;
-        dmma884(w0, w1, ua0, w.x);
-        dmma884(z0, z1, ua0, z.x);
-        dmma884(w0, w1, ua1, w.y);
-        dmma884(z0, z1, ua1, z.y);
-        dmma884(m0, m1, z0, w0);
-        dmma884(m0, m1, z1, w1);
-        sts64(d0, w0);
-        sts64(d1, w1);
-        sts64(d0 + vbytes, z0);
-        sts64(d1 + vbytes, z1);
-      } else {
-        const double2 x = lds128(la);
-        double x0 = 0.0, x1 = 0.0;
-        dmma884(x0, x1, ua0, x.x);
-        dmma884(x0, x1, ua1, x.y);
-        sts64(d0, x0);
-        sts64(d1, x1);
+      for (int it = warp; it < nit; it += kDWarps, ++j) {
+        const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
+        const unsigned la = sm_u32 + (b16 ^ sl16);
+        const unsigned d0 = sm_u32 + (b16 ^ so0), d1 = sm_u32 + (b16 ^ so1);
+        if (NVEC == 2) {
+          const double2 w = lds128(la);
+          const double2 z = lds128(la + vbytes);
+          double w0 = 0.0, w1 = 0.0, z0 = 0.0, z1 = 0.0;
+          dmma884(w0, w1, ua0, w.x);
+          dmma884(z0, z1, ua0, z.x);
+          dmma884(w0, w1, ua1, w.y);
+          dmma884(z0, z1, ua1, z.y);
+          dmma884(m0, m1, z0, w0);
+          dmma884(m0, m1, z1, w1);
+          sts64(d0, w0);
+          sts64(d1, w1);
+          sts64(d0 + vbytes, z0);
+          sts64(d1 + vbytes, z1);
+        } else {
+          const double2 x = lds128(la);
+          double x0 = 0.0, x1 = 0.0;
+          dmma884(x0, x1, ua0, x.x);
+          dmma884(x0, x1, ua1, x.y);
+          sts64(d0, x0);
+          sts64(d1, x1);
+        }
+      }
+    } else {
+      // fused step: stage A, lane ^ 4 exchange (re/im lane bit <-> r0 register bit), stage B
+#pragma unroll 2
+      for (int it = warp; it < nit; it += kDWarps, ++j) {
+        const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
+        const unsigned la = sm_u32 + (b16 ^ sl16);
+        const unsigned d0 = sm_u32 + (b16 ^ so0), d1 = sm_u32 + (b16 ^ so1);
+        if (NVEC == 2) {
+          const double2 w = lds128(la);
+          const double2 z = lds128(la + vbytes);
+          double w0 = 0.0, w1 = 0.0, z0 = 0.0, z1 = 0.0;
+          dmma884(w0, w1, ua0, w.x);
+          dmma884(z0, z1, ua0, z.x);
+          dmma884(w0, w1, ua1, w.y);
+          dmma884(z0, z1, ua1, z.y);
+          dmma884(m0, m1, z0, w0);
+          dmma884(m0, m1, z1, w1);
+          const double wr = __shfl_xor_sync(0xffffffffu, hi ? w0 : w1, 4);
+          const double zr = __shfl_xor_sync(0xffffffffu, hi ? z0 : z1, 4);
+          const double wx = hi ? wr : w0, wy = hi ? w1 : wr;
+          const double zx = hi ? zr : z0, zy = hi ? z1 : zr;
+          double v0 = 0.0, v1 = 0.0, y0 = 0.0, y1 = 0.0;
+          dmma884(v0, v1, ub0, wx);
+          dmma884(y0, y1, ub0, zx);
+          dmma884(v0, v1, ub1, wy);
+          dmma884(y0, y1, ub1, zy);
+          dmma884(n0, n1, y0, v0);
+          dmma884(n0, n1, y1, v1);
+          sts64(d0, v0);
+          sts64(d1, v1);
+          sts64(d0 + vbytes, y0);
+          sts64(d1 + vbytes, y1);
+        } else {
+          const double2 x = lds128(la);
+          double x0 = 0.0, x1 = 0.0;
+          dmma884(x0, x1, ua0, x.x);
+          dmma884(x0, x1, ua1, x.y);
+          const double xr = __shfl_xor_sync(0xffffffffu, hi ? x0 : x1, 4);
+          const double xx = hi ? xr : x0, xy = hi ? x1 : xr;
+          double v0 = 0.0, v1 = 0.0;
+          dmma884(v0, v1, ub0, xx);
+          dmma884(v0, v1, ub1, xy);
+          sts64(d0, v0);
+          sts64(d1, v1);
+        }
       }
     }
     if (NVEC == 2) {
       // The warp's partial R[cz = lane >> 2][cw = 2 (lane & 3) + {0, 1}] (8x8 real cross products)
       // folds into the 4x4 complex M = sum z w^H with one exchange between the lanes holding Re z
       // and Im z (lane ^ 4): lane (az, 0, aw) ends with Re M[az][aw], lane (az, 1, aw) with Im.
+      double* part = s_mpart + (size_t)(step & 1) * 2 * kDWarps * 32;  // [set][warp][32]
       const double recv = __shfl_xor_sync(0xffffffffu, m1, 4);
-      const double mc = (lane & 4) ? (m0 - recv) : (m0 + recv);
-      s_mpart[((s & 1) * kDWarps + warp) * 32 + lane] = mc;
+      part[warp * 32 + lane] = hi ? (m0 - recv) : (m0 + recv);
+      if (paired) {
+        const double recv2 = __shfl_xor_sync(0xffffffffu, n1, 4);
+        part[(kDWarps + warp) * 32 + lane] = hi ? (n0 - recv2) : (n0 + recv2);
+      }
       __syncthreads();
-      if (warp == (s & (kDWarps - 1))) {
-        const double* pp = s_mpart + (s & 1) * kDWarps * 32;
+      const int red0 = step & (kDWarps - 1), red1 = (step + kDWarps / 2) & (kDWarps - 1);
+      if (warp == red0 || (paired && warp == red1)) {
+        const int set = (warp == red0) ? 0 : 1;
+        const double* pp = part + (size_t)set * kDWarps * 32;
         double r0 = 0.0;
 #pragma unroll
         for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 32 + lane];
-        atomicAdd(gmp + (size_t)s * 64, r0);
+        atomicAdd(gmp + (size_t)(set == 0 ? sA : sB) * 64, r0);
       }
     } else {
       __syncthreads();
     }
-    ua0 = na0, ua1 = na1, dl = nl;
+    c0 = nc0, c1 = nc1, e0 = ne0, e1 = ne1, dl = nl;
+    s = snext;
   }
 
 #pragma unroll

@@ -1530,6 +1530,7 @@ static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, con
   return AQC_OK;
 }
 
+static int env_int(const char* name, int dflt);
 // ---- dense-stage engine: host side ----------------------------------------------------------------
 template <int NVEC>
 static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
@@ -1876,7 +1877,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     Program* progs[3] = {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag};
     DenseTables* tabs[3] = {&sv->dt_grad, &sv->dt_fwd, &sv->dt_dag};
     for (int i = 0; i < 3; ++i) {
-      if (!build_dense_tables(*progs[i], *tabs[i])) {
+      if (!build_dense_tables(*progs[i], *tabs[i], env_int("AQC_DENSE_PAIRS", 1))) {
         fail(AQC_EINVAL, "internal: dense engine needs tiles of >= %d bits", kDMinTileBits);
         return bail(AQC_EINVAL);
       }
@@ -2512,9 +2513,25 @@ extern "C" int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int til
 // shared-memory lane tables, so that the CPU test-suite can emulate the DMMA data flow.
 // Layout: npasses, then per pass {tb, nstages, nouter, bitpos[16], outerpos[48], per stage
 // {p, q, nunits, (kind, flags, theta) x kStageUnits, r0, r1, r2, (sl, so0, so1, sb) x 8 warps x 32}}.
+static int debug_dense_program_impl(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
+                                    int reversed, int fuse_pairs, int32_t* out, int64_t cap, int64_t* needed);
+
 extern "C" int aqc_debug_dense_program(const aqc_circuit* circ, int log2_cols, int tile_bits,
                                        int low_bits, int reversed, int32_t* out, int64_t cap,
                                        int64_t* needed) {
+  return debug_dense_program_impl(circ, log2_cols, tile_bits, low_bits, reversed, 0, out, cap, needed);
+}
+
+// Same with the fused steps the production tables use (flags kPairFirst = 0x8000 / kPairSwap = 0x4000
+// in the `sl` word of a step's first stage; the partner stage's own table is then unused).
+extern "C" int aqc_debug_dense_program_fused(const aqc_circuit* circ, int log2_cols, int tile_bits,
+                                             int low_bits, int reversed, int32_t* out, int64_t cap,
+                                             int64_t* needed) {
+  return debug_dense_program_impl(circ, log2_cols, tile_bits, low_bits, reversed, 1, out, cap, needed);
+}
+
+static int debug_dense_program_impl(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
+                                    int reversed, int fuse_pairs, int32_t* out, int64_t cap, int64_t* needed) {
   if (!circ || !needed) return fail(AQC_EINVAL, "null argument");
   if (tile_bits < kDMinTileBits || tile_bits > kMaxTileBits) return fail(AQC_EINVAL, "bad tile_bits");
   if (circ->n + log2_cols < kDMinTileBits) return fail(AQC_EINVAL, "state too small for the dense engine");
@@ -2522,7 +2539,7 @@ extern "C" int aqc_debug_dense_program(const aqc_circuit* circ, int log2_cols, i
   build_program(*circ, log2_cols, circ->n + log2_cols, tile_bits, low_bits, reversed != 0, p,
                 kStageUnits, true);
   DenseTables dt;
-  if (!build_dense_tables(p, dt)) return fail(AQC_EINVAL, "tile too small for the dense engine");
+  if (!build_dense_tables(p, dt, fuse_pairs)) return fail(AQC_EINVAL, "tile too small for the dense engine");
   std::vector<int32_t> w;
   w.push_back((int32_t)p.passes.size());
   for (const PassDesc& pd : p.passes) {

@@ -56,9 +56,11 @@ class CircuitHandle:
         return (self.num_qubits, self.entangler, self.trotter, self.blocks.tobytes())
 
     def debug_program(self, log2_cols: int, tile_bits: int, low_bits: int, reversed_: bool,
-                      dense: bool = False):
+                      dense: bool = False, fused: bool = False):
         """Serialised tile-pass program (host-only; see aqc_debug_program / aqc_debug_dense_program)."""
         fn = self._lib.aqc_debug_dense_program if dense else self._lib.aqc_debug_program
+        if dense and fused:
+            fn = self._lib.aqc_debug_dense_program_fused
         need = ct.c_int64(0)
         _lib.check(
             fn(

@@ -177,6 +177,9 @@ int aqc_debug_program(const aqc_circuit* circ, int log2_cols, int tile_bits, int
  * kernel (layout documented in csrc/aqc_sv.cu), so CPU tests can emulate its data flow. */
 int aqc_debug_dense_program(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
                             int reversed, int32_t* out, int64_t cap, int64_t* needed);
+/* ... with the fused two-stage steps of the production tables (flags in the `sl` word). */
+int aqc_debug_dense_program_fused(const aqc_circuit* circ, int log2_cols, int tile_bits, int low_bits,
+                            int reversed, int32_t* out, int64_t cap, int64_t* needed);
 /* Device-pointer access for zero-copy callers (torch tensors): address of slot. */
 void* aqc_sv_slot_ptr(aqc_sv* sv, int slot);
 /* CUDA stream handle (cudaStream_t) the workspace launches on. */

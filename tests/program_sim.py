@@ -9,6 +9,8 @@ The CUDA arithmetic itself is validated by the ``-m gpu`` parity tests.
 import numpy as np
 from oracle import sv_oracle as O
 
+NWARPS = 8  # kDWarps of aqc_dense.cuh (warps per CTA of dense_pass_kernel)
+
 U_FRONT_LO, U_FRONT_HI, U_BLOCK_CHI, U_BLOCK_CLO = 1, 2, 3, 4
 F_PRE, F_POST = 1, 2
 
@@ -41,8 +43,8 @@ def parse_program(words: np.ndarray, dense: bool = False):
             if dense:
                 rbits = w[pos : pos + 3]
                 pos += 3
-                lanes = np.array(w[pos : pos + 8 * 32 * 4], dtype=np.int64).reshape(8, 32, 4)
-                pos += 8 * 32 * 4
+                lanes = np.array(w[pos : pos + NWARPS * 32 * 4], dtype=np.int64).reshape(NWARPS, 32, 4)
+                pos += NWARPS * 32 * 4
                 stages.append((p, q, units, rbits, lanes))
             else:
                 stages.append((p, q, units))
@@ -165,18 +167,42 @@ def stage_unitary(units, entangler, thetas, dagger):
     return np.stack(cols, axis=1)  # U[i][k]
 
 
+PAIR_FIRST, PAIR_SWAP, SL_MASK = 0x8000, 0x4000, 0x0FFF  # flags in the `sl` word (aqc_dense.cuh)
+
+
+def dense_steps(stages):
+    """Splits a pass's stage list into steps: (first, second | None) stage indices in run order."""
+    out, s = [], 0
+    while s < len(stages):
+        sl0 = int(stages[s][4][0, 0, 0])
+        if sl0 & PAIR_FIRST:
+            a = s + (1 if sl0 & PAIR_SWAP else 0)
+            out.append((a, 2 * s + 1 - a, s))
+            s += 2
+        else:
+            out.append((s, None, s))
+            s += 1
+    return out
+
+
 def dense_check_tables(passes):
-    """Every stage's load and store tables address each tile element exactly once."""
+    """Every step's load and store tables address each tile element exactly once."""
     for ps in passes:
         tb = ps["tb"]
         nit = 1 << (tb - 5)
-        for p, q, units, rbits, lanes in ps["stages"]:
-            assert len({p, q, *rbits}) == 5 and all(0 <= r < tb for r in rbits)
+        for sa, sb_, st in dense_steps(ps["stages"]):
+            p, q, units, rbits, lanes = ps["stages"][st]
+            if sb_ is None:
+                assert len({p, q, *rbits}) == 5 and all(0 <= r < tb for r in rbits)
+            else:
+                pa, qa = ps["stages"][sa][0], ps["stages"][sa][1]
+                pb, qb = ps["stages"][sb_][0], ps["stages"][sb_][1]
+                assert len({pa, qa, pb, qb}) == 4  # fused stages act on disjoint bit pairs
             slots, dslots = [], []
             for it in range(nit):
-                w, j = it % 8, it // 8
+                w, j = it % NWARPS, it // NWARPS
                 b = lanes[w, j, 3]
-                slots += list(b ^ lanes[w, :, 0])
+                slots += list(b ^ (lanes[w, :, 0] & SL_MASK))
                 dslots += list((b << 1) ^ lanes[w, :, 1]) + list((b << 1) ^ lanes[w, :, 2])
             assert sorted(slots) == list(range(1 << tb))
             assert sorted(dslots) == list(range(2 << tb))
@@ -187,7 +213,7 @@ def dense_bank_conflicts(passes):
     worst_l = worst_s = 1
     for ps in passes:
         for p, q, units, rbits, lanes in ps["stages"]:
-            sl = lanes[0, :, 0]
+            sl = lanes[0, :, 0] & SL_MASK
             for qw in range(4):  # LDS.128: quarter warps, 8 bank groups of 16 bytes
                 groups = [int(x) & 7 for x in sl[8 * qw : 8 * qw + 8]]
                 worst_l = max(worst_l, max(groups.count(g) for g in set(groups)))
@@ -224,17 +250,24 @@ def dense_emulate(passes, entangler, thetas, vecs, dagger, grad):
             for v in range(nv):
                 sm[v][2 * swz] = vecs[v][idx].real
                 sm[v][2 * swz + 1] = vecs[v][idx].imag
-            for si, (p, q, units, rbits, lanes) in enumerate(ps["stages"]):
+            def real_form(units):
                 U = stage_unitary(units, entangler, thetas, dagger)
                 ua0, ua1 = np.zeros((8, 4)), np.zeros((8, 4))
                 for i in range(4):
                     ua0[2 * i], ua1[2 * i] = U[i].real, -U[i].imag
                     ua0[2 * i + 1], ua1[2 * i + 1] = U[i].imag, U[i].real
+                return ua0, ua1
+
+            for sa, sb_, st in dense_steps(ps["stages"]):
+                lanes = ps["stages"][st][4]
+                ua0, ua1 = real_form(ps["stages"][sa][2])
+                if sb_ is not None:
+                    ub0, ub1 = real_form(ps["stages"][sb_][2])
                 for it in range(nit):
-                    w, j = it % 8, it // 8
+                    w, j = it % NWARPS, it // NWARPS
                     b = int(lanes[w, j, 3])
                     lane = np.arange(32)
-                    slot = b ^ lanes[w, :, 0]
+                    slot = b ^ (lanes[w, :, 0] & SL_MASK)
                     outs = []
                     for v in range(nv):
                         b0 = np.zeros((4, 8))
@@ -242,12 +275,30 @@ def dense_emulate(passes, entangler, thetas, vecs, dagger, grad):
                         b0[lane & 3, lane >> 2] = sm[v][2 * slot]
                         b1[lane & 3, lane >> 2] = sm[v][2 * slot + 1]
                         outs.append(ua0 @ b0 + ua1 @ b1)  # D[c][g]
+                    if grad:
+                        rmats[sa] += outs[1] @ outs[0].T  # R[cz][cw] = sum_g Z[cz][g] W[cw][g]
+                    if sb_ is not None:
+                        # lane ^ 4 exchange: the lane keeps slot i = (lane >> 2) & 1 of its pair and
+                        # receives the other real component of that amplitude from its partner
+                        outs2 = []
+                        for v in range(nv):
+                            d = outs[v]
+                            hi = (lane >> 2) & 1
+                            cre, cim = (lane >> 2) & ~1, (lane >> 2) | 1
+                            col = 2 * (lane & 3) + hi
+                            xr, xi = d[cre, col], d[cim, col]
+                            b0 = np.zeros((4, 8))
+                            b1 = np.zeros((4, 8))
+                            b0[lane & 3, lane >> 2] = xr
+                            b1[lane & 3, lane >> 2] = xi
+                            outs2.append(ub0 @ b0 + ub1 @ b1)
+                        if grad:
+                            rmats[sb_] += outs2[1] @ outs2[0].T
+                        outs = outs2
                     for v in range(nv):
                         d = outs[v]
                         sm[v][(b << 1) ^ lanes[w, :, 1]] = d[lane >> 2, 2 * (lane & 3)]
                         sm[v][(b << 1) ^ lanes[w, :, 2]] = d[lane >> 2, 2 * (lane & 3) + 1]
-                    if grad:
-                        rmats[si] += outs[1] @ outs[0].T  # R[cz][cw] = sum_g Z[cz][g] W[cw][g]
             for v in range(nv):
                 vecs[v][idx] = sm[v][2 * swz] + 1j * sm[v][2 * swz + 1]
         if grad:

@@ -37,15 +37,17 @@ def _circuits(n):
     yield "spin3", ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "spin", "full", 7, 3))
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("n,tb,low", [(5, 5, 2), (6, 5, 1), (6, 6, 4), (7, 6, 3), (8, 11, 4)])
-def test_dense_program_and_emulation(n, tb, low):
+def test_dense_program_and_emulation(n, tb, low, fused):
+    """fused = True: the production tables, consecutive stages on disjoint bit pairs run as one step."""
     np.random.seed(4000 + 10 * n + tb)
     for name, circ in _circuits(n):
         h = CircuitHandle(circ)
         th = utils.rand_thetas(circ.num_thetas)
         x, y = utils.rand_state(n), utils.rand_state(n)
         for rev in (False, True):
-            prog = parse_program(h.debug_program(0, tb, low, rev, dense=True), dense=True)
+            prog = parse_program(h.debug_program(0, tb, low, rev, dense=True, fused=fused), dense=True)
             check_structure(prog, n)
             dense_check_tables(prog)
             units = sum(len(st[2]) for ps in prog for st in ps["stages"])
@@ -56,7 +58,7 @@ def test_dense_program_and_emulation(n, tb, low):
             (v,), _ = dense_emulate(prog, circ.entangler, th, [y], dagger=rev, grad=False)
             assert _rel(v, ref) < TOL, (name, rev)
         z0 = O.apply_v(circ, th, y, dagger=True)
-        prog = parse_program(h.debug_program(0, tb, low, False, dense=True), dense=True)
+        prog = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=fused), dense=True)
         gref = O.grad_sweep(circ, th, x, z0)
         (w, z), g = replay(prog, circ.entangler, th, [x, z0], dagger=False, grad=True)
         assert _rel(g, gref) < TOL, name
@@ -96,3 +98,16 @@ def test_dense_front_merge_and_bank_conflicts():
         nstages = sum(len(ps["stages"]) for ps in prog)
         assert nstages <= pair_runs + n // 4, (nstages, pair_runs)
         assert dense_bank_conflicts(prog) == (1, 1)
+
+
+def test_fused_steps_at_benchmark_size():
+    """Most stages of the n = 28 gradient program pair up into fused steps."""
+    from program_sim import dense_steps
+
+    n = 28
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 4), True)
+    prog = parse_program(CircuitHandle(circ).debug_program(0, 11, 4, False, dense=True, fused=True), dense=True)
+    dense_check_tables(prog)
+    stages = sum(len(ps["stages"]) for ps in prog)
+    steps = sum(len(dense_steps(ps["stages"])) for ps in prog)
+    assert steps < 0.7 * stages, (steps, stages)
