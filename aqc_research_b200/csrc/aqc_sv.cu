@@ -1215,6 +1215,7 @@ struct aqc_sv {
   double* d_gacc = nullptr;
   double* d_scratch = nullptr;     // small outputs (gather / vdot)
   long long* d_idx = nullptr;
+  std::vector<int64_t> idx_cached;  // host copy of what d_idx holds (gather_async)
   size_t idx_cap = 0, scratch_cap = 0;
   double* h_pinned = nullptr;  // pinned staging for thetas and small results
   size_t pinned_cap = 0;
@@ -1273,6 +1274,7 @@ static int ensure_idx(aqc_sv* sv, size_t count) {
   if (count <= sv->idx_cap) return AQC_OK;
   if (sv->d_idx) cudaFree(sv->d_idx);
   sv->d_idx = nullptr;
+  sv->idx_cached.clear();
   sv->idx_cap = 0;
   CU(cudaMalloc(&sv->d_idx, count * sizeof(long long)));
   sv->idx_cap = count;
@@ -2062,8 +2064,13 @@ static int gather_async(aqc_sv* sv, int slot, const int64_t* idx, int count) {
   if (rc) return rc;
   for (int i = 0; i < count; ++i)
     if (idx[i] < 0 || idx[i] >= sv->size) return fail(AQC_EINVAL, "gather index out of range");
-  CU(cudaMemcpyAsync(sv->d_idx, idx, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice,
-                     sv->stream));
+  // the index list is the same on every objective call: upload it only when it changes (a copy from
+  // pageable host memory stalls the submitting thread)
+  if (sv->idx_cached.size() != (size_t)count || memcmp(sv->idx_cached.data(), idx, (size_t)count * sizeof(int64_t))) {
+    sv->idx_cached.assign(idx, idx + count);
+    CU(cudaStreamSynchronize(sv->stream));  // a previous gather may still read d_idx
+    CU(cudaMemcpy(sv->d_idx, sv->idx_cached.data(), (size_t)count * sizeof(long long), cudaMemcpyHostToDevice));
+  }
   gather_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
       sv->slots[slot], sv->size, sv->d_idx, count, (double2*)sv->d_scratch);
   CU(cudaGetLastError());
@@ -2357,6 +2364,7 @@ extern "C" int aqc_sv_gather_target_columns(aqc_sv* sv, const int64_t* idx, int 
   CU(cudaSetDevice(sv->device));
   rc = ensure_idx(sv, (size_t)count);
   if (rc) return rc;
+  sv->idx_cached.clear();  // d_idx is about to hold something else
   CU(cudaMemcpyAsync(sv->d_idx, idx, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice, sv->stream));
   const long long tot = (long long)d * m;
   gather_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, sv->stream>>>(sv->d_target, sv->d_idx, d, m,
