@@ -167,3 +167,48 @@ def test_function_level_shims():
     assert _rel(mpsop.mps_to_vector(vhy), z0) < TOL
     g = fast_dot_gradient(circ, th, mx, vhy, block_range=(3, 9), front_layer=False)
     assert _rel(g, O.grad_sweep(circ, th, x, z0, (3, 9), False)) < TOL
+
+
+def test_full_size_properties_n50():
+    """
+    BASELINE.json configs[3] at full size (n = 50, chi_max = 64, Trotter ansatz depth 20) through
+    size-independent properties: a physical target (Trotter-evolved Neel state, bonds stay small at
+    this evolution time, so nothing is truncated), angles near the Trotter point.
+      * V^H is norm preserving: <z0|z0> = 1;
+      * the gradient sweep carries z0 = V^H y back to V V^H y = y and |0..> to V|neel>: both
+        overlaps are checked through MPS dots;
+      * the complex gradient of <V x|y> agrees with central finite differences of the overlap.
+    """
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trotop
+
+    n, layers = 50, 20
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    th_t = trotop.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=1.0, delta=1.0)
+    rng = np.random.RandomState(50)
+    th = th_t + 0.02 * (2 * rng.rand(circ.num_thetas) - 1)
+    ws = MpsWorkspace(circ, num_slots=6, chi_max=64, trunc_thr=1e-16)
+    neel = sum(1 << q for q in range(0, n, 2))
+    ws.set_product(0, neel)
+    ws.apply(th_t, 0, 0)  # target y = Trotter(1.0) |neel>
+    assert abs(ws.dot(0, 0) - 1) < 1e-10
+    assert max(M.bond_dims(ws.download(0))) < 64  # no bond saturates: the 1e-16 rule drops noise only
+    idx = np.array([neel] + [neel ^ (1 << q) for q in range(n)], dtype=np.int64)
+    hs = ws.objective(th, 0, 1, idx)  # slot 1 = z0 = V^H y
+    assert abs(ws.dot(1, 1) - 1) < 1e-9
+    assert abs(np.ravel(hs)[0]) ** 2 > 0.5  # near the Trotter point the fidelity is O(1)
+    g = ws.grad(th, x_basis=neel, z0=1, w=2, z=3)  # slot 2 = V x, slot 3 = V V^H y
+    assert abs(abs(ws.dot(3, 0)) - 1) < 1e-7
+    f0 = ws.dot(2, 0)  # <V x | y>
+    assert abs(f0 - np.ravel(hs)[0]) < 1e-7
+    # finite differences of f(theta) = <V(theta) x | y> = conj(<y| V(theta) x>) for a few angles
+    ws.set_product(4, neel)
+    for k in (1, 3 * n + 5, 3 * n + 4 * 137 + 2, circ.num_thetas - 3):
+        vals = []
+        for sgn in (+1, -1):
+            t2 = th.copy()
+            t2[k] += sgn * 1e-4
+            ws.apply(t2, 4, 5)
+            vals.append(ws.dot(5, 0))
+        fd = (vals[0] - vals[1]) / 2e-4
+        assert abs(fd - g[k]) < 1e-6 * max(1.0, abs(g[k])), (k, fd, g[k])
+    ws.close()
