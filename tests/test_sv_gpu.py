@@ -171,3 +171,35 @@ def test_large_properties():
     # d/dt0 + ... ; cheap global check: the gradient is finite and not identically zero
     assert np.all(np.isfinite(g)) and np.linalg.norm(g) > 0
     ws.close()
+
+
+def test_full_size_properties_n28():
+    """
+    BASELINE.json configs[4] at full size (n = 28, 4 layers, 2nd-order Trotter) through
+    size-independent properties: V^H is norm preserving, the gradient sweep ends with
+    (w, z) = (V e0, V V^H y = y), <V e0|y> = hs[0], and the complex gradient of <V e0|y> agrees with
+    central finite differences for angles of the front layer, a full layer and the re-used half layer.
+    """
+    n = 28
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 4), True)
+    np.random.seed(28)
+    th = utils.rand_thetas(circ.num_thetas)
+    ws = SvWorkspace(circ, num_slots=5)
+    ws.fill_random(0, 11)
+    idx = O.basis_state_indices(n)
+    hs = ws.objective(th, 0, 1, idx)[0]
+    assert abs(ws.vdot(1, 1)[0] - 1) < 1e-10
+    g = ws.grad(th, x_basis=0, z0=1, w=2, z=3)[0]
+    assert abs(ws.vdot(3, 0)[0] - 1) < 1e-10  # z came back to the target
+    assert abs(ws.vdot(2, 0)[0] - hs[0]) < 1e-10  # <V e0 | y> = <e0 | V^H y>
+    for k in (2, 3 * n + 1, 3 * n + 4 * 100 + 2, circ.num_thetas - 1):
+        vals = []
+        for sgn in (+1, -1):
+            t2 = th.copy()
+            t2[k] += sgn * 1e-4
+            ws.set_basis(4, 0)
+            ws.apply(t2, 4, 4, dagger=False)
+            vals.append(ws.vdot(4, 0)[0])
+        fd = (vals[0] - vals[1]) / 2e-4
+        assert abs(fd - g[k]) < 1e-7 * max(1.0, abs(g[k])) + 1e-9, (k, fd, g[k])
+    ws.close()
