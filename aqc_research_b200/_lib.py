@@ -51,6 +51,11 @@ SIGNATURES = {
         ct.c_int,
         [ct.c_void_p, c_double_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p],
     ),
+    "aqc_sv_grad_begin": (
+        ct.c_int,
+        [ct.c_void_p, c_double_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int],
+    ),
+    "aqc_sv_grad_end": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "aqc_sv_objective": (
         ct.c_int,
         [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p],

@@ -1236,6 +1236,7 @@ struct aqc_sv {
   double *d_albuf = nullptr, *d_aebuf = nullptr, *d_arescale = nullptr;
   // dense-stage engine (aqc_dense.cuh): DMMA sweeps; the default whenever the tile has >= 5 bits
   bool dense = false;
+  bool grad_pending = false;  // aqc_sv_grad_begin enqueued, results not collected yet
   int num_sms = 148;
   DenseTables dt_grad, dt_fwd, dt_dag;
   double *d_umat = nullptr, *d_gm = nullptr;
@@ -1253,6 +1254,10 @@ struct aqc_sv {
 };
 
 static int ensure_pinned(aqc_sv* sv, size_t doubles) {
+  if (sv->grad_pending) {  // an uncollected gradient sweep still owns the staging buffer: drop it
+    CU(cudaStreamSynchronize(sv->stream));
+    sv->grad_pending = false;
+  }
   if (doubles <= sv->pinned_cap) return AQC_OK;
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
   sv->h_pinned = nullptr;
@@ -2399,8 +2404,8 @@ extern "C" int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slo
   return AQC_OK;
 }
 
-extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis,
-                           int z0_slot, int w_slot, int z_slot, double* grad_out) {
+extern "C" int aqc_sv_grad_begin(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis,
+                                 int z0_slot, int w_slot, int z_slot) {
   int rc = check_slot(sv, z0_slot);
   if (rc) return rc;
   rc = check_slot(sv, w_slot);
@@ -2415,7 +2420,7 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
   }
   if (w_slot == z_slot || w_slot == z0_slot || (x_slot >= 0 && x_slot == z_slot))
     return fail(AQC_EINVAL, "slot aliasing: w must differ from z/z0 and x from z");
-  if (!thetas || !grad_out) return fail(AQC_EINVAL, "null pointer argument");
+  if (!thetas) return fail(AQC_EINVAL, "null pointer argument");
   CU(cudaSetDevice(sv->device));
   sv->last_launches = 0;
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
@@ -2446,6 +2451,16 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
   CU(cudaEventRecord(sv->ev1, sv->stream));
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
                      sv->stream));
+  sv->grad_pending = true;
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_grad_end(aqc_sv* sv, double* grad_out) {
+  if (!sv || !grad_out) return fail(AQC_EINVAL, "null pointer argument");
+  if (!sv->grad_pending) return fail(AQC_EINVAL, "no gradient sweep in flight (aqc_sv_grad_begin)");
+  CU(cudaSetDevice(sv->device));
+  sv->grad_pending = false;
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   CU(cudaStreamSynchronize(sv->stream));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
   // raw sums -> 0.5j <P w|z>: Ry 0.5, Rz/Rx 0.5j, CPhase -i
@@ -2477,6 +2492,14 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
     }
   }
   return AQC_OK;
+}
+
+extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis,
+                           int z0_slot, int w_slot, int z_slot, double* grad_out) {
+  if (!grad_out) return fail(AQC_EINVAL, "null pointer argument");
+  int rc = aqc_sv_grad_begin(sv, thetas, x_slot, x_basis, z0_slot, w_slot, z_slot);
+  if (rc) return rc;
+  return aqc_sv_grad_end(sv, grad_out);
 }
 
 

@@ -192,6 +192,16 @@ class SvWorkspace:
         )
         return out
 
+    def grad_begin(self, thetas: np.ndarray, *, z0: int, w: int, z: int, x_slot: int = -1, x_basis: int = 0):
+        """Enqueues the gradient sweep and returns at once; collect the result with ``grad_end``."""
+        _, ptr = _thetas_ptr(thetas, self.batch * self.num_thetas)
+        _lib.check(self._lib.aqc_sv_grad_begin(self.handle, ptr, x_slot, int(x_basis), z0, w, z))
+
+    def grad_end(self) -> np.ndarray:
+        out = np.empty((self.batch, self.num_thetas), dtype=np.complex128)
+        _lib.check(self._lib.aqc_sv_grad_end(self.handle, _dptr(out)))
+        return out
+
     def coord_descent(self, thetas: np.ndarray, *, target: int, w: int, z: int, num_sweeps: int = 1):
         """
         ``num_sweeps`` coordinate-descent sweeps (coord_descent_single_sweep,

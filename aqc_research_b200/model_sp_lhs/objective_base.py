@@ -335,6 +335,7 @@ class SpLHSObjectiveBase(ABC):
         self._target = target
         self._ws.upload(SLOT_TARGET, target)
         self._last_thetas = np.empty(0)  # cached V^H target is stale
+        self._early_thetas = None  # an early gradient sweep (if any) belongs to the old target
 
     def set_target_random(self, seed: int) -> None:
         """Synthetic target generated on the device (distribution of utils.rand_state)."""

@@ -15,7 +15,7 @@ import numpy as np
 from .. import checking as chk
 from ..core_operations import mask_gradient
 from ..parametric_circuit import ParametricCircuit
-from .objective_base import SpLHSObjectiveBase
+from .objective_base import SLOT_VH_TARGET, SLOT_W, SLOT_Z, SpLHSObjectiveBase
 
 
 class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
@@ -45,6 +45,14 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         self._grad_scaler = grad_scaler
         self._hs = np.zeros(self._num_states, dtype=np.complex128)
         self._max_no = 0
+        # Early start of the gradient sweep: scipy's L-BFGS-B asks for jac(theta) right after
+        # fun(theta) (optimizer.py:585-590), so once that pattern has been seen twice objective()
+        # enqueues the first gradient term (state 0, always needed, :150-165) before returning and
+        # gradient() only collects it; an objective() call that finds an uncollected sweep (an
+        # optimiser that does not ask for gradients) switches the early start off again.
+        self._early_hits = 0
+        self._early_on = False
+        self._early_thetas = None
 
     def objective(self, thetas: np.ndarray) -> float:
         self._store_latest_thetas(thetas)
@@ -59,16 +67,33 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         w = self._weight
         self._fobj = float(1.0 - (1.0 - w) * self._hs2[0] - w * self._hs2[self._max_no])
         self._fidelity = float(self._hs2[0])
+        if self._early_thetas is not None:  # the previous early sweep was never collected
+            self._early_thetas, self._early_on, self._early_hits = None, False, 0
+        if self._early_on and not self._dense:
+            self._ws.grad_begin(thetas, x_basis=int(self._state_handler.state_indices[0]),
+                                z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
+            self._early_thetas = self._last_thetas
         self._service.on_end_objective()
         return self._fobj
 
+    def _first_term(self, thetas: np.ndarray) -> np.ndarray:
+        """Raw gradient of the state-0 term: collected from the early sweep if one is in flight."""
+        early, self._early_thetas = self._early_thetas, None
+        if early is not None and early.shape == thetas.shape and np.array_equal(early, thetas):
+            return self._ws.grad_end()[0]
+        # (a different theta: the next workspace call drops the uncollected sweep)
+        return self._raw_gradient(thetas, 0)
+
     def gradient(self, thetas: np.ndarray) -> np.ndarray:
         self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)  # may raise: early stop
+        same = self._last_thetas.shape == np.shape(thetas) and np.array_equal(self._last_thetas, thetas)
+        self._early_hits = self._early_hits + 1 if same else 0
+        self._early_on = self._early_hits >= 2
         self._calc_objective_before_gradient(thetas)
         circ = self._circuit
         front = bool(self._front_layer or self._block_range == (0, circ.num_blocks))
 
-        g0 = mask_gradient(circ, self._raw_gradient(thetas, 0), self._block_range, front)
+        g0 = mask_gradient(circ, self._first_term(thetas), self._block_range, front)
         if self._max_no == 0:
             full = np.real(-2.0 * np.conj(self._hs[0]) * g0)
         else:

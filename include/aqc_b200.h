@@ -119,6 +119,14 @@ int aqc_sv_apply(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int
  * grad_out: complex128[batch * num_thetas]. */
 int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
                 int w_slot, int z_slot, double* grad_out);
+/* The same sweep split in two: _begin enqueues everything (angles from a pinned staging buffer,
+ * kernels, the copy of the raw sums back to the host) and returns at once; _end waits for it and
+ * writes grad_out.  Lets a caller that knows the optimiser asks for the gradient right after the
+ * objective at the same angles (scipy's L-BFGS-B does, optimizer.py:585-590) start the sweep while
+ * the host is still busy.  Any other compute call on the workspace drops an uncollected sweep. */
+int aqc_sv_grad_begin(aqc_sv* sv, const double* thetas, int x_slot, int64_t x_basis, int z0_slot,
+                      int w_slot, int z_slot);
+int aqc_sv_grad_end(aqc_sv* sv, double* grad_out);
 
 /* Fused objective step of the state-preparation objectives
  * (objective_lhs_sur_max.py:98-106): z0_slot = V^H target_slot; hs_out[b*count+i] =

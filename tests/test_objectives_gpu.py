@@ -166,3 +166,50 @@ def test_lbfgs_run_matches_reference_trajectory():
     assert abs(res.fun - float(g["lb_fun"])) < 1e-9
     assert rel(res.x, g["lb_x"]) < 1e-7
     assert abs(objv.fidelity - float(g["lb_fidelity"])) < 1e-9
+
+
+def test_early_gradient_start_and_its_fallbacks():
+    """
+    After two fun(theta) / jac(theta) pairs the objective starts the gradient sweep before returning
+    (aqc_sv_grad_begin / _end).  Results must not depend on it: pairs, a gradient at OTHER angles
+    while a sweep is in flight, objective-only stretches (early start switches off), set_target in
+    between -- all against the oracle.
+    """
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200 import utils
+
+    n = 8
+    np.random.seed(88)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    target = utils.rand_state(n)
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    objv.set_target(target)
+
+    def check(th, do_obj=True):
+        w_before, max_before = objv.weight, objv.max_no
+        if do_obj:
+            objv.objective(th)
+        g = objv.gradient(th)
+        f_ref, _, g_ref, _ = O.sur_max_value_and_grad(circ, th, target, w_before, objv.max_no)
+        assert rel(g, g_ref) < TOL, (objv._early_on, max_before)
+
+    ths = [utils.rand_thetas(circ.num_thetas) for _ in range(9)]
+    for th in ths[:4]:  # the pattern is learnt after two pairs; pairs 3 and 4 use the early sweep
+        check(th)
+    assert objv._early_on
+    objv.objective(ths[4])  # early sweep in flight for ths[4] ...
+    check(ths[5], do_obj=False)  # ... but the gradient is asked at other angles
+    assert not objv._early_on
+    check(ths[6])
+    check(ths[6])
+    assert objv._early_on
+    objv.objective(ths[7])
+    objv.objective(ths[8])  # objective-only: the uncollected sweep switches the early start off
+    assert not objv._early_on
+    check(ths[8], do_obj=False)
+    check(ths[0])
+    check(ths[1])
+    objv.objective(ths[2])  # early sweep in flight, then the target changes
+    target = utils.rand_state(n)
+    objv.set_target(target)
+    check(ths[3])
