@@ -44,6 +44,7 @@ WORKLOADS = {  # name -> (num_qubits, layers)
     "sv24": (24, 4),
     "sv28": (28, 4),
     "sv30": (30, 4),
+    "sv31": (31, 4),
 }
 METRIC = "objective+gradient evals/sec"
 UNIT = "evals/s"
