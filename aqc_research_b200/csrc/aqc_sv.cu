@@ -2811,7 +2811,34 @@ __global__ void exchange_kernel(const ExchangeArgs A) {
   const double2* __restrict__ s = A.src[r] + (long long)A.rank * A.chunk;
   double2* __restrict__ d = A.dst + (long long)r * A.chunk;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.chunk; i += stride) d[i] = s[i];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < A.chunk; i += 4 * stride) {  // four peer loads in flight per thread
+    const double2 v0 = s[i], v1 = s[i + stride], v2 = s[i + 2 * stride], v3 = s[i + 3 * stride];
+    d[i] = v0, d[i + stride] = v1, d[i + 2 * stride] = v2, d[i + 3 * stride] = v3;
+  }
+  for (; i < A.chunk; i += stride) d[i] = s[i];
+}
+
+struct PushArgs {
+  const double2* src;  // this rank's source slot
+  double2* dst[16];    // dst[r] = rank r's destination slot
+  long long chunk;
+  int world, rank;
+};
+
+// The same block transpose as remote STORES: (rank r).dst[chunk my_rank] = src[chunk r].  Stores over
+// NVLink are fire-and-forget, so the link is not throttled by outstanding read requests.
+__global__ void exchange_push_kernel(const PushArgs A) {
+  const int r = blockIdx.y;
+  const double2* __restrict__ s = A.src + (long long)r * A.chunk;
+  double2* __restrict__ d = A.dst[r] + (long long)A.rank * A.chunk;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < A.chunk; i += 4 * stride) {
+    const double2 v0 = s[i], v1 = s[i + stride], v2 = s[i + 2 * stride], v3 = s[i + 3 * stride];
+    d[i] = v0, d[i + stride] = v1, d[i + 2 * stride] = v2, d[i + 3 * stride] = v3;
+  }
+  for (; i < A.chunk; i += stride) d[i] = s[i];
 }
 
 extern "C" int aqc_sv_exchange(aqc_sv* sv, int src_slot, int dst_slot) {
@@ -2833,9 +2860,35 @@ extern "C" int aqc_sv_exchange(aqc_sv* sv, int src_slot, int dst_slot) {
     if (!a.src[r]) return fail(AQC_EINVAL, "peer %d slot %d was not imported", r, src_slot);
   }
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  const unsigned gx = (unsigned)std::min<long long>((a.chunk + 255) / 256, 148 * 4);
-  exchange_kernel<<<dim3(gx, a.world), 256, 0, sv->stream>>>(a);
-  CU(cudaGetLastError());
+  // AQC_EXCHANGE = kernel (SM peer loads, default) | memcpy (one copy-engine transfer per peer chunk)
+  static const int mode = [] {
+    const char* e = getenv("AQC_EXCHANGE");
+    return (e && std::string(e) == "memcpy") ? 1 : ((e && std::string(e) == "push") ? 2 : 0);
+  }();
+  if (mode == 2) {
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.src = sv->slots[src_slot];
+    pa.chunk = a.chunk;
+    pa.world = a.world;
+    pa.rank = a.rank;
+    for (int r = 0; r < a.world; ++r) {
+      pa.dst[r] = (r == sv->rank) ? sv->slots[dst_slot] : const_cast<double2*>(sv->peer[dst_slot][r]);
+      if (!pa.dst[r]) return fail(AQC_EINVAL, "peer %d slot %d was not imported", r, dst_slot);
+    }
+    const unsigned gx = (unsigned)std::min<long long>((a.chunk + 255) / 256, 148 * 4);
+    exchange_push_kernel<<<dim3(gx, a.world), 256, 0, sv->stream>>>(pa);
+    CU(cudaGetLastError());
+  } else
+  if (mode == 1) {
+    for (int r = 0; r < a.world; ++r)
+      CU(cudaMemcpyAsync(a.dst + (long long)r * a.chunk, a.src[r] + (long long)a.rank * a.chunk,
+                         (size_t)a.chunk * sizeof(double2), cudaMemcpyDefault, sv->stream));
+  } else {
+    const unsigned gx = (unsigned)std::min<long long>((a.chunk + 255) / 256, 148 * 4);
+    exchange_kernel<<<dim3(gx, a.world), 256, 0, sv->stream>>>(a);
+    CU(cudaGetLastError());
+  }
   CU(cudaEventRecord(sv->ev1, sv->stream));
   CU(cudaStreamSynchronize(sv->stream));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
