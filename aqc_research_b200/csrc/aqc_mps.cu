@@ -1149,6 +1149,125 @@ __device__ void env_step(const EnvArgs& A, int k, double2* X) {
   }
 }
 
+// The same transfer step as two chained tensor-core GEMMs per physical index b (bond capacity >= 32):
+//   X = E . Az[b]  (wi x zi . zi x zo),   E' += conj(Aw[b])^T . X  (wo x wi . wi x zo)
+// real form on mma.sync.m8n8k4.f64; X stays in shared memory as split re/im planes and is the B
+// operand of the second product.  grid (ntasks), 256 threads, warp w owns output rows 8w .. 8w + 7.
+constexpr int kEnvSmemDoubles = 2 * 64 * kThLdA + 2 * 16 * kThLdB + 2 * 64 * kThLdB;
+
+template <bool RIGHT>
+__device__ void env_step_dmma(const EnvArgs& A, int k, double* dsm) {
+  double* sAr = dsm;
+  double* sAi = sAr + 64 * kThLdA;
+  double* sBr = sAi + 64 * kThLdA;
+  double* sBi = sBr + 16 * kThLdB;
+  double* Xr = sBi + 16 * kThLdB;
+  double* Xi = Xr + 64 * kThLdB;
+  const int C = A.C;
+  const int wl = A.w.dims[k], wr = A.w.dims[k + 1], zl = A.z.dims[k], zr = A.z.dims[k + 1];
+  const int wi = RIGHT ? wr : wl, wo = RIGHT ? wl : wr;  // contracted / new bond of w
+  const int zi = RIGHT ? zr : zl, zo = RIGHT ? zl : zr;
+  const double2* E = RIGHT ? A.envR + (size_t)(k + 1) * C * C : A.envL + (size_t)k * C * C;
+  double2* Eo = RIGHT ? A.envR + (size_t)k * C * C : A.envL + (size_t)(k + 1) * C * C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double ore[8][2], oim[8][2];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) ore[q][0] = ore[q][1] = oim[q][0] = oim[q][1] = 0.0;
+
+  for (int b = 0; b < 2; ++b) {
+    double xre[8][2], xim[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xre[q][0] = xre[q][1] = xim[q][0] = xim[q][1] = 0.0;
+    for (int j0 = 0; j0 < zi; j0 += 16) {
+      for (int e = tid; e < 64 * 16; e += 256) {
+        const int kk = e & 15, i = e >> 4;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < wi && j0 + kk < zi) v = E[(size_t)i * C + j0 + kk];
+        sAr[i * kThLdA + kk] = v.x;
+        sAi[i * kThLdA + kk] = v.y;
+      }
+      for (int e = tid; e < 16 * 64; e += 256) {
+        const int j = e & 63, kk = e >> 6;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < zo && j0 + kk < zi) v = site_elem<RIGHT>(A.z, k, b, j0 + kk, j, C);
+        sBr[kk * kThLdB + j] = v.x;
+        sBi[kk * kThLdB + j] = v.y;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 16; ks += 4) {
+        const int ai = (8 * warp + (lane >> 2)) * kThLdA + ks + (lane & 3);
+        const double ar = sAr[ai], aim = sAi[ai], nai = -aim;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int bi = (ks + (lane & 3)) * kThLdB + 8 * q + (lane >> 2);
+          const double br = sBr[bi], bim = sBi[bi];
+          mps_dmma884(xre[q][0], xre[q][1], ar, br);
+          mps_dmma884(xre[q][0], xre[q][1], nai, bim);
+          mps_dmma884(xim[q][0], xim[q][1], ar, bim);
+          mps_dmma884(xim[q][0], xim[q][1], aim, br);
+        }
+      }
+      __syncthreads();
+    }
+    // X -> shared memory planes (row = 8 warp + lane / 4, columns 8 q + 2 (lane & 3) + h)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int idx = (8 * warp + (lane >> 2)) * kThLdB + 8 * q + 2 * (lane & 3) + h;
+        Xr[idx] = xre[q][h];
+        Xi[idx] = xim[q][h];
+      }
+    __syncthreads();
+    for (int i0 = 0; i0 < wi; i0 += 16) {
+      // A planes: row i' (new bond of w), depth i: conj(Aw[b](i -> i'))
+      for (int e = tid; e < 64 * 16; e += 256) {
+        const int kk = e & 15, ip = e >> 4;
+        double2 v = make_double2(0.0, 0.0);
+        if (ip < wo && i0 + kk < wi) v = site_elem<RIGHT>(A.w, k, b, i0 + kk, ip, C);
+        sAr[ip * kThLdA + kk] = v.x;
+        sAi[ip * kThLdA + kk] = -v.y;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 16; ks += 4) {
+        const int ai = (8 * warp + (lane >> 2)) * kThLdA + ks + (lane & 3);
+        const double ar = sAr[ai], aim = sAi[ai], nai = -aim;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int bi = (i0 + ks + (lane & 3)) * kThLdB + 8 * q + (lane >> 2);
+          const double br = Xr[bi], bim = Xi[bi];
+          mps_dmma884(ore[q][0], ore[q][1], ar, br);
+          mps_dmma884(ore[q][0], ore[q][1], nai, bim);
+          mps_dmma884(oim[q][0], oim[q][1], ar, bim);
+          mps_dmma884(oim[q][0], oim[q][1], aim, br);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int ip = 8 * warp + (lane >> 2);
+  if (ip < wo) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 8 * q + 2 * (lane & 3) + h;
+        if (j < zo) Eo[(size_t)ip * C + j] = make_double2(ore[q][h], oim[q][h]);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) mps_env_dmma_kernel(const EnvArgs A) {
+  extern __shared__ double env_dsm[];
+  const EnvTask tk = A.tasks[blockIdx.x];
+  if (tk.dir == 0)
+    env_step_dmma<false>(A, tk.site, env_dsm);
+  else
+    env_step_dmma<true>(A, tk.site, env_dsm);
+}
+
 __global__ void __launch_bounds__(512) mps_env_kernel(const EnvArgs A) {
   extern __shared__ double2 smem_x[];
   const EnvTask tk = A.tasks[blockIdx.x];
@@ -1465,6 +1584,9 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(mps_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mps_env_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(kEnvSmemDoubles * sizeof(double)));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(mps_rho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1734,7 +1856,10 @@ static int env_launch(aqc_mps* m, int wslot, int zslot, int count, const EnvTask
   ea.envL = m->d_envL;
   ea.envR = m->d_envR;
   ea.C = m->C;
-  mps_env_kernel<<<(unsigned)count, 512, 64 * 1024, m->stream>>>(ea);
+  if (m->C >= 32 && m->C <= 64 && !m->theta_scalar)
+    mps_env_dmma_kernel<<<(unsigned)count, 256, kEnvSmemDoubles * sizeof(double), m->stream>>>(ea);
+  else
+    mps_env_kernel<<<(unsigned)count, 512, 64 * 1024, m->stream>>>(ea);
   MCU(cudaGetLastError());
   m->last_launches++;
   return AQC_OK;
