@@ -24,6 +24,10 @@
 //           values, k-steps = the two quad slots a lane holds -> no shuffles, no re-reads.
 //   (the post kernel pulls M_out = U M_in U^H back through the stage).
 //
+// Two consecutive stages on disjoint bit pairs are fused into one step (see build_dense_tables and
+// dense_pass_kernel): the first stage's output fragments become the second stage's B fragments with
+// one lane ^ 4 exchange, so a shared-memory round trip and a CTA barrier serve two stages.
+//
 // Shared memory holds the tile with an XOR swizzle, slot(i) = i ^ fold3(i >> 3), so that the LDS.128
 // of a quarter warp and the STS.64 of a half warp are bank-conflict free whenever the stage's bits
 // (q, p) and the three quad-slot bits (r0, r1, r2) chosen by the host have suitable residues mod 3
@@ -53,12 +57,8 @@ struct DenseTables {
   DLane* d_lanes = nullptr;
 };
 
+// rank of three 3-bit vectors over GF(2)
 static int gf2_rank3(unsigned a, unsigned b, unsigned c) {
-  int best = 0;
-  for (unsigned m = 1; m < 8; ++m) {
-    (void)m;
-  }
-  // rank of three 3-bit vectors over GF(2)
   unsigned v[3] = {a, b, c};
   int rank = 0;
   for (int bit = 0; bit < 3; ++bit) {
@@ -74,7 +74,6 @@ static int gf2_rank3(unsigned a, unsigned b, unsigned c) {
       if (i != rank && (v[i] >> bit & 1u)) v[i] ^= v[rank];
     ++rank;
   }
-  (void)best;
   return rank;
 }
 

@@ -730,8 +730,8 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   // 4 rows per lane => 32 complex numbers in registers) and orthogonalises all 28 column pairs of
   // the block in registers (7 inner rounds of 4 independent rotations), so every column is loaded
   // and stored once per 7 rotations instead of once per rotation: the plain cyclic scheme is bound
-  // by per-SM L2 bandwidth (16 KiB moved per rotation).  The rotations are recorded in shared
-  // memory and replayed on the 8 matching columns of V.
+  // by per-SM L2 bandwidth (16 KiB moved per rotation).  V is not accumulated: the other set of
+  // singular vectors is recovered from the untouched working matrix after convergence (below).
   const int ng = (Cc + 3) / 4;       // column groups
   const int ne = (ng + 1) & ~1;      // even number of players (one phantom group if ng is odd)
   const int npairs = ne / 2;
