@@ -408,7 +408,7 @@ def measure_mps(n=50, chi=64, layers=20, steps=3, warmup=1, device=0, with_cpu=T
         "e2e_value": 1.0 / float(np.mean(wall)),
         "kernel_ms": {"objective": float(np.mean(obj_ms)), "gradient": float(np.mean(grad_ms))},
         "gpu_launches": launches,
-        "dominant_kernel": "mps_svd_kernel (block one-sided Jacobi, FP64 FMA pipe; ~97% of device time)",
+        "dominant_kernel": "mps_svd_kernel (block one-sided Jacobi, FP64 FMA pipe; ~85-89% of device time, profiles/r01_ncu_mps50.md)",
     }
     if with_cpu:
         # reference-equivalent cost: its gradient makes `dots` full-chain mps_dot calls (plus one
