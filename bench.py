@@ -230,6 +230,8 @@ def cpu_port_eval_seconds(n, layers, seed):
     from aqc_research_b200 import utils
     from oracle import c_oracle as C
 
+    C.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1
+
     circ = make_circuit(n, layers)
     rng = np.random.RandomState(seed)
     th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
@@ -463,6 +465,7 @@ def measure_mat7(batch=64, layers=40, steps=5, warmup=2, device=0, with_cpu=True
     if with_cpu:
         from oracle import c_oracle as C
 
+        C.use_all_cores()
         t0 = time.perf_counter()
         z0 = C.apply_v(circ, ths[0], target.ravel(), dagger=True, log2_cols=n)
         C.grad_sweep(circ, ths[0], np.eye(2**n, dtype=np.complex128).ravel(), z0, log2_cols=n, inplace=False)

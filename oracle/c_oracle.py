@@ -41,6 +41,13 @@ def num_threads() -> int:
     return int(_load().orc_num_threads())
 
 
+def use_all_cores() -> int:
+    """All host cores for the OpenMP loops, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    lib = _load()
+    lib.orc_set_num_threads(int(os.cpu_count() or 1))
+    return num_threads()
+
+
 def _desc(circ, as_generic):
     trot = 0
     if hasattr(circ, "is_second_order") and not as_generic:

@@ -38,6 +38,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline wants every host core */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static inline int64_t insert0(int64_t j, int bit) {
   const int64_t lo = j & (((int64_t)1 << bit) - 1);
   return ((j - lo) << 1) | lo;
