@@ -17,6 +17,10 @@ Reference (qiskit-community/aqc-research) locations restated here, paths relativ
   matrix variants             aqc_research/core_op_matrix.py:480-762
   surrogate objective         aqc_research/model_sp_lhs/objective_lhs_sur_max.py:82-191
   sketching objective         aqc_research/model_sketching/sk_core.py:167-222
+  coordinate descent          aqc_research/core_op_matrix.py:765-917   (coord_descent_sweep; pinned by
+                              tests/golden/cd_cases.npz: 8 reference runs of 4 consecutive sweeps)
+  sketching generators        aqc_research/model_sketching/sk_core.py:329-464   (SketchOracle; pinned by
+                              tests/golden/sketch_cases.npz: 7 generator + objective sequences)
 
 The restatement is deliberately written differently from the reference (one generic
 ``(-1, 2, stride)`` reshape per gate instead of half-slice arithmetic) so that agreement is
