@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   // cluster barriers.  Rank 0 finishes (sort, truncate, split).
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
-  const int t = blockIdx.x / csize, s = blockIdx.y, C = A.C;
+  const int crank_hw = (int)cluster.block_rank(), csize_hw = (int)cluster.num_blocks();
+  const int t = blockIdx.x / csize_hw, s = blockIdx.y, C = A.C;
   const MpsTask tk = A.tasks[t];
   const StateMut S = A.st[s];
   const int k = tk.site;
@@ -644,6 +644,19 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   double2* V = A.vmat + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
   const double2* B0 = A.work0 + ((size_t)s * A.maxtasks + t) * (size_t)LD * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // Small matrices (<= 32 columns: at most 4 block pairs per round) are done by ONE CTA with CTA
+  // barriers; the other CTAs of the cluster leave before any cluster barrier is used.  Production
+  // runs (trunc_thr = 1e-6, physical targets) live in this regime: a cluster barrier per round costs
+  // more than the round itself.
+  const bool solo = Cc <= 32;
+  if (solo && crank_hw != 0) return;
+  const int crank = solo ? 0 : crank_hw, csize = solo ? 1 : csize_hw;
+  auto team_sync = [&]() {
+    if (solo)
+      __syncthreads();
+    else
+      cluster.sync();
+  };
 
   int* conv = A.conv + ((size_t)s * A.maxtasks + t) * 32;
   if (crank == 0 && tid < 32) conv[tid] = 0;
@@ -724,7 +737,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     __syncthreads();
   }
   __threadfence();
-  cluster.sync();
+  team_sync();
 
   // Block one-sided Jacobi.  Columns are grouped in fours; a warp takes a PAIR of groups (8 columns,
   // 4 rows per lane => 32 complex numbers in registers) and orthogonalises all 28 column pairs of
@@ -908,7 +921,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
         __syncwarp();
       }
       __threadfence();
-      cluster.sync();
+      team_sync();
     }
     if (tid == 0 && A.sweeps && crank == 0) A.sweeps[s * A.maxtasks + t] = sweep + 1;
     const int mine = __syncthreads_or(rotated);
@@ -917,7 +930,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     } else {
       if (tid == 0 && mine) atomicAdd(conv + sweep, 1);
       __threadfence();
-      cluster.sync();
+      team_sync();
       if (*(volatile int*)(conv + sweep) == 0) break;
     }
   }
