@@ -745,6 +745,17 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   // and stored once per 7 rotations instead of once per rotation: the plain cyclic scheme is bound
   // by per-SM L2 bandwidth (16 KiB moved per rotation).  V is not accumulated: the other set of
   // singular vectors is recovered from the untouched working matrix after convergence (below).
+  // solo mode: the working matrix (Rj x Cc <= 1024 elements) moves into shared memory for the sweeps,
+  // so a block visit costs shared-memory instead of L2 latency (the sweeps of small matrices are a
+  // chain of dependent rounds, not throughput)
+  double2* Bw = B;
+  int ldw = LD;
+  if (solo && Rj * Cc <= 8 * 2 * kMaxChi) {
+    Bw = s_ga;
+    ldw = Rj;
+    for (int e = tid; e < Rj * Cc; e += blockDim.x) Bw[e] = B[(e % Rj) + (size_t)(e / Rj) * LD];
+    __syncthreads();
+  }
   const int ng = (Cc + 3) / 4;       // column groups
   const int ne = (ng + 1) & ~1;      // even number of players (one phantom group if ng is odd)
   const int npairs = ne / 2;
@@ -783,7 +794,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = lane + 32 * e;
-            x[c][e] = (col[c] < Cc && r < Rj) ? B[r + (size_t)col[c] * LD] : make_double2(0.0, 0.0);
+            x[c][e] = (col[c] < Cc && r < Rj) ? Bw[r + (size_t)col[c] * ldw] : make_double2(0.0, 0.0);
           }
         // squared column norms of the block: computed once per visit, then tracked through the
         // rotations (|p'|^2 = |p|^2 - t|g|, |q'|^2 = |q|^2 + t|g| with t|g| = kappa |g|^2), so the inner
@@ -916,7 +927,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = lane + 32 * e;
-            if (col[c] < Cc && r < Rj) B[r + (size_t)col[c] * LD] = x[c][e];
+            if (col[c] < Cc && r < Rj) Bw[r + (size_t)col[c] * ldw] = x[c][e];
           }
         __syncwarp();
       }
@@ -935,6 +946,11 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     }
   }
   if (crank != 0) return;
+  if (Bw != B) {  // back to global memory for the split below
+    __syncthreads();
+    for (int e = tid; e < Rj * Cc; e += blockDim.x) B[(e % Rj) + (size_t)(e / Rj) * LD] = Bw[e];
+    __syncthreads();
+  }
 
   // singular values = column norms
   for (int c = warp; c < Cc; c += nwarps) {
