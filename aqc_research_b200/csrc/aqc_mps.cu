@@ -886,14 +886,22 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
           // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
           const double g2 = gr * gr + gi * gi;
           const bool doit = (g2 > tol2 * al * be) && g2 > 0.0;
+          // with hh = d^2 + 4|g|^2, h = sqrt(hh), q = |d| + h:  1 + kappa^2 |g|^2 = 2h / q, hence
+          //   cs = sqrt(q / 2h),  cs kappa = sign(d) sqrt(2 / (q h)),  kappa |g|^2 = 2 sign(d) |g|^2 / q
+          // -- two dependent special-function steps (rsqrt, then rsqrt and sqrt side by side) instead
+          // of the sqrt -> divide -> rsqrt chain; the inner rounds are latency bound
           const double d = be - al;
-          const double h = sqrt(fma(d, d, 4.0 * g2));
-          const double kappa = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);
-          const double csl = rsqrt(fma(kappa * kappa, g2, 1.0));
-          const double my_dn = doit ? kappa * g2 : 0.0;
+          const double hh = fma(d, d, 4.0 * g2);
+          const double rh = rsqrt(hh);
+          const double q = fma(hh, rh, fabs(d));
+          const double rq = rsqrt(q), srh = sqrt(rh);
+          const double sgn = (d >= 0.0) ? 1.0 : -1.0;
+          const double csl = (q * rq) * (srh * 0.70710678118654752440);
+          const double sf = sgn * 1.41421356237309504880 * (srh * rq);
+          const double my_dn = doit ? (2.0 * sgn) * g2 * (rq * rq) : 0.0;
           const double my_cs = doit ? csl : 1.0;
-          const double my_sr = doit ? csl * kappa * gr : 0.0;
-          const double my_si = doit ? csl * kappa * gi : 0.0;
+          const double my_sr = doit ? sf * gr : 0.0;
+          const double my_si = doit ? sf * gi : 0.0;
 #pragma unroll
           for (int ip = 0; ip < 4; ++ip) {
             const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
