@@ -42,6 +42,7 @@ SIGNATURES = {
     "aqc_sv_upload": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int64]),
     "aqc_sv_download": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int64]),
     "aqc_sv_set_basis": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int64]),
+    "aqc_sv_set_sparse": (ct.c_int, [ct.c_void_p, ct.c_int, c_int64_p, ct.c_void_p, ct.c_int]),
     "aqc_sv_set_identity": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "aqc_sv_fill_random": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_uint64]),
     "aqc_sv_gather": (ct.c_int, [ct.c_void_p, ct.c_int, c_int64_p, ct.c_int, ct.c_void_p]),

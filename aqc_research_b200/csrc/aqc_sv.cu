@@ -1122,6 +1122,18 @@ __global__ void set_basis_kernel(double2* __restrict__ v, long long size, long l
   v[(long long)blockIdx.y * stride + i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
 }
 
+struct SparseInit {
+  long long index[8];
+  double2 amp[8];
+  int count;
+};
+
+// amplitudes of a few basis states on top of a zeroed vector (later entries win on equal indices)
+__global__ void set_sparse_kernel(double2* __restrict__ v, long long stride, SparseInit s) {
+  if (threadIdx.x == 0)
+    for (int k = 0; k < s.count; ++k) v[(long long)blockIdx.x * stride + s.index[k]] = s.amp[k];
+}
+
 __global__ void set_identity_kernel(double2* __restrict__ v, long long size, long long stride,
                                     int log2_cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2030,6 +2042,26 @@ extern "C" int aqc_sv_set_basis(aqc_sv* sv, int slot, int64_t index) {
       sv->slots[slot], sv->size, sv->size, index);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(sv->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_sv_set_sparse(aqc_sv* sv, int slot, const int64_t* indices, const double* amps,
+                                 int count) {
+  int rc = check_slot(sv, slot);
+  if (rc) return rc;
+  if (!indices || !amps) return fail(AQC_EINVAL, "null pointer argument");
+  if (count < 1 || count > 8) return fail(AQC_EINVAL, "a sparse state holds 1 to 8 basis amplitudes");
+  SparseInit init;
+  init.count = count;
+  for (int k = 0; k < count; ++k) {
+    if (indices[k] < 0 || indices[k] >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
+    init.index[k] = indices[k];
+    init.amp[k] = make_double2(amps[2 * k], amps[2 * k + 1]);
+  }
+  CU(cudaSetDevice(sv->device));
+  CU(cudaMemsetAsync(sv->slots[slot], 0, (size_t)sv->batch * sv->size * sizeof(double2), sv->stream));
+  set_sparse_kernel<<<sv->batch, 32, 0, sv->stream>>>(sv->slots[slot], sv->size, init);
+  CU(cudaGetLastError());
   return AQC_OK;
 }
 

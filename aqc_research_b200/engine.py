@@ -136,6 +136,18 @@ class SvWorkspace:
     def set_basis(self, slot: int, index: int):
         _lib.check(self._lib.aqc_sv_set_basis(self.handle, slot, int(index)))
 
+    def set_sparse(self, slot: int, indices: Sequence[int], amplitudes: Sequence[complex]):
+        """slot = sum_k amplitudes[k] |indices[k]> (at most 8 terms); stream ordered, does not wait."""
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        amp = np.ascontiguousarray(amplitudes, dtype=np.complex128)
+        if idx.ndim != 1 or idx.shape != amp.shape:
+            raise ValueError("indices and amplitudes must be 1D sequences of equal length")
+        _lib.check(
+            self._lib.aqc_sv_set_sparse(
+                self.handle, slot, idx.ctypes.data_as(_lib.c_int64_p), _dptr(amp), idx.size
+            )
+        )
+
     def set_identity(self, slot: int):
         _lib.check(self._lib.aqc_sv_set_identity(self.handle, slot))
 

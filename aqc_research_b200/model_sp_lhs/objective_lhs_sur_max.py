@@ -15,7 +15,7 @@ import numpy as np
 from .. import checking as chk
 from ..core_operations import mask_gradient
 from ..parametric_circuit import ParametricCircuit
-from .objective_base import SLOT_VH_TARGET, SLOT_W, SLOT_Z, SpLHSObjectiveBase
+from .objective_base import SLOT_STATE, SLOT_VH_TARGET, SLOT_W, SLOT_Z, SpLHSObjectiveBase
 
 
 class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
@@ -53,6 +53,7 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         self._early_hits = 0
         self._early_on = False
         self._early_thetas = None
+        self._sweep_key = None
 
     def objective(self, thetas: np.ndarray) -> float:
         self._store_latest_thetas(thetas)
@@ -70,19 +71,47 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         if self._early_thetas is not None:  # the previous early sweep was never collected
             self._early_thetas, self._early_on, self._early_hits = None, False, 0
         if self._early_on and not self._dense:
-            self._ws.grad_begin(thetas, x_basis=int(self._state_handler.state_indices[0]),
-                                z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
+            self._begin_sweep(thetas)
             self._early_thetas = self._last_thetas
         self._service.on_end_objective()
         return self._fobj
 
-    def _first_term(self, thetas: np.ndarray) -> np.ndarray:
-        """Raw gradient of the state-0 term: collected from the early sweep if one is in flight."""
+    def _begin_sweep(self, thetas: np.ndarray):
+        """
+        Enqueues the one gradient sweep an evaluation needs (basis flip states).  <V x|t> is
+        antilinear in x, so the two weighted terms of :150-186,
+            Re(-2(1-w) conj(hs_0) d<V s_0|t>) + Re(-2w conj(hs_max) d<V s_max|t>),
+        are the real part of d<V x|t> for x = -2(1-w) hs_0 |s_0> - 2w hs_max |s_max>: one sweep of
+        (w, z) instead of the reference's two.  With max_no == 0 the sweep starts from |s_0> and
+        the factor -2 conj(hs_0) is applied afterwards, as in the reference.
+        """
+        idx = self._state_handler.state_indices
+        if self._max_no == 0:
+            self._ws.grad_begin(thetas, x_basis=int(idx[0]), z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
+        else:
+            w, m = self._weight, self._max_no
+            self._ws.set_sparse(SLOT_W, [int(idx[0]), int(idx[m])],
+                                [-2.0 * (1.0 - w) * self._hs[0], -2.0 * w * self._hs[m]])
+            self._ws.grad_begin(thetas, x_slot=SLOT_W, z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
+        self._sweep_key = (self._max_no, self._weight)
+
+    def _sweep(self, thetas: np.ndarray) -> np.ndarray:
+        """Raw result of ``_begin_sweep``: collected from the early sweep if one is in flight."""
         early, self._early_thetas = self._early_thetas, None
-        if early is not None and early.shape == thetas.shape and np.array_equal(early, thetas):
-            return self._ws.grad_end()[0]
-        # (a different theta: the next workspace call drops the uncollected sweep)
-        return self._raw_gradient(thetas, 0)
+        if (early is None or early.shape != thetas.shape or not np.array_equal(early, thetas)
+                or self._sweep_key != (self._max_no, self._weight)):
+            # (a stale early sweep is dropped by the next workspace call)
+            self._begin_sweep(thetas)
+        return self._ws.grad_end()[0]
+
+    def _dense_terms(self, thetas: np.ndarray) -> np.ndarray:
+        """Generic (dense) flip states: the same single sweep, started from the uploaded combination."""
+        hnd, w, m = self._state_handler, self._weight, self._max_no
+        if m == 0:
+            return -2.0 * np.conj(self._hs[0]) * self._raw_gradient(thetas, 0)
+        x = (-2.0 * (1.0 - w) * self._hs[0]) * hnd.init_state(0) + (-2.0 * w * self._hs[m]) * hnd.init_state(m)
+        self._ws.upload(SLOT_STATE, x)
+        return self._ws.grad(thetas, x_slot=SLOT_STATE, z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)[0]
 
     def gradient(self, thetas: np.ndarray) -> np.ndarray:
         self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)  # may raise: early stop
@@ -93,15 +122,13 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         circ = self._circuit
         front = bool(self._front_layer or self._block_range == (0, circ.num_blocks))
 
-        g0 = mask_gradient(circ, self._first_term(thetas), self._block_range, front)
-        if self._max_no == 0:
-            full = np.real(-2.0 * np.conj(self._hs[0]) * g0)
+        if self._dense:
+            raw = self._dense_terms(thetas)
         else:
-            w = self._weight
-            full = np.real(-2.0 * (1.0 - w) * np.conj(self._hs[0]) * g0)
-            gm = mask_gradient(circ, self._raw_gradient(thetas, self._max_no), self._block_range, front)
-            full = full + np.real(-2.0 * w * np.conj(self._hs[self._max_no]) * gm)
-        full = np.ascontiguousarray(full, dtype=np.float64)
+            raw = self._sweep(thetas)
+            if self._max_no == 0:
+                raw = -2.0 * np.conj(self._hs[0]) * raw
+        full = np.ascontiguousarray(np.real(mask_gradient(circ, raw, self._block_range, front)), dtype=np.float64)
         if self._grad_scaler:
             full *= self._grad_scaler.estimate(self._fobj)
         self._weight += self._gamma * (float(np.sqrt(abs(self._fobj))) - self._weight)

@@ -88,6 +88,11 @@ int aqc_sv_upload(aqc_sv* sv, int slot, int batch_index, const double* host, int
 int aqc_sv_download(aqc_sv* sv, int slot, int batch_index, double* host, int64_t count);
 /* slot[b] = |index>  for all b (ThinStateHandler states, objective_base.py:42-173). */
 int aqc_sv_set_basis(aqc_sv* sv, int slot, int64_t index);
+/* slot[b] = sum_k (amps[2k] + i amps[2k+1]) |indices[k]>  for all b, 1 <= count <= 8.  Stream
+ * ordered, returns without waiting.  The weighted two-term gradient of the surrogate objective
+ * (objective_lhs_sur_max.py:150-186) is antilinear in the flip states, so both terms are taken in
+ * ONE sweep started from -2(1-w) hs_0 |s_0> - 2 w hs_max |s_max>. */
+int aqc_sv_set_sparse(aqc_sv* sv, int slot, const int64_t* indices, const double* amps, int count);
 /* slot[b] = identity matrix (requires log2_cols == n), FullRangeSketchingVectors
  * (sk_core.py:317-326). */
 int aqc_sv_set_identity(aqc_sv* sv, int slot);

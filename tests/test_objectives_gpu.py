@@ -213,3 +213,39 @@ def test_early_gradient_start_and_its_fallbacks():
     target = utils.rand_state(n)
     objv.set_target(target)
     check(ths[3])
+
+
+def test_set_sparse_and_fused_two_term_sweep():
+    """
+    aqc_sv_set_sparse writes a few basis amplitudes; one sweep started from the weighted combination
+    of two flip states equals the weighted sum of the two single-state gradients (antilinearity of
+    <V x|t> in x), which is what the reference adds up (objective_lhs_sur_max.py:150-186).
+    """
+    from aqc_research_b200 import circuit_structures as cs, utils
+    from aqc_research_b200.engine import SvWorkspace
+
+    n = 7
+    np.random.seed(707)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    th, target = utils.rand_thetas(circ.num_thetas), utils.rand_state(n)
+    ws = SvWorkspace(circ, num_slots=4)
+    a = np.array([0.3 - 0.2j, -1.1 + 0.7j])
+    ws.set_sparse(2, [5, 96], a)
+    x = ws.download(2)
+    ref = np.zeros(2**n, dtype=np.complex128)
+    ref[5], ref[96] = a
+    assert np.array_equal(x, ref)
+    with pytest.raises(Exception):
+        ws.set_sparse(2, [2**n], [1.0])
+    with pytest.raises(Exception):
+        ws.set_sparse(2, list(range(9)), [1.0] * 9)
+    ws.upload(0, target)
+    ws.apply(th, 0, 1, dagger=True)
+    g5 = ws.grad(th, x_basis=5, z0=1, w=2, z=3)[0]
+    ws.apply(th, 0, 1, dagger=True)
+    g96 = ws.grad(th, x_basis=96, z0=1, w=2, z=3)[0]
+    ws.apply(th, 0, 1, dagger=True)
+    ws.set_sparse(2, [5, 96], a)
+    both = ws.grad(th, x_slot=2, z0=1, w=2, z=3)[0]
+    assert rel(both, np.conj(a[0]) * g5 + np.conj(a[1]) * g96) < TOL
+    ws.close()
