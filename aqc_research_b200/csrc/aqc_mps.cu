@@ -1479,14 +1479,21 @@ __global__ void mps_amplitude_kernel(StateView S, const long long* __restrict__ 
   if (tid == 0) out[blockIdx.x] = v[cur][0];
 }
 
-__global__ void mps_set_product_kernel(StateMut S, long long index, int n, int C) {
+// |index> as a bond-1 MPS; site `site` (if >= 0) holds a0 |0> + a1 |1> instead of a basis vector
+__global__ void mps_set_product_kernel(StateMut S, long long index, int n, int C, int site, double2 a0,
+                                       double2 a1) {
   const int k = blockIdx.x;
   double2* G = S.gam + (size_t)k * 2 * C * C;
   for (int i = threadIdx.x; i < 2 * C * C; i += blockDim.x) G[i] = make_double2(0.0, 0.0);
   __syncthreads();
   if (threadIdx.x == 0) {
     const int b = (int)((index >> k) & 1);
-    G[(size_t)b * C * C] = make_double2(1.0, 0.0);
+    if (k == site) {
+      G[0] = a0;
+      G[(size_t)C * C] = a1;
+    } else {
+      G[(size_t)b * C * C] = make_double2(1.0, 0.0);
+    }
     S.dims[k] = 1;
     if (k == n - 1) S.dims[n] = 1;
   }
@@ -1680,8 +1687,9 @@ static int copy_state_async(aqc_mps* m, int src, int dst) {
   return AQC_OK;
 }
 
-static int set_product_async(aqc_mps* m, int slot, long long index) {
-  mps_set_product_kernel<<<m->n, 256, 0, m->stream>>>(mut(m, slot), index, m->n, m->C);
+static int set_product_async(aqc_mps* m, int slot, long long index, int site = -1,
+                             double2 a0 = make_double2(0.0, 0.0), double2 a1 = make_double2(0.0, 0.0)) {
+  mps_set_product_kernel<<<m->n, 256, 0, m->stream>>>(mut(m, slot), index, m->n, m->C, site, a0, a1);
   MCU(cudaGetLastError());
   m->last_launches++;
   return AQC_OK;
@@ -1693,6 +1701,19 @@ extern "C" int aqc_mps_set_product(aqc_mps* m, int slot, int64_t index) {
   if (index < 0 || (m->n < 63 && index >= (1ll << m->n))) return aqc_fail(AQC_EINVAL, "basis index out of range");
   MCU(cudaSetDevice(m->device));
   rc = set_product_async(m, slot, index);
+  if (rc) return rc;
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
+
+extern "C" int aqc_mps_set_product_site(aqc_mps* m, int slot, int64_t index, int site, const double* amps) {
+  int rc = mps_check_slot(m, slot);
+  if (rc) return rc;
+  if (!amps) return aqc_fail(AQC_EINVAL, "null argument");
+  if (index < 0 || (m->n < 63 && index >= (1ll << m->n))) return aqc_fail(AQC_EINVAL, "basis index out of range");
+  if (site < 0 || site >= m->n) return aqc_fail(AQC_EINVAL, "site out of range");
+  MCU(cudaSetDevice(m->device));
+  rc = set_product_async(m, slot, index, site, make_double2(amps[0], amps[1]), make_double2(amps[2], amps[3]));
   if (rc) return rc;
   MCU(cudaStreamSynchronize(m->stream));
   return AQC_OK;

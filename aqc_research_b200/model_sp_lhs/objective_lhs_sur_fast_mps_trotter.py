@@ -86,20 +86,39 @@ class SpSurrogateObjectiveFastMpsTrotter(SpLHSObjectiveBase):
         g = self._mps.grad(thetas, x_basis=idx, z0=_SLOT_VH, w=_SLOT_W, z=_SLOT_Z)
         return mask_gradient(self._circuit, g, block_range, front)
 
+    def _raw_pair(self, thetas, block_range, front):
+        """
+        Both weighted terms of the reference (:190-227) from ONE sweep: <V x|t> is antilinear in x
+        and  -2(1-w) hs_0 |s_0> - 2w hs_max |s_max>  is a product state again (the two basis states
+        differ in one qubit), so the sweep starts from that bond-1 MPS, normalised, and the norm
+        is multiplied back.
+        """
+        idx, w, m = self._state_handler.state_indices, self._weight, self._max_no
+        i0, flip = int(idx[0]), int(idx[0]) ^ int(idx[m])
+        if flip == 0 or flip & (flip - 1):  # not a single flip: two sweeps, as the reference
+            g0 = self._raw(thetas, 0, block_range, front)
+            gm = self._raw(thetas, m, block_range, front)
+            return -2.0 * (1.0 - w) * np.conj(self._hs[0]) * g0 - 2.0 * w * np.conj(self._hs[m]) * gm
+        site = flip.bit_length() - 1
+        a0, am = -2.0 * (1.0 - w) * self._hs[0], -2.0 * w * self._hs[m]
+        scale = float(np.hypot(abs(a0), abs(am)))
+        if scale == 0.0:
+            return np.zeros(self._circuit.num_thetas, dtype=np.complex128)
+        amps = (a0 / scale, am / scale) if (i0 >> site) & 1 == 0 else (am / scale, a0 / scale)
+        self._mps.set_product_site(_SLOT_W, i0, site, amps[0], amps[1])
+        g = self._mps.grad(thetas, x_slot=_SLOT_W, z0=_SLOT_VH, w=_SLOT_W, z=_SLOT_Z)
+        return scale * mask_gradient(self._circuit, g, block_range, front)
+
     def gradient(self, thetas: np.ndarray) -> np.ndarray:
         self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)
         self._calc_objective_before_gradient(thetas)
         circ = self._circuit
         block_range = layer_to_block_range(circ, self._layer_range)
         front = first_layer_included(circ, self._layer_range)
-        g0 = self._raw(thetas, 0, block_range, front)
         if self._max_no == 0:
-            full = np.real(-2.0 * np.conj(self._hs[0]) * g0)
+            full = np.real(-2.0 * np.conj(self._hs[0]) * self._raw(thetas, 0, block_range, front))
         else:
-            w = self._weight
-            full = np.real(-2.0 * (1.0 - w) * np.conj(self._hs[0]) * g0)
-            gm = self._raw(thetas, self._max_no, block_range, front)
-            full = full + np.real(-2.0 * w * np.conj(self._hs[self._max_no]) * gm)
+            full = np.real(self._raw_pair(thetas, block_range, front))
         full = np.ascontiguousarray(full, dtype=np.float64)
         if self._grad_scaler:
             full *= self._grad_scaler.estimate(self._fobj)

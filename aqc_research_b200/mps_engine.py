@@ -89,6 +89,11 @@ class MpsWorkspace:
     def set_product(self, slot: int, index: int):
         _lib.check(self._lib.aqc_mps_set_product(self.handle, slot, int(index)))
 
+    def set_product_site(self, slot: int, index: int, site: int, amp0: complex, amp1: complex):
+        """|index> with qubit ``site`` replaced by amp0 |0> + amp1 |1> (bond dimension 1)."""
+        amps = np.array([amp0, amp1], dtype=np.complex128)
+        _lib.check(self._lib.aqc_mps_set_product_site(self.handle, slot, int(index), int(site), _dptr(amps)))
+
     def apply(self, thetas: np.ndarray, src: int, dst: int, dagger: bool = False):
         _, ptr = _thetas_ptr(thetas, self.num_thetas)
         _lib.check(self._lib.aqc_mps_apply(self.handle, ptr, int(dagger), src, dst))

@@ -259,6 +259,11 @@ int aqc_mps_download(aqc_mps* mps, int slot, double* gam, double* lam, int32_t* 
 /* slot = |index> as a bond-dimension-1 MPS (MpsStateHandler states for X-type preparations,
  * objective_base.py:345-398). */
 int aqc_mps_set_product(aqc_mps* mps, int slot, int64_t index);
+/* The same product state except that qubit `site` holds (amps[0] + i amps[1]) |0> +
+ * (amps[2] + i amps[3]) |1>: a weighted pair of states that differ by one flip is still a
+ * product state (the caller keeps the pair at unit norm), so both terms of the surrogate gradient
+ * (objective_lhs_sur_fast_mps_trotter.py:190-227) come from one sweep. */
+int aqc_mps_set_product_site(aqc_mps* mps, int slot, int64_t index, int site, const double* amps);
 /* dst = V src (dagger 0, v_mul_mps mps_operations.py:326-346) or V^H src (dagger 1,
  * v_dagger_mul_mps :349-371), with truncation. */
 int aqc_mps_apply(aqc_mps* mps, const double* thetas, int dagger, int src_slot, int dst_slot);

@@ -212,3 +212,32 @@ def test_full_size_properties_n50():
         fd = (vals[0] - vals[1]) / 2e-4
         assert abs(fd - g[k]) < 1e-6 * max(1.0, abs(g[k])), (k, fd, g[k])
     ws.close()
+
+
+def test_set_product_site_and_fused_two_term_sweep():
+    """
+    aqc_mps_set_product_site: a product state with one qubit in superposition; one gradient sweep
+    from the weighted pair of flip states equals the weighted sum of two sweeps (antilinearity).
+    """
+    rng = np.random.RandomState(77)
+    n = 6
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    ws = MpsWorkspace(circ, num_slots=4, chi_max=64, trunc_thr=1e-16)
+    index, site = 0b010101, 2  # bit 2 of the index is set
+    a_same, a_flip = np.array([0.6 - 0.3j, -0.2 + 0.7j]) / np.sqrt(0.98)  # unit norm, as the caller keeps it
+    ws.set_product_site(2, index, site, a_flip, a_same)  # |0> carries the flipped state here
+    vec = M.mps_to_vector(ws.download(2))
+    ref = np.zeros(2**n, dtype=np.complex128)
+    ref[index], ref[index ^ (1 << site)] = a_same, a_flip
+    assert _rel(vec, ref) < 1e-15
+    with pytest.raises(Exception):
+        ws.set_product_site(2, index, n, 1.0, 0.0)
+    ws.upload(0, M.vector_to_mps(_rand_vec(n, rng)))
+    ws.apply(th, 0, 1, dagger=True)
+    g_same = ws.grad(th, x_basis=index, z0=1, w=2, z=3)
+    g_flip = ws.grad(th, x_basis=index ^ (1 << site), z0=1, w=2, z=3)
+    ws.set_product_site(2, index, site, a_flip, a_same)
+    both = ws.grad(th, x_slot=2, z0=1, w=2, z=3)
+    assert _rel(both, np.conj(a_same) * g_same + np.conj(a_flip) * g_flip) < TOL
+    ws.close()
