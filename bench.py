@@ -586,6 +586,48 @@ def measure_sketch(n=12, m=64, layers=4, steps=3, device=0, with_cpu=True):
     return out
 
 
+def measure_lbfgs(n=12, layers=2, maxiter=40, evol_time=1.0, device=0, with_cpu=True):
+    """
+    BASELINE.json configs[1] end to end: the optimisation loop the reference
+    runs (optimizer.py:585-590 -> scipy L-BFGS-B, fun = objv.objective, jac = objv.gradient) on
+    the Neel state, target = Trotter evolution with 10x finer steps (generated on the device),
+    theta_0 = init_ansatz_to_trotter.  Wall clock of the whole minimize() call, host side included.
+    """
+    from scipy.optimize import minimize
+    from aqc_research_b200.model_sp_lhs.objective_lhs_sur_max import SpSurrogateObjectiveMax
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trot
+
+    circ = make_circuit(n, layers)
+    th0 = trot.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=evol_time, delta=1.0)
+    target = trot.trotter_state(n, evol_time=evol_time, num_steps=10 * layers, delta=1.0,
+                                second_order=True, ini_state=trot.neel_init_state(n))
+    params = dict(num_qubits=n, max_flips=1, maxiter=maxiter, verbose=0, enable_optim_stats=False,
+                  num_simulations=1, trunc_thr=1e-6, state_prep_func=trot.neel_init_state, device=device)
+    best = None
+    for _ in range(2):  # the first run pays for allocation and table upload
+        objv = SpSurrogateObjectiveMax(user_parameters=params, circ=circ, front_layer=True)
+        objv.set_target(target)
+        t0 = time.perf_counter()
+        res = minimize(fun=objv.objective, x0=th0.copy(), jac=objv.gradient, method="L-BFGS-B",
+                       options=dict(maxfun=5 * maxiter, maxiter=maxiter, ftol=10 * np.finfo(float).eps, eps=1e-8))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out = {
+        "workload": f"L-BFGS-B run, n={n}, {layers} layers 2nd-order Trotter ansatz, maxiter={maxiter}, Neel state, "
+                    f"Trotter target (t={evol_time})",
+        "num_thetas": circ.num_thetas, "iterations": int(res.nit), "evaluations": int(res.nfev),
+        "wall_s": best, "value": float(res.nfev) / best, "unit": UNIT,
+        "final_fobj": float(res.fun), "final_fidelity": float(objv.fidelity),
+    }
+    if with_cpu:
+        secs = min(cpu_port_eval_seconds(n, layers, 11 + k)[0] for k in range(3))  # first call starts the threads
+        from oracle import c_oracle as C
+
+        out["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": C.num_threads(), "kind": "port",
+                               "sample": f"1 objective+gradient, best of 3 ({secs * 1e3:.2f} ms); the run needs {int(res.nfev)}"}
+    return out
+
+
 def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
     """
     BASELINE.json configs[4], second half: ONE state vector over `world` GPUs (global-qubit
@@ -792,6 +834,7 @@ def main():
             line["extra_workloads"]["mat7"] = measure_mat7(device=local_rank, with_cpu=not args.no_cpu_baseline)
             line["extra_workloads"]["cd7"] = measure_cd7(device=local_rank, with_cpu=not args.no_cpu_baseline)
             line["extra_workloads"]["sketch12"] = measure_sketch(device=local_rank, with_cpu=not args.no_cpu_baseline)
+            line["extra_workloads"]["lbfgs12"] = measure_lbfgs(device=local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as ex:  # extras must never break the headline line
             line["extra_workloads"]["error"] = repr(ex)
     print(json.dumps(line), flush=True)
