@@ -601,6 +601,117 @@ __global__ void __launch_bounds__(256) mps_theta_dmma_kernel(const ThetaArgs A) 
     }
 }
 
+// One inner round of the register-resident block Jacobi: 4 disjoint column pairs of the 8 columns a
+// warp holds (4 rows per lane) are rotated side by side.  CROSS = false: round IR of the 7-round
+// tournament over all 28 pairs; CROSS = true: pairs (i, 4 + (i + IR) % 4), i.e. only pairs across
+// the two column groups (4 rounds cover the 16 of them).
+template <int IR, bool CROSS>
+__device__ __forceinline__ void jacobi_pair(int ip, int& pa, int& pb) {
+  if (CROSS) {
+    pa = ip;
+    pb = 4 + (ip + IR) % 4;
+  } else {
+    const int a_ = (ip == 0) ? 7 : (IR + ip) % 7;
+    const int b_ = (ip == 0) ? IR : (IR + 7 - ip) % 7;
+    pa = a_ < b_ ? a_ : b_;
+    pb = a_ < b_ ? b_ : a_;
+  }
+}
+
+template <int IR, bool CROSS>
+__device__ __forceinline__ void jacobi_inner(double2 (&x)[8][4], double (&nrm)[8], int lane, double tol2,
+                                             bool& any) {
+  // the 4 disjoint pairs of this inner round: partial cross products of all four ...
+  double pv[8];
+  double al = 0.0, be = 0.0;
+#pragma unroll
+  for (int ip = 0; ip < 4; ++ip) {
+    int pa, pb;
+    jacobi_pair<IR, CROSS>(ip, pa, pb);
+    double gr = 0.0, gi = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double2 u = x[pa][e], v = x[pb][e];
+      gr = fma(u.x, v.x, fma(u.y, v.y, gr));   // Re conj(p) q
+      gi = fma(u.x, v.y, fma(-u.y, v.x, gi));  // Im conj(p) q
+    }
+    pv[ip * 2 + 0] = gr, pv[ip * 2 + 1] = gi;
+    if ((lane >> 3) == ip) al = nrm[pa], be = nrm[pb];
+  }
+  // ... reduced over the warp with a transposing butterfly (7 + 2 shuffles): afterwards
+  // lane L holds entry (L >> 2) & 7, i.e. the 8 lanes of group ip = L >> 3 hold pair ip
+  double red;
+  {
+    double w4[4], w2[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double send = u16 ? pv[i] : pv[i + 4];
+      const double keep = u16 ? pv[i + 4] : pv[i];
+      w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = u8 ? w4[i] : w4[i + 2];
+      const double keep = u8 ? w4[i + 2] : w4[i];
+      w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double send = u4 ? w2[0] : w2[1];
+    const double keep = u4 ? w2[1] : w2[0];
+    red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    red += __shfl_xor_sync(0xffffffffu, red, 2);
+    red += __shfl_xor_sync(0xffffffffu, red, 1);
+  }
+  const int gbase = lane & 0x18;
+  const double gr = __shfl_sync(0xffffffffu, red, gbase | 0);
+  const double gi = __shfl_sync(0xffffffffu, red, gbase | 4);
+  // every 8-lane group computes the rotation of ITS pair (4 pairs in parallel):
+  // tan t = 2|g| sign(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = |q|^2 - |p|^2; the phase
+  // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
+  const double g2 = gr * gr + gi * gi;
+  const bool doit = (g2 > tol2 * al * be) && g2 > 0.0;
+  // with hh = d^2 + 4|g|^2, h = sqrt(hh), q = |d| + h:  1 + kappa^2 |g|^2 = 2h / q, hence
+  //   cs = sqrt(q / 2h),  cs kappa = sign(d) sqrt(2 / (q h)),  kappa |g|^2 = 2 sign(d) |g|^2 / q
+  // -- two dependent special-function steps (rsqrt, then rsqrt and sqrt side by side) instead
+  // of the sqrt -> divide -> rsqrt chain; the inner rounds are latency bound
+  const double d = be - al;
+  const double hh = fma(d, d, 4.0 * g2);
+  const double rh = rsqrt(hh);
+  const double q = fma(hh, rh, fabs(d));
+  const double rq = rsqrt(q), srh = sqrt(rh);
+  const double sgn = (d >= 0.0) ? 1.0 : -1.0;
+  const double csl = (q * rq) * (srh * 0.70710678118654752440);
+  const double sf = sgn * 1.41421356237309504880 * (srh * rq);
+  const double my_dn = doit ? (2.0 * sgn) * g2 * (rq * rq) : 0.0;
+  const double my_cs = doit ? csl : 1.0;
+  const double my_sr = doit ? sf * gr : 0.0;
+  const double my_si = doit ? sf * gi : 0.0;
+#pragma unroll
+  for (int ip = 0; ip < 4; ++ip) {
+    int pa, pb;
+    jacobi_pair<IR, CROSS>(ip, pa, pb);
+    const double cs = __shfl_sync(0xffffffffu, my_cs, ip << 3);
+    const double sr = __shfl_sync(0xffffffffu, my_sr, ip << 3);
+    const double si = __shfl_sync(0xffffffffu, my_si, ip << 3);
+    const double dn = __shfl_sync(0xffffffffu, my_dn, ip << 3);
+    nrm[pa] -= dn;
+    nrm[pb] += dn;
+    any = any || (sr != 0.0) || (si != 0.0);
+    // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q   (identity if not rotated)
+    const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double2 u = x[pa][e], v = x[pb][e];
+      double2 nu = make_double2(cs * u.x, cs * u.y);
+      cfma(nu, fm, v);
+      double2 nv = make_double2(cs * v.x, cs * v.y);
+      cfma(nv, fp, u);
+      x[pa][e] = nu;
+      x[pb][e] = nv;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel: one-sided Jacobi SVD of the working matrix + truncation + split into Gamma, lambda
 // ------------------------------------------------------------------------------------------
@@ -833,100 +944,24 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
           for (int c = 0; c < 8; ++c)
             nrm[c] = __shfl_sync(0xffffffffu, red, ((c >> 2) & 1) * 16 + ((c >> 1) & 1) * 8 + (c & 1) * 4);
         }
+        // Round 0 of a sweep orthogonalises all 28 pairs of the 8 columns (7 inner rounds); in it every
+        // column group meets exactly one partner, so the 6 pairs INSIDE each group are covered once
+        // per sweep there.  The other rounds only take the 16 pairs ACROSS the two groups (4 inner
+        // rounds): repeating the inside pairs in all ne-1 rounds cost 12 of every 28 rotations.
         bool any = false;
-#pragma unroll
-        for (int ir = 0; ir < 7; ++ir) {
-          // the 4 disjoint pairs of this inner round: partial cross products of all four ...
-          double pv[8];
-          double al = 0.0, be = 0.0;
-#pragma unroll
-          for (int ip = 0; ip < 4; ++ip) {
-            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
-            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
-            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
-            double gr = 0.0, gi = 0.0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const double2 u = x[pa][e], v = x[pb][e];
-              gr = fma(u.x, v.x, fma(u.y, v.y, gr));   // Re conj(p) q
-              gi = fma(u.x, v.y, fma(-u.y, v.x, gi));  // Im conj(p) q
-            }
-            pv[ip * 2 + 0] = gr, pv[ip * 2 + 1] = gi;
-            if ((lane >> 3) == ip) al = nrm[pa], be = nrm[pb];
-          }
-          // ... reduced over the warp with a transposing butterfly (7 + 2 shuffles): afterwards
-          // lane L holds entry (L >> 2) & 7, i.e. the 8 lanes of group ip = L >> 3 hold pair ip
-          double red;
-          {
-            double w4[4], w2[2];
-            const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const double send = u16 ? pv[i] : pv[i + 4];
-              const double keep = u16 ? pv[i + 4] : pv[i];
-              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const double send = u8 ? w4[i] : w4[i + 2];
-              const double keep = u8 ? w4[i + 2] : w4[i];
-              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            const double send = u4 ? w2[0] : w2[1];
-            const double keep = u4 ? w2[1] : w2[0];
-            red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            red += __shfl_xor_sync(0xffffffffu, red, 2);
-            red += __shfl_xor_sync(0xffffffffu, red, 1);
-          }
-          const int gbase = lane & 0x18;
-          const double gr = __shfl_sync(0xffffffffu, red, gbase | 0);
-          const double gi = __shfl_sync(0xffffffffu, red, gbase | 4);
-          // every 8-lane group computes the rotation of ITS pair (4 pairs in parallel):
-          // tan t = 2|g| sign(d) / (|d| + sqrt(d^2 + 4|g|^2)), d = |q|^2 - |p|^2; the phase
-          // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
-          const double g2 = gr * gr + gi * gi;
-          const bool doit = (g2 > tol2 * al * be) && g2 > 0.0;
-          // with hh = d^2 + 4|g|^2, h = sqrt(hh), q = |d| + h:  1 + kappa^2 |g|^2 = 2h / q, hence
-          //   cs = sqrt(q / 2h),  cs kappa = sign(d) sqrt(2 / (q h)),  kappa |g|^2 = 2 sign(d) |g|^2 / q
-          // -- two dependent special-function steps (rsqrt, then rsqrt and sqrt side by side) instead
-          // of the sqrt -> divide -> rsqrt chain; the inner rounds are latency bound
-          const double d = be - al;
-          const double hh = fma(d, d, 4.0 * g2);
-          const double rh = rsqrt(hh);
-          const double q = fma(hh, rh, fabs(d));
-          const double rq = rsqrt(q), srh = sqrt(rh);
-          const double sgn = (d >= 0.0) ? 1.0 : -1.0;
-          const double csl = (q * rq) * (srh * 0.70710678118654752440);
-          const double sf = sgn * 1.41421356237309504880 * (srh * rq);
-          const double my_dn = doit ? (2.0 * sgn) * g2 * (rq * rq) : 0.0;
-          const double my_cs = doit ? csl : 1.0;
-          const double my_sr = doit ? sf * gr : 0.0;
-          const double my_si = doit ? sf * gi : 0.0;
-#pragma unroll
-          for (int ip = 0; ip < 4; ++ip) {
-            const int a_ = (ip == 0) ? 7 : (ir + ip) % 7;
-            const int b_ = (ip == 0) ? ir : (ir + 7 - ip) % 7;
-            const int pa = a_ < b_ ? a_ : b_, pb = a_ < b_ ? b_ : a_;
-            const double cs = __shfl_sync(0xffffffffu, my_cs, ip << 3);
-            const double sr = __shfl_sync(0xffffffffu, my_sr, ip << 3);
-            const double si = __shfl_sync(0xffffffffu, my_si, ip << 3);
-            const double dn = __shfl_sync(0xffffffffu, my_dn, ip << 3);
-            nrm[pa] -= dn;
-            nrm[pb] += dn;
-            any = any || (sr != 0.0) || (si != 0.0);
-            // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q   (identity if not rotated)
-            const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const double2 u = x[pa][e], v = x[pb][e];
-              double2 nu = make_double2(cs * u.x, cs * u.y);
-              cfma(nu, fm, v);
-              double2 nv = make_double2(cs * v.x, cs * v.y);
-              cfma(nv, fp, u);
-              x[pa][e] = nu;
-              x[pb][e] = nv;
-            }
-          }
+        if (round == 0) {
+          jacobi_inner<0, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<1, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<2, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<3, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<4, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<5, false>(x, nrm, lane, tol2, any);
+          jacobi_inner<6, false>(x, nrm, lane, tol2, any);
+        } else {
+          jacobi_inner<0, true>(x, nrm, lane, tol2, any);
+          jacobi_inner<1, true>(x, nrm, lane, tol2, any);
+          jacobi_inner<2, true>(x, nrm, lane, tol2, any);
+          jacobi_inner<3, true>(x, nrm, lane, tol2, any);
         }
         if (!any) continue;  // warp-uniform
         rotated = 1;
