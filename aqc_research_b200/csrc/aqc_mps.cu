@@ -618,8 +618,8 @@ __device__ __forceinline__ void jacobi_pair(int ip, int& pa, int& pb) {
   }
 }
 
-template <int IR, bool CROSS>
-__device__ __forceinline__ void jacobi_inner(double2 (&x)[8][4], double (&nrm)[8], int lane, double tol2,
+template <int IR, bool CROSS, int NE>
+__device__ __forceinline__ void jacobi_inner(double2 (&x)[8][NE], double (&nrm)[8], int lane, double tol2,
                                              bool& any) {
   // the 4 disjoint pairs of this inner round: partial cross products of all four ...
   double pv[8];
@@ -630,7 +630,7 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][4], double (&nrm)[8
     jacobi_pair<IR, CROSS>(ip, pa, pb);
     double gr = 0.0, gi = 0.0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       const double2 u = x[pa][e], v = x[pb][e];
       gr = fma(u.x, v.x, fma(u.y, v.y, gr));   // Re conj(p) q
       gi = fma(u.x, v.y, fma(-u.y, v.x, gi));  // Im conj(p) q
@@ -700,7 +700,7 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][4], double (&nrm)[8
     // p' = cs p - sn e^{-i phi} q ;  q' = sn e^{i phi} p + cs q   (identity if not rotated)
     const double2 fm = make_double2(-sr, si), fp = make_double2(sr, si);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       const double2 u = x[pa][e], v = x[pb][e];
       double2 nu = make_double2(cs * u.x, cs * u.y);
       cfma(nu, fm, v);
@@ -708,6 +708,145 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][4], double (&nrm)[8
       cfma(nv, fp, u);
       x[pa][e] = nu;
       x[pb][e] = nv;
+    }
+  }
+}
+
+// The Jacobi sweeps of one SVD on the matrix Bw (Rj x Cc, leading dimension ldw; global or shared
+// memory), shared by `csize` CTAs (crank = this CTA).  NE = rows per lane: 32 NE >= Rj, so a small
+// matrix does not pay for the zero rows of the 128-row layout (a warp with an SM sub-partition to
+// itself is bound by FP64 issue: 2 cycles per instruction).
+template <int NE>
+__device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int Cc, bool solo, int crank,
+                                              int csize, int* conv, int* sweeps_out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  auto team_sync = [&]() {
+    if (solo)
+      __syncthreads();
+    else
+      cluster.sync();
+  };
+  const int ng = (Cc + 3) / 4;       // column groups
+  const int ne = (ng + 1) & ~1;      // even number of players (one phantom group if ng is odd)
+  const int npairs = ne / 2;
+  // convergence: |<p, q>| <= tol |p| |q| with tol ~ 2 sqrt(R) eps (LAPACK xGESVJ uses sqrt(m) eps);
+  // a tighter value sits below the rounding noise of the inner product and never converges
+  const double tol = 2.0 * sqrt((double)Rj) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    int rotated = 0;
+    const int nrounds = (ne > 1) ? ne - 1 : 1;
+    for (int round = 0; round < nrounds; ++round) {
+      for (int pi = warp * csize + crank; pi < npairs; pi += nwarps * csize) {
+        int gI, gJ;
+        if (ne == 1 || ng == 1) {
+          gI = 0;
+          gJ = 1;  // single group: the second group is empty
+        } else if (pi == 0) {
+          gI = ne - 1;
+          gJ = round;
+        } else {
+          gI = (round + pi) % (ne - 1);
+          gJ = (round + ne - 1 - pi) % (ne - 1);
+        }
+        if (gI > gJ) {
+          const int tmp = gI;
+          gI = gJ;
+          gJ = tmp;
+        }
+        if (gI >= ng) continue;
+        int col[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) col[c] = 4 * gI + c, col[4 + c] = 4 * gJ + c;
+        double2 x[8][NE];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int r = lane + 32 * e;
+            x[c][e] = (col[c] < Cc && r < Rj) ? Bw[r + (size_t)col[c] * ldw] : make_double2(0.0, 0.0);
+          }
+        // squared column norms of the block: computed once per visit, then tracked through the
+        // rotations (|p'|^2 = |p|^2 - t|g|, |q'|^2 = |q|^2 + t|g| with t|g| = kappa |g|^2), so the inner
+        // rounds only need the cross products <p|q>
+        double nrm[8];
+        {
+          double pn[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) acc = fma(x[c][e].x, x[c][e].x, fma(x[c][e].y, x[c][e].y, acc));
+            pn[c] = acc;
+          }
+          double w4[4], w2[2];
+          const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = u16 ? pn[i] : pn[i + 4];
+            const double keep = u16 ? pn[i + 4] : pn[i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = u8 ? w4[i] : w4[i + 2];
+            const double keep = u8 ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          const double send = u4 ? w2[0] : w2[1];
+          const double keep = u4 ? w2[1] : w2[0];
+          double red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          red += __shfl_xor_sync(0xffffffffu, red, 2);
+          red += __shfl_xor_sync(0xffffffffu, red, 1);
+          // lane L holds column ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            nrm[c] = __shfl_sync(0xffffffffu, red, ((c >> 2) & 1) * 16 + ((c >> 1) & 1) * 8 + (c & 1) * 4);
+        }
+        // Round 0 of a sweep orthogonalises all 28 pairs of the 8 columns (7 inner rounds); in it every
+        // column group meets exactly one partner, so the 6 pairs INSIDE each group are covered once
+        // per sweep there.  The other rounds only take the 16 pairs ACROSS the two groups (4 inner
+        // rounds): repeating the inside pairs in all ne-1 rounds cost 12 of every 28 rotations.
+        bool any = false;
+        if (round == 0) {
+          jacobi_inner<0, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<1, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<2, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<3, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<4, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<5, false, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<6, false, NE>(x, nrm, lane, tol2, any);
+        } else {
+          jacobi_inner<0, true, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<1, true, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<2, true, NE>(x, nrm, lane, tol2, any);
+          jacobi_inner<3, true, NE>(x, nrm, lane, tol2, any);
+        }
+        if (!any) continue;  // warp-uniform
+        rotated = 1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int r = lane + 32 * e;
+            if (col[c] < Cc && r < Rj) Bw[r + (size_t)col[c] * ldw] = x[c][e];
+          }
+        __syncwarp();
+      }
+      __threadfence();
+      team_sync();
+    }
+    if (tid == 0 && sweeps_out && crank == 0) *sweeps_out = sweep + 1;
+    const int mine = __syncthreads_or(rotated);
+    if (csize == 1) {
+      if (mine == 0) break;
+    } else {
+      if (tid == 0 && mine) atomicAdd(conv + sweep, 1);
+      __threadfence();
+      team_sync();
+      if (*(volatile int*)(conv + sweep) == 0) break;
     }
   }
 }
@@ -867,127 +1006,13 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     for (int e = tid; e < Rj * Cc; e += blockDim.x) Bw[e] = B[(e % Rj) + (size_t)(e / Rj) * LD];
     __syncthreads();
   }
-  const int ng = (Cc + 3) / 4;       // column groups
-  const int ne = (ng + 1) & ~1;      // even number of players (one phantom group if ng is odd)
-  const int npairs = ne / 2;
-  // convergence: |<p, q>| <= tol |p| |q| with tol ~ 2 sqrt(R) eps (LAPACK xGESVJ uses sqrt(m) eps);
-  // a tighter value sits below the rounding noise of the inner product and never converges
-  const double tol = 2.0 * sqrt((double)Rj) * 2.220446049250313e-16;
-  const double tol2 = tol * tol;
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    int rotated = 0;
-    const int nrounds = (ne > 1) ? ne - 1 : 1;
-    for (int round = 0; round < nrounds; ++round) {
-      for (int pi = warp * csize + crank; pi < npairs; pi += nwarps * csize) {
-        int gI, gJ;
-        if (ne == 1 || ng == 1) {
-          gI = 0;
-          gJ = 1;  // single group: the second group is empty
-        } else if (pi == 0) {
-          gI = ne - 1;
-          gJ = round;
-        } else {
-          gI = (round + pi) % (ne - 1);
-          gJ = (round + ne - 1 - pi) % (ne - 1);
-        }
-        if (gI > gJ) {
-          const int tmp = gI;
-          gI = gJ;
-          gJ = tmp;
-        }
-        if (gI >= ng) continue;
-        int col[8];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) col[c] = 4 * gI + c, col[4 + c] = 4 * gJ + c;
-        double2 x[8][4];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = lane + 32 * e;
-            x[c][e] = (col[c] < Cc && r < Rj) ? Bw[r + (size_t)col[c] * ldw] : make_double2(0.0, 0.0);
-          }
-        // squared column norms of the block: computed once per visit, then tracked through the
-        // rotations (|p'|^2 = |p|^2 - t|g|, |q'|^2 = |q|^2 + t|g| with t|g| = kappa |g|^2), so the inner
-        // rounds only need the cross products <p|q>
-        double nrm[8];
-        {
-          double pn[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            double acc = 0.0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc = fma(x[c][e].x, x[c][e].x, fma(x[c][e].y, x[c][e].y, acc));
-            pn[c] = acc;
-          }
-          double w4[4], w2[2];
-          const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double send = u16 ? pn[i] : pn[i + 4];
-            const double keep = u16 ? pn[i + 4] : pn[i];
-            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double send = u8 ? w4[i] : w4[i + 2];
-            const double keep = u8 ? w4[i + 2] : w4[i];
-            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-          const double send = u4 ? w2[0] : w2[1];
-          const double keep = u4 ? w2[1] : w2[0];
-          double red = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          red += __shfl_xor_sync(0xffffffffu, red, 2);
-          red += __shfl_xor_sync(0xffffffffu, red, 1);
-          // lane L holds column ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            nrm[c] = __shfl_sync(0xffffffffu, red, ((c >> 2) & 1) * 16 + ((c >> 1) & 1) * 8 + (c & 1) * 4);
-        }
-        // Round 0 of a sweep orthogonalises all 28 pairs of the 8 columns (7 inner rounds); in it every
-        // column group meets exactly one partner, so the 6 pairs INSIDE each group are covered once
-        // per sweep there.  The other rounds only take the 16 pairs ACROSS the two groups (4 inner
-        // rounds): repeating the inside pairs in all ne-1 rounds cost 12 of every 28 rotations.
-        bool any = false;
-        if (round == 0) {
-          jacobi_inner<0, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<1, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<2, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<3, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<4, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<5, false>(x, nrm, lane, tol2, any);
-          jacobi_inner<6, false>(x, nrm, lane, tol2, any);
-        } else {
-          jacobi_inner<0, true>(x, nrm, lane, tol2, any);
-          jacobi_inner<1, true>(x, nrm, lane, tol2, any);
-          jacobi_inner<2, true>(x, nrm, lane, tol2, any);
-          jacobi_inner<3, true>(x, nrm, lane, tol2, any);
-        }
-        if (!any) continue;  // warp-uniform
-        rotated = 1;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = lane + 32 * e;
-            if (col[c] < Cc && r < Rj) Bw[r + (size_t)col[c] * ldw] = x[c][e];
-          }
-        __syncwarp();
-      }
-      __threadfence();
-      team_sync();
-    }
-    if (tid == 0 && A.sweeps && crank == 0) A.sweeps[s * A.maxtasks + t] = sweep + 1;
-    const int mine = __syncthreads_or(rotated);
-    if (csize == 1) {
-      if (mine == 0) break;
-    } else {
-      if (tid == 0 && mine) atomicAdd(conv + sweep, 1);
-      __threadfence();
-      team_sync();
-      if (*(volatile int*)(conv + sweep) == 0) break;
-    }
-  }
+  int* sweeps_out = A.sweeps ? A.sweeps + s * A.maxtasks + t : nullptr;
+  if (Rj <= 32)
+    jacobi_sweeps<1>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
+  else if (Rj <= 64)
+    jacobi_sweeps<2>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
+  else
+    jacobi_sweeps<4>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
   if (crank != 0) return;
   if (Bw != B) {  // back to global memory for the split below
     __syncthreads();
