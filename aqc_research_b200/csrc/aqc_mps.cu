@@ -670,19 +670,19 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][NE], double (&nrm)[
   // e^{i phi} = g / |g| only enters as sn e^{i phi} = cs kappa g
   const double g2 = gr * gr + gi * gi;
   const bool doit = (g2 > tol2 * al * be) && g2 > 0.0;
-  // with hh = d^2 + 4|g|^2, h = sqrt(hh), q = |d| + h:  1 + kappa^2 |g|^2 = 2h / q, hence
-  //   cs = sqrt(q / 2h),  cs kappa = sign(d) sqrt(2 / (q h)),  kappa |g|^2 = 2 sign(d) |g|^2 / q
-  // -- two dependent special-function steps (rsqrt, then rsqrt and sqrt side by side) instead
-  // of the sqrt -> divide -> rsqrt chain; the inner rounds are latency bound
+  // with hh = d^2 + 4|g|^2, h = sqrt(hh), q = |d| + h:  1 + kappa^2 |g|^2 = 2h / q, hence with
+  // y = q / 2h (in [1/2, 1]):  cs = sqrt(y),  cs kappa = sign(d) / (h sqrt(y)),  kappa = sign(d) / (h y)
+  // -- two special functions in all, rsqrt(hh) and rsqrt(y), instead of the sqrt -> divide -> rsqrt
+  // chain: the inner rounds are bound by FP64 issue and by this dependent chain
   const double d = be - al;
   const double hh = fma(d, d, 4.0 * g2);
-  const double rh = rsqrt(hh);
-  const double q = fma(hh, rh, fabs(d));
-  const double rq = rsqrt(q), srh = sqrt(rh);
-  const double sgn = (d >= 0.0) ? 1.0 : -1.0;
-  const double csl = (q * rq) * (srh * 0.70710678118654752440);
-  const double sf = sgn * 1.41421356237309504880 * (srh * rq);
-  const double my_dn = doit ? (2.0 * sgn) * g2 * (rq * rq) : 0.0;
+  const double rh = rsqrt(hh);                     // 1 / h
+  const double y = fma(0.5 * fabs(d), rh, 0.5);    // (|d| + h) / 2h
+  const double ry = rsqrt(y);
+  const double sgn_rh = (d >= 0.0) ? rh : -rh;
+  const double csl = y * ry;
+  const double sf = sgn_rh * ry;
+  const double my_dn = doit ? (sgn_rh * g2) * (ry * ry) : 0.0;
   const double my_cs = doit ? csl : 1.0;
   const double my_sr = doit ? sf * gr : 0.0;
   const double my_si = doit ? sf * gi : 0.0;
