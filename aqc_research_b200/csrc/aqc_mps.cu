@@ -125,6 +125,7 @@ struct aqc_mps {
   int* d_conv = nullptr;       // [2][maxtasks][32]
   int num_sms = 148;
   bool svd_precond = true;    // AQC_MPS_SVD=plain: Jacobi directly on the working matrix
+  bool svd_fence = false;     // AQC_MPS_FENCE=1
   bool theta_scalar = false;  // AQC_MPS_THETA=scalar: thread-per-column contraction instead of the DMMA GEMM
   double* h_pinned = nullptr;
   size_t pinned_cap = 0;
@@ -718,7 +719,7 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][NE], double (&nrm)[
 // itself is bound by FP64 issue: 2 cycles per instruction).
 template <int NE>
 __device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int Cc, bool solo, int crank,
-                                              int csize, int* conv, int* sweeps_out) {
+                                              int csize, int* conv, int* sweeps_out, bool fence) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -835,7 +836,10 @@ __device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int 
           }
         __syncwarp();
       }
-      __threadfence();
+      // cluster.sync() is barrier.cluster.arrive.release + wait.acquire: it orders the global-memory
+      // columns between the CTAs of the cluster by itself; the device-scope fence in front of it was
+      // 9 % of the stall samples (ERRBAR).  AQC_MPS_FENCE=1 puts it back.
+      if (fence) __threadfence();
       team_sync();
     }
     if (tid == 0 && sweeps_out && crank == 0) *sweeps_out = sweep + 1;
@@ -844,7 +848,7 @@ __device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int 
       if (mine == 0) break;
     } else {
       if (tid == 0 && mine) atomicAdd(conv + sweep, 1);
-      __threadfence();
+      if (fence) __threadfence();
       team_sync();
       if (*(volatile int*)(conv + sweep) == 0) break;
     }
@@ -865,6 +869,7 @@ struct SvdArgs {
   int* sweeps;  // [state][maxtasks] Jacobi sweeps used (diagnostics)
   int* conv;    // [state][maxtasks][32] rotations counted per sweep (cluster-wide convergence)
   int precond;  // 1: Householder QR first, Jacobi on R^H (Drmac-Veselic preconditioning)
+  int fence;    // 1: device-scope fence in front of every cluster barrier (AQC_MPS_FENCE=1)
 };
 
 __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
@@ -944,27 +949,48 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
       __syncthreads();
       const double beta = s_beta;
       if (beta != 0.0) {
-        for (int c = j + 1 + warp; c < Cc; c += nwarps) {
-          double2 a[4];
-          double2 dot = make_double2(0.0, 0.0);
+        // four columns per warp in flight: the update is a chain of L2 round trips otherwise
+        double2 hv[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = j + lane + 32 * e;
-            a[e] = (r < R) ? B[r + (size_t)c * LD] : make_double2(0.0, 0.0);
-            if (r < R) cfma_conj(dot, s_v[r - j], a[e]);
+        for (int e = 0; e < 4; ++e) {
+          const int r = j + lane + 32 * e;
+          hv[e] = (r < R) ? s_v[r - j] : make_double2(0.0, 0.0);
+        }
+        for (int cb = j + 1 + warp; cb < Cc; cb += 4 * nwarps) {
+          double2 a[4][4], dot[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = cb + u * nwarps;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int r = j + lane + 32 * e;
+              a[u][e] = (c < Cc && r < R) ? B[r + (size_t)c * LD] : make_double2(0.0, 0.0);
+            }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o);
-            dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
-          }
-          const double2 f = make_double2(-beta * dot.x, -beta * dot.y);
+          for (int u = 0; u < 4; ++u) {
+            dot[u] = make_double2(0.0, 0.0);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = j + lane + 32 * e;
-            if (r < R) {
-              cfma(a[e], s_v[r - j], f);
-              B[r + (size_t)c * LD] = a[e];
+            for (int e = 0; e < 4; ++e) cfma_conj(dot[u], hv[e], a[u][e]);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              dot[u].x += __shfl_xor_sync(0xffffffffu, dot[u].x, o);
+              dot[u].y += __shfl_xor_sync(0xffffffffu, dot[u].y, o);
+            }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = cb + u * nwarps;
+            const double2 f = make_double2(-beta * dot[u].x, -beta * dot[u].y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int r = j + lane + 32 * e;
+              if (c < Cc && r < R) {
+                cfma(a[u][e], hv[e], f);
+                B[r + (size_t)c * LD] = a[u][e];
+              }
             }
           }
         }
@@ -986,7 +1012,7 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
     }
     __syncthreads();
   }
-  __threadfence();
+  if (A.fence) __threadfence();
   team_sync();
 
   // Block one-sided Jacobi.  Columns are grouped in fours; a warp takes a PAIR of groups (8 columns,
@@ -1008,11 +1034,11 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   }
   int* sweeps_out = A.sweeps ? A.sweeps + s * A.maxtasks + t : nullptr;
   if (Rj <= 32)
-    jacobi_sweeps<1>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
+    jacobi_sweeps<1>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
   else if (Rj <= 64)
-    jacobi_sweeps<2>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
+    jacobi_sweeps<2>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
   else
-    jacobi_sweeps<4>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out);
+    jacobi_sweeps<4>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
   if (crank != 0) return;
   if (Bw != B) {  // back to global memory for the split below
     __syncthreads();
@@ -1673,6 +1699,8 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
     m->theta_scalar = th && std::string(th) == "scalar";
     const char* sv = getenv("AQC_MPS_SVD");
     m->svd_precond = !(sv && std::string(sv) == "plain");
+    const char* fe = getenv("AQC_MPS_FENCE");
+    m->svd_fence = fe && std::string(fe) == "1";
   }
   for (MpsProgram* p : {&m->fwd, &m->dag}) {
     alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
@@ -1855,6 +1883,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   sa.sweeps = m->d_sweeps;
   sa.conv = m->d_conv;
   sa.precond = m->svd_precond ? 1 : 0;
+  sa.fence = m->svd_fence ? 1 : 0;
   // as many CTAs per SVD as fit in one wave (cluster of 1, 2 or 4)
   int csize = 1;
   const int nsvd = st.ntasks * nstates;
