@@ -62,10 +62,13 @@ def test_roundtrip_dot_amplitudes(n):
     ws.close()
 
 
-@pytest.mark.parametrize("n", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 8, 12])
 def test_untruncated_apply_and_gradient_vs_statevector(n):
+    """n = 12: bonds up to 64, i.e. 128 x 128 SVDs shared by a cluster (all register layouts of the sweeps)."""
     rng = np.random.RandomState(100 + n)
     for name, circ in _circuits(n, rng):
+        if n == 12 and name not in ("t2", "cx"):
+            continue
         th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
         y = _rand_vec(n, rng)
         ws = MpsWorkspace(circ, num_slots=5, chi_max=64, trunc_thr=1e-16)
