@@ -379,7 +379,7 @@ def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
         assert np.isfinite(f) and np.all(np.isfinite(g))
         two_term = {"e2e_value": 1.0 / float(np.mean(t2_s)), "unit": UNIT, "steps": len(t2_s),
                     "target": "random (rand_state distribution, generated on the device)",
-                    "gradient_sweeps_per_eval": 1}
+                    "gradient_sweeps_per_eval": 1, "scope": "one GPU (rank 0), end to end through the objective class"}
     T = circ.num_thetas
     return {
         "two_term": two_term,
