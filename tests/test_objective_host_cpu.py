@@ -1,0 +1,252 @@
+"""
+Host logic of SpSurrogateObjectiveMax on CPU: hysteresis of ``max_no``, weight smoothing, the ONE
+fused sweep for the two weighted gradient terms, the early start of the gradient and its fallbacks.
+
+The GPU workspace is replaced by a stand-in that answers the same calls (objective, set_sparse,
+grad_begin / grad_end, grad, upload) with the NumPy oracle, so what is checked here is the Python
+layer above the C-ABI -- against the golden call sequences recorded from the unmodified reference
+(tests/golden/objective_sequences.npz; objective_lhs_sur_max.py:82-191).  The kernels themselves are
+checked by the ``-m gpu`` tests.
+"""
+
+import numpy as np
+import pytest
+
+from golden_util import load, rel
+from aqc_research_b200.engine import CircuitHandle
+from aqc_research_b200.model_sp_lhs import objective_base
+from aqc_research_b200.model_sp_lhs.objective_lhs_sur_max import SpSurrogateObjectiveMax
+from aqc_research_b200.parametric_circuit import TrotterAnsatz
+from oracle import sv_oracle as O
+
+TOL = 1e-10
+
+
+class OracleWorkspace:
+    """Answers the SvWorkspace calls the objective makes, with oracle/sv_oracle.py underneath."""
+
+    calls = []
+
+    def __init__(self, circ, num_slots, device=0):
+        self.circ = circ
+        self.circuit = CircuitHandle(circ)  # host-only part of the C-ABI (no GPU needed)
+        self.size = 2**circ.num_qubits
+        self.slots = [np.zeros(self.size, dtype=np.complex128) for _ in range(num_slots)]
+        self.pending = None
+
+    def upload(self, slot, data, batch_index=-1):
+        self.slots[slot] = np.array(data, dtype=np.complex128).ravel()
+
+    def objective(self, thetas, target, z0, indices):
+        self.pending = None  # a new call drops an uncollected sweep
+        self.slots[z0] = O.apply_v(self.circ, np.asarray(thetas), self.slots[target], dagger=True)
+        OracleWorkspace.calls.append("objective")
+        return self.slots[z0][np.asarray(indices)][None, :]
+
+    def set_sparse(self, slot, indices, amplitudes):
+        assert 1 <= len(indices) <= 8
+        v = np.zeros(self.size, dtype=np.complex128)
+        for i, a in zip(indices, amplitudes):
+            v[int(i)] = a
+        self.slots[slot] = v
+        OracleWorkspace.calls.append("set_sparse")
+
+    def grad_begin(self, thetas, *, z0, w, z, x_slot=-1, x_basis=0):
+        if x_slot >= 0:
+            x = self.slots[x_slot].copy()
+        else:
+            x = np.zeros(self.size, dtype=np.complex128)
+            x[int(x_basis)] = 1.0
+        self.pending = O.grad_sweep(self.circ, np.asarray(thetas), x, self.slots[z0])
+        OracleWorkspace.calls.append("sweep")
+
+    def grad_end(self):
+        assert self.pending is not None, "no gradient sweep in flight"
+        out, self.pending = self.pending, None
+        return out[None, :]
+
+    def grad(self, thetas, **kw):
+        self.grad_begin(thetas, **kw)
+        return self.grad_end()
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def fake_gpu(monkeypatch):
+    monkeypatch.setattr(objective_base, "SvWorkspace", OracleWorkspace)
+    OracleWorkspace.calls = []
+    yield OracleWorkspace
+
+
+def _params(n, **kw):
+    p = dict(num_qubits=n, max_flips=1, maxiter=10, verbose=0, enable_optim_stats=False,
+             num_simulations=1, trunc_thr=1e-6, state_prep_func=None)
+    p.update(kw)
+    return p
+
+
+def test_golden_sequences_with_one_sweep_per_evaluation(fake_gpu):
+    g = load("objective_sequences.npz")
+    seen_two_term = False
+    for c in range(int(g["num_sp"])):
+        p = f"sp{c}_"
+        n, _, steps = [int(v) for v in g[p + "meta"]]
+        if n > 8:
+            continue
+        circ = TrotterAnsatz(n, g[p + "blocks"], True)
+        objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+        objv.set_target(g[p + "target"])
+        for s in range(steps):
+            th = g[p + "thetas"][s]
+            fake_gpu.calls.clear()
+            assert abs(objv.objective(th) - g[p + "f"][s]) < TOL
+            assert objv.max_no == int(g[p + "max_no"][s])
+            grad = objv.gradient(th)
+            assert rel(grad, g[p + "grad"][s]) < TOL
+            assert abs(objv.weight - g[p + "weight"][s]) < TOL
+            # one V^H sweep and ONE gradient sweep, also when two weighted terms are needed
+            assert fake_gpu.calls.count("objective") == 1 and fake_gpu.calls.count("sweep") == 1
+            if objv.max_no != 0:
+                seen_two_term = True
+                assert "set_sparse" in fake_gpu.calls
+    assert seen_two_term
+
+
+def test_dense_state_handler_uses_one_sweep_too(fake_gpu):
+    g = load("objective_sequences.npz")
+    p = "sp3_"  # n = 7, max_no = 7 throughout
+    n, _, steps = [int(v) for v in g[p + "meta"]]
+    circ = TrotterAnsatz(n, g[p + "blocks"], True)
+    dense = np.zeros((n + 1, 2**n), dtype=np.complex128)
+    for i, k in enumerate(O.basis_state_indices(n, 0)):
+        dense[i, k] = 1
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n, state_prep_func=lambda nq: dense), circ=circ,
+                                   front_layer=True)
+    objv.set_target(g[p + "target"])
+    # the dense handler takes its overlaps through vdot
+    OracleWorkspace.vdot = lambda self, a, b: np.array([np.vdot(self.slots[a], self.slots[b])])
+    OracleWorkspace.apply = lambda self, th, src, dst, dagger=False: self.slots.__setitem__(
+        dst, O.apply_v(self.circ, np.asarray(th), self.slots[src], dagger=dagger))
+    for s in range(steps):
+        th = g[p + "thetas"][s]
+        fake_gpu.calls.clear()
+        assert abs(objv.objective(th) - g[p + "f"][s]) < TOL
+        assert rel(objv.gradient(th), g[p + "grad"][s]) < TOL
+        assert fake_gpu.calls.count("sweep") == 1
+        assert abs(objv.weight - g[p + "weight"][s]) < TOL
+
+
+def test_early_start_follows_the_fun_jac_pattern(fake_gpu):
+    g = load("objective_sequences.npz")
+    p = "sp2_"  # n = 4, five steps, max_no != 0
+    n, _, steps = [int(v) for v in g[p + "meta"]]
+    circ = TrotterAnsatz(n, g[p + "blocks"], True)
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    objv.set_target(g[p + "target"])
+    order = []
+    for s in range(steps):
+        th = g[p + "thetas"][s]
+        fake_gpu.calls.clear()
+        objv.objective(th)
+        order.append("sweep" in fake_gpu.calls)  # was the sweep enqueued by objective() already?
+        assert rel(objv.gradient(th), g[p + "grad"][s]) < TOL
+        assert fake_gpu.calls.count("sweep") == 1
+    assert order == [False, False] + [True] * (steps - 2)  # learnt after two fun/jac pairs
+    # a gradient asked at OTHER angles while an early sweep is in flight: recomputed, early start off
+    th_a, th_b = g[p + "thetas"][0], g[p + "thetas"][1]
+    objv.objective(th_a)
+    w_before = objv.weight
+    grad_b = objv.gradient(th_b)
+    _, _, ref_b, _ = O.sur_max_value_and_grad(circ, th_b, g[p + "target"], w_before, objv.max_no)
+    assert rel(grad_b, ref_b) < TOL
+    assert not objv._early_on
+
+
+class OracleMpsWorkspace:
+    """Stand-in for MpsWorkspace: states kept as dense vectors (no truncation), oracle underneath."""
+
+    calls = []
+
+    def __init__(self, circ, num_slots, chi_max=64, trunc_thr=1e-16, device=0):
+        self.circ = circ
+        self.size = 2**circ.num_qubits
+        self.slots = [np.zeros(self.size, dtype=np.complex128) for _ in range(num_slots)]
+
+    def upload(self, slot, mps):
+        from oracle import mps_oracle as M
+
+        self.slots[slot] = M.mps_to_vector(mps)
+
+    def objective(self, thetas, target, z0, indices):
+        self.slots[z0] = O.apply_v(self.circ, np.asarray(thetas), self.slots[target], dagger=True)
+        return self.slots[z0][np.asarray(indices)]
+
+    def set_product_site(self, slot, index, site, amp0, amp1):
+        v = np.zeros(self.size, dtype=np.complex128)
+        v[index & ~(1 << site)] = amp0  # qubit `site` in |0>
+        v[index | (1 << site)] = amp1   # ... in |1>
+        assert abs(abs(amp0) ** 2 + abs(amp1) ** 2 - 1.0) < 1e-14  # the caller keeps the pair normalised
+        self.slots[slot] = v
+        OracleMpsWorkspace.calls.append("set_product_site")
+
+    def grad(self, thetas, *, z0, w, z, x_slot=-1, x_basis=0):
+        if x_slot >= 0:
+            x = self.slots[x_slot].copy()
+        else:
+            x = np.zeros(self.size, dtype=np.complex128)
+            x[int(x_basis)] = 1.0
+        OracleMpsWorkspace.calls.append("sweep")
+        return O.grad_sweep(self.circ, np.asarray(thetas), x, self.slots[z0])
+
+    def close(self):
+        pass
+
+
+def test_mps_objective_two_terms_from_one_product_state(monkeypatch):
+    """
+    SpSurrogateObjectiveFastMpsTrotter: the weighted pair (s_0, X_i s_0) is one product state with
+    qubit i in superposition; which amplitude sits on |0> depends on the bit of s_0 (Neel state:
+    both cases occur).  Golden values: the reference's state-vector objective on the same states.
+    """
+    from aqc_research_b200.model_sp_lhs import objective_lhs_sur_fast_mps_trotter as mod
+    from oracle import mps_oracle as M
+
+    monkeypatch.setattr(mod, "MpsWorkspace", OracleMpsWorkspace)
+    OracleMpsWorkspace.calls = []
+    g = load("objective_sequences.npz")
+    for p in ("sp2_", "sp3_"):
+        n, _, steps = [int(v) for v in g[p + "meta"]]
+        circ = TrotterAnsatz(n, g[p + "blocks"], True)
+        objv = mod.SpSurrogateObjectiveFastMpsTrotter(
+            user_parameters=_params(n, trunc_thr=1e-16), circ=circ)
+        objv.set_target(M.vector_to_mps(g[p + "target"]))
+        for s in range(steps):
+            th = g[p + "thetas"][s]
+            OracleMpsWorkspace.calls.clear()
+            assert abs(objv.objective(th) - g[p + "f"][s]) < TOL
+            assert objv.max_no == int(g[p + "max_no"][s]) and objv.max_no != 0
+            assert rel(objv.gradient(th), g[p + "grad"][s]) < TOL
+            assert OracleMpsWorkspace.calls == ["set_product_site", "sweep"]
+    # Neel preparation: flipped qubits with bit 1 (even sites) and bit 0 (odd sites) in s_0
+    n = 4
+    np.random.seed(5)
+    from aqc_research_b200 import circuit_structures as cs, utils
+
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    target, neel = utils.rand_state(n), 0b0101
+    objv = mod.SpSurrogateObjectiveFastMpsTrotter(
+        user_parameters=_params(n, trunc_thr=1e-16, state_prep_func=lambda nq: neel), circ=circ)
+    objv.set_target(M.vector_to_mps(target))
+    seen = set()
+    for _ in range(12):
+        th = utils.rand_thetas(circ.num_thetas)
+        w_before = objv.weight
+        objv.objective(th)
+        grad = objv.gradient(th)
+        _, _, ref, _ = O.sur_max_value_and_grad(circ, th, target, w_before, objv.max_no, init_index=neel)
+        assert rel(grad, ref) < TOL
+        if objv.max_no:
+            seen.add((neel >> (objv.max_no - 1)) & 1)
+    assert seen == {0, 1}
