@@ -119,6 +119,9 @@ SIGNATURES = {
     "aqc_mps_bond_capacity": (ct.c_int, [ct.c_void_p]),
     "aqc_mps_upload": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p, c_int32_p]),
     "aqc_mps_download": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p, c_int32_p]),
+    "aqc_prim_apply": (ct.c_int, [ct.c_int, ct.c_void_p, ct.c_int64, ct.c_int, c_int64_p, c_int32_p, ct.c_void_p]),
+    "aqc_prim_dot": (ct.c_int, [ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_int64, c_int64_p, c_int32_p, ct.c_void_p,
+                                ct.c_void_p]),
     "aqc_mps_set_product": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int64]),
     "aqc_mps_set_product_site": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_void_p]),
     "aqc_mps_apply": (ct.c_int, [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, ct.c_int]),

@@ -120,3 +120,149 @@ def mask_gradient(circ, grad, block_range, front_layer) -> np.ndarray:
     if not front_layer:
         circ.subset1q(grad)[:] = 0
     return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# Gate-by-gate primitives (core_operations.py:34-603 of the reference): what its unit tests and tools
+# call directly.  Same names, argument order and in-place behaviour; the gate runs on the GPU
+# (csrc/aqc_prim.cu) on a copy of the host vector.  The workspace arguments are checked like the
+# reference checks them but are not needed.  Qubit ``pos`` is index bit ``n - 1 - pos``.
+# ------------------------------------------------------------------------------------------------
+from . import _prim  # noqa: E402
+from . import elementary_operations as _eo  # noqa: E402
+
+_P00 = np.array([[1, 0], [0, 0]], dtype=np.complex128)
+_P11 = np.array([[0, 0], [0, 1]], dtype=np.complex128)
+
+
+def bit2bit_transform(n: int, i: int) -> int:
+    """Qubit position -> bit of the flat index (Qiskit bit order, core_operations.py:34-43)."""
+    return n - 1 - i
+
+
+def _stride(n: int, pos: int) -> int:
+    return 1 << (n - 1 - pos)
+
+
+def _check_vec(n: int, *vecs) -> None:
+    for v in vecs:
+        assert isinstance(v, np.ndarray) and v.shape == (2**n,) and v.dtype == np.complex128
+        assert v.flags.c_contiguous
+
+
+def gate2x2_mul_vec(num_qubits: int, pos: int, gate2x2: np.ndarray, vec: np.ndarray, out: np.ndarray,
+                    inplace: bool) -> np.ndarray:
+    """``(I (x) G (x) I) @ vec`` into ``vec`` (inplace) or into ``out`` (core_operations.py:46-119)."""
+    assert 0 <= pos < num_qubits and gate2x2.shape == (2, 2)
+    _check_vec(num_qubits, vec, out)
+    assert not np.may_share_memory(vec, out)
+    dst = vec
+    if not inplace:
+        np.copyto(out, vec)
+        dst = out
+    return _prim.apply_gates(dst, [(_stride(num_qubits, pos), 0, 0, gate2x2)])
+
+
+def proj00_mul_vec(num_qubits: int, pos: int, vec: np.ndarray) -> np.ndarray:
+    """|0><0| on qubit ``pos``, in place (:122-140)."""
+    assert 0 <= pos < num_qubits
+    _check_vec(num_qubits, vec)
+    return _prim.apply_gates(vec, [(_stride(num_qubits, pos), 0, 0, _P00)])
+
+
+def proj11_mul_vec(num_qubits: int, pos: int, vec: np.ndarray) -> np.ndarray:
+    """|1><1| on qubit ``pos``, in place (:143-161)."""
+    assert 0 <= pos < num_qubits
+    _check_vec(num_qubits, vec)
+    return _prim.apply_gates(vec, [(_stride(num_qubits, pos), 0, 0, _P11)])
+
+
+def _rot_mul_vec(make, n, pos, angle, vec, temp):
+    assert 0 <= pos < n and chk.is_float(angle)
+    _check_vec(n, vec)
+    assert temp is None or (isinstance(temp, np.ndarray) and temp.shape == vec.shape)
+    return _prim.apply_gates(vec, [(_stride(n, pos), 0, 0, make(float(angle)))])
+
+
+def rx_mul_vec(n: int, pos: int, angle: float, vec: np.ndarray, temp: np.ndarray) -> np.ndarray:
+    """Rx(angle) on qubit ``pos``, in place (:164-197)."""
+    return _rot_mul_vec(_eo.np_rx, n, pos, angle, vec, temp)
+
+
+def ry_mul_vec(n: int, pos: int, angle: float, vec: np.ndarray, temp: np.ndarray) -> np.ndarray:
+    """Ry(angle) on qubit ``pos``, in place (:200-233)."""
+    return _rot_mul_vec(_eo.np_ry, n, pos, angle, vec, temp)
+
+
+def rz_mul_vec(n: int, pos: int, angle: float, vec: np.ndarray, _: Optional[np.ndarray] = None) -> np.ndarray:
+    """Rz(angle) on qubit ``pos``, in place (:236-264)."""
+    return _rot_mul_vec(_eo.np_rz, n, pos, angle, vec, None)
+
+
+def _pauli_dot(pauli, n, pos, w_vec, z_vec, temp) -> np.complex128:
+    assert 0 <= pos < n
+    _check_vec(n, w_vec, z_vec, temp)
+    return np.complex128(0.5j * _prim.gate_vdot(w_vec, z_vec, (_stride(n, pos), 0, 0, pauli)))
+
+
+def dot_x(n: int, pos: int, w_vec: np.ndarray, z_vec: np.ndarray, temp: np.ndarray) -> np.complex128:
+    """``0.5j <X w|z>`` (:267-293)."""
+    return _pauli_dot(_eo.np_x(), n, pos, w_vec, z_vec, temp)
+
+
+def dot_y(n: int, pos: int, w_vec: np.ndarray, z_vec: np.ndarray, temp: np.ndarray) -> np.complex128:
+    """``0.5j <Y w|z>`` (:296-322)."""
+    return _pauli_dot(_eo.np_y(), n, pos, w_vec, z_vec, temp)
+
+
+def dot_z(n: int, pos: int, w_vec: np.ndarray, z_vec: np.ndarray, temp: np.ndarray) -> np.complex128:
+    """``0.5j <Z w|z>`` (:325-351)."""
+    return _pauli_dot(_eo.np_z(), n, pos, w_vec, z_vec, temp)
+
+
+def block_mul_vec(n: int, c: int, t: int, c_mat: np.ndarray, t_mat: np.ndarray, g_mat: np.ndarray,
+                  vec: np.ndarray, workspace: np.ndarray, dagger: bool) -> np.ndarray:
+    """
+    ``vec <- (c_mat (x) t_mat) . controlled-g_mat . vec`` in place; ``dagger=True`` only flips the
+    order of the two factors, the matrices are taken as given (:354-419).
+    """
+    assert 0 <= c < n and 0 <= t < n and c != t
+    assert c_mat.shape == t_mat.shape == g_mat.shape == (2, 2)
+    _check_vec(n, vec)
+    assert workspace.shape == (2, vec.size) and not np.may_share_memory(vec, workspace)
+    ent = (_stride(n, t), _stride(n, c), 1, g_mat)
+    local = [(_stride(n, c), 0, 0, c_mat), (_stride(n, t), 0, 0, t_mat)]
+    return _prim.apply_gates(vec, local + [ent] if dagger else [ent] + local)
+
+
+def _ctrl_mul_vec(gate, n, c, t, vec, temp):
+    assert 0 <= c < n and 0 <= t < n and c != t
+    _check_vec(n, vec)
+    assert temp is None or (isinstance(temp, np.ndarray) and temp.shape == vec.shape)
+    return _prim.apply_gates(vec, [(_stride(n, t), _stride(n, c), 1, gate)])
+
+
+def cx_mul_vec(n: int, c: int, t: int, _: float, vec: np.ndarray, temp: np.ndarray) -> np.ndarray:
+    """CX with control ``c`` and target ``t``, in place (:422-465)."""
+    return _ctrl_mul_vec(_eo.np_x(), n, c, t, vec, temp)
+
+
+def cz_mul_vec(n: int, c: int, t: int, _: float, vec: np.ndarray, temp: np.ndarray) -> np.ndarray:
+    """CZ, in place (:468-511)."""
+    return _ctrl_mul_vec(_eo.np_z(), n, c, t, vec, temp)
+
+
+def cp_mul_vec(n: int, c: int, t: int, angle: float, vec: np.ndarray, temp: np.ndarray) -> np.ndarray:
+    """CPhase(angle), in place (:514-558)."""
+    assert chk.is_float(angle)
+    return _ctrl_mul_vec(_eo.np_phase(float(angle)), n, c, t, vec, temp)
+
+
+def derv_cphase_mul_vec(n: int, c: int, t: int, angle: float, vec: np.ndarray, out: np.ndarray) -> np.ndarray:
+    """``out = (|1><1|_c (x) dP(angle)/d angle _t) vec`` (:561-603); ``vec`` is not modified."""
+    assert 0 <= c < n and 0 <= t < n and c != t and chk.is_float(angle)
+    _check_vec(n, vec, out)
+    assert not np.may_share_memory(vec, out)
+    np.copyto(out, vec)
+    dgate = np.array([[0, 0], [0, 1j * np.exp(1j * float(angle))]], dtype=np.complex128)
+    return _prim.apply_gates(out, [(_stride(n, t), _stride(n, c), 2, dgate)])

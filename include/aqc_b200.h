@@ -285,6 +285,24 @@ int aqc_mps_debug_sweeps(aqc_mps* mps, int32_t* out, int cap);
 float aqc_mps_last_kernel_ms(const aqc_mps* mps);
 int aqc_mps_last_num_launches(const aqc_mps* mps);
 
+/* ---------------------------------------------------------------------------------------------
+ * Single-gate primitives (csrc/aqc_prim.cu): the gate-by-gate functions the reference's unit tests
+ * and tools call directly -- core_operations.py:46-603 (gate2x2_mul_vec, proj00/11_mul_vec,
+ * rx/ry/rz_mul_vec, cx/cz/cp_mul_vec, block_mul_vec, derv_cphase_mul_vec, dot_x/y/z) and
+ * core_op_matrix.py:32-477 (the same on (2^n, m) matrices, x/y/z_dot_mat, derv_cphase).  Host arrays
+ * in and out (complex128, interleaved); NOT the hot path, which fuses whole pair-runs per pass.
+ *
+ * Gate k acts on the index bit of stride strides[2k] (element i pairs with i + stride where
+ * (i / stride) is even) with the row-major complex 2x2 matrix gates[8k .. 8k+7]; modes[k]: 0 plain,
+ * 1 controlled by the bit of stride strides[2k+1] (identity where it is 0), 2 controlled with ZERO
+ * where the control bit is 0 (|1><1| (x) G).  Vectors: stride = 2^(n-1-pos); matrices with m columns:
+ * stride = m 2^qubit. */
+int aqc_prim_apply(int device, double* host, int64_t count, int num_gates, const int64_t* strides,
+                   const int32_t* modes, const double* gates);
+/* out[0..1] = sum_i conj((G w)_i) z_i for ONE gate G described as above (np.vdot(G w, z)). */
+int aqc_prim_dot(int device, const double* host_w, const double* host_z, int64_t count,
+                 const int64_t* strides, const int32_t* modes, const double* gates, double* out);
+
 #ifdef __cplusplus
 }
 #endif

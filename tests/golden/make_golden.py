@@ -300,7 +300,84 @@ def sketch_cases():
     print("sketch_cases:", case)
 
 
+def primitive_cases():
+    """
+    Gate-by-gate primitives of the reference (core_operations.py:46-603, core_op_matrix.py:32-477,
+    elementary_operations.py:39-291) on seeded inputs: every function, every qubit position.
+    """
+    cop, cpm, eo = R.cop, R.cpm, R.eo
+    rng = np.random.RandomState(0xA11)
+    out = {}
+    n = 4
+    dim = 2**n
+
+    def rvec():
+        return (rng.randn(dim) + 1j * rng.randn(dim)).astype(np.complex128)
+
+    g = (rng.randn(2, 2) + 1j * rng.randn(2, 2)).astype(np.complex128)
+    cm, tm, gm = [(rng.randn(2, 2) + 1j * rng.randn(2, 2)).astype(np.complex128) for _ in range(3)]
+    ang = 0.7321
+    out["n"], out["gate"], out["angle"] = np.array(n), g, np.array(ang)
+    out["c_mat"], out["t_mat"], out["g_mat"] = cm, tm, gm
+    v0, z0 = rvec(), rvec()
+    out["vec"], out["zvec"] = v0, z0
+    tmp = np.zeros(dim, dtype=np.complex128)
+    for pos in range(n):
+        out[f"gate2x2_{pos}"] = cop.gate2x2_mul_vec(n, pos, g, v0.copy(), tmp.copy(), True).copy()
+        o = np.zeros(dim, dtype=np.complex128)
+        cop.gate2x2_mul_vec(n, pos, g, v0.copy(), o, False)
+        out[f"gate2x2_out_{pos}"] = o
+        out[f"proj00_{pos}"] = cop.proj00_mul_vec(n, pos, v0.copy()).copy()
+        out[f"proj11_{pos}"] = cop.proj11_mul_vec(n, pos, v0.copy()).copy()
+        for nm in ("rx", "ry", "rz"):
+            out[f"{nm}_{pos}"] = getattr(cop, nm + "_mul_vec")(n, pos, ang, v0.copy(), tmp.copy()).copy()
+        for nm in ("dot_x", "dot_y", "dot_z"):
+            out[f"{nm}_{pos}"] = np.array(getattr(cop, nm)(n, pos, v0.copy(), z0.copy(), tmp.copy()))
+    for c in range(n):
+        for t in range(n):
+            if c == t:
+                continue
+            for nm in ("cx", "cz", "cp"):
+                out[f"{nm}_{c}{t}"] = getattr(cop, nm + "_mul_vec")(n, c, t, ang, v0.copy(), tmp.copy()).copy()
+            o = np.zeros(dim, dtype=np.complex128)
+            out[f"dcp_{c}{t}"] = cop.derv_cphase_mul_vec(n, c, t, ang, v0.copy(), o).copy()
+            for dag in (False, True):
+                ws = np.zeros((2, dim), dtype=np.complex128)
+                out[f"block_{c}{t}_{int(dag)}"] = cop.block_mul_vec(n, c, t, cm, tm, gm, v0.copy(), ws, dag).copy()
+            out[f"np_block_{c}{t}"] = eo.np_block_matrix(n, c, t, cm, tm, gm)
+            out[f"np_cx_{c}{t}"] = eo.np_cx_matrix(n, c, t)
+    for nm in ("np_rx", "np_ry", "np_rz", "np_phase"):
+        out[nm] = getattr(eo, nm)(ang)
+    out["np_x"], out["np_z"] = eo.np_x(), eo.np_z()
+    # matrices: square and ragged (m = 5 columns)
+    for m in (dim, 5):
+        m0 = (rng.randn(dim, m) + 1j * rng.randn(dim, m)).astype(np.complex128)
+        zm = (rng.randn(dim, m) + 1j * rng.randn(dim, m)).astype(np.complex128)
+        out[f"mat_{m}"], out[f"zmat_{m}"] = m0, zm
+        ws = np.zeros(dim * m, dtype=np.complex128)
+        for q in range(n):
+            out[f"m{m}_gate2x2_{q}"] = cpm.gate2x2_mul_mat(q, g, m0.copy(), ws.copy()).copy()
+            for nm in ("rx", "ry", "rz"):
+                out[f"m{m}_{nm}_{q}"] = getattr(cpm, nm + "_mul_mat")(ang, q, m0.copy(), ws.copy()).copy()
+            for nm in ("x", "y", "z"):
+                out[f"m{m}_{nm}dot_{q}"] = np.array(getattr(cpm, nm + "_dot_mat")(q, m0.copy(), zm.copy(), ws.copy()))
+        for c in range(n):
+            for t in range(n):
+                if c == t:
+                    continue
+                for nm in ("cx", "cz", "cp"):
+                    out[f"m{m}_{nm}_{c}{t}"] = getattr(cpm, nm + "_mul_mat")(c, t, ang, m0.copy(), ws.copy()).copy()
+                out[f"m{m}_dcp_{c}{t}"] = np.array(cpm.derv_cphase(c, t, m0.copy(), zm.copy(), ws.copy()))
+    np.savez_compressed(os.path.join(HERE, "primitive_cases.npz"), **out)
+    print("primitive_cases:", len(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # e.g. `make_golden.py primitive_cases`
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
+    primitive_cases()
     sv_cases()
     mat_cases()
     objective_sequences()
