@@ -101,3 +101,29 @@ def v_dagger_mul_mps(circ: ParametricCircuit, thetas: np.ndarray, mps_vec: Qiski
     out = ws.download(1)
     ws.close()
     return out
+
+
+def rand_mps_vec(num_qubits: int, out_state: Optional[np.ndarray] = None, num_layers: int = 3) -> QiskitMPS:
+    """
+    Random state in MPS format (mps_operations.py:301-323): a random-angle "spin" ansatz of
+    ``num_layers * (num_qubits - 1)`` unit blocks with a randomly chosen entangler applied to
+    |0...0>, evaluated by the GPU MPS engine without truncation (the reference builds the Qiskit
+    circuit and runs qiskit-aer).  ``out_state``, if given, receives the dense state vector.
+    """
+    from . import circuit_structures as cs  # pylint: disable=import-outside-toplevel
+    from . import utils  # pylint: disable=import-outside-toplevel
+
+    assert isinstance(num_qubits, (int, np.integer)) and num_qubits >= 2
+    assert isinstance(num_layers, (int, np.integer)) and num_layers > 0
+    blocks = cs.create_ansatz_structure(num_qubits, "spin", "full", num_layers * (num_qubits - 1))
+    circ = ParametricCircuit(num_qubits, str(np.random.choice(["cx", "cz", "cp"])), blocks)
+    thetas = utils.rand_thetas(circ.num_thetas)
+    ws = _workspace(circ, _NO_TRUNCATION_THR, slots=1)
+    ws.set_product(0, 0)
+    ws.apply(thetas, 0, 0, dagger=False)
+    mps = ws.download(0)
+    ws.close()
+    if out_state is not None:
+        assert out_state.shape == (2**num_qubits,)
+        np.copyto(out_state, mps_to_vector(mps))
+    return mps

@@ -244,3 +244,45 @@ def test_set_product_site_and_fused_two_term_sweep():
     both = ws.grad(th, x_slot=2, z0=1, w=2, z=3)
     assert _rel(both, np.conj(a_same) * g_same + np.conj(a_flip) * g_flip) < TOL
     ws.close()
+
+
+def test_rand_mps_vec():
+    """rand_mps_vec (mps_operations.py:301-323): a valid, normalised MPS whose dense form is returned."""
+    from aqc_research_b200 import mps_operations as mpsop
+
+    np.random.seed(3)
+    n = 6
+    dense = np.zeros(2**n, dtype=np.complex128)
+    mps = mpsop.rand_mps_vec(n, out_state=dense, num_layers=2)
+    assert mpsop.check_mps(mps) and len(mps[0]) == n
+    assert abs(np.linalg.norm(dense) - 1.0) < 1e-12
+    assert _rel(M.mps_to_vector(mps), dense) < 1e-14
+    assert abs(mpsop.mps_dot(mps, mps) - 1.0) < 1e-12
+    other = mpsop.rand_mps_vec(n)
+    assert abs(mpsop.mps_dot(mps, other) - np.vdot(dense, M.mps_to_vector(other))) < 1e-12
+
+
+def test_gate_by_gate_helpers_vs_dense_oracle():
+    """
+    x/y/z_mul_mps, rx/ry/rz_mul_mps, cx/cz/cp_mul_mps, dot_x/y/z (mps_dot_objective.py:245-516)
+    against the dense gates of the oracle (qubit k = bit k of the flat index, as mps_to_vector).
+    """
+    from aqc_research_b200 import mps_dot_objective as mdo
+
+    rng = np.random.RandomState(21)
+    n, ang = 5, 0.9173
+    v, z = _rand_vec(n, rng), _rand_vec(n, rng)
+    mv, mz = M.vector_to_mps(v), M.vector_to_mps(z)
+    for q in range(n):
+        for fn, g in ((mdo.x_mul_mps, O.PAULI_X), (mdo.y_mul_mps, O.PAULI_Y), (mdo.z_mul_mps, O.PAULI_Z)):
+            assert _rel(M.mps_to_vector(fn(q, mv)), O.op1(v.copy(), q, g)) < TOL, (fn.__name__, q)
+        for fn, mk in ((mdo.rx_mul_mps, O.rx), (mdo.ry_mul_mps, O.ry), (mdo.rz_mul_mps, O.rz)):
+            assert _rel(M.mps_to_vector(fn(ang, q, mv)), O.op1(v.copy(), q, mk(ang))) < TOL, (fn.__name__, q)
+        for fn, g in ((mdo.dot_x, O.PAULI_X), (mdo.dot_y, O.PAULI_Y), (mdo.dot_z, O.PAULI_Z)):
+            assert abs(fn(q, mv, mz) - 0.5j * np.vdot(O.op1(v.copy(), q, g), z)) < TOL, (fn.__name__, q)
+    for c, t in ((0, 1), (1, 0), (3, 2), (3, 4)):
+        assert _rel(M.mps_to_vector(mdo.cx_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_X)) < TOL
+        assert _rel(M.mps_to_vector(mdo.cz_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_Z)) < TOL
+        assert _rel(M.mps_to_vector(mdo.cp_mul_mps(ang, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.phase(ang))) < TOL
+    with pytest.raises(Exception):
+        mdo.cx_mul_mps(0.0, 0, 2, mv)  # non-adjacent qubits: no swap network in the engine

@@ -250,3 +250,40 @@ def test_mps_objective_two_terms_from_one_product_state(monkeypatch):
         if objv.max_no:
             seen.add((neel >> (objv.max_no - 1)) & 1)
     assert seen == {0, 1}
+
+
+def test_mps_gate_helpers_host_logic(monkeypatch):
+    """
+    The gate-by-gate MPS helpers (mps_dot_objective.py:245-516 of the reference) are tiny circuits
+    pushed through the engine: angles, cancelling blocks, the factor i of the Pauli gates.  Checked
+    here with the dense stand-in; tests/test_mps_gpu.py repeats it on the GPU engine.
+    """
+    from aqc_research_b200 import mps_dot_objective as mdo
+    from aqc_research_b200 import mps_operations as mpsop
+    from oracle import mps_oracle as M
+
+    class Dense(OracleMpsWorkspace):
+        def apply(self, thetas, src, dst, dagger=False):
+            self.slots[dst] = O.apply_v(self.circ, np.asarray(thetas), self.slots[src], dagger=dagger)
+
+        def download(self, slot):
+            return M.vector_to_mps(self.slots[slot])
+
+        def dot(self, a, b):
+            return complex(np.vdot(self.slots[a], self.slots[b]))
+
+    monkeypatch.setattr(mpsop, "MpsWorkspace", Dense)
+    rng = np.random.RandomState(21)
+    n, ang = 4, 0.9173
+    v = rng.randn(2**n) + 1j * rng.randn(2**n)
+    v /= np.linalg.norm(v)
+    mv = M.vector_to_mps(v)
+    for q in range(n):
+        for fn, g in ((mdo.x_mul_mps, O.PAULI_X), (mdo.y_mul_mps, O.PAULI_Y), (mdo.z_mul_mps, O.PAULI_Z)):
+            assert rel(M.mps_to_vector(fn(q, mv)), O.op1(v.copy(), q, g)) < TOL, (fn.__name__, q)
+        for fn, mk in ((mdo.rx_mul_mps, O.rx), (mdo.ry_mul_mps, O.ry), (mdo.rz_mul_mps, O.rz)):
+            assert rel(M.mps_to_vector(fn(ang, q, mv)), O.op1(v.copy(), q, mk(ang))) < TOL, (fn.__name__, q)
+    for c, t in ((0, 1), (1, 0), (3, 2)):
+        assert rel(M.mps_to_vector(mdo.cx_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_X)) < TOL
+        assert rel(M.mps_to_vector(mdo.cz_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_Z)) < TOL
+        assert rel(M.mps_to_vector(mdo.cp_mul_mps(ang, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.phase(ang))) < TOL
