@@ -103,3 +103,46 @@ def contiguous_c128(*arrays) -> bool:
         isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags.c_contiguous
         for a in arrays
     )
+
+
+# -- remaining predicates of the reference's checking.py (same names and meaning) ------------------
+_INT = (np.int32, np.int64)
+
+
+def is_complex(x, cond: bool = True) -> bool:
+    return isinstance(x, (complex, np.complexfloating)) and bool(cond)
+
+
+def complex_or_float_1d(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX + _FLOAT + (np.float32, np.complex64), 1, cond)
+
+
+def complex_3d(x, cond: bool = True) -> bool:
+    return _arr(x, _COMPLEX + (np.complex64,), 3, cond)
+
+
+def int_1d(x, cond: bool = True) -> bool:
+    return _arr(x, _INT, 1, cond)
+
+
+def int_2d(x, cond: bool = True) -> bool:
+    return _arr(x, _INT, 2, cond)
+
+
+def bool_1d(x, cond: bool = True) -> bool:
+    return _arr(x, (np.bool_,), 1, cond)
+
+
+def check_sim_complex_vecs4(a, b, c, d) -> bool:
+    """Four complex128 vectors of one shape, each contiguous (checking.py:176-195)."""
+    vecs = (a, b, c, d)
+    return all(complex_1d(v) and v.flags.c_contiguous for v in vecs) and all(v.shape == a.shape for v in vecs)
+
+
+def check_permutation(x) -> bool:
+    """A 1D integer array holding every number of 0..size-1 once (checking.py:213-222)."""
+    return int_1d(x) and bool(np.array_equal(np.sort(x), np.arange(x.size)))
+
+
+def none_or_type(entity, entity_type) -> bool:
+    return entity is None or isinstance(entity, entity_type)

@@ -354,3 +354,152 @@ class SpLHSObjectiveBase(ABC):
     def workspace(self) -> Optional[SvWorkspace]:
         """The GPU workspace (bench/profiling introspection)."""
         return self._ws
+
+
+# ------------------------------------------------------------------------------------------------
+# State handlers under the names of the reference (objective_base.py:42-429), for code that
+# constructs them directly.  The objective classes above use make_state_handler().
+# ------------------------------------------------------------------------------------------------
+def _check_coefs(coefs: np.ndarray, count: int) -> None:
+    assert chk.complex_or_float_1d(coefs, coefs.size == count)
+    assert abs(np.linalg.norm(coefs) - 1) < np.sqrt(np.finfo(np.float64).eps)
+
+
+class ThinStateHandler(BasisStateHandler):
+    """
+    |0> and the flip states X_i|0>, X_i X_j|0>, ... kept as basis indices and materialised on demand
+    (objective_base.py:42-256), including the sparse linear combinations of the reference.
+    """
+
+    def __init__(self, num_qubits: int, max_flips: int, verbose: bool = False):
+        super().__init__(num_qubits, max_flips, 0, verbose=verbose)
+        self._state = np.zeros(2**num_qubits, dtype=np.complex128)
+
+    def init_state(self, state_no: int) -> np.ndarray:
+        """The internal array re-initialised to the requested state (:95-112)."""
+        assert chk.is_int(state_no, 0 <= state_no < self.num_states)
+        self._state.fill(0)
+        self._state[self._state_idx[state_no]] = 1
+        return self._state
+
+    def init_composite_state_no_zero(self, coefs: np.ndarray) -> np.ndarray:
+        """sum_i coefs_i |flip state i>, |0> excluded (:119-140)."""
+        _check_coefs(coefs, self.num_states - 1)
+        self._state.fill(0)
+        self._state[self._state_idx[1:]] = coefs
+        return self._state
+
+    def init_composite_state(self, coefs: np.ndarray) -> np.ndarray:
+        """sum_i coefs_i |state i> over all states (:142-162)."""
+        _check_coefs(coefs, self.num_states)
+        self._state.fill(0)
+        self._state[self._state_idx] = coefs
+        return self._state
+
+    def state_dot_vector(self, state_no: int, vec: np.ndarray) -> np.complex128:
+        assert chk.is_int(state_no, 0 <= state_no < self.num_states)
+        assert chk.complex_1d(vec, vec.size == 2**self._num_qubits)
+        return vec[self._state_idx[state_no]]
+
+    def composite_state_dot_vector_no_zero(self, coefs: np.ndarray, vec: np.ndarray) -> np.complex128:
+        """<composite state|vec> over the few non-zero entries (:175-195)."""
+        _check_coefs(coefs, self.num_states - 1)
+        assert chk.complex_1d(vec, vec.size == 2**self._num_qubits)
+        return np.complex128(np.vdot(coefs, vec[self._state_idx[1:]]))
+
+    def composite_state_dot_vector(self, coefs: np.ndarray, vec: np.ndarray) -> np.complex128:
+        """(:197-216)"""
+        _check_coefs(coefs, self.num_states)
+        assert chk.complex_1d(vec, vec.size == 2**self._num_qubits)
+        return np.complex128(np.vdot(coefs, vec[self._state_idx]))
+
+
+def _prepared_handler(num_qubits: int, max_flips: int, state_prep_func: Optional[Callable]):
+    assert chk.is_int(num_qubits, num_qubits >= 2)
+    assert chk.is_int(max_flips, 0 <= max_flips <= num_qubits)
+    assert state_prep_func is None or callable(state_prep_func)
+    if max_flips > 1:
+        raise ValueError("expects 'max_flips <= 1' to save memory")
+    return make_state_handler(num_qubits, max_flips, state_prep_func)
+
+
+class GenericStateHandler(DenseStateHandler):
+    """
+    Explicit dense states S|0>, S X_i|0> (objective_base.py:258-342).  ``state_prep_func(num_qubits)``
+    returns what make_state_handler() accepts: a basis index, the X-gate positions, an (n+1, 2^n)
+    array, or a Qiskit circuit when Qiskit is installed.
+    """
+
+    def __init__(self, num_qubits: int, max_flips: int, state_prep_func: Optional[Callable] = None,
+                 verbose: bool = False):
+        inner = _prepared_handler(num_qubits, max_flips, state_prep_func)
+        states = np.array([inner.init_state(i) for i in range(inner.num_states)], dtype=np.complex128)
+        super().__init__(states)
+
+    def state_dot_vector(self, state_no: int, vec: np.ndarray) -> np.complex128:
+        assert chk.is_int(state_no, 0 <= state_no < self.num_states)
+        return super().state_dot_vector(state_no, vec)
+
+    def init_composite_state_no_zero(self, _: np.ndarray) -> np.ndarray:
+        raise NotImplementedError("composite states exist for ThinStateHandler only, as in the reference")
+
+    init_composite_state = init_composite_state_no_zero
+
+    def composite_state_dot_vector_no_zero(self, _: np.ndarray, __: np.ndarray) -> np.complex128:
+        raise NotImplementedError("composite states exist for ThinStateHandler only, as in the reference")
+
+    composite_state_dot_vector = composite_state_dot_vector_no_zero
+
+
+class MpsStateHandler:
+    """
+    The same n+1 states in MPS format (objective_base.py:345-429).  Preparations that are products of
+    X gates give bond-dimension-1 states, written down directly; ``state_dot_vector`` is one
+    ``mps_dot`` on the GPU.
+    """
+
+    def __init__(self, num_qubits: int, max_flips: int, state_prep_func: Optional[Callable] = None,
+                 verbose: bool = False):
+        inner = _prepared_handler(num_qubits, max_flips, state_prep_func)
+        if not isinstance(inner, BasisStateHandler):
+            raise ValueError("MpsStateHandler supports basis-state (X-type) preparations only")
+        self._num_qubits = num_qubits
+        self._state_idx = inner.state_indices
+        one, zero = np.ones((1, 1), dtype=np.complex128), np.zeros((1, 1), dtype=np.complex128)
+        self._states = []
+        for index in self._state_idx:
+            gam = [((zero, one) if (int(index) >> q) & 1 else (one, zero)) for q in range(num_qubits)]
+            lam = [np.ones(1, dtype=np.float64) for _ in range(num_qubits - 1)]
+            self._states.append((gam, lam))
+
+    @property
+    def num_states(self) -> int:
+        return len(self._states)
+
+    @property
+    def state_indices(self) -> np.ndarray:
+        return self._state_idx
+
+    def init_state(self, state_no: int):
+        assert chk.is_int(state_no, 0 <= state_no < self.num_states)
+        return self._states[state_no]
+
+    @property
+    def state0(self):
+        return self._states[0]
+
+    def state_dot_vector(self, state_no: int, vec) -> np.complex128:
+        from ..mps_operations import mps_dot  # pylint: disable=import-outside-toplevel
+
+        assert chk.is_int(state_no, 0 <= state_no < self.num_states)
+        return np.complex128(mps_dot(self._states[state_no], vec))
+
+    def init_composite_state_no_zero(self, _: np.ndarray) -> np.ndarray:
+        raise NotImplementedError("composite states exist for ThinStateHandler only, as in the reference")
+
+    init_composite_state = init_composite_state_no_zero
+
+    def composite_state_dot_vector_no_zero(self, _: np.ndarray, __: np.ndarray) -> np.complex128:
+        raise NotImplementedError("composite states exist for ThinStateHandler only, as in the reference")
+
+    composite_state_dot_vector = composite_state_dot_vector_no_zero

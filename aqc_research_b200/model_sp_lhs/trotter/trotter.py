@@ -114,3 +114,122 @@ def trotter_state(num_qubits: int, *, evol_time: float, num_steps: int, delta: f
         vec[index] = 1
     out = np.empty_like(vec)
     return v_mul_vec(circ, thetas, vec, out)
+
+
+class Trotter:
+    """
+    Trotter evolution under the XXZ chain Hamiltonian, first or second order (trotter.py:40-180 of
+    the reference, where it wraps a Qiskit circuit).  Here the Trotter circuit is the
+    ``TrotterAnsatz`` with the angles of ``init_ansatz_to_trotter`` and runs on the GPU; an initial
+    state is a dense vector, a basis index or the list of X-gate positions that the reference's
+    preparation circuits (``neel_init_state`` ...) stand for.
+    """
+
+    def __init__(self, *, num_qubits: int, evol_time: float, num_steps: int, delta: float = 1.0,
+                 second_order: bool):
+        assert chk.is_int(num_qubits, num_qubits >= 2)
+        assert chk.is_float(evol_time, evol_time > 0)
+        assert chk.is_int(num_steps, num_steps >= 1)
+        assert chk.is_float(delta, delta > 0)
+        assert isinstance(second_order, bool)
+        self._num_qubits = int(num_qubits)
+        self._evol_time = float(evol_time)
+        self._num_trotter_steps = int(num_steps)
+        self._delta = float(delta)
+        self._dt = float(evol_time) / float(num_steps)
+        self._second_order = second_order
+
+    @property
+    def evol_time(self) -> float:
+        return self._evol_time
+
+    @property
+    def time_step(self) -> float:
+        return self._dt
+
+    @property
+    def num_trotter_steps(self) -> int:
+        return self._num_trotter_steps
+
+    def as_vector(self, ini_state: Union[int, List[int], np.ndarray]) -> np.ndarray:
+        """``Trotter |ini_state>`` as a dense vector (:97-127); one ``v_mul_vec`` on the GPU."""
+        return trotter_state(self._num_qubits, evol_time=self._evol_time, num_steps=self._num_trotter_steps,
+                             delta=self._delta, second_order=self._second_order, ini_state=ini_state)
+
+    def as_mps(self, ini_state: Union[int, List[int]], trunc_thr: Optional[float] = None,
+               out_state: Optional[np.ndarray] = None):
+        """``Trotter |ini_state>`` in MPS format (:137-163); ``ini_state`` is a basis state."""
+        from ...circuit_structures import make_trotter_like_circuit  # pylint: disable=import-outside-toplevel
+        from ...mps_engine import MpsWorkspace  # pylint: disable=import-outside-toplevel
+        from ... import mps_operations as mpsop  # pylint: disable=import-outside-toplevel
+
+        n = self._num_qubits
+        circ = TrotterAnsatz(n, make_trotter_like_circuit(n, self._num_trotter_steps), self._second_order)
+        thetas = init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=self._evol_time, delta=self._delta)
+        index = int(ini_state) if isinstance(ini_state, (int, np.integer)) else basis_index(ini_state)
+        thr = mpsop.no_truncation_threshold() if trunc_thr is None else float(trunc_thr)
+        ws = MpsWorkspace(circ, num_slots=1, chi_max=64, trunc_thr=thr)
+        ws.set_product(0, index)
+        ws.apply(thetas, 0, 0, dagger=False)
+        mps = ws.download(0)
+        ws.close()
+        if out_state is not None:
+            np.copyto(out_state, mpsop.mps_to_vector(mps))
+        return mps
+
+    def as_qcircuit(self, ini_state):
+        """The reference returns a Qiskit ``QuantumCircuit`` (:129-135); Qiskit is not part of this package."""
+        raise NotImplementedError("Trotter.as_qcircuit needs Qiskit; use as_vector / as_mps, or "
+                                  "init_ansatz_to_trotter for the angles of the equivalent TrotterAnsatz")
+
+
+def make_hamiltonian(num_qubits: int, delta: float) -> np.ndarray:
+    """
+    Dense XXZ chain Hamiltonian  H = -1/4 sum_k (X_k X_{k+1} + Y_k Y_{k+1} + delta Z_k Z_{k+1})
+    (half-spin matrices; trotter.py:183-230).  Testing aid, O(4^n) memory.  Built from index
+    arithmetic: XX + YY exchanges the two bits of a neighbouring pair when they differ (amplitude 2),
+    ZZ is +1 for equal and -1 for different bits; the chain is mirror symmetric, so the bit order is
+    immaterial.
+    """
+    assert chk.is_int(num_qubits, num_qubits >= 2) and chk.is_float(delta)
+    dim = 2**num_qubits
+    idx = np.arange(dim)
+    ham = np.zeros((dim, dim), dtype=np.complex128)
+    for k in range(num_qubits - 1):
+        b0, b1 = (idx >> k) & 1, (idx >> (k + 1)) & 1
+        differ = b0 != b1
+        ham[idx, idx] += -0.25 * delta * np.where(differ, -1.0, 1.0)
+        flipped = idx ^ ((1 << k) | (1 << (k + 1)))
+        ham[flipped[differ], idx[differ]] += -0.25 * 2.0
+    return ham
+
+
+def exact_evolution(hamiltonian: np.ndarray, ini_state: Union[int, List[int], np.ndarray],
+                    evol_time: float) -> np.ndarray:
+    """``exp(-i t H) |ini_state>`` by dense matrix exponential (trotter.py:233-266); testing aid."""
+    from scipy.linalg import expm  # pylint: disable=import-outside-toplevel
+
+    assert chk.complex_2d(hamiltonian) and hamiltonian.shape[0] == hamiltonian.shape[1]
+    assert chk.is_float(evol_time, evol_time > 0)
+    if isinstance(ini_state, np.ndarray) and ini_state.ndim == 1 and ini_state.size == hamiltonian.shape[0]:
+        vec = ini_state.astype(np.complex128)
+    else:
+        vec = np.zeros(hamiltonian.shape[0], dtype=np.complex128)
+        vec[int(ini_state) if isinstance(ini_state, (int, np.integer)) else basis_index(ini_state)] = 1
+    return expm((-1.0j * evol_time) * hamiltonian) @ vec
+
+
+def trotter_global_phase(num_qubits: int, num_steps: int, second_order: bool) -> float:
+    """
+    Global phase the reference attaches to a Trotter circuit (trotter.py:286-314): pi/4 per block of
+    the ``num_steps`` full layers, plus pi/4 times ``num_qubits`` (even) or ``num_qubits - 1`` (odd)
+    for the second order -- the reference's own count, kept as it is.  For the first order
+    ``e^{i phase} Trotter|psi>`` approaches ``exp(-i t H)|psi>`` as the steps get finer
+    (tests/test_trotter_cpu.py).
+    """
+    assert chk.is_int(num_qubits, num_qubits >= 2) and chk.is_int(num_steps, num_steps >= 1)
+    assert isinstance(second_order, bool)
+    blocks = (num_qubits - 1) * num_steps
+    if second_order:
+        blocks += num_qubits if num_qubits % 2 == 0 else num_qubits - 1
+    return 0.25 * np.pi * blocks

@@ -206,3 +206,48 @@ def test_full_size_properties_n28():
         fd = (vals[0] - vals[1]) / 2e-4
         assert abs(fd - g[k]) < 1e-7 * max(1.0, abs(g[k])) + 1e-9, (k, fd, g[k])
     ws.close()
+
+
+def test_circuit_transform_and_trotter_class():
+    """
+    ansatz_to_numpy_fast / ansatz_to_numpy_trotter (circuit_transform.py:273-390) against the dense
+    oracle; Trotter.as_vector / as_mps (trotter.py:97-163) against the oracle's Trotter circuit.
+    """
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200 import circuit_transform as ctr
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trot
+    from aqc_research_b200.parametric_circuit import ParametricCircuit, TrotterAnsatz
+    from oracle import mps_oracle as M
+    from oracle import sv_oracle as O
+
+    rng = np.random.RandomState(77)
+    n = 4
+    circ = ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "spin", "full", 7))
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    eye = np.eye(2**n, dtype=np.complex128)
+    ref_mat = O.apply_v(circ, th, eye.copy().ravel(), ncols=2**n).reshape(2**n, 2**n)
+    assert np.linalg.norm(ctr.ansatz_to_numpy_fast(circ, th) - ref_mat) < 1e-12
+    tro = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    th = np.pi * (2 * rng.rand(tro.num_thetas) - 1)
+    cols = np.stack([O.apply_v(tro, th, eye[:, k].copy()) for k in range(2**n)], axis=1)
+    got = ctr.ansatz_to_numpy_trotter(tro, th)
+    assert np.linalg.norm(got - cols) < 1e-12 and np.linalg.norm(got.conj().T @ got - eye) < 1e-12
+    with pytest.raises(ValueError):
+        ctr.ansatz_to_numpy_fast(tro, th)
+    with pytest.raises(NotImplementedError):
+        ctr.ansatz_to_qcircuit(circ, th)
+    # Trotter class: the TrotterAnsatz at the init_ansatz_to_trotter angles
+    tr = trot.Trotter(num_qubits=5, evol_time=0.9, num_steps=3, delta=1.1, second_order=True)
+    neel = trot.neel_init_state(5)
+    c5 = TrotterAnsatz(5, cs.make_trotter_like_circuit(5, 3), True)
+    t5 = trot.init_ansatz_to_trotter(c5, np.zeros(c5.num_thetas), evol_time=0.9, delta=1.1)
+    v0 = np.zeros(32, dtype=np.complex128)
+    v0[trot.basis_index(neel)] = 1
+    want = O.apply_v(c5, t5, v0)
+    assert np.linalg.norm(tr.as_vector(neel) - want) < 1e-12
+    assert np.linalg.norm(tr.as_vector(v0) - want) < 1e-12
+    dense = np.zeros(32, dtype=np.complex128)
+    mps = tr.as_mps(neel, out_state=dense)
+    assert np.linalg.norm(dense - want) < 1e-10 and np.linalg.norm(M.mps_to_vector(mps) - want) < 1e-10
+    exact = trot.exact_evolution(trot.make_hamiltonian(5, 1.1), neel, 0.9)
+    assert 1.0 - abs(np.vdot(exact, want)) < 1e-3
