@@ -287,3 +287,64 @@ def test_mps_gate_helpers_host_logic(monkeypatch):
         assert rel(M.mps_to_vector(mdo.cx_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_X)) < TOL
         assert rel(M.mps_to_vector(mdo.cz_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_Z)) < TOL
         assert rel(M.mps_to_vector(mdo.cp_mul_mps(ang, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.phase(ang))) < TOL
+
+
+class OracleMatWorkspace:
+    """Stand-in for the matrix-path SvWorkspace used by SketchingObjectiveEx (dense oracle underneath)."""
+
+    def __init__(self, circ, num_slots, device=0, log2_cols=0, batch=1, as_generic=False):
+        self.circ, self.ncols = circ, 1 << log2_cols
+        self.size = (2**circ.num_qubits) * self.ncols
+        self.slots = [np.zeros(self.size, dtype=np.complex128) for _ in range(num_slots)]
+        self.sweeps = 0
+
+    def upload(self, slot, data, batch_index=-1):
+        self.slots[slot] = np.array(data, dtype=np.complex128).ravel()
+
+    def set_identity(self, slot):
+        self.slots[slot] = np.eye(2**self.circ.num_qubits, dtype=np.complex128).ravel()
+
+    def apply(self, thetas, src, dst, dagger=False):
+        self.slots[dst] = O.apply_v(self.circ, np.asarray(thetas), self.slots[src], dagger=dagger, ncols=self.ncols)
+
+    def vdot(self, a, b):
+        return np.array([np.vdot(self.slots[a], self.slots[b])])
+
+    def grad(self, thetas, *, z0, w, z, x_slot=-1, x_basis=0):
+        self.sweeps += 1
+        return O.grad_sweep(self.circ, np.asarray(thetas), self.slots[x_slot], self.slots[z0], ncols=self.ncols)[None, :]
+
+    def close(self):
+        pass
+
+
+def test_sketching_objective_host_logic(monkeypatch):
+    """
+    SketchingObjectiveEx + FullRangeSketchingVectors (sk_core.py:94-326): f = 1 - Re Tr(V^H U) / d,
+    g = -Re(grad) / d, the (f, g) cache keyed on theta, best-point bookkeeping -- against the golden
+    sequences of the reference, with the oracle standing in for the GPU workspace.
+    """
+    from golden_util import KINDS
+    from aqc_research_b200.model_sketching import sk_core
+    from aqc_research_b200.parametric_circuit import ParametricCircuit
+
+    monkeypatch.setattr(sk_core, "SvWorkspace", OracleMatWorkspace)
+    g = load("objective_sequences.npz")
+    for c in range(int(g["num_sk"])):
+        p = f"sk{c}_"
+        n, kind = [int(v) for v in g[p + "meta"]]
+        circ = ParametricCircuit(n, KINDS[kind], g[p + "blocks"])
+        objv = sk_core.SketchingObjectiveEx(circ, sk_core.FullRangeSketchingVectors(g[p + "target"]), enable_stats=True)
+        ths = g[p + "thetas"]
+        for s in range(ths.shape[0]):
+            assert abs(objv.objective(ths[s]) - g[p + "f"][s]) < TOL
+            before = objv.workspace.sweeps
+            assert rel(objv.gradient(ths[s]), g[p + "grad"][s]) < TOL
+            assert objv.workspace.sweeps == before  # same theta: the cached gradient is returned
+        assert objv.num_iterations == ths.shape[0]
+        grad = objv.gradient(ths[0])  # gradient first at other angles: objective is recomputed
+        assert rel(grad, g[p + "grad"][0]) < TOL and objv.num_iterations == ths.shape[0] + 1
+        res = objv.optim_results
+        best = int(np.argmin(g[p + "f"]))
+        assert abs(res["cost"] - g[p + "f"][best]) < TOL and np.array_equal(res["thetas"], ths[best])
+        assert objv.statistics["nit"] == ths.shape[0] + 1
