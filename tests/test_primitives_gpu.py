@@ -68,6 +68,37 @@ def test_projector_does_not_spread_non_finite_values():
     assert np.all(np.isfinite(out)) and np.all(out[: 2 ** (n - 1)] == 1) and np.all(out[2 ** (n - 1):] == 0)
 
 
+def test_degenerate_gates_and_blocks_vs_kronecker():
+    """
+    gate2x2_mul_vec with every zero pattern of the 2x2 gate (the reference special-cases them,
+    core_operations.py:76-119; its test_core_operations.py:124-196) and block_mul_vec for all
+    (ctrl, targ) against the dense Kronecker matrices of elementary_operations (qubit 0 leftmost).
+    """
+    from aqc_research_b200 import elementary_operations as eo
+
+    rng = np.random.RandomState(5)
+    n = 3
+    a, b, c, d = (rng.randn(4) + 1j * rng.randn(4))
+    patterns = [[[a, 0], [0, d]], [[0, b], [c, 0]], [[a, b], [0, 0]], [[0, 0], [c, d]],
+                [[a, 0], [c, 0]], [[0, b], [0, d]], [[a, 0], [0, 0]], [[0, 0], [0, d]], [[0, 0], [0, 0]]]
+    v0 = rng.randn(2**n) + 1j * rng.randn(2**n)
+    for pat in patterns:
+        g = np.array(pat, dtype=np.complex128)
+        for pos in range(n):
+            want = eo._embed(n, {pos: g}) @ v0
+            got = cop.gate2x2_mul_vec(n, pos, g, v0.copy(), np.zeros_like(v0), True)
+            assert np.linalg.norm(got - want) <= TOL * np.linalg.norm(v0), (pat, pos)
+    cm, tm, gm = [rng.randn(2, 2) + 1j * rng.randn(2, 2) for _ in range(3)]
+    for ctrl in range(n):
+        for targ in range(n):
+            if ctrl == targ:
+                continue
+            ws = np.zeros((2, v0.size), dtype=np.complex128)
+            want = eo.np_block_matrix(n, ctrl, targ, cm, tm, gm) @ v0
+            assert rel(cop.block_mul_vec(n, ctrl, targ, cm, tm, gm, v0.copy(), ws, False), want) < TOL
+            assert rel(cop.cx_mul_vec(n, ctrl, targ, 0.0, v0.copy(), ws[0]), eo.np_cx_matrix(n, ctrl, targ) @ v0) < TOL
+
+
 @pytest.mark.parametrize("m", [16, 5])
 def test_matrix_primitives_match_the_reference(m):
     g = load("primitive_cases.npz")

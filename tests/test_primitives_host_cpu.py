@@ -50,6 +50,7 @@ def test_vector_primitives_host_logic():
     gpu_tests.test_vector_primitives_match_the_reference()
     gpu_tests.test_projector_does_not_spread_non_finite_values()
     gpu_tests.test_bad_arguments_raise()
+    gpu_tests.test_degenerate_gates_and_blocks_vs_kronecker()
 
 
 @pytest.mark.parametrize("m", [16, 5])
