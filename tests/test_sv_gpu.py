@@ -251,3 +251,34 @@ def test_circuit_transform_and_trotter_class():
     assert np.linalg.norm(dense - want) < 1e-10 and np.linalg.norm(M.mps_to_vector(mps) - want) < 1e-10
     exact = trot.exact_evolution(trot.make_hamiltonian(5, 1.1), neel, 0.9)
     assert 1.0 - abs(np.vdot(exact, want)) < 1e-3
+
+
+@pytest.mark.parametrize("ent,m", [("cx", 8), ("cz", 5), ("cp", 8)])
+def test_matrix_gradient_equals_parameter_shift(ent, m):
+    """
+    grad_of_matrix_dot_product against the EXACT parameter-shift gradient of f = <V X, Y>_F, the
+    reference's strongest check of the matrix path (test_core_op_matrix.py:115-140, 305-336): every
+    rotation angle enters as cos / sin of theta/2 (shift pi, scale 1/4), the CPhase angle as e^{i phi}
+    (shift pi/2, scale 1/2).  Nothing but v_mul_mat is used for f.
+    """
+    rng = np.random.RandomState(len(ent) * 100 + m)
+    n = 3
+    circ = ParametricCircuit(n, ent, cs.create_ansatz_structure(n, "spin", "full", 5))
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    x = np.ascontiguousarray(rng.randn(2**n, m) + 1j * rng.randn(2**n, m))
+    y = np.ascontiguousarray(rng.randn(2**n, m) + 1j * rng.randn(2**n, m))
+
+    def fobj(angles):
+        return np.vdot(cpm.v_mul_mat(circ, angles, x.copy()), y)
+
+    grad = cpm.grad_of_matrix_dot_product(circ, th, x.copy(), cpm.v_dagger_mul_mat(circ, th, y.copy()))
+    tpb = 5 if ent == "cp" else 4
+    shifted = np.zeros(circ.num_thetas, dtype=np.complex128)
+    for k in range(circ.num_thetas):
+        is_phase = ent == "cp" and k >= 3 * n and (k - 3 * n) % tpb == 4
+        shift, scale = (0.5 * np.pi, 0.5) if is_phase else (np.pi, 0.25)
+        tp, tm = th.copy(), th.copy()
+        tp[k] += shift
+        tm[k] -= shift
+        shifted[k] = scale * (fobj(tp) - fobj(tm))
+    assert _rel(grad, shifted) < 1e-10
