@@ -44,7 +44,7 @@ def _needs_qiskit(name: str):
         raise NotImplementedError(f"{name} converts to / from Qiskit objects; Qiskit is not part of this package")
 
     _fn.__name__ = name
-    _fn.__doc__ = f"Qiskit converter of the reference (circuit_transform.py); unavailable without Qiskit."
+    _fn.__doc__ = "Qiskit converter of the reference (circuit_transform.py); unavailable without Qiskit."
     return _fn
 
 

@@ -12,7 +12,7 @@ starts per GPU) in one launch sequence.
 
 from abc import ABC, abstractmethod
 from time import perf_counter
-from typing import Optional, Tuple
+from typing import Tuple
 import numpy as np
 from .. import checking as chk
 from ..engine import SvWorkspace

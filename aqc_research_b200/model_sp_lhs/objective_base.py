@@ -8,7 +8,7 @@ inside an ``SvWorkspace``; only thetas go down and (hs, gradient) come back per 
 
 import itertools
 from abc import ABC, abstractmethod
-from typing import Callable, List, Optional, Sequence, Tuple, Union
+from typing import Callable, List, Optional, Tuple
 import numpy as np
 from .. import checking as chk
 from ..engine import SvWorkspace

@@ -5,7 +5,7 @@ Function-level drop-ins of the reference's MPS helpers (aqc_research/mps_operati
 format utilities (pure NumPy, as in the reference :87-189).
 """
 
-from typing import List, Optional, Tuple
+from typing import List, Optional
 import numpy as np
 from .mps_engine import MpsWorkspace, QiskitMPS
 from .parametric_circuit import ParametricCircuit
