@@ -36,3 +36,19 @@ def rand_state(num_qubits: int) -> np.ndarray:
     state = np.random.rand(dim) + 1j * np.random.rand(dim)
     state /= np.linalg.norm(state)
     return state
+
+
+def zero_state(num_qubits: int) -> np.ndarray:
+    """The state |0...0> as a dense complex128 vector (utils.py:82-89)."""
+    assert isinstance(num_qubits, (int, np.integer)) and num_qubits >= 2
+    state = np.zeros(2**num_qubits, dtype=np.complex128)
+    state[0] = 1
+    return state
+
+
+def num_cpus() -> int:
+    """Number of host CPUs, 1 if it cannot be determined (utils.py:42-48)."""
+    import os  # pylint: disable=import-outside-toplevel
+
+    count = os.cpu_count()
+    return int(count) if isinstance(count, int) and count > 0 else 1
