@@ -148,7 +148,7 @@ class AqcError(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compiles the shared library in-tree with nvcc for sm_100a. Returns its path."""
-    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True, check=False)
+    res = subprocess.run(["make", "-j4", "-C", CSRC_DIR], capture_output=True, text=True, check=False)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)

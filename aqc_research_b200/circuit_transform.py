@@ -14,13 +14,13 @@ import numpy as np
 from . import checking as chk
 from .core_op_matrix import v_mul_mat
 from .core_operations import v_mul_vec
-from .parametric_circuit import ParametricCircuit, TrotterAnsatz
+from .parametric_circuit import ParametricCircuit, TrotterAnsatz, is_parametric_circuit, is_trotter_ansatz
 
 
 def ansatz_to_numpy_fast(circ: ParametricCircuit, thetas: np.ndarray) -> np.ndarray:
     """Circuit matrix of a generic (non-Trotter) ansatz (:273-287)."""
-    assert isinstance(circ, ParametricCircuit) and chk.float_1d(thetas)
-    if isinstance(circ, TrotterAnsatz):
+    assert is_parametric_circuit(circ) and chk.float_1d(thetas)
+    if is_trotter_ansatz(circ):
         raise ValueError("ansatz_to_numpy_fast does not support TrotterAnsatz; use ansatz_to_numpy_trotter")
     mat = np.eye(circ.dimension, dtype=np.complex128)
     return v_mul_mat(circ, thetas, mat, workspace=None)
@@ -28,7 +28,7 @@ def ansatz_to_numpy_fast(circ: ParametricCircuit, thetas: np.ndarray) -> np.ndar
 
 def ansatz_to_numpy_trotter(circ: ParametricCircuit, thetas: np.ndarray) -> np.ndarray:
     """Circuit matrix of any ansatz, Trotterized ones included (:290-390)."""
-    assert isinstance(circ, ParametricCircuit) and chk.float_1d(thetas)
+    assert is_parametric_circuit(circ) and chk.float_1d(thetas)
     dim = circ.dimension
     mat = np.empty((dim, dim), dtype=np.complex128)
     col, out = np.zeros(dim, dtype=np.complex128), np.empty(dim, dtype=np.complex128)

@@ -10,7 +10,7 @@ from typing import Optional
 import numpy as np
 from . import checking as chk
 from .core_operations import _workspace
-from .parametric_circuit import ParametricCircuit
+from .parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 
 def _pad_cols(mat: np.ndarray, log2_cols: int) -> np.ndarray:
@@ -27,7 +27,7 @@ def _log2_cols(m: int) -> int:
 
 
 def _check(circ, thetas, *mats):
-    assert isinstance(circ, ParametricCircuit)
+    assert is_parametric_circuit(circ)
     assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
     for m in mats:
         assert chk.complex_2d(m, m.shape[0] == circ.dimension and 1 <= m.shape[1] <= m.shape[0])
@@ -86,7 +86,7 @@ def coord_descent_single_sweep(
     (core_op_matrix.py:765-917): ``thetas`` is modified IN PLACE, the objective at the end of the
     sweep is returned.  cx / cz entanglers only, as in the reference (:818-819).
     """
-    assert isinstance(circ, ParametricCircuit)
+    assert is_parametric_circuit(circ)
     assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
     assert chk.complex_2d(target, target.shape[0] == target.shape[1] == circ.dimension)
     if circ.entangler == "cp":

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 from . import checking as chk
 from .engine import SvWorkspace
-from .parametric_circuit import ParametricCircuit
+from .parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 _CACHE_SIZE = 4
 _workspaces: "OrderedDict[tuple, SvWorkspace]" = OrderedDict()
@@ -50,7 +50,7 @@ def clear_workspace_cache():
 
 
 def _check_vectors(circ, thetas, *vecs):
-    assert isinstance(circ, ParametricCircuit)
+    assert is_parametric_circuit(circ)
     assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
     for v in vecs:
         assert chk.complex_1d(v, v.size == circ.dimension) and v.flags.c_contiguous

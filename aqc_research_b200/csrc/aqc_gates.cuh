@@ -194,221 +194,3 @@ __device__ __forceinline__ void block_unit(cd (&a)[NVEC][4], const double2* __re
     }
   }
 }
-
-
-// ------------------------------------------------------------------------------------------------
-// Scale-free ("fast Givens") forms used by the gradient sweep.
-//
-// Both swept vectors w and z go through the same gates and only inner products <P w|z> are wanted,
-// so a common complex scalar on w and z matters only through its squared modulus.  Hence
-//   Rz(phi)   = e^{-i phi/2} diag(1, e^{i phi})      -> multiply a1 by e^{i phi}      (no scale)
-//   Ry(theta) = c [[1, -t], [t, 1]],   t = s / c      -> one FMA per component        (scale c)
-//             = s [[r, -1], [1, r]],   r = c / s      (used when |c| is small)        (scale s)
-//   Rx(theta) = c [[1, -i t], [-i t, 1]] = s [[r, -i], [-i, r]]
-// The dropped real scale factors are tracked by the prep kernel (aqc_sv.cu): the raw inner
-// product taken after a rotation is multiplied by the squared cumulative scale afterwards.
-// Parameter encoding (double2 p): Ry / Rx: p.x = t or r, p.y = 0 (c-form) or 1 (s-form);
-// Rz / CPhase: p = (cos phi, sin phi) of the FULL angle.
-// ------------------------------------------------------------------------------------------------
-template <bool HI, int ROT, bool CFORM = false>
-__device__ __forceinline__ void srot1q(cd (&a)[2][4], const double2 p, double* acc) {
-  constexpr int I0a = 0, I0b = HI ? 1 : 2;          // the two pairs (i0, i1 = i0 + step)
-  constexpr int STEP = HI ? 2 : 1;
-  if (ROT == ROT_Z) {
-#pragma unroll
-    for (int v = 0; v < 2; ++v) mul_cs(a[v][I0a + STEP], p.x, p.y), mul_cs(a[v][I0b + STEP], p.x, p.y);
-  } else if (CFORM || p.y == 0.0) {  // c-form
-    const double t = p.x;
-#pragma unroll
-    for (int v = 0; v < 2; ++v)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
-        const cd b0 = a[v][i0], b1 = a[v][i1];
-        if (ROT == ROT_Y) {
-          a[v][i0].x = fma(-t, b1.x, b0.x), a[v][i0].y = fma(-t, b1.y, b0.y);
-          a[v][i1].x = fma(t, b0.x, b1.x), a[v][i1].y = fma(t, b0.y, b1.y);
-        } else {  // Rx: a0 - i t a1 ; a1 - i t a0
-          a[v][i0].x = fma(t, b1.y, b0.x), a[v][i0].y = fma(-t, b1.x, b0.y);
-          a[v][i1].x = fma(t, b0.y, b1.x), a[v][i1].y = fma(-t, b0.x, b1.y);
-        }
-      }
-  } else {  // s-form
-    const double rr = p.x;
-#pragma unroll
-    for (int v = 0; v < 2; ++v)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
-        const cd b0 = a[v][i0], b1 = a[v][i1];
-        if (ROT == ROT_Y) {  // r a0 - a1 ; a0 + r a1
-          a[v][i0].x = fma(rr, b0.x, -b1.x), a[v][i0].y = fma(rr, b0.y, -b1.y);
-          a[v][i1].x = fma(rr, b1.x, b0.x), a[v][i1].y = fma(rr, b1.y, b0.y);
-        } else {  // Rx: r a0 - i a1 ; r a1 - i a0
-          a[v][i0].x = fma(rr, b0.x, b1.y), a[v][i0].y = fma(rr, b0.y, -b1.x);
-          a[v][i1].x = fma(rr, b1.x, b0.y), a[v][i1].y = fma(rr, b1.y, -b0.x);
-        }
-      }
-  }
-  // raw inner products after the rotation (same forms as rot1q)
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
-    if (ROT == ROT_Y) {
-      cdot_add(acc, a[0][i0], a[1][i1]);
-      cdot_sub(acc, a[0][i1], a[1][i0]);
-    }
-    if (ROT == ROT_Z) {
-      cdot_add(acc, a[0][i0], a[1][i0]);
-      cdot_sub(acc, a[0][i1], a[1][i1]);
-    }
-    if (ROT == ROT_X) {
-      cdot_add(acc, a[0][i1], a[1][i0]);
-      cdot_add(acc, a[0][i0], a[1][i1]);
-    }
-  }
-}
-
-template <bool HI>
-__device__ __forceinline__ void sfront_unit(cd (&a)[2][4], const double2* __restrict__ p, double* acc) {
-  srot1q<HI, ROT_Z>(a, p[2], acc + 4);
-  srot1q<HI, ROT_Y>(a, p[1], acc + 2);
-  srot1q<HI, ROT_Z>(a, p[0], acc + 0);
-}
-
-// Unit block of the gradient sweep with scale-free rotations.  PRE / POST: -1 = runtime flags,
-// 0 / 1 = compile-time (the Trotter triplet specialisation).
-template <int ENT, bool CHI, int PRE, int POST, bool CFORM = false>
-__device__ __forceinline__ void sblock_unit(cd (&a)[2][4], const double2* __restrict__ p, int flags,
-                                            double* acc) {
-  constexpr int C1A = CHI ? 2 : 1;
-  constexpr int T1A = CHI ? 1 : 2;
-  constexpr int ROT_S = (ENT == AQC_ENT_CX) ? ROT_X : ROT_Z;
-  const bool pre = (PRE < 0) ? (flags & F_PRE) != 0 : (PRE != 0);
-  const bool post = (POST < 0) ? (flags & F_POST) != 0 : (POST != 0);
-  if (pre) {
-#pragma unroll
-    for (int v = 0; v < 2; ++v) mul_mi(a[v][C1A]), mul_mi(a[v][3]);
-  }
-  if (ENT == AQC_ENT_CX) {
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const cd t = a[v][C1A];
-      a[v][C1A] = a[v][3];
-      a[v][3] = t;
-    }
-  } else if (ENT == AQC_ENT_CZ) {
-#pragma unroll
-    for (int v = 0; v < 2; ++v) a[v][3].x = -a[v][3].x, a[v][3].y = -a[v][3].y;
-  } else {
-    cdot_add(acc + 8, a[0][3], a[1][3]);
-#pragma unroll
-    for (int v = 0; v < 2; ++v) mul_cs(a[v][3], p[4].x, p[4].y);
-  }
-  srot1q<CHI, ROT_Y, CFORM>(a, p[0], acc + 0);
-  srot1q<CHI, ROT_Z, CFORM>(a, p[1], acc + 2);
-  srot1q<!CHI, ROT_Y, CFORM>(a, p[2], acc + 4);
-  srot1q<!CHI, ROT_S, CFORM>(a, p[3], acc + 6);
-  if (post) {
-#pragma unroll
-    for (int v = 0; v < 2; ++v) mul_pi(a[v][T1A]), mul_pi(a[v][3]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Scale-free forms for the single-vector sweeps V x / V^H x (no inner products).  The dropped
-// complex scalars (signed cos / sin factors, e^{-i phi/2} of every Rz) are collected by the prep
-// kernel and multiplied back when the last pass stores the tile.  The parameter table is built for
-// the NEGATED angles in the daggered sweep, so DAG only reverses the order of the rotations.
-// ------------------------------------------------------------------------------------------------
-template <bool HI, int ROT>
-__device__ __forceinline__ void arot1q(cd (&a)[4], const double2 p) {
-  constexpr int I0a = 0, I0b = HI ? 1 : 2;
-  constexpr int STEP = HI ? 2 : 1;
-  if (ROT == ROT_Z) {
-    mul_cs(a[I0a + STEP], p.x, p.y);
-    mul_cs(a[I0b + STEP], p.x, p.y);
-    return;
-  }
-  const double t = p.x;
-  if (p.y == 0.0) {  // c-form
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
-      const cd b0 = a[i0], b1 = a[i1];
-      if (ROT == ROT_Y) {
-        a[i0].x = fma(-t, b1.x, b0.x), a[i0].y = fma(-t, b1.y, b0.y);
-        a[i1].x = fma(t, b0.x, b1.x), a[i1].y = fma(t, b0.y, b1.y);
-      } else {
-        a[i0].x = fma(t, b1.y, b0.x), a[i0].y = fma(-t, b1.x, b0.y);
-        a[i1].x = fma(t, b0.y, b1.x), a[i1].y = fma(-t, b0.x, b1.y);
-      }
-    }
-  } else {  // s-form
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int i0 = r ? I0b : I0a, i1 = i0 + STEP;
-      const cd b0 = a[i0], b1 = a[i1];
-      if (ROT == ROT_Y) {
-        a[i0].x = fma(t, b0.x, -b1.x), a[i0].y = fma(t, b0.y, -b1.y);
-        a[i1].x = fma(t, b1.x, b0.x), a[i1].y = fma(t, b1.y, b0.y);
-      } else {
-        a[i0].x = fma(t, b0.x, b1.y), a[i0].y = fma(t, b0.y, -b1.x);
-        a[i1].x = fma(t, b1.x, b0.y), a[i1].y = fma(t, b1.y, -b0.x);
-      }
-    }
-  }
-}
-
-template <bool HI, bool DAG>
-__device__ __forceinline__ void afront_unit(cd (&a)[4], const double2* __restrict__ p) {
-  if (!DAG) {
-    arot1q<HI, ROT_Z>(a, p[2]);
-    arot1q<HI, ROT_Y>(a, p[1]);
-    arot1q<HI, ROT_Z>(a, p[0]);
-  } else {
-    arot1q<HI, ROT_Z>(a, p[0]);
-    arot1q<HI, ROT_Y>(a, p[1]);
-    arot1q<HI, ROT_Z>(a, p[2]);
-  }
-}
-
-template <int ENT, bool CHI, bool DAG>
-__device__ __forceinline__ void ablock_unit(cd (&a)[4], const double2* __restrict__ p, int flags) {
-  constexpr int C1A = CHI ? 2 : 1;
-  constexpr int T1A = CHI ? 1 : 2;
-  constexpr int ROT_S = (ENT == AQC_ENT_CX) ? ROT_X : ROT_Z;
-  if (!DAG) {
-    if (flags & F_PRE) mul_mi(a[C1A]), mul_mi(a[3]);
-    if (ENT == AQC_ENT_CX) {
-      const cd t = a[C1A];
-      a[C1A] = a[3];
-      a[3] = t;
-    } else if (ENT == AQC_ENT_CZ) {
-      a[3].x = -a[3].x, a[3].y = -a[3].y;
-    } else {
-      mul_cs(a[3], p[4].x, p[4].y);
-    }
-    arot1q<CHI, ROT_Y>(a, p[0]);
-    arot1q<CHI, ROT_Z>(a, p[1]);
-    arot1q<!CHI, ROT_Y>(a, p[2]);
-    arot1q<!CHI, ROT_S>(a, p[3]);
-    if (flags & F_POST) mul_pi(a[T1A]), mul_pi(a[3]);
-  } else {
-    if (flags & F_POST) mul_mi(a[T1A]), mul_mi(a[3]);
-    arot1q<!CHI, ROT_S>(a, p[3]);
-    arot1q<!CHI, ROT_Y>(a, p[2]);
-    arot1q<CHI, ROT_Z>(a, p[1]);
-    arot1q<CHI, ROT_Y>(a, p[0]);
-    if (ENT == AQC_ENT_CX) {
-      const cd t = a[C1A];
-      a[C1A] = a[3];
-      a[3] = t;
-    } else if (ENT == AQC_ENT_CZ) {
-      a[3].x = -a[3].x, a[3].y = -a[3].y;
-    } else {
-      mul_cs(a[3], p[4].x, p[4].y);  // table holds the negated angle
-    }
-    if (flags & F_PRE) mul_pi(a[C1A]), mul_pi(a[3]);
-  }
-}

@@ -7,7 +7,7 @@ import ctypes as ct
 from typing import Optional, Sequence
 import numpy as np
 from . import _lib
-from .parametric_circuit import ParametricCircuit, TrotterAnsatz
+from .parametric_circuit import ParametricCircuit, is_parametric_circuit, is_trotter_ansatz
 
 _ENT_CODE = {"cx": 0, "cz": 1, "cp": 2}
 
@@ -27,13 +27,13 @@ class CircuitHandle:
     """Owns an ``aqc_circuit`` built from a ParametricCircuit / TrotterAnsatz description."""
 
     def __init__(self, circ: ParametricCircuit, as_generic: bool = False):
-        assert isinstance(circ, ParametricCircuit)
+        assert is_parametric_circuit(circ)
         self._lib = _lib.load()
         self.num_qubits = circ.num_qubits
         self.num_thetas = circ.num_thetas
         self.entangler = circ.entangler
         trotter = 0
-        if isinstance(circ, TrotterAnsatz) and not as_generic:
+        if is_trotter_ansatz(circ) and not as_generic:
             trotter = 2 if circ.is_second_order else 1
         self.trotter = trotter
         blocks = np.ascontiguousarray(circ.blocks, dtype=np.int32)

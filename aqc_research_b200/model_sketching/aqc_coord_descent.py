@@ -11,7 +11,7 @@ ONE kernel (one CTA per start) that updates all angles of all starts on the devi
 from typing import Optional
 import numpy as np
 from ..engine import SvWorkspace
-from ..parametric_circuit import ParametricCircuit
+from ..parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 SLOT_TARGET, SLOT_W, SLOT_Z = 0, 1, 2
 
@@ -20,7 +20,7 @@ class BatchedCoordinateDescent:
     """``batch`` independent coordinate-descent runs against one target unitary."""
 
     def __init__(self, circ: ParametricCircuit, target: np.ndarray, batch: int = 1, device: int = 0):
-        assert isinstance(circ, ParametricCircuit)
+        assert is_parametric_circuit(circ)
         if circ.entangler == "cp":
             raise NotImplementedError("CPhase entangler is not supported yet")
         target = np.ascontiguousarray(target, dtype=np.complex128)

@@ -16,7 +16,7 @@ from typing import Tuple
 import numpy as np
 from .. import checking as chk
 from ..engine import SvWorkspace
-from ..parametric_circuit import ParametricCircuit
+from ..parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 _SLOT_Y, _SLOT_Z, _SLOT_X, _SLOT_TMP = 0, 1, 2, 3
 
@@ -144,7 +144,7 @@ class EigenSketchingVectors(SketchingVectorsBase):
     on_device = True
 
     def generate_device(self, ws, x, y, tmp, circ=None, thetas=None) -> None:
-        assert isinstance(circ, ParametricCircuit)
+        assert is_parametric_circuit(circ)
         assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
         assert circ.dimension == self._target_mat.shape[0]
         dim, m = circ.dimension, self.num_skvecs
@@ -212,7 +212,7 @@ class SketchingObjectiveEx:
         logger=None,
         device: int = 0,
     ):
-        assert isinstance(circ, ParametricCircuit) and isinstance(skvecs, SketchingVectorsBase)
+        assert is_parametric_circuit(circ) and isinstance(skvecs, SketchingVectorsBase)
         self._circ = circ
         self._skvecs = skvecs
         self._target = skvecs.target_matrix

@@ -12,7 +12,7 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 from .. import checking as chk
 from ..engine import SvWorkspace
-from ..parametric_circuit import ParametricCircuit
+from ..parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 # workspace slot roles
 SLOT_TARGET, SLOT_VH_TARGET, SLOT_W, SLOT_Z, SLOT_STATE = 0, 1, 2, 3, 4
@@ -144,7 +144,7 @@ class SpService:
     """
 
     def __init__(self, user_parameters: dict, circuit: ParametricCircuit, num_states: int, verbose: bool = False):
-        assert chk.is_dict(user_parameters) and isinstance(circuit, ParametricCircuit)
+        assert chk.is_dict(user_parameters) and is_parametric_circuit(circuit)
         assert chk.is_int(num_states, num_states >= 1)
         self._params = user_parameters
         self._circuit = circuit
@@ -228,7 +228,7 @@ class SpLHSObjectiveBase(ABC):
     """
 
     def __init__(self, user_parameters: dict, circuit: ParametricCircuit, use_mps: bool = False, verbose: bool = False):
-        assert isinstance(user_parameters, dict) and isinstance(circuit, ParametricCircuit)
+        assert isinstance(user_parameters, dict) and is_parametric_circuit(circuit)
         self._params = user_parameters
         self._circuit = circuit
         self._use_mps = bool(use_mps)

@@ -14,7 +14,7 @@ from .. import checking as chk
 from ..core_operations import mask_gradient
 from ..mps_engine import MpsWorkspace
 from ..mps_operations import check_mps
-from ..parametric_circuit import TrotterAnsatz, first_layer_included, layer_to_block_range
+from ..parametric_circuit import TrotterAnsatz, first_layer_included, is_trotter_ansatz, layer_to_block_range
 from .objective_base import BasisStateHandler, SpLHSObjectiveBase, make_state_handler
 
 _SLOT_TARGET, _SLOT_VH, _SLOT_W, _SLOT_Z = 0, 1, 2, 3
@@ -35,7 +35,7 @@ class SpSurrogateObjectiveFastMpsTrotter(SpLHSObjectiveBase):
         verbose: bool = False,
         grad_scaler=None,
     ):
-        if not isinstance(circ, TrotterAnsatz):
+        if not is_trotter_ansatz(circ):
             raise ValueError("expects Trotterized ansatz")
         super().__init__(user_parameters, circ, use_mps=True, verbose=verbose)
         if user_parameters["max_flips"] != 1:

@@ -11,7 +11,7 @@ Trotter.as_qcircuit, ...) are callers outside the hot path and are not rebuilt; 
 from typing import List, Optional, Tuple, Union
 import numpy as np
 from ... import checking as chk
-from ...parametric_circuit import ParametricCircuit, TrotterAnsatz, first_layer_included
+from ...parametric_circuit import ParametricCircuit, TrotterAnsatz, first_layer_included, is_trotter_ansatz
 
 
 def trotter_alphas(dt: float, delta: float) -> np.ndarray:
@@ -56,7 +56,7 @@ def state_difference(state1: np.ndarray, state2: np.ndarray) -> float:
 
 def slice2q(circ: ParametricCircuit, vec: np.ndarray, *, layer_range: Optional[Tuple[int, int]] = None):
     """View (layers, n-1 triplets, 12 angles) of the block part of a theta-sized vector."""
-    if not isinstance(circ, TrotterAnsatz):
+    if not is_trotter_ansatz(circ):
         raise ValueError("expects Trotterized ansatz")
     assert isinstance(vec, np.ndarray) and vec.shape == (circ.num_thetas,)
     layers = circ.num_layers

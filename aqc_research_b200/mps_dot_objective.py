@@ -8,7 +8,7 @@ from . import checking as chk
 from .core_operations import mask_gradient
 from .mps_engine import MpsWorkspace, QiskitMPS
 from .mps_operations import no_truncation_threshold
-from .parametric_circuit import ParametricCircuit
+from .parametric_circuit import ParametricCircuit, is_parametric_circuit
 
 
 def fast_dot_gradient(
@@ -25,7 +25,7 @@ def fast_dot_gradient(
     Complex gradient of ``<lvec|V^H|phi>`` given ``vh_phi = V^H|phi>``; entries outside
     ``block_range`` / of a disabled front layer are zero, as in the reference.
     """
-    assert isinstance(circ, ParametricCircuit)
+    assert is_parametric_circuit(circ)
     assert chk.float_1d(thetas, thetas.size == circ.num_thetas)
     assert isinstance(lvec, tuple) and isinstance(vh_phi, tuple)
     block_range = (0, circ.num_blocks) if block_range is None else block_range

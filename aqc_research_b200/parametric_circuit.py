@@ -192,6 +192,22 @@ class TrotterAnsatz(ParametricCircuit):
                 raise ValueError("unexpected layout of the leading half-layer")
 
 
+def is_parametric_circuit(circ) -> bool:
+    """
+    Structural test used at every boundary of this package instead of ``isinstance``: a circuit built
+    by the reference's own ``aqc_research.parametric_circuit`` (parametric_circuit.py:37-70) passes as
+    well as ours -- the engine reads only these attributes.
+    """
+    return all(hasattr(circ, a) for a in ("num_qubits", "entangler", "blocks", "num_blocks", "num_thetas"))
+
+
+def is_trotter_ansatz(circ) -> bool:
+    """A circuit with the Trotterized layout (parametric_circuit.py:267-423), ours or the reference's."""
+    return is_parametric_circuit(circ) and hasattr(circ, "is_second_order") and hasattr(
+        circ, "half_layer_num_blocks"
+    )
+
+
 def layer_to_block_range(
     circ: ParametricCircuit, layer_range: Union[Tuple[int, int], None]
 ) -> Tuple[int, int]:
