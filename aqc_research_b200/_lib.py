@@ -138,6 +138,7 @@ SIGNATURES = {
     "aqc_mps_debug_sweeps": (ct.c_int, [ct.c_void_p, c_int32_p, ct.c_int]),
     "aqc_mps_last_kernel_ms": (ct.c_float, [ct.c_void_p]),
     "aqc_mps_last_num_launches": (ct.c_int, [ct.c_void_p]),
+    "aqc_mps_truncation_stats": (ct.c_int, [ct.c_void_p, c_double_p]),
     "aqc_sv_stream": (ct.c_void_p, [ct.c_void_p]),
 }
 

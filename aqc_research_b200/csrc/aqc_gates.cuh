@@ -14,6 +14,7 @@ enum UnitKind : int32_t {
   U_FRONT_HI = 2,
   U_BLOCK_CHI = 3,  // unit block, control on the high register bit
   U_BLOCK_CLO = 4,
+  U_SWAP = 5,  // MPS swap network only (aqc_mps.cu)
 };
 enum UnitFlags : int32_t {
   F_PRE = 1,   // Trotter Rz(-pi/2) on control before the block (i % 3 == 0)

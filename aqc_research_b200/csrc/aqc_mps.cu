@@ -121,6 +121,7 @@ struct aqc_mps {
   double* d_gacc = nullptr;     // [nthetas] complex raw sums
   double2* d_small = nullptr;   // small outputs
   long long* d_idx = nullptr;
+  double* d_trunc = nullptr;   // [4] truncation record of the current call (see SvdArgs)
   int* d_sweeps = nullptr;     // [2][maxtasks]
   int* d_conv = nullptr;       // [2][maxtasks][32]
   int num_sms = 148;
@@ -158,17 +159,31 @@ static int build_mps_program(const aqc_circuit* c, bool reversed, MpsProgram& pr
     int lo, kind, flags, theta;
   };
   std::vector<Blk> blks;
+  // A unit-block on non-adjacent qubits (the reference accepts any (ctrl, targ):
+  // mps_dot_objective.py:380-468, test_mps_fast_dot_gradient.py:119-153) runs through a swap network:
+  // adjacent SWAPs bring the upper qubit down next to the lower one, the block acts on the
+  // neighbouring sites, and the SWAPs are undone.  A SWAP that would directly follow the same SWAP
+  // (back-to-back blocks on one distant pair) cancels against it.
+  auto push_swap = [&](int lo) {
+    if (!blks.empty() && blks.back().kind == U_SWAP && blks.back().lo == lo)
+      blks.pop_back();
+    else
+      blks.push_back({lo, U_SWAP, 0, 0});
+  };
   for (int i = 0; i < nb + half; ++i) {
     const int k = nb > 0 ? i % nb : 0;
     const int cq = aqc_circ_ctrl(c, k), tq = aqc_circ_targ(c, k);
-    if (std::abs(cq - tq) != 1) {
-      err = "the MPS path supports unit-blocks on adjacent qubits only";
+    const int lo = std::min(cq, tq), hi = std::max(cq, tq);
+    if (hi - lo != 1 && trot) {
+      err = "a Trotterized ansatz has unit-blocks on adjacent qubits only";
       return AQC_EINVAL;
     }
     int flags = 0;
     if (trot && i % 3 == 0) flags |= F_PRE;
     if (trot && i % 3 == 2) flags |= F_POST;
-    blks.push_back({std::min(cq, tq), cq > tq ? U_BLOCK_CHI : U_BLOCK_CLO, flags, 3 * n + tpb * k});
+    for (int s = hi - 1; s > lo; --s) push_swap(s);  // qubit `hi` travels down to site lo + 1
+    blks.push_back({lo, cq > tq ? U_BLOCK_CHI : U_BLOCK_CLO, flags, 3 * n + tpb * k});
+    for (int s = lo + 1; s < hi; ++s) push_swap(s);  // ... and back
   }
   // level[s] = index of the last step that touched site s; open task of that site (if the last
   // thing that touched both sites of a pair is the same task, a block can be chained onto it)
@@ -285,6 +300,12 @@ __global__ void mps_algebra_kernel(const MpsTask* __restrict__ tasks, int ntasks
     for (int u = 0; u < tk.nunits; ++u) {
       double2 tr[5];
       const int kind = tk.kind[u];
+      if (kind == U_SWAP) {  // parameter-free, self-inverse
+        const cd t = a[0][1];
+        a[0][1] = a[0][2];
+        a[0][2] = t;
+        continue;
+      }
       const int np = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 3 : NP;
       for (int k = 0; k < np; ++k) {
         const double th = thetas[tk.theta[u] + k];
@@ -323,6 +344,15 @@ __global__ void mps_algebra_kernel(const MpsTask* __restrict__ tasks, int ntasks
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc[k] = 0.0;
       const int kind = tk.kind[u];
+      if (kind == U_SWAP) {  // both swept vectors go through the SWAP; nothing to differentiate
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const cd t = a[v][1];
+          a[v][1] = a[v][2];
+          a[v][2] = t;
+        }
+        continue;
+      }
       const bool front = (kind == U_FRONT_LO || kind == U_FRONT_HI);
       const int np = front ? 3 : NP;
       for (int k = 0; k < np; ++k) {
@@ -870,6 +900,10 @@ struct SvdArgs {
   int* conv;    // [state][maxtasks][32] rotations counted per sweep (cluster-wide convergence)
   int precond;  // 1: Householder QR first, Jacobi on R^H (Drmac-Veselic preconditioning)
   int fence;    // 1: device-scope fence in front of every cluster barrier (AQC_MPS_FENCE=1)
+  // truncation record of the current public call: [0] sum of discarded weights (sum of squared Schmidt
+  // values relative to the split's total), [1] largest single discard, [2] part of [0] that only the
+  // chi_max cap removed (beyond the trunc_thr rule), [3] number of splits the cap cut
+  double* trunc_stats;
 };
 
 __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
@@ -1086,6 +1120,21 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
       double nrm = 0.0;
       for (int i = 0; i < keep; ++i) nrm += s_sig[s_order[i]] * s_sig[s_order[i]];
       scale = 1.0 / sqrt(nrm);
+      // what was cut: everything beyond `keep`; the cap's share is what lies beyond chi_max
+      double cut = 0.0, capcut = 0.0;
+      for (int i = keep; i < total; ++i) cut += s_sig[s_order[i]] * s_sig[s_order[i]];
+      for (int i = A.chi_max; i < total; ++i) capcut += s_sig[s_order[i]] * s_sig[s_order[i]];
+      const double all = nrm + cut;
+      if (A.trunc_stats && all > 0.0) {
+        atomicAdd(A.trunc_stats + 0, cut / all);
+        // (non-negative doubles order like their bit patterns)
+        atomicMax(reinterpret_cast<unsigned long long*>(A.trunc_stats + 1),
+                  (unsigned long long)__double_as_longlong(cut / all));
+        if (total > A.chi_max) {
+          atomicAdd(A.trunc_stats + 2, capcut / all);
+          atomicAdd(A.trunc_stats + 3, 1.0);
+        }
+      }
     }
     s_keep = keep;
     s_total = total;
@@ -1629,7 +1678,8 @@ extern "C" void aqc_mps_destroy(aqc_mps* m) {
   for (void* p : {(void*)m->d_thetas, (void*)m->d_gate, (void*)m->d_theta0, (void*)m->d_work,
                   (void*)m->d_vmat, (void*)m->d_work0, (void*)m->d_envL, (void*)m->d_envR, (void*)m->d_rho,
                   (void*)m->d_gacc, (void*)m->d_small, (void*)m->d_idx, (void*)m->fwd.d_tasks,
-                  (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env, (void*)m->d_sweeps, (void*)m->d_conv})
+                  (void*)m->dag.d_tasks, (void*)m->fwd.d_env, (void*)m->dag.d_env, (void*)m->d_sweeps, (void*)m->d_conv,
+                  (void*)m->d_trunc})
     if (p) cudaFree(p);
   if (m->h_pinned) cudaFreeHost(m->h_pinned);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -1692,6 +1742,8 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
   alloc((void**)&m->d_small, 4096 * sizeof(double2));
   alloc((void**)&m->d_idx, 4096 * sizeof(long long));
   alloc((void**)&m->d_sweeps, 2 * mt * sizeof(int));
+  alloc((void**)&m->d_trunc, 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(m->d_trunc, 0, 4 * sizeof(double));
   alloc((void**)&m->d_conv, 2 * mt * 32 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
   {
@@ -1880,6 +1932,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   sa.maxtasks = m->maxtasks;
   sa.chi_max = m->chi_max;
   sa.trunc_thr = m->trunc_thr;
+  sa.trunc_stats = m->d_trunc;
   sa.sweeps = m->d_sweeps;
   sa.conv = m->d_conv;
   sa.precond = m->svd_precond ? 1 : 0;
@@ -1942,6 +1995,7 @@ extern "C" int aqc_mps_apply(aqc_mps* m, const double* thetas, int dagger, int s
   if (!thetas) return aqc_fail(AQC_EINVAL, "thetas is null");
   MCU(cudaSetDevice(m->device));
   m->last_launches = 0;
+  cudaMemsetAsync(m->d_trunc, 0, 4 * sizeof(double), m->stream);
   MCU(cudaEventRecord(m->ev0, m->stream));
   rc = apply_async(m, thetas, dagger, src_slot, dst_slot);
   if (rc) return rc;
@@ -1982,6 +2036,7 @@ extern "C" int aqc_mps_objective(aqc_mps* m, const double* thetas, int target_sl
   if (!thetas || !idx || !hs_out || count <= 0) return aqc_fail(AQC_EINVAL, "bad arguments");
   MCU(cudaSetDevice(m->device));
   m->last_launches = 0;
+  cudaMemsetAsync(m->d_trunc, 0, 4 * sizeof(double), m->stream);
   MCU(cudaEventRecord(m->ev0, m->stream));
   rc = apply_async(m, thetas, 1, target_slot, z0_slot);
   if (rc) return rc;
@@ -2038,6 +2093,7 @@ extern "C" int aqc_mps_dot(aqc_mps* m, int slot_a, int slot_b, double* out) {
   if (!out) return aqc_fail(AQC_EINVAL, "out is null");
   MCU(cudaSetDevice(m->device));
   m->last_launches = 0;
+  cudaMemsetAsync(m->d_trunc, 0, 4 * sizeof(double), m->stream);
   rc = env_full_sweeps(m, slot_a, slot_b, true);
   if (rc) return rc;
   MCU(cudaMemcpyAsync((void*)out, m->d_envL + (size_t)m->n * m->C * m->C,
@@ -2061,6 +2117,7 @@ extern "C" int aqc_mps_grad(aqc_mps* m, const double* thetas, int x_slot, int64_
   if (!thetas || !grad_out) return aqc_fail(AQC_EINVAL, "null argument");
   MCU(cudaSetDevice(m->device));
   m->last_launches = 0;
+  cudaMemsetAsync(m->d_trunc, 0, 4 * sizeof(double), m->stream);
   const int n = m->n;
   auto done = [&](int code) {
     cudaStreamSynchronize(m->stream);
@@ -2177,6 +2234,18 @@ extern "C" int aqc_mps_grad(aqc_mps* m, const double* thetas, int x_slot, int64_
 }
 
 extern "C" float aqc_mps_last_kernel_ms(const aqc_mps* m) { return m ? m->last_ms : 0.f; }
+
+// Truncation record of the most recent apply / objective / grad call on this workspace:
+// out[0] sum over all splits of the discarded weight (squared Schmidt values, relative to the split),
+// out[1] largest single discard, out[2] the part of out[0] removed by the chi_max cap alone (beyond the
+// trunc_thr rule of mps_operations.py:248-265, which has no cap), out[3] number of splits the cap cut.
+extern "C" int aqc_mps_truncation_stats(aqc_mps* m, double* out4) {
+  if (!m || !out4) return aqc_fail(AQC_EINVAL, "null argument");
+  MCU(cudaSetDevice(m->device));
+  MCU(cudaMemcpyAsync(out4, m->d_trunc, 4 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  MCU(cudaStreamSynchronize(m->stream));
+  return AQC_OK;
+}
 extern "C" int aqc_mps_last_num_launches(const aqc_mps* m) { return m ? m->last_launches : 0; }
 
 // Diagnostics: Jacobi sweeps used by the SVDs of the most recent two-qubit step

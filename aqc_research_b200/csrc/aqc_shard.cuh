@@ -29,11 +29,10 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   int rc = ensure_pinned(sv, tot * 2 + 64);
   if (rc) return rc;
-  rc = upload_thetas(sv, thetas);
+  rc = upload_thetas(sv, thetas, !sv->dense);
   if (rc) return rc;
   if (sv->dense) {
-    if (mode == 0) CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
-    if ((rc = dense_prepare(sv, mode))) return rc;
+    if ((rc = dense_prepare(sv, mode))) return rc;  // (clears the gradient sums too)
   } else if (mode == 0) {
     CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
   }
@@ -86,7 +85,12 @@ extern "C" int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   int rc = ensure_pinned(sv, tot * 2 + 64);
   if (rc) return rc;
-  if (sv->dense && (rc = dense_collect(sv))) return rc;
+  if (sv->dense) {  // the epilogue kernel converts and writes the (partial) gradient into h_pinned
+    if ((rc = dense_collect(sv))) return rc;
+    CU(cudaStreamSynchronize(sv->stream));
+    memcpy(grad_out, sv->h_pinned, tot * 2 * sizeof(double));
+    return AQC_OK;
+  }
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
                      sv->stream));
   CU(cudaStreamSynchronize(sv->stream));

@@ -27,11 +27,19 @@ constexpr int kSOffHoff = kSOffPart + kSGroups * kSPartDoubles * 8;  // per prod
 constexpr int kSOffTile = kSOffHoff + kSGroups * 64 * 8;           // [group][buffer] tile id (-1: no more tiles)
 constexpr int kSOffNext = kSOffTile + 32;                          // CTA-local tile counter
 constexpr int kSOffBar = kSOffTile + 64;                           // mbarriers full[group][buffer], done[group][buffer]
-constexpr int kSSmemBytes = kSOffBar + 4 * kSGroups * 8;
+// Per-group running sums of the stage matrices M = sum z w^H of the first kSAccStages stages of a pass:
+// they collect every tile the group processes and reach global memory (red.global.add.f64) once per
+// pass instead of once per tile (n = 28: 590 tiles per group and pass); later stages of very long
+// passes (one-pass matrix programs) keep the per-tile global adds.
+constexpr int kSAccStages = 12;
+constexpr int kSOffAcc = kSOffBar + 4 * kSGroups * 8 + 16;
+constexpr int kSSmemBytes = kSOffAcc + kSGroups * kSAccStages * 32 * 8;
 static_assert(kSSmemBytes <= 227 * 1024, "stream kernel shared memory");
-// register budget: 896 threads start with 72 registers each; the compute warpgroups take 80, the
-// producer warpgroup gives its share back (setmaxnreg)
-constexpr int kSRegsCompute = 80, kSRegsProducer = 32;
+// Register budget: 896 threads are launched with 72 registers each (64512 in the CTA's pool); the six
+// compute warpgroups take 80 (61440), which the producer warpgroup must pay for by keeping 24 (3072) --
+// setmaxnreg.inc blocks until the CTA's OWN pool can serve it, so the budget has to balance exactly.
+constexpr int kSRegsCompute = 80, kSRegsProducer = 24;
+static_assert(kSGroups * kDWarps * 32 * kSRegsCompute + 128 * kSRegsProducer <= kSThreads * 72, "register pool");
 
 struct StreamArgs {
   const PassDesc* passes;  // device copy of the program's passes
@@ -71,16 +79,25 @@ __device__ __forceinline__ bool mbar_test(unsigned addr, unsigned parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+// Waits are bounded: a wait that lasts longer than ~10 s of SM clocks is a protocol bug, and a trapped
+// kernel (an error the host sees) is better than a hung GPU.
+constexpr long long kSWatchdogClocks = 20000000000ll;
+__device__ __forceinline__ bool mbar_try(unsigned addr, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(addr),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  if (mbar_try(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity))
+    if (clock64() - t0 > kSWatchdogClocks) __trap();
 }
 __device__ __forceinline__ void group_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kDThreads) : "memory");
@@ -103,15 +120,17 @@ __device__ __forceinline__ void stream_grid_barrier(unsigned long long* bar, vol
     const unsigned long long old = atomicAdd(bar, 1ull);
     const unsigned long long target = (old / n + 1ull) * n;
     unsigned long long seen;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+      if (clock64() - t0 > kSWatchdogClocks) __trap();
     } while (seen < target);
     __threadfence();
   }
   __syncthreads();
 }
 
-template <int NVEC>
+template <int NVEC, bool REBAL>
 __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const StreamArgs A) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int tid = threadIdx.x;
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
   // The two roles run the same pass loop in separate code regions, each behind its own setmaxnreg, so
   // that the register allocator gives the compute warps 80 registers and the producers 32.
   if (producer) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSRegsProducer));
+    if (REBAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSRegsProducer));
     unsigned pdone = 0;  // phase parity of done[g][b] (bit b)
   for (int p = A.pass_begin; p < A.pass_end; ++p) {
     const PassDesc* __restrict__ pd = A.passes + p;
@@ -250,9 +269,12 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
     if (p + 1 < A.pass_end) stream_grid_barrier(A.grid_bar, s_next);
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSRegsCompute));
+    if (REBAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSRegsCompute));
     unsigned pfull = 0;  // phase parity of full[g][b] (bit b)
     int step = 0;        // steps so far (parity selects the partial-sum buffer, also across tiles)
+    for (int k = wg * 32 + lane; k < kSAccStages * 32; k += kDThreads)
+      reinterpret_cast<double*>(s_raw + kSOffAcc)[(size_t)g * kSAccStages * 32 + k] = 0.0;
+    group_bar(g + 1);
   for (int p = A.pass_begin; p < A.pass_end; ++p) {
     const PassDesc* __restrict__ pd = A.passes + p;
     const int tb = pd->tb, nstages = pd->nstages, stage0 = pd->stage0, nouter = pd->nouter;
@@ -266,6 +288,20 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
       // ---------------------------------------------------------------- compute group
       const int nit = tsize >> 5;
       double* part_g = reinterpret_cast<double*>(s_raw + kSOffPart) + (size_t)g * kSPartDoubles;
+      double* acc_g = reinterpret_cast<double*>(s_raw + kSOffAcc) + (size_t)g * kSAccStages * 32;
+      long long y_acc = -1;  // batch element the running sums belong to
+      // running sums -> global memory (all warps of the group; the sums are left at zero)
+      auto flush_acc = [&]() {
+        if (NVEC != 2 || y_acc < 0) return;
+        group_bar(g + 1);  // the last reducing warp has finished
+        double* gdst = A.gm + ((size_t)y_acc * A.nstages_total + stage0) * 64 + lane;
+        for (int sidx = wg; sidx < nstages && sidx < kSAccStages; sidx += kDWarps) {
+          const double v = acc_g[sidx * 32 + lane];
+          acc_g[sidx * 32 + lane] = 0.0;
+          atomicAdd(gdst + (size_t)sidx * 64, v);
+        }
+        group_bar(g + 1);
+      };
       for (int b = 0;; b ^= 1) {
         const int i = 2 * g + b;
         mbar_wait(bar0 + 8 * i, (pfull >> b) & 1);
@@ -273,6 +309,10 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
         const int t = s_tile[i];
         if (t < 0) break;
         const long long y = (long long)t >> nouter;
+        if (y != y_acc) {
+          flush_acc();
+          y_acc = y;
+        }
         const unsigned sm_u32 = sm0 + (unsigned)i * kSBufBytes;
         const size_t sbase = (size_t)y * A.nstages_total + stage0;
         const double* __restrict__ um = A.umat + sbase * 64 + lane;
@@ -409,7 +449,11 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
               double r0 = 0.0;
 #pragma unroll
               for (int w = 0; w < kDWarps; ++w) r0 += pp[w * 32 + lane];
-              atomicAdd(gmp + (size_t)(set == 0 ? sA : sB) * 64, r0);
+              const int sidx = set == 0 ? sA : sB;
+              if (sidx < kSAccStages)
+                acc_g[sidx * 32 + lane] += r0;  // this warp owns the slot until the next group barrier
+              else
+                atomicAdd(gmp + (size_t)sidx * 64, r0);
             }
           } else {
             group_bar(g + 1);
@@ -420,8 +464,162 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
         if (nstages == 0) group_bar(g + 1);
         if (wg == 0 && lane == 0) mbar_arrive(bar0 + 8 * (2 * kSGroups + i));
       }
+      flush_acc();
     }
     if (p + 1 < A.pass_end) stream_grid_barrier(A.grid_bar, s_next);
   }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prologue and epilogue of a sweep (one small launch each, no host copies in between):
+//   sweep_prologue_kernel : stage matrices U_s(theta) of one program straight from the angles (the host
+//                           writes them into pinned, device-mapped memory -- no H2D copy, no (cos, sin)
+//                           table), and the zeroing of the gradient accumulators;
+//   grad_epilogue_kernel  : per-rotation inner products from the accumulated stage matrices
+//                           (see dense_grad_kernel), the 0.5 / 0.5j / -i factors of the reference
+//                           (core_operations.py:317-351, 972-975) and the write of the finished complex
+//                           gradient into pinned host memory by the last CTA that completes.
+// ------------------------------------------------------------------------------------------------
+template <int ENT, bool DAG, int NVEC>
+__device__ __forceinline__ void unit_from_theta(const UnitDesc& u, const double* __restrict__ th, cd (&a)[NVEC][4],
+                                                double* acc) {
+  const bool front = u.kind == U_FRONT_LO || u.kind == U_FRONT_HI;
+  const int np = front ? 3 : (ENT == AQC_ENT_CP ? 5 : 4);
+  double2 tr[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k < np) {
+      const double t = th[u.theta + k];
+      double s, c;
+      sincos(k == 4 ? t : 0.5 * t, &s, &c);  // full angle for the CPhase parameter
+      tr[k] = make_double2(c, s);
+    }
+  }
+  switch (u.kind) {
+    case U_FRONT_LO: front_unit<NVEC, false, DAG>(a, tr, acc); break;
+    case U_FRONT_HI: front_unit<NVEC, true, DAG>(a, tr, acc); break;
+    case U_BLOCK_CHI: block_unit<NVEC, ENT, true, DAG>(a, tr, u.flags, acc); break;
+    case U_BLOCK_CLO: block_unit<NVEC, ENT, false, DAG>(a, tr, u.flags, acc); break;
+    default: break;
+  }
+}
+
+struct PrologueArgs {
+  const StageDesc* stages;
+  int nstages, nthetas, batch;
+  const double* thetas;  // [batch][nthetas], pinned host memory mapped into the device address space
+  double* umat;          // [batch][nstages][64]
+  double* zero0;         // two arrays to clear (stage-matrix sums, per-angle sums); may be null
+  long long nzero0;
+  double* zero1;
+  long long nzero1;
+};
+
+template <int ENT, bool DAG>
+__global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
+  for (long long i = gt; i < A.nzero1; i += gsz) A.zero1[i] = 0.0;
+  for (long long t = gt; t < (long long)A.batch * A.nstages * 4; t += gsz) {
+    const int k = (int)(t & 3), s = (int)((t >> 2) % A.nstages), b = (int)((t >> 2) / A.nstages);
+    const StageDesc sd = A.stages[s];
+    const double* th = A.thetas + (size_t)b * A.nthetas;
+    cd a[1][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
+    for (int u = 0; u < sd.nunits; ++u) unit_from_theta<ENT, DAG, 1>(sd.u[u], th, a, nullptr);
+    double* um = A.umat + ((size_t)b * A.nstages + s) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]; DMMA A-fragment order (see dense_umat_kernel)
+      um[(2 * i) * 4 + k] = a[0][i].x;
+      um[32 + (2 * i) * 4 + k] = -a[0][i].y;
+      um[(2 * i + 1) * 4 + k] = a[0][i].y;
+      um[32 + (2 * i + 1) * 4 + k] = a[0][i].x;
+    }
+  }
+}
+
+struct EpilogueArgs {
+  const StageDesc* stages;
+  int nstages, nthetas, batch, n3, tpb;
+  const double* thetas;
+  const double* gm;        // [batch][nstages][64] accumulated stage matrices
+  double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
+  double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
+  unsigned* ticket;        // completion counter (left at zero)
+};
+
+template <int ENT>
+__global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
+  __shared__ int s_last;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.batch * A.nstages * 4) {
+    const int r = t & 3, s = (t >> 2) % A.nstages, b = (t >> 2) / A.nstages;
+    const StageDesc sd = A.stages[s];
+    const double* th = A.thetas + (size_t)b * A.nthetas;
+    const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
+    // virtual quadruple r: w' = e_r, z' = M_out[:, r]; pull both back through the stage, then run it
+    // forward with the reference's gate-by-gate accumulation (dense_grad_kernel)
+    cd a[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
+      a[1][i].x = Mq[(i << 3) | r];
+      a[1][i].y = Mq[(i << 3) | 4 | r];
+    }
+    constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (int u = sd.nunits - 1; u >= 0; --u) unit_from_theta<ENT, true, 2>(sd.u[u], th, a, acc);
+    double* g = A.gacc + (size_t)b * A.nthetas * 2;
+    for (int u = 0; u < sd.nunits; ++u) {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      unit_from_theta<ENT, false, 2>(sd.u[u], th, a, acc);
+      const int kind = sd.u[u].kind;
+      const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
+      double* gu = g + 2 * (size_t)sd.u[u].theta;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k)
+        if (k < nval) atomicAdd(gu + k, acc[k]);
+    }
+  }
+  // the CTA that finishes last converts the raw sums and hands the gradient to the host
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int total = A.batch * A.nthetas;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k = i % A.nthetas;
+    const double re = __ldcg(A.gacc + 2 * (size_t)i), im = __ldcg(A.gacc + 2 * (size_t)i + 1);
+    int kind;  // 0: Ry (0.5), 1: Rz / Rx (0.5j), 2: CPhase (-i)
+    if (k < A.n3)
+      kind = (k % 3 == 1) ? 0 : 1;
+    else {
+      const int q = (k - A.n3) % A.tpb;
+      kind = (q == 4) ? 2 : ((q == 0 || q == 2) ? 0 : 1);
+    }
+    double2 v;
+    if (kind == 0)
+      v = make_double2(0.5 * re, 0.5 * im);
+    else if (kind == 1)
+      v = make_double2(-0.5 * im, 0.5 * re);
+    else
+      v = make_double2(im, -re);
+    reinterpret_cast<double2*>(A.out)[i] = v;
+  }
+  if (threadIdx.x == 0) *A.ticket = 0u;
+}
+
+// hs[b][i] = v[b][idx[i]] written straight into pinned host memory
+__global__ void gather_out_kernel(const double2* __restrict__ v, long long stride, const long long* __restrict__ idx,
+                                  int count, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[(size_t)blockIdx.y * count + i] = v[(long long)blockIdx.y * stride + idx[i]];
 }

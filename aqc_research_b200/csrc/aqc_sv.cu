@@ -99,7 +99,9 @@ struct aqc_sv {
   long long* d_idx = nullptr;
   std::vector<int64_t> idx_cached;  // host copy of what d_idx holds (gather_async)
   size_t idx_cap = 0, scratch_cap = 0;
-  double* h_pinned = nullptr;  // pinned staging for thetas and small results
+  double* h_pinned = nullptr;  // pinned staging for small results (the device writes them directly)
+  double* h_thetas = nullptr;  // pinned, device-readable copy of the angles of the call in flight
+  unsigned* d_ticket = nullptr;  // completion counter of grad_epilogue_kernel
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -189,14 +191,18 @@ static int launch_pass_e(aqc_sv* sv, const PassArgs& args) {
   }
 }
 
-// NOTE: callers size the pinned staging buffer (ensure_pinned) BEFORE calling this, so that it
-// is never re-allocated while the asynchronous copy below is in flight.
-static int upload_thetas(aqc_sv* sv, const double* thetas) {
+// Stages the angles of a call in pinned host memory, where the prologue / epilogue kernels of the dense
+// engine read them directly (no H2D copy, no (cos, sin) table).  `to_device` additionally copies them
+// to d_thetas and builds the (cos, sin) table: the legacy engine and coordinate descent need that.
+static int upload_thetas(aqc_sv* sv, const double* thetas, bool to_device) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
-  if (sv->pinned_cap < tot) return fail(AQC_EINVAL, "internal: pinned buffer too small");
-  memcpy(sv->h_pinned, thetas, tot * sizeof(double));
-  CU(cudaMemcpyAsync(sv->d_thetas, sv->h_pinned, tot * sizeof(double), cudaMemcpyHostToDevice,
-                     sv->stream));
+  if (sv->grad_pending) {  // an uncollected gradient sweep still reads the staged angles: drop it
+    CU(cudaStreamSynchronize(sv->stream));
+    sv->grad_pending = false;
+  }
+  memcpy(sv->h_thetas, thetas, tot * sizeof(double));
+  if (!to_device) return AQC_OK;
+  CU(cudaMemcpyAsync(sv->d_thetas, sv->h_thetas, tot * sizeof(double), cudaMemcpyHostToDevice, sv->stream));
   const int thr = 128;
   trig_kernel<<<(unsigned)((tot + thr - 1) / thr), thr, 0, sv->stream>>>(
       sv->d_thetas, sv->d_trig, (long long)tot, sv->circ.nthetas, 3 * sv->circ.n, sv->circ.tpb);
@@ -260,55 +266,68 @@ static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
   return AQC_OK;
 }
 
-// stage matrices of one program for the uploaded angles (mode 0 gradient, 1 V, 2 V^H)
+// Prologue of a sweep: stage matrices of one program from the staged angles (mode 0 gradient, 1 V,
+// 2 V^H); the gradient prologue also clears the stage-matrix sums and the per-angle sums.
 static int dense_prepare(aqc_sv* sv, int mode) {
   const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
-  const int ns = (int)p.stages.size();
-  if (ns == 0) return AQC_OK;
-  const dim3 grid((unsigned)((ns * 4 + 127) / 128), (unsigned)sv->batch);
+  PrologueArgs a;
+  memset(&a, 0, sizeof(a));
+  a.stages = p.d_stages;
+  a.nstages = (int)p.stages.size();
+  a.nthetas = sv->circ.nthetas;
+  a.batch = sv->batch;
+  a.thetas = sv->h_thetas;
+  a.umat = sv->d_umat;
+  if (mode == 0) {
+    a.zero0 = sv->d_gm;
+    a.nzero0 = (long long)sv->batch * a.nstages * 64;
+    a.zero1 = sv->d_gacc;
+    a.nzero1 = (long long)sv->batch * sv->circ.nthetas * 2;
+  }
+  const long long work = std::max<long long>((long long)sv->batch * a.nstages * 4, std::max(a.nzero0, a.nzero1) / 8);
+  if (work == 0) return AQC_OK;
+  const unsigned grid = (unsigned)std::min<long long>((work + 127) / 128, 4 * sv->num_sms);
   const bool dag = mode == 2;
-#define AQC_UMAT(E)                                                                                  \
-  do {                                                                                               \
-    if (dag)                                                                                         \
-      dense_umat_kernel<E, true><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,          \
-                                                               sv->circ.nthetas, sv->d_umat);       \
-    else                                                                                             \
-      dense_umat_kernel<E, false><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,         \
-                                                                sv->circ.nthetas, sv->d_umat);      \
+#define AQC_PRO(E)                                                         \
+  do {                                                                     \
+    if (dag)                                                               \
+      sweep_prologue_kernel<E, true><<<grid, 128, 0, sv->stream>>>(a);     \
+    else                                                                   \
+      sweep_prologue_kernel<E, false><<<grid, 128, 0, sv->stream>>>(a);    \
   } while (0)
   switch (sv->circ.ent) {
-    case AQC_ENT_CX: AQC_UMAT(AQC_ENT_CX); break;
-    case AQC_ENT_CZ: AQC_UMAT(AQC_ENT_CZ); break;
-    default: AQC_UMAT(AQC_ENT_CP);
+    case AQC_ENT_CX: AQC_PRO(AQC_ENT_CX); break;
+    case AQC_ENT_CZ: AQC_PRO(AQC_ENT_CZ); break;
+    default: AQC_PRO(AQC_ENT_CP);
   }
-#undef AQC_UMAT
+#undef AQC_PRO
   CU(cudaGetLastError());
   sv->last_launches += 1;
-  if (mode == 0)
-    CU(cudaMemsetAsync(sv->d_gm, 0, (size_t)sv->batch * ns * 64 * sizeof(double), sv->stream));
   return AQC_OK;
 }
 
-// raw per-rotation sums (the format of pass_kernel) from the accumulated stage matrices
+// Epilogue of the gradient sweep: complex gradient 0.5j <P w|z> from the accumulated stage matrices,
+// written by the device into the pinned result buffer (h_pinned[0 .. 2 batch T)).
 static int dense_collect(aqc_sv* sv) {
   const Program& p = sv->prog_grad;
-  const int ns = (int)p.stages.size();
-  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
-  CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
-  if (ns == 0) return AQC_OK;
-  const dim3 grid((unsigned)((ns * 4 + 127) / 128), (unsigned)sv->batch);
+  EpilogueArgs a;
+  memset(&a, 0, sizeof(a));
+  a.stages = p.d_stages;
+  a.nstages = (int)p.stages.size();
+  a.nthetas = sv->circ.nthetas;
+  a.batch = sv->batch;
+  a.n3 = 3 * sv->circ.n;
+  a.tpb = sv->circ.tpb;
+  a.thetas = sv->h_thetas;
+  a.gm = sv->d_gm;
+  a.gacc = sv->d_gacc;
+  a.out = sv->h_pinned;
+  a.ticket = sv->d_ticket;
+  const unsigned grid = (unsigned)std::max<long long>(1, ((long long)sv->batch * a.nstages * 4 + 127) / 128);
   switch (sv->circ.ent) {
-    case AQC_ENT_CX:
-      dense_grad_kernel<AQC_ENT_CX><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
-                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
-      break;
-    case AQC_ENT_CZ:
-      dense_grad_kernel<AQC_ENT_CZ><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
-                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
-      break;
-    default:
-      dense_grad_kernel<AQC_ENT_CP><<<grid, 128, 0, sv->stream>>>(p.d_stages, ns, sv->d_trig,
-                                                                  sv->circ.nthetas, sv->d_gm, sv->d_gacc);
+    case AQC_ENT_CX: grad_epilogue_kernel<AQC_ENT_CX><<<grid, 128, 0, sv->stream>>>(a); break;
+    case AQC_ENT_CZ: grad_epilogue_kernel<AQC_ENT_CZ><<<grid, 128, 0, sv->stream>>>(a); break;
+    default: grad_epilogue_kernel<AQC_ENT_CP><<<grid, 128, 0, sv->stream>>>(a);
   }
   CU(cudaGetLastError());
   sv->last_launches += 1;
@@ -323,8 +342,10 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
   const bool coop = env_int("AQC_STREAM_COOP", 1) != 0;
   static bool configured[16] = {false};
   if (!configured[sv->device & 15]) {
-    CU(cudaFuncSetAttribute(dense_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    CU(cudaFuncSetAttribute(dense_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
     configured[sv->device & 15] = true;
   }
   StreamArgs a;
@@ -353,7 +374,10 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
       a.xamp = sv->d_one;
     }
     void* params[] = {(void*)&a};
-    const void* fn = mode == 0 ? (const void*)dense_stream_kernel<2> : (const void*)dense_stream_kernel<1>;
+    // AQC_STREAM_REBAL=1: development variant with setmaxnreg register rebalancing (80 / 24 registers)
+    const bool rebal = env_int("AQC_STREAM_REBAL", 0) != 0;
+    const void* fn = mode == 0 ? (rebal ? (const void*)dense_stream_kernel<2, true> : (const void*)dense_stream_kernel<2, false>)
+                               : (rebal ? (const void*)dense_stream_kernel<1, true> : (const void*)dense_stream_kernel<1, false>);
     if (a.pass_end - a.pass_begin > 1)
       CU(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sv->stream_grid), dim3(kSThreads), params, kSSmemBytes,
                                      sv->stream));
@@ -474,6 +498,8 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
                   (void*)sv->dt_dag.d_lanes})
     if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
+  if (sv->h_thetas) cudaFreeHost(sv->h_thetas);
+  if (sv->d_ticket) cudaFree(sv->d_ticket);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages), cudaFree(p->d_passes);
   if (sv->ev0) cudaEventDestroy(sv->ev0);
@@ -545,6 +571,9 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMalloc(&sv->d_thetas, tot * sizeof(double)));
   CUB(cudaMalloc(&sv->d_trig, tot * sizeof(double2)));
   CUB(cudaMalloc(&sv->d_gacc, tot * 2 * sizeof(double)));
+  CUB(cudaMallocHost(&sv->h_thetas, std::max<size_t>(tot, 1) * sizeof(double)));
+  CUB(cudaMalloc(&sv->d_ticket, sizeof(unsigned)));
+  CUB(cudaMemset(sv->d_ticket, 0, sizeof(unsigned)));
 #undef CUB
   // Tile shape.  States beyond the L2 (> 64 MiB) want 256-byte contiguous runs (4 low bits); L2-resident
   // states (nbits <= 22) spend the low bits on gate qubits instead (fewer passes).  The persistent sweep
@@ -749,20 +778,26 @@ extern "C" int aqc_sv_fill_random(aqc_sv* sv, int slot, uint64_t seed) {
   return AQC_OK;
 }
 
-static int gather_async(aqc_sv* sv, int slot, const int64_t* idx, int count) {
+// The index list of a gather is the same on every objective call: it is uploaded only when it changes
+// (a copy from pageable host memory stalls the submitting thread).
+static int gather_indices(aqc_sv* sv, const int64_t* idx, int count) {
   int rc = ensure_idx(sv, (size_t)count);
-  if (rc) return rc;
-  rc = ensure_scratch(sv, (size_t)2 * count * sv->batch);
   if (rc) return rc;
   for (int i = 0; i < count; ++i)
     if (idx[i] < 0 || idx[i] >= sv->size) return fail(AQC_EINVAL, "gather index out of range");
-  // the index list is the same on every objective call: upload it only when it changes (a copy from
-  // pageable host memory stalls the submitting thread)
   if (sv->idx_cached.size() != (size_t)count || memcmp(sv->idx_cached.data(), idx, (size_t)count * sizeof(int64_t))) {
     sv->idx_cached.assign(idx, idx + count);
     CU(cudaStreamSynchronize(sv->stream));  // a previous gather may still read d_idx
     CU(cudaMemcpy(sv->d_idx, sv->idx_cached.data(), (size_t)count * sizeof(long long), cudaMemcpyHostToDevice));
   }
+  return AQC_OK;
+}
+
+static int gather_async(aqc_sv* sv, int slot, const int64_t* idx, int count) {
+  int rc = gather_indices(sv, idx, count);
+  if (rc) return rc;
+  rc = ensure_scratch(sv, (size_t)2 * count * sv->batch);
+  if (rc) return rc;
   gather_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
       sv->slots[slot], sv->size, sv->d_idx, count, (double2*)sv->d_scratch);
   CU(cudaGetLastError());
@@ -802,10 +837,11 @@ extern "C" int aqc_sv_vdot(aqc_sv* sv, int slot_a, int slot_b, double* out) {
   return AQC_OK;
 }
 
-static int apply_async(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int dst_slot) {
+static int apply_async(aqc_sv* sv, const double* thetas, int dagger, int src_slot, int dst_slot,
+                       bool thetas_to_device = false) {
   int rc = ensure_pinned(sv, (size_t)sv->batch * sv->circ.nthetas * 2 + 64);
   if (rc) return rc;
-  rc = upload_thetas(sv, thetas);
+  rc = upload_thetas(sv, thetas, thetas_to_device || !sv->dense);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev0, sv->stream));
   if (sv->dense) {
@@ -884,7 +920,7 @@ extern "C" int aqc_sv_coord_descent(aqc_sv* sv, double* thetas, int target_slot,
   a.fobj = sv->d_cd_fobj;
   for (int sweep = 0; sweep < num_sweeps; ++sweep) {
     // z = V(thetas)^H target (thetas uploaded to d_thetas on the way), w = I
-    rc = apply_async(sv, thetas, 1, target_slot, z_slot);
+    rc = apply_async(sv, thetas, 1, target_slot, z_slot, true);  // the sweep kernel updates d_thetas
     if (rc) return rc;
     set_identity_kernel<<<grid1d(sv->size, sv->batch, 256), 256, 0, sv->stream>>>(
         sv->slots[w_slot], sv->size, sv->size, sv->log2_cols);
@@ -1075,13 +1111,15 @@ extern "C" int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slo
   const size_t nout = (size_t)2 * count * sv->batch;
   rc = ensure_pinned(sv, nout + (size_t)sv->batch * sv->circ.nthetas * 2 + 64);
   if (rc) return rc;
+  rc = gather_indices(sv, idx, count);
+  if (rc) return rc;
   rc = apply_async(sv, thetas, 1, target_slot, z0_slot);
   if (rc) return rc;
-  rc = gather_async(sv, z0_slot, idx, count);
-  if (rc) return rc;
+  // the gathered amplitudes go straight into the pinned result buffer
+  gather_out_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
+      sv->slots[z0_slot], sv->size, sv->d_idx, count, reinterpret_cast<double2*>(sv->h_pinned));
+  CU(cudaGetLastError());
   sv->last_launches += 1;
-  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_scratch, nout * sizeof(double), cudaMemcpyDeviceToHost,
-                     sv->stream));
   CU(cudaStreamSynchronize(sv->stream));
   memcpy(hs_out, sv->h_pinned, nout * sizeof(double));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
@@ -1110,9 +1148,9 @@ extern "C" int aqc_sv_grad_begin(aqc_sv* sv, const double* thetas, int x_slot, i
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   rc = ensure_pinned(sv, tot * 2 + 64);
   if (rc) return rc;
-  rc = upload_thetas(sv, thetas);
+  rc = upload_thetas(sv, thetas, !sv->dense);
   if (rc) return rc;
-  CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
+  if (!sv->dense) CU(cudaMemsetAsync(sv->d_gacc, 0, tot * 2 * sizeof(double), sv->stream));
   CU(cudaEventRecord(sv->ev0, sv->stream));
   if (sv->dense) {
     rc = dense_prepare(sv, 0);
@@ -1127,8 +1165,8 @@ extern "C" int aqc_sv_grad_begin(aqc_sv* sv, const double* thetas, int x_slot, i
   }
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev1, sv->stream));
-  CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,
-                     sv->stream));
+  if (!sv->dense)  // (the dense epilogue has written the finished gradient into h_pinned itself)
+    CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost, sv->stream));
   sv->grad_pending = true;
   return AQC_OK;
 }
@@ -1141,10 +1179,12 @@ extern "C" int aqc_sv_grad_end(aqc_sv* sv, double* grad_out) {
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   CU(cudaStreamSynchronize(sv->stream));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
-  // raw sums -> 0.5j <P w|z>: Ry 0.5, Rz/Rx 0.5j, CPhase -i
+  if (sv->dense) {
+    memcpy(grad_out, sv->h_pinned, tot * 2 * sizeof(double));
+    return AQC_OK;
+  }
+  // legacy engine: raw sums -> 0.5j <P w|z>: Ry 0.5, Rz/Rx 0.5j, CPhase -i
   const int n3 = 3 * sv->circ.n, tpb = sv->circ.tpb, T = sv->circ.nthetas;
-  const bool cx = sv->circ.ent == AQC_ENT_CX;
-  (void)cx;
   for (int b = 0; b < sv->batch; ++b) {
     const double* raw = sv->h_pinned + (size_t)b * T * 2;
     double* g = grad_out + (size_t)b * T * 2;

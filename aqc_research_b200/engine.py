@@ -23,6 +23,15 @@ def _thetas_ptr(thetas: np.ndarray, expected: int):
     return th, th.ctypes.data_as(_lib.c_double_p)
 
 
+def circuit_signature(circ, as_generic: bool = False):
+    """Hashable description of a circuit structure, computed on the host without a C handle."""
+    trotter = 0
+    if is_trotter_ansatz(circ) and not as_generic:
+        trotter = 2 if circ.is_second_order else 1
+    blocks = np.ascontiguousarray(circ.blocks, dtype=np.int32)
+    return (int(circ.num_qubits), circ.entangler, trotter, blocks.tobytes())
+
+
 class CircuitHandle:
     """Owns an ``aqc_circuit`` built from a ParametricCircuit / TrotterAnsatz description."""
 

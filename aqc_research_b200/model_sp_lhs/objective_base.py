@@ -11,8 +11,10 @@ from abc import ABC, abstractmethod
 from typing import Callable, List, Optional, Tuple
 import numpy as np
 from .. import checking as chk
-from ..engine import SvWorkspace
+from ..engine import SvWorkspace, circuit_signature
 from ..parametric_circuit import ParametricCircuit, is_parametric_circuit
+
+_SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))  # theta-cache tolerance (objective_base.py:728-730)
 
 # workspace slot roles
 SLOT_TARGET, SLOT_VH_TARGET, SLOT_W, SLOT_Z, SLOT_STATE = 0, 1, 2, 3, 4
@@ -234,6 +236,8 @@ class SpLHSObjectiveBase(ABC):
         self._use_mps = bool(use_mps)
         self._verbose = bool(verbose)
         self._target = None
+        self._target_seed = None  # set_target_random: the target is regenerated after a structure change
+        self._blocks_seen = circuit.blocks
         self._last_thetas = np.empty(0)
         num_qubits = user_parameters["num_qubits"]
         assert num_qubits == circuit.num_qubits
@@ -247,10 +251,11 @@ class SpLHSObjectiveBase(ABC):
             self._num_states = self._state_handler.num_states
             self._dense = isinstance(self._state_handler, DenseStateHandler)
             self._ws = SvWorkspace(circuit, num_slots=5 if self._dense else 4, device=self._device)
-            self._structure = self._ws.circuit.signature()
+            self._structure = circuit_signature(circuit)
             self._init_common()
         else:
             self._num_states = num_qubits + 1  # finalised by the MPS subclass
+            self._structure = circuit_signature(circuit)
 
     def _init_common(self):
         self._service = SpService(self._params, self._circuit, self._num_states, verbose=self._verbose)
@@ -259,16 +264,28 @@ class SpLHSObjectiveBase(ABC):
         self._weight = 1.0
 
     # -- GPU residency ----------------------------------------------------------------------
+    def _structure_changed(self) -> bool:
+        """True once after ``insert_unit_blocks`` / ``update_structure`` changed the circuit."""
+        blocks = self._circuit.blocks
+        if blocks is self._blocks_seen:  # both code bases REPLACE the array on a structure change
+            return False
+        self._blocks_seen = blocks
+        sig = circuit_signature(self._circuit)
+        if sig == self._structure:
+            return False
+        self._structure = sig
+        self._last_thetas = np.empty(0)  # cached objective belongs to the old structure
+        self._early_thetas = None
+        return True
+
     def _refresh_workspace(self):
         """Re-creates the GPU workspace if the circuit structure changed (insert_unit_blocks)."""
-        from ..engine import CircuitHandle  # pylint: disable=import-outside-toplevel
-
-        sig = CircuitHandle(self._circuit).signature()
-        if sig != self._structure:
+        if self._structure_changed():
             self._ws.close()
             self._ws = SvWorkspace(self._circuit, num_slots=5 if self._dense else 4, device=self._device)
-            self._structure = sig
-            if self._target is not None:
+            if self._target_seed is not None:
+                self._ws.fill_random(SLOT_TARGET, self._target_seed)
+            elif self._target is not None:
                 self._ws.upload(SLOT_TARGET, self._target)
 
     def _hs_products(self, thetas: np.ndarray) -> np.ndarray:
@@ -300,10 +317,16 @@ class SpLHSObjectiveBase(ABC):
         self._last_thetas = np.array(thetas, dtype=np.float64, copy=True)
 
     def _calc_objective_before_gradient(self, thetas: np.ndarray):
-        tol = float(np.sqrt(np.finfo(np.float64).eps))
+        if not self._use_mps:
+            self._refresh_workspace()  # a structure change invalidates the cached objective
         last = self._last_thetas
-        if last.size != thetas.size or not np.allclose(thetas, last, atol=tol, rtol=tol):
-            self.objective(thetas)
+        if last.size == thetas.size:
+            if np.array_equal(thetas, last):  # the optimiser's fun(x), jac(x) pair: nothing to do
+                return
+            tol = _SQRT_EPS
+            if np.allclose(thetas, last, atol=tol, rtol=tol):
+                return
+        self.objective(thetas)
 
     @abstractmethod
     def objective(self, thetas: np.ndarray) -> float:
@@ -333,6 +356,8 @@ class SpLHSObjectiveBase(ABC):
         assert not self._use_mps
         assert chk.complex_1d(target, target.size == self._circuit.dimension)
         self._target = target
+        self._target_seed = None
+        self._refresh_workspace()
         self._ws.upload(SLOT_TARGET, target)
         self._last_thetas = np.empty(0)  # cached V^H target is stale
         self._early_thetas = None  # an early gradient sweep (if any) belongs to the old target
@@ -340,8 +365,11 @@ class SpLHSObjectiveBase(ABC):
     def set_target_random(self, seed: int) -> None:
         """Synthetic target generated on the device (distribution of utils.rand_state)."""
         self._target = "device-random"
+        self._target_seed = int(seed)
+        self._refresh_workspace()
         self._ws.fill_random(SLOT_TARGET, seed)
         self._last_thetas = np.empty(0)
+        self._early_thetas = None
 
     @property
     def statistics(self) -> dict:

@@ -58,15 +58,26 @@ class SpSurrogateObjectiveFastMpsTrotter(SpLHSObjectiveBase):
         self._mps = MpsWorkspace(circ, num_slots=4, chi_max=self._chi_max, trunc_thr=self._trunc_thr,
                                  device=self._device)
 
+    def _refresh_mps_workspace(self):
+        """Re-creates the MPS workspace after a structure change (insert_unit_blocks / update_structure)."""
+        if self._structure_changed():
+            self._mps.close()
+            self._mps = MpsWorkspace(self._circuit, num_slots=4, chi_max=self._chi_max, trunc_thr=self._trunc_thr,
+                                     device=self._device)
+            if self._target is not None:
+                self._mps.upload(_SLOT_TARGET, self._target)
+
     def set_target(self, target) -> None:
         assert check_mps(target) and len(target[0]) == self._circuit.num_qubits
         self._target = target
+        self._refresh_mps_workspace()
         self._mps.upload(_SLOT_TARGET, target)
         self._last_thetas = np.empty(0)
 
     def objective(self, thetas: np.ndarray) -> float:
         if self._target is None:
             raise RuntimeError("set_target() must be called before objective()")
+        self._refresh_mps_workspace()
         self._store_latest_thetas(thetas)
         self._hs[:] = self._mps.objective(thetas, _SLOT_TARGET, _SLOT_VH, self._state_handler.state_indices)
         np.copyto(self._hs2, np.abs(self._hs) ** 2)
@@ -111,6 +122,7 @@ class SpSurrogateObjectiveFastMpsTrotter(SpLHSObjectiveBase):
 
     def gradient(self, thetas: np.ndarray) -> np.ndarray:
         self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)
+        self._refresh_mps_workspace()
         self._calc_objective_before_gradient(thetas)
         circ = self._circuit
         block_range = layer_to_block_range(circ, self._layer_range)

@@ -157,8 +157,12 @@ class Trotter:
                              delta=self._delta, second_order=self._second_order, ini_state=ini_state)
 
     def as_mps(self, ini_state: Union[int, List[int]], trunc_thr: Optional[float] = None,
-               out_state: Optional[np.ndarray] = None):
-        """``Trotter |ini_state>`` in MPS format (:137-163); ``ini_state`` is a basis state."""
+               out_state: Optional[np.ndarray] = None, chi_max: int = 64):
+        """
+        ``Trotter |ini_state>`` in MPS format (:137-163); ``ini_state`` is a basis state.  ``chi_max``
+        (<= 64) is the bond-dimension cap of the GPU engine; ``BondCapacityError`` is raised if the cap
+        removes more weight than ``trunc_thr`` allows (the reference's qiskit-aer run has no cap).
+        """
         from ...circuit_structures import make_trotter_like_circuit  # pylint: disable=import-outside-toplevel
         from ...mps_engine import MpsWorkspace  # pylint: disable=import-outside-toplevel
         from ... import mps_operations as mpsop  # pylint: disable=import-outside-toplevel
@@ -168,11 +172,14 @@ class Trotter:
         thetas = init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=self._evol_time, delta=self._delta)
         index = int(ini_state) if isinstance(ini_state, (int, np.integer)) else basis_index(ini_state)
         thr = mpsop.no_truncation_threshold() if trunc_thr is None else float(trunc_thr)
-        ws = MpsWorkspace(circ, num_slots=1, chi_max=64, trunc_thr=thr)
-        ws.set_product(0, index)
-        ws.apply(thetas, 0, 0, dagger=False)
-        mps = ws.download(0)
-        ws.close()
+        ws = MpsWorkspace(circ, num_slots=1, chi_max=chi_max, trunc_thr=thr)
+        try:
+            ws.set_product(0, index)
+            ws.apply(thetas, 0, 0, dagger=False)
+            ws.check_cap("Trotter.as_mps")
+            mps = ws.download(0)
+        finally:
+            ws.close()
         if out_state is not None:
             np.copyto(out_state, mpsop.mps_to_vector(mps))
         return mps

@@ -45,8 +45,8 @@ def fast_dot_gradient(
 #   * a 1-qubit gate is the front layer Rz(t0) Ry(t1) Rz(t2) of an ansatz whose two unit blocks
 #     (same pair, zero angles) cancel: CX CX = 1.  Rx(a) = Rz(-pi/2) Ry(a) Rz(pi/2); the Pauli gates
 #     are i R(pi), the factor i goes into the first site tensor;
-#   * CX / CZ / CP(angle) is a single unit block with zero rotation angles (adjacent qubits only --
-#     the engine has no swap network, the reference leaves that to qiskit-aer).
+#   * CX / CZ / CP(angle) is a single unit block with zero rotation angles, on any (ctrl, targ) pair
+#     (non-adjacent pairs run through the engine's swap network, csrc/aqc_mps.cu build_mps_program).
 # The hot path (fast_dot_gradient above) does not use them: it takes all derivatives of a pair-run
 # from one reduced overlap matrix.
 # ------------------------------------------------------------------------------------------------

@@ -13,6 +13,10 @@ from .parametric_circuit import ParametricCircuit
 QiskitMPS = Tuple[List[Tuple[np.ndarray, np.ndarray]], List[np.ndarray]]
 
 
+class BondCapacityError(RuntimeError):
+    """The bond-dimension cap of the GPU MPS engine truncated a state the caller wanted exact."""
+
+
 def pack_mps(mps: QiskitMPS, capacity: int):
     """QiskitMPS -> (gam[n][2][C][C], lam[n+1][C], dims[n+1]) padded arrays."""
     gammas, lambdas = mps
@@ -127,6 +131,28 @@ class MpsWorkspace:
         out = np.empty(self.num_thetas, dtype=np.complex128)
         _lib.check(self._lib.aqc_mps_grad(self.handle, ptr, x_slot, int(x_basis), z0, w, z, _dptr(out)))
         return out
+
+    def truncation_stats(self) -> dict:
+        """
+        What the SVD splits of the most recent apply / objective / grad call discarded:
+        ``discarded_weight`` (sum over splits of the dropped squared Schmidt values, relative to each
+        split), ``max_discarded``, ``cap_discarded`` (the share removed only because of the ``chi_max``
+        cap -- the reference's qiskit-aer run has no cap) and ``cap_hits`` (splits the cap cut).
+        """
+        out = np.zeros(4, dtype=np.float64)
+        _lib.check(self._lib.aqc_mps_truncation_stats(self.handle, out.ctypes.data_as(_lib.c_double_p)))
+        return {"discarded_weight": float(out[0]), "max_discarded": float(out[1]),
+                "cap_discarded": float(out[2]), "cap_hits": int(out[3])}
+
+    def check_cap(self, what: str):
+        """Raises if the chi_max cap (not the trunc_thr rule) removed more weight than trunc_thr allows."""
+        st = self.truncation_stats()
+        if st["cap_hits"] and st["cap_discarded"] > max(self.trunc_thr, 1e-14):
+            raise BondCapacityError(
+                f"{what}: the bond-dimension cap chi_max = {self.chi_max} removed a weight of "
+                f"{st['cap_discarded']:.3e} in {st['cap_hits']} splits (trunc_thr = {self.trunc_thr:g}); "
+                "the reference (qiskit-aer) has no cap -- raise chi_max (<= 64) or trunc_thr"
+            )
 
     @property
     def last_kernel_ms(self) -> float:

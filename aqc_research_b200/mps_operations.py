@@ -61,8 +61,8 @@ def mps_to_vector(qiskit_mps: QiskitMPS) -> np.ndarray:
     return psi.reshape(-1)
 
 
-def _workspace(circ: ParametricCircuit, trunc_thr: float, slots: int = 4) -> MpsWorkspace:
-    return MpsWorkspace(circ, num_slots=slots, chi_max=_CHI_MAX, trunc_thr=trunc_thr)
+def _workspace(circ: ParametricCircuit, trunc_thr: float, slots: int = 4, chi_max: int = _CHI_MAX) -> MpsWorkspace:
+    return MpsWorkspace(circ, num_slots=slots, chi_max=chi_max, trunc_thr=trunc_thr)
 
 
 def mps_dot(qiskit_mps1: QiskitMPS, qiskit_mps2: QiskitMPS) -> np.complex128:
@@ -82,25 +82,33 @@ def mps_dot(qiskit_mps1: QiskitMPS, qiskit_mps2: QiskitMPS) -> np.complex128:
 
 
 def v_mul_mps(circ: ParametricCircuit, thetas: np.ndarray, mps_vec: QiskitMPS, *,
-              trunc_thr: Optional[float] = _NO_TRUNCATION_THR) -> QiskitMPS:
-    """``V @ mps_vec`` (mps_operations.py:326-346)."""
-    ws = _workspace(circ, trunc_thr, slots=2)
-    ws.upload(0, mps_vec)
-    ws.apply(thetas, 0, 1, dagger=False)
-    out = ws.download(1)
-    ws.close()
-    return out
+              trunc_thr: Optional[float] = _NO_TRUNCATION_THR, chi_max: int = _CHI_MAX) -> QiskitMPS:
+    """
+    ``V @ mps_vec`` (mps_operations.py:326-346).  Deviation from the reference: the GPU engine caps the
+    bond dimension at ``chi_max`` (<= 64); if the cap -- rather than ``trunc_thr`` -- removes more weight
+    than ``trunc_thr``, ``BondCapacityError`` is raised instead of returning a silently truncated state.
+    """
+    ws = _workspace(circ, trunc_thr, slots=2, chi_max=chi_max)
+    try:
+        ws.upload(0, mps_vec)
+        ws.apply(thetas, 0, 1, dagger=False)
+        ws.check_cap("v_mul_mps")
+        return ws.download(1)
+    finally:
+        ws.close()
 
 
 def v_dagger_mul_mps(circ: ParametricCircuit, thetas: np.ndarray, mps_vec: QiskitMPS, *,
-                     trunc_thr: Optional[float] = _NO_TRUNCATION_THR) -> QiskitMPS:
-    """``V^H @ mps_vec`` (mps_operations.py:349-371)."""
-    ws = _workspace(circ, trunc_thr, slots=2)
-    ws.upload(0, mps_vec)
-    ws.apply(thetas, 0, 1, dagger=True)
-    out = ws.download(1)
-    ws.close()
-    return out
+                     trunc_thr: Optional[float] = _NO_TRUNCATION_THR, chi_max: int = _CHI_MAX) -> QiskitMPS:
+    """``V^H @ mps_vec`` (mps_operations.py:349-371); the bond cap is reported as in ``v_mul_mps``."""
+    ws = _workspace(circ, trunc_thr, slots=2, chi_max=chi_max)
+    try:
+        ws.upload(0, mps_vec)
+        ws.apply(thetas, 0, 1, dagger=True)
+        ws.check_cap("v_dagger_mul_mps")
+        return ws.download(1)
+    finally:
+        ws.close()
 
 
 def rand_mps_vec(num_qubits: int, out_state: Optional[np.ndarray] = None, num_layers: int = 3) -> QiskitMPS:
@@ -119,10 +127,13 @@ def rand_mps_vec(num_qubits: int, out_state: Optional[np.ndarray] = None, num_la
     circ = ParametricCircuit(num_qubits, str(np.random.choice(["cx", "cz", "cp"])), blocks)
     thetas = utils.rand_thetas(circ.num_thetas)
     ws = _workspace(circ, _NO_TRUNCATION_THR, slots=1)
-    ws.set_product(0, 0)
-    ws.apply(thetas, 0, 0, dagger=False)
-    mps = ws.download(0)
-    ws.close()
+    try:
+        ws.set_product(0, 0)
+        ws.apply(thetas, 0, 0, dagger=False)
+        ws.check_cap("rand_mps_vec")
+        mps = ws.download(0)
+    finally:
+        ws.close()
     if out_state is not None:
         assert out_state.shape == (2**num_qubits,)
         np.copyto(out_state, mps_to_vector(mps))

@@ -60,51 +60,68 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# DRAM bytes per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum +
-# dram__bytes_write.sum; summaries under profiles/): workload -> bytes
-NCU_TRAFFIC = {
-    "sv28": 17.12e9,  # profiles/r01_ncu_dense_sv28.md: one read + one write of w and z (8.59 + 8.53 GB)
-    "sv20": 33.6e6,   # same file, n = 20 paragraph: one read of w and z; the L2 absorbs the write-back
-}
-FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (scripts/ubench_fp64.cu, profiles/r01_ubench_fp64.txt);
-#                          DMMA (mma.sync.m8n8k4.f64) and DFMA share this one FP64 pipe
+def fp64_peak():
+    """
+    FP64 pipe peak (DMMA and DFMA share it) measured on this pool's B200 with scripts/ubench_fp64.cu;
+    the record is profiles/fp64_peak.json (MEASURED_PEAKS.json holds no FP64 figure).
+    """
+    path = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    try:
+        with open(path, encoding="utf-8") as fh:
+            rec = json.load(fh)
+        return float(rec["fp64_tflops"]), f"measured (profiles/fp64_peak.json: {rec.get('source', '')})"
+    except (OSError, KeyError, ValueError):
+        return 148 * 1.965e9 * 128 / 1e12, "nominal (148 SMs x 1965 MHz x 128 flop/clk)"
 
 
-def roofline_block(workload, n, P, passes_grad, passes_dag, stages_grad, stages_dag, grad_s, obj_s):
+def ncu_traffic(workload):
     """
-    Roofline of the dominant kernel, dense_pass_kernel<2> (the gradient tile pass).
-      achieved / peak / frac : SURVEY 8(d) contract -- ALGORITHMIC bytes at pair-run granularity
-          (4 * 16 * 2^n * P per gradient sweep, spread over its launches) / measured launch time,
-          against the measured HBM copy peak.  Because a tile pass fuses several pair-runs, the
-          kernel moves fewer DRAM bytes than that, so this fraction exceeds 1 and the binding roofs
-          are the two below:
-      dram   : bytes the launch really moves (one read + one write of w and z) / launch time;
-      fp64   : DMMA flops the launch really issues (6 m8n8k4 per 8 quadruples and stage) against
-               the measured FP64 pipe peak.
+    dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    `ncu --set full` capture that scripts/ncu_summary.py condensed into profiles/ncu_traffic.json
+    (with the git hash of the build that was profiled); None if this workload was not captured.
     """
-    peak, peak_src = measured_peaks()
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path, encoding="utf-8") as fh:
+            rec = json.load(fh).get(workload)
+        return rec if rec else None
+    except (OSError, ValueError):
+        return None
+
+
+def roofline_block(workload, n, P, stages_grad, stages_dag, grad_kernel_s, obj_kernel_s, step_s, grad_launches):
+    """
+    Roofline of the dominant kernel, the gradient sweep kernel (one launch runs every tile pass of the
+    sweep).  The SURVEY 8(d) pair-run byte figure exceeds the HBM peak because a tile pass fuses several
+    pair-runs per DRAM round trip, so the binding roof is the FP64 pipe:
+      frac / achieved / peak : DMMA flops the sweep issues (6 m8n8k4 = 6 x 512 flop per 8 amplitude
+          quadruples and stage) / CUDA-event time of the sweep, against the measured FP64 pipe peak;
+      hbm_pairrun : the 8(d) contract figure, ALGORITHMIC bytes at pair-run granularity
+          (4 * 16 * 2^n * P per gradient sweep) / sweep time, against the measured HBM copy peak;
+      traffic: ncu dram bytes per launch of the profiled build (profiles/ncu_traffic.json) or null;
+      eval_frac_*: the same two figures for the whole step (V^H sweep + gradient sweep) on ms_per_step.
+    """
+    hbm_peak, hbm_src = measured_peaks()
+    f64_peak, f64_src = fp64_peak()
     V = 16.0 * 2**n
-    per_launch_s = grad_s / passes_grad
-    per_launch_alg = 4.0 * V * P / passes_grad
-    achieved = per_launch_alg / per_launch_s / 1e9
-    dram_per_launch = 4.0 * V
     dmma_grad = stages_grad * (2**n / 32.0) * 6 * 512.0
     dmma_apply = stages_dag * (2**n / 32.0) * 2 * 512.0
+    alg_bytes = 4.0 * V * P
+    achieved = dmma_grad / grad_kernel_s / 1e12
+    tr = ncu_traffic(workload)
     return {
-        "bound": "hbm", "kernel": "dense_pass_kernel<2> (gradient tile pass: cp.async tile load, DMMA stages)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": NCU_TRAFFIC.get(workload), "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": per_launch_alg, "launch_ms": per_launch_s * 1e3,
-        "eval_frac": (6.0 * V * P / (obj_s + grad_s)) / 1e9 / peak,
-        "dram": {"bytes_per_launch": dram_per_launch, "achieved_gbs": dram_per_launch / per_launch_s / 1e9,
-                 "frac_of_measured_peak": dram_per_launch / per_launch_s / 1e9 / peak},
-        "fp64": {"dmma_tflops_gradient_kernel": dmma_grad / grad_s / 1e12,
-                 "dmma_tflops_eval": (dmma_grad + dmma_apply) / (grad_s + obj_s) / 1e12,
-                 "peak_tflops": FP64_PEAK_TFLOPS,
-                 "frac_gradient_kernel": dmma_grad / grad_s / 1e12 / FP64_PEAK_TFLOPS,
-                 "frac_eval": (dmma_grad + dmma_apply) / (grad_s + obj_s) / 1e12 / FP64_PEAK_TFLOPS},
-        "note": "frac > 1: tile passes fuse several pair-runs per DRAM round trip; the kernel is bound by "
-                "the FP64 (DMMA) pipe first and DRAM second -- see the dram / fp64 sub-objects",
+        "bound": "fp64", "kernel": "gradient sweep kernel (tile passes: cp.async tile staging, DMMA stage matrices)",
+        "achieved": achieved, "peak": f64_peak, "unit": "TFLOP/s", "frac": achieved / f64_peak,
+        "peak_source": f64_src, "launch_ms": grad_kernel_s * 1e3 / max(1, grad_launches),
+        "launches_per_sweep": grad_launches, "dmma_flop_per_sweep": dmma_grad,
+        "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_capture": tr,
+        "hbm_pairrun": {"algorithmic_bytes_per_sweep": alg_bytes, "achieved_gbs": alg_bytes / grad_kernel_s / 1e9,
+                        "peak_gbs": hbm_peak, "frac": alg_bytes / grad_kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "note": "SURVEY 8(d) pair-run granularity; > 1 because a tile pass fuses several pair-runs"},
+        "eval_frac_fp64": (dmma_grad + dmma_apply) / step_s / 1e12 / f64_peak,
+        "eval_frac_hbm_pairrun": (6.0 * V * P / step_s) / 1e9 / hbm_peak,
+        "fp64_eval_kernels": {"dmma_tflops": (dmma_grad + dmma_apply) / (grad_kernel_s + obj_kernel_s) / 1e12,
+                              "frac": (dmma_grad + dmma_apply) / (grad_kernel_s + obj_kernel_s) / 1e12 / f64_peak},
     }
 
 
@@ -113,6 +130,17 @@ def make_circuit(n, layers):
     from aqc_research_b200.parametric_circuit import TrotterAnsatz
 
     return TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+
+
+def workload_config(workload, n, layers):
+    """The `config` object of the JSON line: identical in the GPU arm and the reference arm."""
+    circ = make_circuit(n, layers)
+    return {
+        "workload": workload, "num_qubits": n, "layers": layers, "ansatz": "TrotterAnsatz 2nd order",
+        "num_thetas": circ.num_thetas, "pair_runs": pair_runs(n, layers), "gate_units": gate_units(circ),
+        "target": "synthetic complex128 state of 2^n amplitudes (the cost does not depend on its values)",
+        "parallelism": "independent evaluations, one per GPU, no collective (multistart / horizons)",
+    }
 
 
 def pair_runs(n, layers):
@@ -284,10 +312,9 @@ def run_reference_arm(args, n, layers):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
         "data": "synthetic",
-        "config": {"workload": args.workload, "num_qubits": n, "layers": layers,
-                   "ansatz": "TrotterAnsatz 2nd order",
-                   "note": "CPU port of the reference algorithm (oracle/sv_oracle.c, OpenMP); the "
-                           "reference itself is pure Python/NumPy, see BASELINE.md section 2"},
+        "config": workload_config(args.workload, n, layers),
+        "details": {"note": "CPU port of the reference algorithm (oracle/sv_oracle.c, OpenMP); the "
+                            "reference itself is pure Python/NumPy, see BASELINE.md section 2"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -332,7 +359,7 @@ def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
             flush.fill_(1)
             torch.cuda.synchronize(device)
 
-    step_ms, obj_ms, grad_ms, launches = [], [], [], 0
+    step_ms, obj_ms, grad_ms, launches, grad_launches = [], [], [], 0, 1
     for it in range(warmup + steps):
         if it == warmup and sampler:
             sampler.start()
@@ -349,6 +376,7 @@ def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
             obj_ms.append(o_ms)
             grad_ms.append(g_ms)
             launches += o_l + g_l
+            grad_launches = g_l
     # end-to-end through the public objective class (host thetas in, f and gradient out)
     e2e_s = []
     for it in range(warmup + steps):
@@ -382,7 +410,7 @@ def measure_gpu(n, layers, steps, warmup, device, flush_l2, sampler=None):
                     "gradient_sweeps_per_eval": 1, "scope": "one GPU (rank 0), end to end through the objective class"}
     T = circ.num_thetas
     return {
-        "two_term": two_term,
+        "two_term": two_term, "grad_launches": grad_launches,
         "circ": circ, "step_ms": step_ms, "obj_ms": obj_ms, "grad_ms": grad_ms, "launches": launches,
         "e2e_s": e2e_s, "fidelity": fidelity, "passes_grad": ws.num_passes(0), "passes_dag": ws.num_passes(2),
         "stages_grad": ws.num_stages(0), "stages_dag": ws.num_stages(2),
@@ -789,18 +817,16 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-        "config": {
-            "workload": args.workload, "num_qubits": n, "layers": layers,
-            "ansatz": "TrotterAnsatz 2nd order", "num_thetas": circ.num_thetas,
-            "pair_runs": P, "gate_units": gate_units(circ),
+        "config": workload_config(args.workload, n, layers),
+        "details": {
             "target": "near: V(theta*)|0>, fidelity %.4f" % res["fidelity"],
             "l2": "flushed between timed steps (256 MiB write)" if flush_l2 else "inputs (3 x %.1f GiB) larger than L2" % (V / 2**30),
-            "parallelism": "1 independent evaluation per GPU (no collective)" if world > 1 else "1 GPU",
+            "gpus": world,
             "tile_passes": {"gradient": res["passes_grad"], "vh_apply": res["passes_dag"]},
             "stages": {"gradient": res["stages_grad"], "vh_apply": res["stages_dag"]},
         },
-        "roofline": roofline_block(args.workload, n, P, res["passes_grad"], res["passes_dag"],
-                                   res["stages_grad"], res["stages_dag"], grad_s, obj_s),
+        "roofline": roofline_block(args.workload, n, P, res["stages_grad"], res["stages_dag"], grad_s, obj_s,
+                                   total_ms * 1e-3 / args.steps, res["grad_launches"]),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
                 "d2h_bytes_per_step": res["d2h"]},
         "gpu_launches": res["launches"],
@@ -826,8 +852,8 @@ def main():
             "kernel_ms": {"vh_apply_sweep": o2 * 1e3, "gradient_sweep": g2 * 1e3},
             "tile_passes": {"gradient": r2["passes_grad"], "vh_apply": r2["passes_dag"]},
             "stages": {"gradient": r2["stages_grad"], "vh_apply": r2["stages_dag"]},
-            "roofline": roofline_block("sv28", n2, p2, r2["passes_grad"], r2["passes_dag"],
-                                       r2["stages_grad"], r2["stages_dag"], g2, o2),
+            "roofline": roofline_block("sv28", n2, p2, r2["stages_grad"], r2["stages_dag"], g2, o2, t2,
+                                       r2["grad_launches"]),
         }}
         try:
             line["extra_workloads"]["mps50"] = measure_mps(device=local_rank, with_cpu=not args.no_cpu_baseline)

@@ -239,9 +239,9 @@ int aqc_debug_program_sharded(const aqc_circuit* circ, int log2_world, int tile_
 
 /* ---------------------------------------------------------------------------
  * MPS workspace on one GPU (Vidal form, bond capacity C = aqc_mps_bond_capacity()).
- * Supports circuits whose unit-blocks act on ADJACENT qubits (TrotterAnsatz, "spin"/"line"
- * layouts) -- the case of SpSurrogateObjectiveFastMpsTrotter
- * (objective_lhs_sur_fast_mps_trotter.py:57-99).  Gate arithmetic that the reference delegates to
+ * Unit-blocks may act on any (ctrl, targ) pair (mps_dot_objective.py:380-468); non-adjacent pairs run
+ * through a swap network of adjacent two-site updates.  The production case is
+ * SpSurrogateObjectiveFastMpsTrotter (objective_lhs_sur_fast_mps_trotter.py:57-99).  Gate arithmetic that the reference delegates to
  * qiskit-aer (mps_operations.py:248-265) runs here: two-site contraction, one-sided Jacobi SVD,
  * truncation rule "drop the smallest Schmidt values while the sum of their squares < trunc_thr,
  * cap at chi_max, renormalise".
@@ -284,6 +284,11 @@ int aqc_mps_grad(aqc_mps* mps, const double* thetas, int x_slot, int64_t x_basis
 int aqc_mps_debug_sweeps(aqc_mps* mps, int32_t* out, int cap);
 float aqc_mps_last_kernel_ms(const aqc_mps* mps);
 int aqc_mps_last_num_launches(const aqc_mps* mps);
+/* Truncation record of the most recent apply / objective / grad call: out4[0] = sum over all splits
+ * of the discarded weight (squared Schmidt values relative to the split), [1] = largest single
+ * discard, [2] = the part of [0] removed ONLY by the chi_max cap (qiskit-aer, which the reference
+ * calls at mps_operations.py:248-265, has no cap), [3] = number of splits the cap cut. */
+int aqc_mps_truncation_stats(aqc_mps* mps, double* out4);
 
 /* ---------------------------------------------------------------------------------------------
  * Single-gate primitives (csrc/aqc_prim.cu): the gate-by-gate functions the reference's unit tests

@@ -37,13 +37,27 @@ def test_roofline_block_keys_and_arithmetic():
     n, layers = 28, 4
     P = bench.pair_runs(n, layers)
     assert P == 27 * 4 + 14  # (n - 1) L + n // 2
-    r = bench.roofline_block("sv28", n, P, passes_grad=20, passes_dag=13, stages_grad=128, stages_dag=122,
-                             grad_s=0.121, obj_s=0.0425)
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "dram", "fp64"):
+    r = bench.roofline_block("sv28", n, P, stages_grad=128, stages_dag=122, grad_kernel_s=0.121,
+                             obj_kernel_s=0.0425, step_s=0.165, grad_launches=1)
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "hbm_pairrun", "eval_frac_fp64"):
         assert key in r
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s"
-    # algorithmic bytes of one gradient sweep = 4 vectors x 16 B x 2^n x P, spread over its launches
-    assert abs(r["algorithmic_bytes_per_launch"] * 20 - 4 * 16 * 2.0**n * P) < 1
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert abs(r["dram"]["bytes_per_launch"] - 4 * 16 * 2.0**n) < 1
-    assert 0 < r["fp64"]["frac_eval"] < 1 and r["traffic"] == 17.12e9
+    # the pair-run byte figure exceeds the HBM peak, so the line names the FP64 pipe as the roof
+    assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s"
+    flops = 128 * 2.0**n / 32 * 6 * 512
+    assert abs(r["achieved"] - flops / 0.121 / 1e12) < 1e-9 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0 < r["frac"] < 1 and 30 < r["peak"] < 45
+    h = r["hbm_pairrun"]
+    assert abs(h["algorithmic_bytes_per_sweep"] - 4 * 16 * 2.0**n * P) < 1 and h["frac"] > 1
+    # whole-step figures are taken on the step time, not on the kernel time
+    assert abs(r["eval_frac_hbm_pairrun"] - 6 * 16 * 2.0**n * P / 0.165 / 1e9 / h["peak_gbs"]) < 1e-9
+    tr = bench.ncu_traffic("sv28")
+    assert r["traffic"] == (tr["dram_bytes_per_launch"] if tr else None)
+
+
+def test_both_arms_describe_the_same_config():
+    import bench
+
+    a = bench.workload_config("sv20", 20, 2)
+    assert a["workload"] == "sv20" and a["num_qubits"] == 20 and a["pair_runs"] == 48 and a["gate_units"] == 164
+    assert set(a) == {"workload", "num_qubits", "layers", "ansatz", "num_thetas", "pair_runs", "gate_units",
+                      "target", "parallelism"}

@@ -117,10 +117,40 @@ def test_truncation_behaviour():
     assert errs[0] < TOL and errs[0] <= errs[1] * 1.0001 + 1e-12 and errs[1] <= errs[2] + 1e-12
 
 
-def test_non_adjacent_blocks_rejected():
-    circ = ParametricCircuit(4, "cx", np.array([[0, 1], [2, 3]]))
-    with pytest.raises(ValueError, match="adjacent"):
-        MpsWorkspace(circ, num_slots=1)
+@pytest.mark.parametrize("ent", ["cx", "cz", "cp"])
+def test_non_adjacent_blocks_random_layouts(ent):
+    """
+    Unit-blocks on ANY (ctrl, targ) pair -- the reference's gradient tests use random layouts
+    (test_mps_fast_dot_gradient.py:119-153, mps_dot_objective.py:380-468): the engine routes them
+    through a swap network.  V|x>, V^H|y>, mps_dot and the whole fast_dot_gradient against the dense
+    oracle, untruncated, n <= 6.
+    """
+    rng = np.random.RandomState(len(ent) + 40)
+    for n in (3, 4, 5, 6):
+        for trial in range(3):
+            nb = int(rng.randint(1, 3 * n))
+            blocks = np.zeros((2, nb), dtype=int)
+            for i in range(nb):
+                blocks[:, i] = rng.choice(n, size=2, replace=False)
+            if trial == 0:  # back-to-back blocks on one distant pair: the inner SWAPs cancel
+                blocks[:, 0] = (0, n - 1)
+                if nb > 1:
+                    blocks[:, 1] = (n - 1, 0)
+            circ = ParametricCircuit(n, ent, blocks)
+            th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+            x, y = _rand_vec(n, rng), _rand_vec(n, rng)
+            ws = MpsWorkspace(circ, num_slots=5, chi_max=64, trunc_thr=1e-16)
+            ws.upload(0, M.vector_to_mps(y))
+            ws.upload(4, M.vector_to_mps(x))
+            ws.apply(th, 4, 1)
+            assert _rel(M.mps_to_vector(ws.download(1)), O.apply_v(circ, th, x)) < TOL, (n, trial, blocks)
+            ws.apply(th, 0, 1, dagger=True)
+            z0 = O.apply_v(circ, th, y, dagger=True)
+            assert _rel(M.mps_to_vector(ws.download(1)), z0) < TOL
+            g = ws.grad(th, x_slot=4, z0=1, w=2, z=3)
+            assert _rel(g, O.grad_sweep(circ, th, x, z0)) < TOL, (n, trial, blocks)
+            assert abs(ws.dot(2, 3) - np.vdot(O.apply_v(circ, th, x), y)) < TOL
+            ws.close()
 
 
 def test_mps_objective_class_reproduces_statevector_golden():
@@ -284,5 +314,6 @@ def test_gate_by_gate_helpers_vs_dense_oracle():
         assert _rel(M.mps_to_vector(mdo.cx_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_X)) < TOL
         assert _rel(M.mps_to_vector(mdo.cz_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_Z)) < TOL
         assert _rel(M.mps_to_vector(mdo.cp_mul_mps(ang, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.phase(ang))) < TOL
-    with pytest.raises(Exception):
-        mdo.cx_mul_mps(0.0, 0, 2, mv)  # non-adjacent qubits: no swap network in the engine
+    for c, t in ((0, 2), (4, 0), (1, 4)):  # non-adjacent pairs go through the engine's swap network
+        assert _rel(M.mps_to_vector(mdo.cx_mul_mps(0.0, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.PAULI_X)) < TOL
+        assert _rel(M.mps_to_vector(mdo.cp_mul_mps(ang, c, t, mv)), O.ctrl_op(v.copy(), c, t, O.phase(ang))) < TOL

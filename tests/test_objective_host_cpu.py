@@ -272,6 +272,9 @@ def test_mps_gate_helpers_host_logic(monkeypatch):
         def dot(self, a, b):
             return complex(np.vdot(self.slots[a], self.slots[b]))
 
+        def check_cap(self, what):  # the dense stand-in never truncates
+            pass
+
     monkeypatch.setattr(mpsop, "MpsWorkspace", Dense)
     rng = np.random.RandomState(21)
     n, ang = 4, 0.9173
@@ -348,3 +351,42 @@ def test_sketching_objective_host_logic(monkeypatch):
         best = int(np.argmin(g[p + "f"]))
         assert abs(res["cost"] - g[p + "f"][best]) < TOL and np.array_equal(res["thetas"], ths[best])
         assert objv.statistics["nit"] == ths.shape[0] + 1
+
+
+def test_structure_change_rebuilds_the_workspace_and_drops_cached_results(fake_gpu):
+    """
+    insert_unit_blocks / update_structure between calls: the next objective OR gradient
+    call must run on the new layout -- also a gradient() on the angles of the last objective() -- and
+    a device-generated random target must survive the rebuild.
+    """
+    from aqc_research_b200 import circuit_structures as cs
+    from aqc_research_b200.parametric_circuit import ParametricCircuit
+
+    rng = np.random.RandomState(3)
+    n = 5
+    circ = ParametricCircuit(n, "cx", cs.create_ansatz_structure(n, "spin", "full", 8))
+    target = rng.rand(2**n) + 1j * rng.rand(2**n)
+    target /= np.linalg.norm(target)
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    objv.set_target(target)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    objv.objective(th)
+    objv.gradient(th)
+    first_ws = objv.workspace
+    th2, new_idx = circ.insert_unit_blocks(4, np.array([[0, 3], [1, 2]]), th)
+    th2[new_idx] = 0.3
+    # gradient straight away on a vector whose size changed: the objective is recomputed on the new layout
+    g = objv.gradient(th2)
+    assert objv.workspace is not first_ws and objv.workspace.circ.num_blocks == 10
+    fresh = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    fresh.set_target(target)
+    fresh.objective(th2)
+    assert rel(objv._hs2, fresh._hs2) < TOL  # |<s_i|V^H t>|^2 of the NEW circuit
+    # same block count, different layout, same angles: the cached objective must not be reused
+    blocks = circ.blocks.copy()
+    blocks[:, 0] = blocks[::-1, 0]
+    circ.update_structure(blocks)
+    fake_gpu.calls.clear()
+    objv.gradient(th2)
+    assert "objective" in fake_gpu.calls and objv.workspace.circ is circ
+    assert np.all(np.isfinite(g))
