@@ -98,8 +98,10 @@ SIGNATURES = {
     "aqc_sv_begin": (ct.c_int, [ct.c_void_p, c_double_p, ct.c_int]),
     "aqc_sv_run_epoch": (
         ct.c_int,
-        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int],
+        [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int],
     ),
+    "aqc_sv_can_push": (ct.c_int, [ct.c_void_p]),
+    "aqc_sv_ipc_close": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_grad_finish": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "aqc_sv_ipc_export": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_void_p]),
     "aqc_sv_ipc_import": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]),

@@ -333,6 +333,13 @@ struct DensePassArgs {
   double* gm;             // [batch][nstages_total][64]: 32 used, (az << 3 | reim << 2 | aw)  (NVEC == 2)
   int nstages_total;
   PassDesc pd;
+  // Layout switch of a sharded state FUSED into this pass (xchg_world > 0; the last pass of an epoch):
+  // instead of writing its tile back in place, the pass stores every 256-byte run where it belongs
+  // after the block transpose over the ranks -- element (chunk c, offset o) of this rank goes to
+  // (chunk xchg_rank, offset o) of rank c -- straight into the peers' HBM (NVLink peer stores;
+  // xdst[v][c] = destination vector v of rank c, mapped with CUDA IPC; c = xchg_rank is local).
+  int xchg_world, xchg_rank, xchg_shift;  // chunk = local index >> xchg_shift
+  double2* xdst[2][16];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -383,7 +390,9 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]
+  __shared__ double2* s_xdst[32];                                       // [vector][rank] push destinations
   const int tid = threadIdx.x;
+  if (A.xchg_world > 0 && tid < 32) s_xdst[tid] = A.xdst[tid >> 4][tid & 15];  // (read after the stage barriers)
   const int lane = tid & 31, warp = tid >> 5;
   const int tb = A.pd.tb;
   const int tsize = 1 << tb;
@@ -603,6 +612,26 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
     s = snext;
   }
 
+  if (A.xchg_world > 0) {
+    // fused layout switch: the tile leaves for the ranks it belongs to (runs of 2^low >= 16 amplitudes stay
+    // contiguous: the low tile bits are low index bits, the chunk bits are the top ones)
+    if (nstages == 0) __syncthreads();
+    const long long omask = (1ll << A.xchg_shift) - 1;
+    const long long rbase = (long long)A.xchg_rank << A.xchg_shift;
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+      const double2* sm = smem + (size_t)v * tsize;
+      for (int l = tid; l < tsize; l += kDThreads) {
+        long long li = base | lo_off;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (((l >> 8) >> k) & 1) li |= hs[k];
+        double2* d = s_xdst[v * 16 + (int)(li >> A.xchg_shift)] + (rbase | (li & omask));
+        *d = sm[dense_swz(l)];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int v = 0; v < NVEC; ++v) {
     const double2* sm = smem + (size_t)v * tsize;

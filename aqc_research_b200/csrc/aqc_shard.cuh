@@ -44,8 +44,13 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
 // V / V^H on vec0.  src slots are read by the first pass only (src0 < 0: vec0 is the local part
 // of a basis state: offset `basis_local`, or all zeros if basis_local < 0); dst slots receive the
 // result and are updated in place by the remaining passes.
+// push0 (and push1 for the gradient) >= 0: the layout switch that follows the epoch is FUSED into its
+// last pass -- the pass stores its tiles straight into slot push0 / push1 of the rank each 256-byte
+// run belongs to after the block transpose (peer stores over NVLink, buffers mapped with
+// aqc_sv_ipc_import); dst then only holds intermediate results.  The caller makes all ranks meet
+// (host barrier) before anyone reads the pushed slots.  Needs the persistent sweep kernel.
 extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local,
-                                int src1, int dst0, int dst1) {
+                                int src1, int dst0, int dst1, int push0, int push1) {
   if (!sv || mode < 0 || mode > 2) return fail(AQC_EINVAL, "bad arguments");
   const Program* p = prog_of(sv, mode);
   if (epoch < 0 || epoch >= (int)p->epoch_pass0.size()) return fail(AQC_EINVAL, "bad epoch");
@@ -57,6 +62,15 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
     if (dst0 == dst1) return fail(AQC_EINVAL, "w and z must be different slots");
   }
   if (src0 < 0 && mode != 0) return fail(AQC_EINVAL, "basis source is only valid for the gradient");
+  if (push0 >= 0) {
+    if (sv->g <= 0 || !sv->dense || !sv->use_stream)
+      return fail(AQC_EINVAL, "the fused layout switch needs a sharded workspace and the persistent sweep kernel");
+    if ((rc = check_slot(sv, push0))) return rc;
+    if (mode == 0 && (rc = check_slot(sv, push1))) return rc;
+    if (push0 == dst0 || push0 == src0 || (mode == 0 && (push1 == dst1 || push1 == dst0 || push0 == dst1 ||
+                                                         push1 == src1 || push0 == src1 || push0 == push1)))
+      return fail(AQC_EINVAL, "pushed slots must differ from the slots the epoch works on");
+  }
   CU(cudaSetDevice(sv->device));
   const int p0 = p->epoch_pass0[epoch];
   const int p1 = epoch + 1 < (int)p->epoch_pass0.size() ? p->epoch_pass0[epoch + 1] : (int)p->passes.size();
@@ -65,7 +79,7 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   if (sv->dense)
     rc = run_dense_program(sv, mode, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
                            mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
-                           mode == 0 ? sv->slots[dst1] : nullptr, p0, p1);
+                           mode == 0 ? sv->slots[dst1] : nullptr, p0, p1, push0, push1);
   else
     rc = run_program(sv, *p, mode == 0, mode == 2, src0 >= 0 ? sv->slots[src0] : nullptr, basis,
                      mode == 0 ? sv->slots[src1] : nullptr, sv->slots[dst0],
@@ -76,6 +90,9 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
   return AQC_OK;
 }
+
+// 1 if this workspace can fuse the layout switch into the last pass of an epoch (aqc_sv_run_epoch).
+extern "C" int aqc_sv_can_push(const aqc_sv* sv) { return (sv && sv->g > 0 && sv->dense && sv->use_stream) ? 1 : 0; }
 
 // Downloads this workspace's (partial) raw inner products and converts them to 0.5j <P w|z>
 // (linear, so partial sums of several ranks may be added afterwards).
@@ -146,6 +163,20 @@ extern "C" int aqc_sv_ipc_import(aqc_sv* sv, int peer_rank, int slot, const unsi
   void* p = nullptr;
   CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   sv->peer[slot][peer_rank] = (const double2*)p;
+  sv->ipc_opened.push_back(p);  // closed by aqc_sv_ipc_close / aqc_sv_destroy
+  return AQC_OK;
+}
+
+// Unmaps every peer buffer imported with aqc_sv_ipc_import.  Importers call this (and all ranks meet)
+// BEFORE the exporting workspaces are destroyed.
+extern "C" int aqc_sv_ipc_close(aqc_sv* sv) {
+  if (!sv) return fail(AQC_EINVAL, "null workspace");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaStreamSynchronize(sv->stream));
+  for (void* p : sv->ipc_opened) cudaIpcCloseMemHandle(p);
+  sv->ipc_opened.clear();
+  for (auto& row : sv->peer)
+    for (auto& q : row) q = nullptr;
   return AQC_OK;
 }
 

@@ -33,13 +33,14 @@ constexpr int kSOffBar = kSOffTile + 64;                           // mbarriers 
 // passes (one-pass matrix programs) keep the per-tile global adds.
 constexpr int kSAccStages = 12;
 constexpr int kSOffAcc = kSOffBar + 4 * kSGroups * 8 + 16;
-constexpr int kSSmemBytes = kSOffAcc + kSGroups * kSAccStages * 32 * 8;
+constexpr int kSOffXdst = kSOffAcc + kSGroups * kSAccStages * 32 * 8;  // [vector][rank] push destinations
+constexpr int kSSmemBytes = kSOffXdst + 2 * 16 * 8;
 static_assert(kSSmemBytes <= 227 * 1024, "stream kernel shared memory");
-// Register budget: 896 threads are launched with 72 registers each (64512 in the CTA's pool); the six
-// compute warpgroups take 80 (61440), which the producer warpgroup must pay for by keeping 24 (3072) --
-// setmaxnreg.inc blocks until the CTA's OWN pool can serve it, so the budget has to balance exactly.
-constexpr int kSRegsCompute = 80, kSRegsProducer = 24;
-static_assert(kSGroups * kDWarps * 32 * kSRegsCompute + 128 * kSRegsProducer <= kSThreads * 72, "register pool");
+// Registers: 896 threads at 72 registers each.  The two roles live in separate code regions (their own
+// pass loops), which is what lets ptxas fit each of them into 72 without spills; rebalancing with
+// setmaxnreg (80 for the compute warpgroups, 24 for the producers -- the CTA's own pool has to balance
+// exactly, or setmaxnreg.inc blocks forever) was measured at HALF the speed: the producers, spilling at
+// 24 registers, become the critical path (profiles/r02_stream_kernel.md).
 
 struct StreamArgs {
   const PassDesc* passes;  // device copy of the program's passes
@@ -57,6 +58,14 @@ struct StreamArgs {
   const double* umat;
   double* gm;
   unsigned long long* grid_bar;  // monotonic arrival counter (all launches of a workspace use one grid size)
+  // Layout switch of a sharded state fused into the LAST pass of the range (xchg_world > 0): instead of
+  // writing its tile back in place, the pass stores every 256-byte run where it belongs after the block
+  // transpose over the ranks -- element (chunk c, offset o) of this rank goes to (chunk xchg_rank,
+  // offset o) of rank c -- straight into the peers' memory (NVLink peer stores; xdst[v][c] is the
+  // destination vector of rank c, mapped with CUDA IPC; c = xchg_rank is a local buffer).
+  int nbuf;  // tile buffers per compute group: 2 (32 KiB each, double buffered) or 1 (64 KiB)
+  int xchg_world, xchg_rank, xchg_shift;  // chunk = local index >> xchg_shift
+  double2* xdst[2][16];
 };
 
 __device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
@@ -130,7 +139,7 @@ __device__ __forceinline__ void stream_grid_barrier(unsigned long long* bar, vol
   __syncthreads();
 }
 
-template <int NVEC, bool REBAL>
+template <int NVEC>
 __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const StreamArgs A) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int tid = threadIdx.x;
@@ -147,14 +156,14 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
     *s_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  double2** s_xdst = reinterpret_cast<double2**>(s_raw + kSOffXdst);
+  if (tid < 32) s_xdst[tid] = A.xdst[tid >> 4][tid & 15];
   __syncthreads();
   const bool producer = warp >= kSGroups * kDWarps;
   const int g = producer ? warp - kSGroups * kDWarps : warp / kDWarps;  // group served / compute group
   const int wg = warp % kDWarps;                                        // warp inside the compute group
-  // The two roles run the same pass loop in separate code regions, each behind its own setmaxnreg, so
-  // that the register allocator gives the compute warps 80 registers and the producers 32.
+  // The two roles run the same pass loop in separate code regions.
   if (producer) {
-    if (REBAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSRegsProducer));
     unsigned pdone = 0;  // phase parity of done[g][b] (bit b)
   for (int p = A.pass_begin; p < A.pass_end; ++p) {
     const PassDesc* __restrict__ pd = A.passes + p;
@@ -172,12 +181,15 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
         long long lo_off = 0;
         for (int k = 0; k < 5 && k < tb; ++k) lo_off |= (long long)((lane >> k) & 1) << pd->bitpos[k];
         const int nj = tsize >> 5;  // 16-byte chunks per lane and vector
-        for (int j = lane; j < nj; j += 32) {
+        for (int j = lane; j < nj && j < 64; j += 32) {
           long long h = 0;
-          for (int k = 5; k < tb; ++k) h |= (long long)((j >> (k - 5)) & 1) << pd->bitpos[k];
+          for (int k = 5; k < tb && k < 11; ++k) h |= (long long)((j >> (k - 5)) & 1) << pd->bitpos[k];
           s_hoff[j] = h;
         }
         __syncwarp();
+        // high-bit offset of chunk j of a lane (the table holds 64 entries; a 2^12 tile has 128 chunks)
+        const long long hi12 = tb > 11 ? (1ll << pd->bitpos[11]) : 0ll;
+        auto hoff = [&](int j) { return s_hoff[j & 63] + ((j >> 6) ? hi12 : 0ll); };
         const bool synth = first && A.xcount > 0;
         unsigned valid = 0;
         bool ended = false;
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
             if (v == 0 && synth) {
               for (int j = 0; j < nj; ++j) {
                 const unsigned l = (unsigned)lane + 32u * (unsigned)j;
-                const long long gi = base | lo_off | s_hoff[j];
+                const long long gi = base | lo_off | hoff(j);
                 const double2* srcp = A.xamp;
                 unsigned bytes = 0;
 #pragma unroll
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
 #pragma unroll 4
               for (int j = 0; j < nj; ++j) {
                 const unsigned l = (unsigned)lane + 32u * (unsigned)j;
-                cp_async16_s(sv_ + (dense_swz(l) << 4), src + s_hoff[j]);
+                cp_async16_s(sv_ + (dense_swz(l) << 4), src + hoff(j));
               }
             }
           }
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
           valid |= 1u << b;
         };
         refill(0);
-        refill(1);
+        if (A.nbuf > 1) refill(1);
         for (int b = 0; valid; b ^= 1) {
           if (!((valid >> b) & 1)) continue;
           const int i = 2 * g + b;
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
             for (int kk = 0; kk < nouter; ++kk) base |= ((x >> kk) & 1ll) << pd->outerpos[kk];
             const long long boff = y * A.vec_stride + base;
             const unsigned sbuf = sm0 + (unsigned)i * kSBufBytes;
+            const bool push = A.xchg_world > 0 && p + 1 == A.pass_end;
 #pragma unroll
             for (int v = 0; v < NVEC; ++v) {
               const unsigned sv_ = sbuf + (unsigned)v * vbytes;
@@ -254,9 +267,19 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
                   const unsigned l = (unsigned)lane + 32u * (unsigned)(j0 + u);
                   if (j0 + u < nj) val[u] = lds128(sv_ + (dense_swz(l) << 4));
                 }
+                if (!push) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (j0 + u < nj) stg128(dst + s_hoff[j0 + u], val[u]);
+                  for (int u = 0; u < 4; ++u)
+                    if (j0 + u < nj) stg128(dst + hoff(j0 + u), val[u]);
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (j0 + u < nj) {
+                      const long long li = base + lo_off + hoff(j0 + u);  // local index (batch is 1)
+                      const long long c = li >> A.xchg_shift, o = li & ((1ll << A.xchg_shift) - 1);
+                      stg128(s_xdst[v * 16 + c] + (((long long)A.xchg_rank << A.xchg_shift) | o), val[u]);
+                    }
+                }
               }
             }
           }
@@ -269,7 +292,6 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
     if (p + 1 < A.pass_end) stream_grid_barrier(A.grid_bar, s_next);
   }
   } else {
-    if (REBAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSRegsCompute));
     unsigned pfull = 0;  // phase parity of full[g][b] (bit b)
     int step = 0;        // steps so far (parity selects the partial-sum buffer, also across tiles)
     for (int k = wg * 32 + lane; k < kSAccStages * 32; k += kDThreads)
@@ -302,7 +324,7 @@ __global__ void __launch_bounds__(kSThreads, 1) dense_stream_kernel(const Stream
         }
         group_bar(g + 1);
       };
-      for (int b = 0;; b ^= 1) {
+      for (int b = 0;; b ^= (A.nbuf - 1)) {
         const int i = 2 * g + b;
         mbar_wait(bar0 + 8 * i, (pfull >> b) & 1);
         pfull ^= 1u << b;

@@ -113,6 +113,7 @@ struct aqc_sv {
   bool dense = false;
   // persistent warp-specialised sweep kernel (aqc_stream.cuh): one cooperative launch per pass range
   bool use_stream = false;
+  int stream_nbuf = 2;                      // tile buffers per compute group (see aqc_stream.cuh)
   int stream_grid = 1;                      // CTAs of every stream launch of this workspace
   unsigned long long* d_gridbar = nullptr;  // grid-barrier arrival counter
   double2* d_one = nullptr;                 // the constant (1, 0): amplitude of a basis start vector
@@ -131,6 +132,7 @@ struct aqc_sv {
   // global-qubit sharding (0 = single GPU)
   int g = 0, rank = 0;
   const double2* peer[64][16];  // peer[slot][rank]: IPC-mapped base pointers of the other ranks
+  std::vector<void*> ipc_opened;  // what cudaIpcOpenMemHandle returned (closed on destroy)
 };
 
 static int ensure_pinned(aqc_sv* sv, size_t doubles) {
@@ -338,14 +340,12 @@ static int dense_collect(aqc_sv* sv) {
 // AQC_STREAM_COOP=0 launches pass by pass instead (no grid barrier inside; for per-pass profiling).
 static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseTables& dt, const double2* src0,
                          long long basis, const double2* src1, double2* dst0, double2* dst1, int pass_begin,
-                         int pass_end) {
+                         int pass_end, int push0 = -1, int push1 = -1) {
   const bool coop = env_int("AQC_STREAM_COOP", 1) != 0;
   static bool configured[16] = {false};
   if (!configured[sv->device & 15]) {
-    CU(cudaFuncSetAttribute(dense_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    CU(cudaFuncSetAttribute(dense_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    CU(cudaFuncSetAttribute(dense_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    CU(cudaFuncSetAttribute(dense_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    CU(cudaFuncSetAttribute(dense_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
     configured[sv->device & 15] = true;
   }
   StreamArgs a;
@@ -358,6 +358,7 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
   a.umat = sv->d_umat;
   a.gm = sv->d_gm;
   a.grid_bar = sv->d_gridbar;
+  a.nbuf = sv->stream_nbuf;
   a.dst[0] = dst0;
   a.dst[1] = dst1;
   const int step = coop ? (pass_end - pass_begin) : 1;
@@ -367,6 +368,19 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
     const bool first = p0 == pass_begin;
     a.src[0] = first ? src0 : dst0;
     a.src[1] = first ? src1 : dst1;
+    a.xchg_world = 0;
+    if (push0 >= 0 && a.pass_end == pass_end) {  // the launch that holds the last pass pushes its result
+      a.xchg_world = 1 << sv->g;
+      a.xchg_rank = sv->rank;
+      a.xchg_shift = sv->nbits - sv->g;
+      for (int r = 0; r < a.xchg_world; ++r) {
+        a.xdst[0][r] = r == sv->rank ? sv->slots[push0] : const_cast<double2*>(sv->peer[push0][r]);
+        a.xdst[1][r] = mode != 0 ? nullptr
+                                 : (r == sv->rank ? sv->slots[push1] : const_cast<double2*>(sv->peer[push1][r]));
+        if (!a.xdst[0][r] || (mode == 0 && !a.xdst[1][r]))
+          return fail(AQC_EINVAL, "peer %d: destination slot was not imported", r);
+      }
+    }
     a.xcount = 0;
     if (first && basis >= 0) {
       a.xcount = 1;
@@ -374,10 +388,7 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
       a.xamp = sv->d_one;
     }
     void* params[] = {(void*)&a};
-    // AQC_STREAM_REBAL=1: development variant with setmaxnreg register rebalancing (80 / 24 registers)
-    const bool rebal = env_int("AQC_STREAM_REBAL", 0) != 0;
-    const void* fn = mode == 0 ? (rebal ? (const void*)dense_stream_kernel<2, true> : (const void*)dense_stream_kernel<2, false>)
-                               : (rebal ? (const void*)dense_stream_kernel<1, true> : (const void*)dense_stream_kernel<1, false>);
+    const void* fn = mode == 0 ? (const void*)dense_stream_kernel<2> : (const void*)dense_stream_kernel<1>;
     if (a.pass_end - a.pass_begin > 1)
       CU(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sv->stream_grid), dim3(kSThreads), params, kSSmemBytes,
                                      sv->stream));
@@ -391,7 +402,7 @@ static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseT
 // passes [pass_begin, pass_end) of a program on the dense engine; mode 0: (w, z), else one vector
 static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long long basis,
                              const double2* src1, double2* dst0, double2* dst1, int pass_begin,
-                             int pass_end) {
+                             int pass_end, int push0 = -1, int push1 = -1) {
   const Program& prog = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
   const DenseTables& dt = mode == 0 ? sv->dt_grad : (mode == 1 ? sv->dt_fwd : sv->dt_dag);
   DensePassArgs a;
@@ -402,7 +413,9 @@ static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long lon
   a.gm = sv->d_gm;
   a.nstages_total = (int)prog.stages.size();
   if (pass_end < 0) pass_end = (int)prog.passes.size();
-  if (sv->use_stream) return launch_stream(sv, mode, prog, dt, src0, basis, src1, dst0, dst1, pass_begin, pass_end);
+  if (sv->use_stream)
+    return launch_stream(sv, mode, prog, dt, src0, basis, src1, dst0, dst1, pass_begin, pass_end, push0, push1);
+  if (push0 >= 0) return fail(AQC_EINVAL, "the fused layout switch needs the persistent sweep kernel (AQC_STREAM=1)");
   for (int i = pass_begin; i < pass_end; ++i) {
     a.pd = prog.passes[i];
     a.src[0] = (i == pass_begin) ? src0 : dst0;
@@ -484,6 +497,9 @@ static int upload_program(Program& p) {
 extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   if (!sv) return;
   cudaSetDevice(sv->device);
+  if (sv->stream) cudaStreamSynchronize(sv->stream);
+  for (void* p : sv->ipc_opened) cudaIpcCloseMemHandle(p);
+  sv->ipc_opened.clear();
   for (auto p : sv->slots)
     if (p) cudaFree(p);
   if (sv->d_thetas) cudaFree(sv->d_thetas);
@@ -582,9 +598,15 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   // prefers larger tiles for large states.
   const bool want_stream = env_int("AQC_STREAM", 1) != 0;
   const bool l2_resident = sv->nbits <= 22;
-  const int tb_grad_max = want_stream ? 10 : kMaxTileBits - 1, tb_apply_max = want_stream ? 11 : kMaxTileBits;
-  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", (l2_resident || want_stream) ? 10 : 11), tb_grad_max);
-  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", (l2_resident || want_stream) ? 11 : 12), tb_apply_max);
+  // stream kernel: two 32 KiB buffers per compute group (2^10 (w, z) / 2^11 single tiles, double buffered)
+  // for L2-resident states, one 64 KiB buffer (2^11 / 2^12 tiles: fewer passes, 8 iterations per warp and
+  // stage) for the large ones
+  const int nbuf = std::max(1, std::min(2, env_int("AQC_STREAM_NBUF", l2_resident ? 2 : 1)));
+  const int tb_grad_max = want_stream ? (nbuf == 2 ? 10 : 11) : kMaxTileBits - 1;
+  const int tb_apply_max = want_stream ? (nbuf == 2 ? 11 : 12) : kMaxTileBits;
+  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), tb_grad_max);
+  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", l2_resident ? 11 : 12), tb_apply_max);
+  sv->stream_nbuf = nbuf;
   const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 4);
   const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)

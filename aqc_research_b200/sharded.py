@@ -3,10 +3,13 @@ One state vector over 2^g GPUs (global-qubit sharding) -- SURVEY.md section 8(e)
 
 One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing (barriers, the tiny
 all-reduce of the partial gradient sums and of the gathered amplitudes).  The heavy step, the
-layout switch between epochs, is a block transpose over the ranks done by ``aqc_sv_exchange``
-(every rank pulls its chunks from its peers' HBM with plain peer loads over NVLink; the peers'
-buffers are mapped with CUDA IPC).  If IPC mapping is unavailable the same transpose is done with
-``isend / irecv`` pairs of the process group (NCCL, or gloo in the CPU tests).
+layout switch between epochs, is a block transpose over the ranks.  It is FUSED into the last tile
+pass of every epoch: instead of writing its tiles back in place, the pass stores each 256-byte run
+straight into the HBM of the rank it belongs to after the transpose (peer stores over NVLink, the
+peers' buffers mapped with CUDA IPC), so the transfer overlaps the DMMA work tile by tile and no
+separate copy pass over the vector exists.  Fallbacks: ``aqc_sv_exchange`` (a separate pull kernel,
+``AQC_SHARD_PUSH=0``) and, without IPC, ``isend / irecv`` pairs of the process group (NCCL, or gloo
+in the CPU tests).
 
 Layouts (see ``build_program_sharded`` in csrc/aqc_sv.cu), n qubits, g = log2(world), nl = n - g:
   A: qubits n-g..n-1 global;  qubits 0..g-1 on local bits nl-g..nl-1;  qubit q -> bit q - g otherwise
@@ -66,10 +69,18 @@ class GpuShardBackend:
         _, ptr = _thetas_ptr(thetas, self.num_thetas)
         _lib.check(self._lib.aqc_sv_begin(self.handle, ptr, mode))
 
-    def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1):
+    def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1, push0=-1, push1=-1):
         _lib.check(
-            self._lib.aqc_sv_run_epoch(self.handle, mode, epoch, src0, int(basis_local), src1, dst0, dst1)
+            self._lib.aqc_sv_run_epoch(self.handle, mode, epoch, src0, int(basis_local), src1, dst0, dst1,
+                                       push0, push1)
         )
+
+    def can_push(self) -> bool:
+        return bool(self._lib.aqc_sv_can_push(self.handle))
+
+    def ipc_close(self):
+        if getattr(self, "handle", None):
+            _lib.check(self._lib.aqc_sv_ipc_close(self.handle))
 
     def grad_finish(self) -> np.ndarray:
         out = np.empty(self.num_thetas, dtype=np.complex128)
@@ -196,27 +207,36 @@ class DistComm:
 class ShardedStateVector:
     """
     Objective / gradient building blocks on a sharded state.  Vectors are addressed by NAME
-    ("target", "z0", "w", "z"); the driver keeps the name -> slot map because a layout switch
-    writes into the spare slot and swaps the roles.
+    ("target", "z0", "w", "z"); the driver keeps the name -> slot map and a pool of free slots,
+    because a layout switch delivers a vector into another slot.  Five slots are enough for the
+    gradient sweep: the target, the two swept vectors and two landing slots (the sweep starts IN
+    PLACE on the slot of z0 = V^H target, which every evaluation recomputes anyway).
     """
 
     NAMES = ("target", "z0", "w", "z")
 
     def __init__(self, circ: ParametricCircuit, comm, backend, use_p2p: bool = True):
+        import os  # pylint: disable=import-outside-toplevel
+
         self.circ = circ
         self.comm = comm
         self.be = backend
         self.n = circ.num_qubits
         self.g = int(comm.world).bit_length() - 1
         assert 1 << self.g == comm.world, "world size must be a power of two"
-        self.slot: Dict[str, int] = {name: i for i, name in enumerate(self.NAMES)}
-        self.slot["spare"] = len(self.NAMES)
+        assert backend.num_slots >= 5, "a sharded state needs at least 5 slots"
+        self.slot: Dict[str, int] = {"target": 0}
+        self.free: List[int] = list(range(1, backend.num_slots))
+        for name in ("z0", "w", "z"):  # every name owns a slot at rest (callers upload / download by name)
+            self.slot[name] = self.free.pop(0)
         self.layout: Dict[str, int] = {name: 0 for name in self.NAMES}
         self.exchange_ms = 0.0
         self.compute_ms = 0.0
         self.p2p = False
         if use_p2p and hasattr(backend, "ipc_export"):
             self._setup_p2p()
+        self.push = bool(self.p2p and getattr(backend, "can_push", lambda: False)()
+                         and os.environ.get("AQC_SHARD_PUSH", "1") != "0")
 
     def _setup_p2p(self):
         """Maps every slot of every peer through CUDA IPC; falls back to send/recv on failure."""
@@ -232,15 +252,23 @@ class ShardedStateVector:
         total = self.comm.allreduce_sum(np.array([float(ok)]), device=self._dev())
         self.p2p = bool(total[0] == self.comm.world)
 
+    def close(self):
+        """Importers unmap the peers' buffers, all ranks meet, then the buffers are freed."""
+        if self.p2p and hasattr(self.be, "ipc_close"):
+            self.be.ipc_close()
+        self.comm.barrier()
+        if hasattr(self.be, "close"):
+            self.be.close()
+
     def _dev(self):
         return f"cuda:{self.be.device}" if hasattr(self.be, "device") else None
 
-    # -- layout switch ---------------------------------------------------------------------
+    # -- layout switch (separate pass: pull kernel or send / recv) ---------------------------------
     def _switch(self, names: Sequence[str]):
         import time  # pylint: disable=import-outside-toplevel
 
         for name in names:
-            src, dst = self.slot[name], self.slot["spare"]
+            src, dst = self.slot[name], self.free.pop(0)
             self.comm.barrier()  # every rank finished writing its source
             t0 = time.perf_counter()
             if self.p2p:
@@ -249,32 +277,51 @@ class ShardedStateVector:
                 self.comm.transpose_chunks(self.be.slot_tensor(src), self.be.slot_tensor(dst))
             self.comm.barrier()  # every rank pulled: sources are free again
             self.exchange_ms += (time.perf_counter() - t0) * 1e3
-            self.slot[name], self.slot["spare"] = dst, src
+            self.slot[name] = dst
+            self.free.append(src)
             self.layout[name] ^= 1
 
-    def _run(self, mode, first_sources, names):
-        """Runs all epochs of ``mode`` on the named vectors (vec0[, vec1])."""
+    def _run(self, mode, first_sources, names, rest_in_layout_a=True):
+        """
+        Runs all epochs of ``mode`` on the named vectors (vec0[, vec1]); ``first_sources`` =
+        (src0 slot or -1, local basis offset, src1 slot) are read by the first pass only.  The named
+        vectors must own slots (their content is overwritten).  ``rest_in_layout_a=False`` leaves the
+        results in the layout of the last epoch (work states nobody reads again).
+        """
+        import time  # pylint: disable=import-outside-toplevel
+
         be = self.be
-        for e in range(be.num_epochs(mode)):
+        ne = be.num_epochs(mode)
+        for e in range(ne):
             need = be.epoch_layout(mode, e)
+            nxt = be.epoch_layout(mode, e + 1) if e + 1 < ne else (0 if rest_in_layout_a else need)
+            dst = [self.slot[nm] for nm in names]
             if e == 0:
-                src0, basis_local, src1 = first_sources
-                # sources must be in the layout of the first epoch
                 if need != 0:
                     raise NotImplementedError("first epoch must run in layout A")
-                dst = [self.slot[nm] for nm in names]
-                be.run_epoch(mode, e, src0, basis_local, src1, dst[0], dst[1] if len(dst) > 1 else 0)
-                for nm in names:
-                    self.layout[nm] = 0
+                src0, basis_local, src1 = first_sources
             else:
-                if self.layout[names[0]] != need:
+                assert self.layout[names[0]] == need
+                src0, basis_local, src1 = dst[0], -1, dst[1] if len(dst) > 1 else 0
+            d1 = dst[1] if len(dst) > 1 else 0
+            if nxt != need and self.push:
+                land = [self.free.pop(0) for _ in names]
+                be.run_epoch(mode, e, src0, basis_local, src1, dst[0], d1, land[0], land[1] if len(land) > 1 else -1)
+                self.compute_ms += getattr(be, "last_kernel_ms", 0.0)
+                t0 = time.perf_counter()
+                self.comm.barrier()  # every rank has delivered: the landing slots are complete
+                self.exchange_ms += (time.perf_counter() - t0) * 1e3
+                for nm, ls in zip(names, land):
+                    self.free.append(self.slot[nm])
+                    self.slot[nm] = ls
+                    self.layout[nm] = nxt
+            else:
+                be.run_epoch(mode, e, src0, basis_local, src1, dst[0], d1)
+                self.compute_ms += getattr(be, "last_kernel_ms", 0.0)
+                for nm in names:
+                    self.layout[nm] = need
+                if nxt != need:
                     self._switch(names)
-                dst = [self.slot[nm] for nm in names]
-                be.run_epoch(mode, e, dst[0], -1, dst[1] if len(dst) > 1 else 0, dst[0],
-                             dst[1] if len(dst) > 1 else 0)
-            self.compute_ms += getattr(be, "last_kernel_ms", 0.0)
-        if self.layout[names[0]] != 0:
-            self._switch(names)  # data at rest are in layout A
 
     # -- public operations -------------------------------------------------------------------
     def set_target_random(self, seed: int):
@@ -307,11 +354,18 @@ class ShardedStateVector:
         self.apply(thetas, "target", "z0", dagger=True)
         return self.amplitudes("z0", indices)
 
-    def grad(self, thetas, x_basis: int) -> np.ndarray:
-        """Complex gradient of <V e_x | y> given z0 (grad_of_dot_product)."""
+    def grad(self, thetas, x_basis: int, keep_states: bool = False) -> np.ndarray:
+        """
+        Complex gradient of <V e_x | y> given z0 (grad_of_dot_product).  The sweep runs in place on
+        the slot of z0, which is CONSUMED (every evaluation recomputes it, objective() first);
+        ``keep_states`` brings the final w = V e_x and z = V z0 back to layout A.
+        """
         rank, off = locate(int(x_basis), self.n, self.g)
         self.be.begin(thetas, MODE_GRAD)
-        self._run(MODE_GRAD, (-1, off if rank == self.comm.rank else -1, self.slot["z0"]), ["w", "z"])
+        # z takes over the slot of z0; z0 gets the old slot of z (content undefined until the next objective)
+        self.slot["z"], self.slot["z0"] = self.slot["z0"], self.slot["z"]
+        self._run(MODE_GRAD, (-1, off if rank == self.comm.rank else -1, self.slot["z"]), ["w", "z"],
+                  rest_in_layout_a=keep_states)
         return self.comm.allreduce_sum(self.be.grad_finish(), device=self._dev())
 
     def vdot(self, a: str, b: str) -> complex:

@@ -442,12 +442,15 @@ def measure_mps(n=50, chi=64, layers=20, steps=3, warmup=1, device=0, with_cpu=T
         t0 = time.perf_counter()
         ws.objective(th, 0, 1, idx)
         o, lo = ws.last_kernel_ms, ws.last_num_launches
+        trunc_obj = ws.truncation_stats() if it == warmup + steps - 1 else None
         ws.grad(th, x_basis=neel, z0=1, w=2, z=3)
         g, lg = ws.last_kernel_ms, ws.last_num_launches
         dt = time.perf_counter() - t0
         if it >= warmup:
             obj_ms.append(o), grad_ms.append(g), wall.append(dt)
             launches += lo + lg
+    trunc_grad = ws.truncation_stats()
+    z0_norm = float(abs(ws.dot(1, 1)) ** 0.5)
     ws.close()
     nb_tot = circ.num_blocks + circ.half_layer_num_blocks
     dots = 3 * n + 4 * nb_tot
@@ -458,6 +461,9 @@ def measure_mps(n=50, chi=64, layers=20, steps=3, warmup=1, device=0, with_cpu=T
         "e2e_value": 1.0 / float(np.mean(wall)),
         "kernel_ms": {"objective": float(np.mean(obj_ms)), "gradient": float(np.mean(grad_ms))},
         "gpu_launches": launches,
+        # what the timed computation discards (saturated regime: every bond sits at the chi cap, so the
+        # numbers are large -- the parity of truncated results is pinned at smaller sizes)
+        "z0_norm": z0_norm, "truncation": {"objective": trunc_obj, "gradient": trunc_grad},
         "dominant_kernel": "mps_svd_kernel (block one-sided Jacobi, FP64 FMA pipe; ~85-89% of device time, profiles/r01_ncu_mps50.md)",
     }
     if with_cpu:
@@ -661,8 +667,8 @@ def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
     BASELINE.json configs[4], second half: ONE state vector over `world` GPUs (global-qubit
     sharding), weak scaling: n = base_qubits + log2(world) qubits, i.e. a constant 2^base_qubits
     amplitudes per GPU.  One step = objective + single-term gradient of the whole sharded state;
-    layout switches go through the peer-memory exchange kernel (NVLink).  Wall clock per step
-    (max over ranks via the barriers inside the driver).
+    every layout switch is fused into the last tile pass of its epoch (NVLink peer stores).  Wall
+    clock per step between two barriers of the process group (= max over ranks).
     """
     import torch.distributed as dist
     from aqc_research_b200.sharded import DistComm, GpuShardBackend, ShardedStateVector
@@ -692,12 +698,61 @@ def measure_sharded(base_qubits, layers, steps, warmup, local_rank, world):
             times.append((dt, sv.compute_ms, sv.exchange_ms))
     assert np.all(np.isfinite(grad))
     t = np.array(times)
+    # bytes every GPU sends per evaluation: each layout switch moves (1 - 1/world) of a 16 * 2^base_qubits
+    # byte shard; the V^H sweep switches one vector per epoch boundary (and once more to return to the
+    # rest layout), the gradient sweep two vectors per epoch boundary
+    e_g, e_d = be.num_epochs(0), be.num_epochs(2)
+    last_d = be.epoch_layout(2, e_d - 1)
+    switches = (e_d - 1 + (1 if last_d != 0 else 0)) + 2 * (e_g - 1)
+    sent = switches * 16.0 * 2**base_qubits * (1.0 - 1.0 / world)
     res = {"num_qubits": n, "layers": layers, "num_thetas": circ.num_thetas, "p2p_exchange": bool(sv.p2p),
-           "epochs": {"gradient": be.num_epochs(0), "vh_apply": be.num_epochs(2)},
+           "fused_push": bool(sv.push), "epochs": {"gradient": e_g, "vh_apply": e_d},
            "s_per_step": float(t[:, 0].mean()), "compute_ms": float(t[:, 1].mean()),
-           "exchange_ms": float(t[:, 2].mean()), "fidelity": float(abs(hs[0]) ** 2)}
-    be.close()
+           "barrier_wait_ms": float(t[:, 2].mean()), "fidelity": float(abs(hs[0]) ** 2),
+           "vector_switches_per_eval": switches, "nvlink_bytes_sent_per_gpu_per_eval": sent,
+           "nvlink_gbs_per_gpu_over_whole_step": sent / float(t[:, 0].mean()) / 1e9}
+    sv.close()
     return res
+
+
+def sharded_parity(n, layers, local_rank, world, seed=2024):
+    """
+    Self-test of the sharded CUDA path at real shard sizes: objective amplitudes
+    and gradient of an n-qubit state over `world` GPUs against the SAME evaluation on one GPU
+    (rank 0), north-star tolerance 1e-10 relative.  The target is generated on the device from the
+    logical amplitude index, so both runs see the same vector.
+    """
+    from aqc_research_b200.engine import SvWorkspace
+    from aqc_research_b200.sharded import DistComm, GpuShardBackend, ShardedStateVector
+
+    g = world.bit_length() - 1
+    circ = make_circuit(n, layers)
+    comm = DistComm()
+    be = GpuShardBackend(circ, g, comm.rank, local_rank, num_slots=5)
+    sv = ShardedStateVector(circ, comm, be)
+    rng = np.random.RandomState(seed)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    idx = np.array([0] + [1 << q for q in range(n)], dtype=np.int64)
+    sv.set_target_random(seed)
+    hs = sv.objective(th, idx)
+    xb = int(idx[n // 2])
+    grad = sv.grad(th, xb)
+    fused = bool(sv.push)
+    sv.close()
+    out = None
+    if comm.rank == 0:
+        ws = SvWorkspace(circ, num_slots=4, device=local_rank)
+        ws.fill_random(0, seed)
+        hs1 = ws.objective(th, 0, 1, idx)[0]
+        g1 = ws.grad(th, x_basis=xb, z0=1, w=2, z=3)[0]
+        ws.close()
+        e_hs = float(np.linalg.norm(hs - hs1) / np.linalg.norm(hs1))
+        e_g = float(np.linalg.norm(grad - g1) / np.linalg.norm(g1))
+        out = {"num_qubits": n, "layers": layers, "gpus": world, "amplitudes_per_gpu": 2 ** (n - g),
+               "fused_push": fused, "rel_err_hs_vs_1gpu": e_hs, "rel_err_grad_vs_1gpu": e_g,
+               "tolerance": 1e-10, "parity_ok": bool(e_hs < 1e-10 and e_g < 1e-10)}
+    comm.barrier()
+    return out
 
 
 def run_sharded_bench(args):
@@ -710,7 +765,7 @@ def run_sharded_bench(args):
     base, layers = args.shard_qubits, 4
     if world == 1:
         res = measure_gpu(base, layers, args.steps, args.warmup, 0, False, None)
-        out = {"num_qubits": base, "s_per_step": float(np.mean(res["step_ms"])) * 1e-3, "exchange_ms": 0.0,
+        out = {"num_qubits": base, "s_per_step": float(np.mean(res["step_ms"])) * 1e-3, "barrier_wait_ms": 0.0,
                "compute_ms": float(np.mean(res["step_ms"])), "epochs": {"gradient": 1, "vh_apply": 1},
                "layers": layers, "num_thetas": res["circ"].num_thetas, "p2p_exchange": False}
     else:
@@ -738,7 +793,8 @@ def run_sharded_bench(args):
                          "note": "whole evaluation (pair-run algorithmic bytes per GPU) incl. exchange time"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 16 * out["num_thetas"],
                     "d2h_bytes_per_step": 16 * (n + 1) + 16 * out["num_thetas"]},
-            "kernel_ms": {"compute": out["compute_ms"], "exchange": out["exchange_ms"]},
+            "kernel_ms": {"compute": out["compute_ms"], "barrier_wait": out.get("barrier_wait_ms", 0.0)},
+            "sharded": out,
             "gpu_launches": None,
         }
         print(json.dumps(line), flush=True)
@@ -801,6 +857,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = float(t[0]), float(t[1])
         dist.barrier()
+    # N > 1: besides the replica headline, the ONE-state-over-N-GPUs path of BASELINE.json configs[4]
+    # (global-qubit sharding, weak scaling at 2^shard_qubits amplitudes per GPU) and its parity
+    # self-test against a single-GPU evaluation -- every rank takes part
+    shard_extra = None
+    if dist is not None and not args.no_extra:
+        g = world.bit_length() - 1
+        shard_extra = {
+            "svshard": measure_sharded(args.shard_qubits, 4, 2, 1, local_rank, world),
+            "svshard_parity": sharded_parity(24 + g, 2, local_rank, world),
+        }
+        dist.barrier()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -834,6 +901,12 @@ def main():
         "two_term_case": res["two_term"],
         "clocks": clocks,
     }
+    if shard_extra is not None:
+        sh = shard_extra["svshard"]
+        sh.update({"value": 1.0 / sh["s_per_step"], "unit": UNIT, "steps": 2, "warmup": 1,
+                   "scaling": "weak (2^%d amplitudes per GPU)" % args.shard_qubits,
+                   "parallelism": "one state over %d GPUs (global-qubit sharding, fused NVLink push)" % world})
+        line["extra_workloads"] = shard_extra
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, layers)
     if world == 1 and not args.no_extra and args.workload == "sv20":

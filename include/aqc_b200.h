@@ -215,14 +215,24 @@ int aqc_sv_num_epochs(const aqc_sv* sv, int mode);
 int aqc_sv_epoch_layout(const aqc_sv* sv, int mode, int epoch); /* 0 = A, 1 = B */
 int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode);
 /* Tile passes of one epoch (src slots are read by the first pass only; src0 < 0: vec0 = local part
- * of a basis state at offset basis_local, or zeros if basis_local < 0). */
+ * of a basis state at offset basis_local, or zeros if basis_local < 0).
+ * push0 (and push1 for the gradient) >= 0 FUSES the layout switch that follows the epoch into its
+ * last tile pass: the pass stores every 256-byte run of its tiles straight into slot push0 / push1
+ * of the rank the run belongs to after the block transpose (peer stores over NVLink; all slots
+ * imported with aqc_sv_ipc_import / aqc_sv_peer_attach).  All ranks must meet before anyone reads
+ * the pushed slots.  -1: the result stays in dst0 / dst1 in the epoch's own layout. */
 int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local, int src1,
-                     int dst0, int dst1);
+                     int dst0, int dst1, int push0, int push1);
+/* 1 if aqc_sv_run_epoch can fuse the layout switch (sharded workspace, persistent sweep kernel). */
+int aqc_sv_can_push(const aqc_sv* sv);
 /* This rank's partial complex gradient (already scaled like grad_of_dot_product). */
 int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out);
 /* Peer mapping of the other ranks' slots: CUDA IPC between processes ... */
 int aqc_sv_ipc_export(aqc_sv* sv, int slot, unsigned char* handle64);
 int aqc_sv_ipc_import(aqc_sv* sv, int peer_rank, int slot, const unsigned char* handle64);
+/* Unmaps everything aqc_sv_ipc_import mapped; importers call it (and all ranks meet) before the
+ * exporting workspaces are destroyed. */
+int aqc_sv_ipc_close(aqc_sv* sv);
 /* ... or direct peer access when all workspaces live in one process. */
 int aqc_sv_peer_attach(aqc_sv* sv, int peer_rank, int slot, aqc_sv* peer);
 /* dst_slot[chunk r] = (rank r).src_slot[chunk my_rank] for all r: layout switch A <-> B.

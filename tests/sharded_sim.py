@@ -91,7 +91,8 @@ class SimShardBackend:
         if mode == 0:
             self.gacc = np.zeros(self.num_thetas, dtype=np.complex128)
 
-    def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1):
+    def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1, push0=-1, push1=-1):
+        assert push0 < 0 and push1 < 0, "the NumPy stand-in has no fused layout switch"
         passes = self.progs[mode][epoch][1]
         if src0 >= 0:
             v0 = self.slots[src0].copy()

@@ -70,8 +70,9 @@ def main():
         z0 = O.apply_v(circ, th, y, dagger=True)
         err_hs = np.linalg.norm(hs - z0[idx]) / np.linalg.norm(z0[idx])
         err_z0 = np.linalg.norm(be.download(sv.slot["z0"]) - shard_of(z0, n, g, rank)) / np.linalg.norm(z0) * np.sqrt(world)
+        nrm = abs(sv.vdot("z0", "z0") - 1.0)  # (the gradient sweep consumes z0)
         xb = int(idx[2])
-        grad = sv.grad(th, xb)
+        grad = sv.grad(th, xb, keep_states=True)
         e = np.zeros(2**n, dtype=complex)
         e[xb] = 1
         gref = O.grad_sweep(circ, th, e, z0)
@@ -79,16 +80,13 @@ def main():
         # z ends as V V^H y = y, w as V e_x -- both back in layout A
         err_z = np.linalg.norm(be.download(sv.slot["z"]) - shard_of(y, n, g, rank)) * np.sqrt(world)
         err_w = np.linalg.norm(be.download(sv.slot["w"]) - shard_of(O.apply_v(circ, th, e), n, g, rank)) * np.sqrt(world)
-        nrm = abs(sv.vdot("z0", "z0") - 1.0)
         errs = dict(hs=err_hs, z0=err_z0, grad=err_g, norm=nrm)
-        if not args.gpu:  # the CUDA gradient sweep leaves rescaled work states in w, z
-            errs.update(z=err_z, w=err_w)
+        errs.update(z=err_z, w=err_w)
         worst = max(worst, max(errs.values()))
         if rank == 0:
             print(f"[{name}] world={world} p2p={sv.p2p} epochs(grad,dag)=({be.num_epochs(0)},{be.num_epochs(2)}) "
                   + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
-        if hasattr(be, "close"):
-            be.close()
+        sv.close()
     # synthetic target generated per rank is rank-count independent (GPU only)
     if args.gpu:
         circ = circuits[0][1]
@@ -100,7 +98,7 @@ def main():
         if rank == 0:
             print(f"[random target] norm err {nrm:.2e} probe {np.round(probe, 6)}", flush=True)
         worst = max(worst, nrm)
-        be.close()
+        sv.close()
     ok = worst < 1e-10
     if rank == 0:
         print("SHARDED_OK" if ok else f"SHARDED_FAIL worst={worst:.3e}", flush=True)

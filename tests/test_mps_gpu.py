@@ -247,6 +247,153 @@ def test_full_size_properties_n50():
     ws.close()
 
 
+def _pair_runs(circ):
+    """Upper bound of the SVD splits one sweep of one state makes (one per pair-run of the program)."""
+    return circ.num_blocks + getattr(circ, "half_layer_num_blocks", 0)
+
+
+@pytest.mark.parametrize("n,evol_time", [(12, 2.5), (14, 2.0)])
+def test_truncated_results_within_the_discarded_weight_bound(n, evol_time):
+    """
+    trunc_thr = 1e-6 (the production setting, user_options.py:55; BASELINE config 4) against the EXACT
+    state-vector oracle, with a bound stated in the weight the splits discarded:
+    a split that drops the weight eps_k moves the (renormalised) state by at most sqrt(2 eps_k), so
+    after K splits  ||z_trunc - z_exact|| <= sum_k sqrt(2 eps_k) <= sqrt(2 K W),  W = sum_k eps_k
+    (``truncation_stats``), K <= pair-runs of the circuit.  hs_i = <s_i|z0> and every gradient entry
+    0.5j <P w|z> inherit the bound (|P| = 1, unit vectors).  The physical target (Trotter-evolved Neel
+    state, 10x finer steps) really is truncated at these evolution times: W > 0 is asserted.
+    """
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trotop
+
+    rng = np.random.RandomState(n)
+    layers = 3
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    fine = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 10 * layers), True)
+    th_f = trotop.init_ansatz_to_trotter(fine, np.zeros(fine.num_thetas), evol_time=evol_time, delta=1.0)
+    th = trotop.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=evol_time, delta=1.0)
+    th = th + 0.05 * (2 * rng.rand(circ.num_thetas) - 1)
+    neel = sum(1 << q for q in range(0, n, 2))
+    e = np.zeros(2**n, dtype=complex)
+    e[neel] = 1
+    # target: the Trotter-evolved Neel state, compressed once on the host to bonds <= 64; the dense
+    # vector of THAT MPS is the exact target of this test
+    y = M.mps_to_vector(M.vector_to_mps(O.apply_v(fine, th_f, e), chop=1e-7))
+    y /= np.linalg.norm(y)
+    mps_y = M.vector_to_mps(y, chop=1e-13)
+    assert max(M.bond_dims(mps_y)) <= 64
+    ws = MpsWorkspace(circ, num_slots=4, chi_max=64, trunc_thr=1e-6)
+    ws.upload(0, mps_y)
+    idx = np.array([neel] + [neel ^ (1 << q) for q in range(n)], dtype=np.int64)
+    hs = np.ravel(ws.objective(th, 0, 1, idx))
+    st_o = ws.truncation_stats()
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    K = _pair_runs(circ)
+    bound_o = np.sqrt(2.0 * K * st_o["discarded_weight"]) + 1e-12
+    assert st_o["cap_hits"] == 0 and st_o["max_discarded"] < 1e-6  # the trunc_thr rule alone was at work
+    assert np.max(np.abs(hs - z0[idx])) <= bound_o, (np.max(np.abs(hs - z0[idx])), bound_o, st_o)
+    assert abs(ws.dot(1, 1) - 1) < 1e-9  # every split renormalises
+    g = ws.grad(th, x_basis=neel, z0=1, w=2, z=3)
+    st_g = ws.truncation_stats()
+    g_ref = O.grad_sweep(circ, th, e, z0)
+    # z starts from the truncated z0 and both swept states are truncated again
+    bound_g = bound_o + np.sqrt(2.0 * 2 * K * st_g["discarded_weight"]) + 1e-12
+    assert np.max(np.abs(g - g_ref)) <= bound_g, (np.max(np.abs(g - g_ref)), bound_g, st_g)
+    assert st_o["discarded_weight"] + st_g["discarded_weight"] > 0  # the case does truncate
+    # the bound is a meaningful one (well below the size of the results, max |g| ~ 0.6) and the actual
+    # deviation is what trunc_thr = 1e-6 suggests (the gate-by-gate CPU rule gives ~5e-3 in the state)
+    print(f"[mps trunc n={n}] max|dhs|={np.max(np.abs(hs - z0[idx])):.2e} (bound {bound_o:.2e}) "
+          f"max|dg|={np.max(np.abs(g - g_ref)):.2e} (bound {bound_g:.2e}) {st_o} {st_g}")
+    assert bound_g < 0.5 and np.max(np.abs(g - g_ref)) < 2e-2 and np.max(np.abs(hs - z0[idx])) < 2e-2
+    ws.close()
+
+
+def test_bond_cap_is_reported_not_silent():
+    """
+    chi_max is a deviation from the reference (qiskit-aer has no cap): when the cap -- not
+    trunc_thr -- removes weight, the statistics say so and the no-truncation helpers raise.
+    """
+    from aqc_research_b200 import mps_operations as mpsop
+    from aqc_research_b200.mps_engine import BondCapacityError
+
+    n = 10
+    rng = np.random.RandomState(3)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 3), True)
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)  # random angles: bonds grow to 2^5 = 32
+    ws = MpsWorkspace(circ, num_slots=2, chi_max=8, trunc_thr=1e-16)
+    ws.set_product(0, 0)
+    ws.apply(th, 0, 1)
+    st = ws.truncation_stats()
+    assert st["cap_hits"] > 0 and st["cap_discarded"] > 1e-6 and st["discarded_weight"] >= st["cap_discarded"]
+    with pytest.raises(BondCapacityError):
+        ws.check_cap("test")
+    ws.close()
+    ws = MpsWorkspace(circ, num_slots=2, chi_max=32, trunc_thr=1e-16)
+    ws.set_product(0, 0)
+    ws.apply(th, 0, 1)
+    st = ws.truncation_stats()
+    assert st["cap_hits"] == 0 and st["discarded_weight"] < 1e-12
+    ws.check_cap("test")
+    ws.close()
+    with pytest.raises(BondCapacityError):
+        mpsop.v_mul_mps(circ, th, M.product_state(n, 0), chi_max=8)
+
+
+def test_saturated_n50_gradient_is_consistent_with_the_truncated_overlap():
+    """
+    n = 50, chi_max = 64, depth 20, trunc_thr = 1e-6 in the regime where bonds DO saturate (VERDICT r01
+    weak #3: the bench workload).  No exact answer exists at this size; what can be checked is that the
+    gradient is the derivative of the overlap the same truncated machinery computes: central finite
+    differences of hs_0(theta) = <x|V^H(theta) y>_trunc, with a tolerance stated in the discarded weight.
+    ||z0|| and the truncation record are printed (bench.py reports them for the timed workload).
+    Two regimes: a physical one (Trotter-evolved target, evolution time 3: bonds reach the cap mildly)
+    where the agreement is tight, and random angles (every bond saturates, large discarded weight) where
+    only the bound -- then O(1) -- and finiteness can be asserted.
+    """
+    from aqc_research_b200.model_sp_lhs.trotter import trotter as trotop
+
+    n, layers = 50, 20
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    K = _pair_runs(circ)
+    neel = sum(1 << q for q in range(0, n, 2))
+    idx = np.array([neel], dtype=np.int64)
+    rng = np.random.RandomState(5050)
+    for regime in ("physical", "random"):
+        if regime == "physical":
+            th_t = trotop.init_ansatz_to_trotter(circ, np.zeros(circ.num_thetas), evol_time=3.0, delta=1.0)
+            th = th_t + 0.01 * (2 * rng.rand(circ.num_thetas) - 1)
+        else:
+            th_t = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+            th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+        ws = MpsWorkspace(circ, num_slots=4, chi_max=64, trunc_thr=1e-6)
+        ws.set_product(0, neel)
+        ws.apply(th_t, 0, 0)  # target
+        st_t = ws.truncation_stats()
+        hs = np.ravel(ws.objective(th, 0, 1, idx))
+        st_o = ws.truncation_stats()
+        z0_norm = abs(ws.dot(1, 1))
+        g = ws.grad(th, x_basis=neel, z0=1, w=2, z=3)
+        st_g = ws.truncation_stats()
+        assert np.all(np.isfinite(g)) and np.isfinite(hs[0]) and abs(z0_norm - 1) < 1e-6
+        W = st_o["discarded_weight"] + st_g["discarded_weight"]
+        bound = np.sqrt(2.0 * 3 * K * W)
+        worst = 0.0
+        for k in (2, 3 * n + 4 * 57 + 1, circ.num_thetas - 2):
+            vals = []
+            for sgn in (+1, -1):
+                t2 = th.copy()
+                t2[k] += sgn * 1e-3
+                vals.append(np.ravel(ws.objective(t2, 0, 1, idx))[0])
+            fd = (vals[0] - vals[1]) / 2e-3  # d<x|V^H y>/dtheta_k = d<V x|y>/dtheta_k
+            worst = max(worst, abs(fd - g[k]))
+        print(f"[mps n=50 {regime}] |hs0|^2={abs(hs[0])**2:.4f} ||z0||={z0_norm:.9f} target trunc {st_t} "
+              f"objective trunc {st_o} gradient trunc {st_g} max|fd-g|={worst:.3e} bound={bound:.3e}")
+        # finite differences of a truncated overlap carry the truncation noise divided by the step
+        assert worst <= bound / 1e-3 + 1e-5, (regime, worst, bound)
+        if regime == "physical":
+            assert abs(hs[0]) ** 2 > 0.3 and worst < 1e-3 * max(1.0, np.max(np.abs(g))), (worst, hs)
+        ws.close()
+
+
 def test_set_product_site_and_fused_two_term_sweep():
     """
     aqc_mps_set_product_site: a product state with one qubit in superposition; one gradient sweep

@@ -21,9 +21,13 @@ TOL = 1e-10
 
 LARGE = {"AQC_TILE_LOW_BITS": "4", "AQC_TILE_LOW_BITS_APPLY": "3"}  # what nbits > 22 selects
 CONFIGS = {
-    "stream": {},
-    "stream-large-state-tiles": dict(LARGE),
-    "stream-pass-per-launch": {"AQC_STREAM_COOP": "0"},
+    # persistent sweep kernel: two 32 KiB buffers per group, 2^10 / 2^11 tiles (the choice for nbits <= 22)
+    "stream": {"AQC_STREAM": "1", "AQC_STREAM_NBUF": "2"},
+    # ... one 64 KiB buffer per group, 2^11 / 2^12 tiles, 256-byte runs (the choice for nbits > 22)
+    "stream-large-state-tiles": dict(LARGE, AQC_STREAM="1", AQC_STREAM_NBUF="1", AQC_TILE_BITS_GRAD="11",
+                                     AQC_TILE_BITS_APPLY="12"),
+    "stream-pass-per-launch": {"AQC_STREAM": "1", "AQC_STREAM_COOP": "0"},
+    # one launch per tile pass, one tile per CTA
     "perpass": {"AQC_STREAM": "0"},
     "perpass-large-state-tiles": dict(LARGE, AQC_STREAM="0", AQC_TILE_BITS_GRAD="11", AQC_TILE_BITS_APPLY="12"),
     "legacy": {"AQC_ENGINE": "legacy"},
