@@ -209,109 +209,156 @@ static bool build_dense_tables(const Program& prog, DenseTables& T, int fuse_pai
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage matrices: one thread per (stage, column) applies the stage's gates to a unit vector with
-// the register-level gate functions of aqc_gates.cuh and writes the column in DMMA A-fragment order
-//   umat[(batch * nstages + stage) * 64 + f * 32 + lane],  lane = c * 4 + k,  c = reim | amp << 1:
-//   f = 0: coefficient of re(x_k) in output component c;  f = 1: coefficient of im(x_k).
+// Prologue and epilogue of a sweep (one small launch each, no host copies in between):
+//   sweep_prologue_kernel : stage matrices U_s(theta) of one program straight from the angles (the host
+//                           writes them into pinned, device-mapped memory -- no H2D copy, no (cos, sin)
+//                           table), and the zeroing of the gradient accumulators;
+//   grad_epilogue_kernel  : per-rotation inner products from the accumulated stage matrices
+//                           (see dense_grad_kernel), the 0.5 / 0.5j / -i factors of the reference
+//                           (core_operations.py:317-351, 972-975) and the write of the finished complex
+//                           gradient into pinned host memory by the last CTA that completes.
 // ------------------------------------------------------------------------------------------------
+template <int ENT, bool DAG, int NVEC>
+__device__ __forceinline__ void unit_from_theta(const UnitDesc& u, const double* __restrict__ th, cd (&a)[NVEC][4],
+                                                double* acc) {
+  const bool front = u.kind == U_FRONT_LO || u.kind == U_FRONT_HI;
+  const int np = front ? 3 : (ENT == AQC_ENT_CP ? 5 : 4);
+  double2 tr[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k < np) {
+      const double t = th[u.theta + k];
+      double s, c;
+      sincos(k == 4 ? t : 0.5 * t, &s, &c);  // full angle for the CPhase parameter
+      tr[k] = make_double2(c, s);
+    }
+  }
+  switch (u.kind) {
+    case U_FRONT_LO: front_unit<NVEC, false, DAG>(a, tr, acc); break;
+    case U_FRONT_HI: front_unit<NVEC, true, DAG>(a, tr, acc); break;
+    case U_BLOCK_CHI: block_unit<NVEC, ENT, true, DAG>(a, tr, u.flags, acc); break;
+    case U_BLOCK_CLO: block_unit<NVEC, ENT, false, DAG>(a, tr, u.flags, acc); break;
+    default: break;
+  }
+}
+
+struct PrologueArgs {
+  const StageDesc* stages;
+  int nstages, nthetas, batch;
+  const double* thetas;  // [batch][nthetas], pinned host memory mapped into the device address space
+  double* umat;          // [batch][nstages][64]
+  double* zero0;         // two arrays to clear (stage-matrix sums, per-angle sums); may be null
+  long long nzero0;
+  double* zero1;
+  long long nzero1;
+};
+
 template <int ENT, bool DAG>
-__device__ __forceinline__ void dense_run_units(const StageDesc& sd, const double2* __restrict__ trig,
-                                                cd (&a)[1][4]) {
-  for (int u = 0; u < sd.nunits; ++u) {
-    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
-    const double2* tr = trig + sd.u[u].theta;
-    switch (kind) {
-      case U_FRONT_LO: front_unit<1, false, DAG>(a, tr, nullptr); break;
-      case U_FRONT_HI: front_unit<1, true, DAG>(a, tr, nullptr); break;
-      case U_BLOCK_CHI: block_unit<1, ENT, true, DAG>(a, tr, flags, nullptr); break;
-      case U_BLOCK_CLO: block_unit<1, ENT, false, DAG>(a, tr, flags, nullptr); break;
-      default: break;
+__global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
+  for (long long i = gt; i < A.nzero1; i += gsz) A.zero1[i] = 0.0;
+  for (long long t = gt; t < (long long)A.batch * A.nstages * 4; t += gsz) {
+    const int k = (int)(t & 3), s = (int)((t >> 2) % A.nstages), b = (int)((t >> 2) / A.nstages);
+    const StageDesc sd = A.stages[s];
+    const double* th = A.thetas + (size_t)b * A.nthetas;
+    cd a[1][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
+    for (int u = 0; u < sd.nunits; ++u) unit_from_theta<ENT, DAG, 1>(sd.u[u], th, a, nullptr);
+    double* um = A.umat + ((size_t)b * A.nstages + s) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]; DMMA A-fragment order (see dense_umat_kernel)
+      um[(2 * i) * 4 + k] = a[0][i].x;
+      um[32 + (2 * i) * 4 + k] = -a[0][i].y;
+      um[(2 * i + 1) * 4 + k] = a[0][i].y;
+      um[32 + (2 * i + 1) * 4 + k] = a[0][i].x;
     }
   }
 }
 
-template <int ENT, bool DAG>
-__global__ void __launch_bounds__(128) dense_umat_kernel(const StageDesc* __restrict__ stages,
-                                                         int nstages, const double2* __restrict__ trig,
-                                                         int nthetas, double* __restrict__ umat) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nstages * 4) return;
-  const int s = t >> 2, k = t & 3, b = blockIdx.y;
-  const StageDesc sd = stages[s];
-  cd a[1][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
-  dense_run_units<ENT, DAG>(sd, trig + (size_t)b * nthetas, a);
-  double* um = umat + ((size_t)b * nstages + s) * 64;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]
-    um[(2 * i) * 4 + k] = a[0][i].x;
-    um[32 + (2 * i) * 4 + k] = -a[0][i].y;
-    um[(2 * i + 1) * 4 + k] = a[0][i].y;
-    um[32 + (2 * i + 1) * 4 + k] = a[0][i].x;
-  }
-}
+struct EpilogueArgs {
+  const StageDesc* stages;
+  int nstages, nthetas, batch, n3, tpb;
+  const double* thetas;
+  const double* gm;        // [batch][nstages][64] accumulated stage matrices
+  double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
+  double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
+  unsigned* ticket;        // completion counter (left at zero)
+};
 
-// ------------------------------------------------------------------------------------------------
-// post-processing: raw per-rotation inner products from the stage matrices M_out.
-// One thread per (stage, virtual quadruple r): w' = e_r, z' = M_out[:, r] (sum_r z'_r w'_r^H = M_out);
-// pull both back through the stage (daggered units in reverse order), then run the stage forward
-// with the reference's gate-by-gate accumulation.  Output format = pass_kernel's raw sums.
-// ------------------------------------------------------------------------------------------------
 template <int ENT>
-__global__ void __launch_bounds__(128) dense_grad_kernel(const StageDesc* __restrict__ stages,
-                                                         int nstages, const double2* __restrict__ trig,
-                                                         int nthetas, const double* __restrict__ gm,
-                                                         double* __restrict__ gacc) {
+__global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
+  __shared__ int s_last;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nstages * 4) return;
-  const int s = t >> 2, r = t & 3, b = blockIdx.y;
-  const StageDesc sd = stages[s];
-  const double2* tg = trig + (size_t)b * nthetas;
-  // M[i][r] = sum z_i conj(w_r): entry (i, r) at [(i << 3) | r] (real part) and [(i << 3) | 4 | r]
-  const double* Mq = gm + ((size_t)b * nstages + s) * 64;
-  cd a[2][4];
+  if (t < A.batch * A.nstages * 4) {
+    const int r = t & 3, s = (t >> 2) % A.nstages, b = (t >> 2) / A.nstages;
+    const StageDesc sd = A.stages[s];
+    const double* th = A.thetas + (size_t)b * A.nthetas;
+    const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
+    // virtual quadruple r: w' = e_r, z' = M_out[:, r]; pull both back through the stage, then run it
+    // forward with the reference's gate-by-gate accumulation (dense_grad_kernel)
+    cd a[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
-    a[1][i].x = Mq[(i << 3) | r];
-    a[1][i].y = Mq[(i << 3) | 4 | r];
-  }
-  constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
-  double dummy[NACC];
-#pragma unroll
-  for (int k = 0; k < NACC; ++k) dummy[k] = 0.0;
-  for (int u = sd.nunits - 1; u >= 0; --u) {
-    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
-    const double2* tr = tg + sd.u[u].theta;
-    switch (kind) {
-      case U_FRONT_LO: front_unit<2, false, true>(a, tr, dummy); break;
-      case U_FRONT_HI: front_unit<2, true, true>(a, tr, dummy); break;
-      case U_BLOCK_CHI: block_unit<2, ENT, true, true>(a, tr, flags, dummy); break;
-      case U_BLOCK_CLO: block_unit<2, ENT, false, true>(a, tr, flags, dummy); break;
-      default: break;
+    for (int i = 0; i < 4; ++i) {
+      a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
+      a[1][i].x = Mq[(i << 3) | r];
+      a[1][i].y = Mq[(i << 3) | 4 | r];
     }
-  }
-  double* g = gacc + (size_t)b * nthetas * 2;
-  for (int u = 0; u < sd.nunits; ++u) {
-    const int kind = sd.u[u].kind, flags = sd.u[u].flags;
-    const double2* tr = tg + sd.u[u].theta;
+    constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    int nval = (ENT == AQC_ENT_CP) ? 10 : 8;
-    switch (kind) {
-      case U_FRONT_LO: front_unit<2, false, false>(a, tr, acc); nval = 6; break;
-      case U_FRONT_HI: front_unit<2, true, false>(a, tr, acc); nval = 6; break;
-      case U_BLOCK_CHI: block_unit<2, ENT, true, false>(a, tr, flags, acc); break;
-      case U_BLOCK_CLO: block_unit<2, ENT, false, false>(a, tr, flags, acc); break;
-      default: nval = 0; break;
-    }
-    double* gu = g + 2 * (size_t)sd.u[u].theta;
+    for (int u = sd.nunits - 1; u >= 0; --u) unit_from_theta<ENT, true, 2>(sd.u[u], th, a, acc);
+    double* g = A.gacc + (size_t)b * A.nthetas * 2;
+    for (int u = 0; u < sd.nunits; ++u) {
 #pragma unroll
-    for (int k = 0; k < NACC; ++k)
-      if (k < nval) atomicAdd(gu + k, acc[k]);
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      unit_from_theta<ENT, false, 2>(sd.u[u], th, a, acc);
+      const int kind = sd.u[u].kind;
+      const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
+      double* gu = g + 2 * (size_t)sd.u[u].theta;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k)
+        if (k < nval) atomicAdd(gu + k, acc[k]);
+    }
   }
+  // the CTA that finishes last converts the raw sums and hands the gradient to the host
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int total = A.batch * A.nthetas;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k = i % A.nthetas;
+    const double re = __ldcg(A.gacc + 2 * (size_t)i), im = __ldcg(A.gacc + 2 * (size_t)i + 1);
+    int kind;  // 0: Ry (0.5), 1: Rz / Rx (0.5j), 2: CPhase (-i)
+    if (k < A.n3)
+      kind = (k % 3 == 1) ? 0 : 1;
+    else {
+      const int q = (k - A.n3) % A.tpb;
+      kind = (q == 4) ? 2 : ((q == 0 || q == 2) ? 0 : 1);
+    }
+    double2 v;
+    if (kind == 0)
+      v = make_double2(0.5 * re, 0.5 * im);
+    else if (kind == 1)
+      v = make_double2(-0.5 * im, 0.5 * re);
+    else
+      v = make_double2(im, -re);
+    reinterpret_cast<double2*>(A.out)[i] = v;
+  }
+  if (threadIdx.x == 0) *A.ticket = 0u;
+}
+
+// hs[b][i] = v[b][idx[i]] written straight into pinned host memory
+__global__ void gather_out_kernel(const double2* __restrict__ v, long long stride, const long long* __restrict__ idx,
+                                  int count, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[(size_t)blockIdx.y * count + i] = v[(long long)blockIdx.y * stride + idx[i]];
 }
 
 // ------------------------------------------------------------------------------------------------

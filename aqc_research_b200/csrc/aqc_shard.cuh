@@ -48,7 +48,7 @@ extern "C" int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode) {
 // last pass -- the pass stores its tiles straight into slot push0 / push1 of the rank each 256-byte
 // run belongs to after the block transpose (peer stores over NVLink, buffers mapped with
 // aqc_sv_ipc_import); dst then only holds intermediate results.  The caller makes all ranks meet
-// (host barrier) before anyone reads the pushed slots.  Needs the persistent sweep kernel.
+// (host barrier) before anyone reads the pushed slots.
 extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local,
                                 int src1, int dst0, int dst1, int push0, int push1) {
   if (!sv || mode < 0 || mode > 2) return fail(AQC_EINVAL, "bad arguments");
@@ -63,8 +63,8 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
   }
   if (src0 < 0 && mode != 0) return fail(AQC_EINVAL, "basis source is only valid for the gradient");
   if (push0 >= 0) {
-    if (sv->g <= 0 || !sv->dense || !sv->use_stream)
-      return fail(AQC_EINVAL, "the fused layout switch needs a sharded workspace and the persistent sweep kernel");
+    if (sv->g <= 0 || !sv->dense)
+      return fail(AQC_EINVAL, "the fused layout switch needs a sharded workspace on the dense engine");
     if ((rc = check_slot(sv, push0))) return rc;
     if (mode == 0 && (rc = check_slot(sv, push1))) return rc;
     if (push0 == dst0 || push0 == src0 || (mode == 0 && (push1 == dst1 || push1 == dst0 || push0 == dst1 ||
@@ -92,7 +92,7 @@ extern "C" int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64
 }
 
 // 1 if this workspace can fuse the layout switch into the last pass of an epoch (aqc_sv_run_epoch).
-extern "C" int aqc_sv_can_push(const aqc_sv* sv) { return (sv && sv->g > 0 && sv->dense && sv->use_stream) ? 1 : 0; }
+extern "C" int aqc_sv_can_push(const aqc_sv* sv) { return (sv && sv->g > 0 && sv->dense) ? 1 : 0; }
 
 // Downloads this workspace's (partial) raw inner products and converts them to 0.5j <P w|z>
 // (linear, so partial sums of several ranks may be added afterwards).

@@ -75,7 +75,6 @@ extern "C" int aqc_device_count(void) {
 #include "aqc_program.h"
 #include "aqc_legacy.cuh"
 #include "aqc_dense.cuh"
-#include "aqc_stream.cuh"
 #include "aqc_cd.cuh"
 #include "aqc_sketch.cuh"
 #include "aqc_small.cuh"
@@ -111,12 +110,6 @@ struct aqc_sv {
   Program prog_grad, prog_fwd, prog_dag;
   // dense-stage engine (aqc_dense.cuh): DMMA sweeps; the default whenever the tile has >= 5 bits
   bool dense = false;
-  // persistent warp-specialised sweep kernel (aqc_stream.cuh): one cooperative launch per pass range
-  bool use_stream = false;
-  int stream_nbuf = 2;                      // tile buffers per compute group (see aqc_stream.cuh)
-  int stream_grid = 1;                      // CTAs of every stream launch of this workspace
-  unsigned long long* d_gridbar = nullptr;  // grid-barrier arrival counter
-  double2* d_one = nullptr;                 // the constant (1, 0): amplitude of a basis start vector
   bool grad_pending = false;  // aqc_sv_grad_begin enqueued, results not collected yet
   int num_sms = 148;
   DenseTables dt_grad, dt_fwd, dt_dag;
@@ -336,69 +329,6 @@ static int dense_collect(aqc_sv* sv) {
   return AQC_OK;
 }
 
-// One cooperative launch of the persistent sweep kernel for the passes [pass_begin, pass_end).
-// AQC_STREAM_COOP=0 launches pass by pass instead (no grid barrier inside; for per-pass profiling).
-static int launch_stream(aqc_sv* sv, int mode, const Program& prog, const DenseTables& dt, const double2* src0,
-                         long long basis, const double2* src1, double2* dst0, double2* dst1, int pass_begin,
-                         int pass_end, int push0 = -1, int push1 = -1) {
-  const bool coop = env_int("AQC_STREAM_COOP", 1) != 0;
-  static bool configured[16] = {false};
-  if (!configured[sv->device & 15]) {
-    CU(cudaFuncSetAttribute(dense_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    CU(cudaFuncSetAttribute(dense_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
-    configured[sv->device & 15] = true;
-  }
-  StreamArgs a;
-  memset(&a, 0, sizeof(a));
-  a.passes = prog.d_passes;
-  a.batch = sv->batch;
-  a.nstages_total = (int)prog.stages.size();
-  a.vec_stride = sv->size;
-  a.lanes = dt.d_lanes;
-  a.umat = sv->d_umat;
-  a.gm = sv->d_gm;
-  a.grid_bar = sv->d_gridbar;
-  a.nbuf = sv->stream_nbuf;
-  a.dst[0] = dst0;
-  a.dst[1] = dst1;
-  const int step = coop ? (pass_end - pass_begin) : 1;
-  for (int p0 = pass_begin; p0 < pass_end; p0 += step) {
-    a.pass_begin = p0;
-    a.pass_end = std::min(pass_end, p0 + step);
-    const bool first = p0 == pass_begin;
-    a.src[0] = first ? src0 : dst0;
-    a.src[1] = first ? src1 : dst1;
-    a.xchg_world = 0;
-    if (push0 >= 0 && a.pass_end == pass_end) {  // the launch that holds the last pass pushes its result
-      a.xchg_world = 1 << sv->g;
-      a.xchg_rank = sv->rank;
-      a.xchg_shift = sv->nbits - sv->g;
-      for (int r = 0; r < a.xchg_world; ++r) {
-        a.xdst[0][r] = r == sv->rank ? sv->slots[push0] : const_cast<double2*>(sv->peer[push0][r]);
-        a.xdst[1][r] = mode != 0 ? nullptr
-                                 : (r == sv->rank ? sv->slots[push1] : const_cast<double2*>(sv->peer[push1][r]));
-        if (!a.xdst[0][r] || (mode == 0 && !a.xdst[1][r]))
-          return fail(AQC_EINVAL, "peer %d: destination slot was not imported", r);
-      }
-    }
-    a.xcount = 0;
-    if (first && basis >= 0) {
-      a.xcount = 1;
-      a.xindex[0] = basis;
-      a.xamp = sv->d_one;
-    }
-    void* params[] = {(void*)&a};
-    const void* fn = mode == 0 ? (const void*)dense_stream_kernel<2> : (const void*)dense_stream_kernel<1>;
-    if (a.pass_end - a.pass_begin > 1)
-      CU(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sv->stream_grid), dim3(kSThreads), params, kSSmemBytes,
-                                     sv->stream));
-    else
-      CU(cudaLaunchKernel(fn, dim3((unsigned)sv->stream_grid), dim3(kSThreads), params, kSSmemBytes, sv->stream));
-    sv->last_launches += 1;
-  }
-  return AQC_OK;
-}
-
 // passes [pass_begin, pass_end) of a program on the dense engine; mode 0: (w, z), else one vector
 static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long long basis,
                              const double2* src1, double2* dst0, double2* dst1, int pass_begin,
@@ -413,9 +343,6 @@ static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long lon
   a.gm = sv->d_gm;
   a.nstages_total = (int)prog.stages.size();
   if (pass_end < 0) pass_end = (int)prog.passes.size();
-  if (sv->use_stream)
-    return launch_stream(sv, mode, prog, dt, src0, basis, src1, dst0, dst1, pass_begin, pass_end, push0, push1);
-  if (push0 >= 0) return fail(AQC_EINVAL, "the fused layout switch needs the persistent sweep kernel (AQC_STREAM=1)");
   for (int i = pass_begin; i < pass_end; ++i) {
     a.pd = prog.passes[i];
     a.src[0] = (i == pass_begin) ? src0 : dst0;
@@ -423,6 +350,19 @@ static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long lon
     a.dst[0] = dst0;
     a.dst[1] = dst1;
     a.basis_index = (i == pass_begin) ? basis : -1;
+    a.xchg_world = 0;
+    if (push0 >= 0 && i + 1 == pass_end) {  // the last pass of the range delivers its result to the peers
+      a.xchg_world = 1 << sv->g;
+      a.xchg_rank = sv->rank;
+      a.xchg_shift = sv->nbits - sv->g;
+      for (int r = 0; r < a.xchg_world; ++r) {
+        a.xdst[0][r] = r == sv->rank ? sv->slots[push0] : const_cast<double2*>(sv->peer[push0][r]);
+        a.xdst[1][r] = mode != 0 ? nullptr
+                                 : (r == sv->rank ? sv->slots[push1] : const_cast<double2*>(sv->peer[push1][r]));
+        if (!a.xdst[0][r] || (mode == 0 && !a.xdst[1][r]))
+          return fail(AQC_EINVAL, "peer %d: destination slot was not imported", r);
+      }
+    }
     const int rc = mode == 0 ? launch_dense_pass<2>(sv, a) : launch_dense_pass<1>(sv, a);
     if (rc) return rc;
     sv->last_launches += 1;
@@ -510,7 +450,7 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   for (void* q : {(void*)sv->d_cd_units, (void*)sv->d_cd_fobj, (void*)sv->d_target, (void*)sv->d_gram,
                   (void*)sv->d_rinv, (void*)sv->d_info})
     if (q) cudaFree(q);
-  for (void* q : {(void*)sv->d_gridbar, (void*)sv->d_one, (void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
+  for (void* q : {(void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
                   (void*)sv->dt_dag.d_lanes})
     if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
@@ -591,22 +531,15 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMalloc(&sv->d_ticket, sizeof(unsigned)));
   CUB(cudaMemset(sv->d_ticket, 0, sizeof(unsigned)));
 #undef CUB
-  // Tile shape.  States beyond the L2 (> 64 MiB) want 256-byte contiguous runs (4 low bits); L2-resident
-  // states (nbits <= 22) spend the low bits on gate qubits instead (fewer passes).  The persistent sweep
-  // kernel (aqc_stream.cuh, AQC_STREAM=1, default) works on 32 KiB tile buffers: 2^10 amplitudes of
-  // (w, z) or 2^11 of one vector; the pass-per-launch kernel (AQC_STREAM=0) takes one tile per CTA and
-  // prefers larger tiles for large states.
-  const bool want_stream = env_int("AQC_STREAM", 1) != 0;
+  // Tile shape.  States beyond the L2 (> 64 MiB) want 256-byte contiguous runs (4 low bits) and the
+  // largest tile; L2-resident states (nbits <= 22) have too few tiles to fill 3 CTAs on each of the
+  // SMs, so they use smaller gradient tiles and spend the low bits on gate qubits instead
+  // (measured at n = 20: 0.42 -> 0.36 ms per evaluation).
   const bool l2_resident = sv->nbits <= 22;
-  // stream kernel: two 32 KiB buffers per compute group (2^10 (w, z) / 2^11 single tiles, double buffered)
-  // for L2-resident states, one 64 KiB buffer (2^11 / 2^12 tiles: fewer passes, 8 iterations per warp and
-  // stage) for the large ones
-  const int nbuf = std::max(1, std::min(2, env_int("AQC_STREAM_NBUF", l2_resident ? 2 : 1)));
-  const int tb_grad_max = want_stream ? (nbuf == 2 ? 10 : 11) : kMaxTileBits - 1;
-  const int tb_apply_max = want_stream ? (nbuf == 2 ? 11 : 12) : kMaxTileBits;
-  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), tb_grad_max);
-  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", l2_resident ? 11 : 12), tb_apply_max);
-  sv->stream_nbuf = nbuf;
+  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), kMaxTileBits - 1);
+  // single-vector sweeps of large states: 2^12-amplitude tiles (64 KiB) with 128-byte runs need fewer
+  // passes (n = 28: 16 -> 13, 47.2 -> 45.5 ms)
+  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", l2_resident ? 11 : 12), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 4);
   const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)
@@ -658,20 +591,10 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     cudaError_t e = cudaMalloc(&sv->d_umat, B * smax * 64 * sizeof(double));
     if (e == cudaSuccess)
       e = cudaMalloc(&sv->d_gm, B * std::max<size_t>(1, sv->prog_grad.stages.size()) * 64 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&sv->d_gridbar, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(sv->d_gridbar, 0, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&sv->d_one, sizeof(double2));
-    const double2 one = make_double2(1.0, 0.0);
-    if (e == cudaSuccess) e = cudaMemcpy(sv->d_one, &one, sizeof(one), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       fail(AQC_ENOMEM, "dense scratch allocation failed: %s", cudaGetErrorString(e));
       return bail(AQC_ENOMEM);
     }
-    sv->use_stream = want_stream;
-    // every stream launch of this workspace uses the same grid (the grid-barrier counter relies on it):
-    // one CTA per SM, fewer if even the finest pass has fewer tiles
-    const long long tiles = ((long long)batch << (sv->nbits - std::min(sv->nbits, std::min(tb_grad, tb_apply))));
-    sv->stream_grid = (int)std::max<long long>(1, std::min<long long>(sv->num_sms, tiles));
   }
   *out = sv;
   return AQC_OK;

@@ -786,11 +786,11 @@ def run_sharded_bench(args):
                        "amplitudes_per_gpu": 2**args.shard_qubits, "parallelism": f"one state over {world} GPUs (global-qubit sharding)",
                        "epochs": out["epochs"], "p2p_exchange": out["p2p_exchange"],
                        "l2": "inputs larger than L2"},
-            "roofline": {"bound": "hbm", "kernel": "dense_pass_kernel<2> (gradient tile pass) + exchange_kernel (NVLink block transpose)",
+            "roofline": {"bound": "hbm", "kernel": "dense_pass_kernel<2> (gradient tile pass; the last pass of every epoch stores its tiles into the peers' HBM over NVLink)",
                          "achieved": 96.0 * 2**n * P * value / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": 96.0 * 2**n * P * value / 1e9 / world / peak, "traffic": None,
                          "peak_source": peak_src,
-                         "note": "whole evaluation (pair-run algorithmic bytes per GPU) incl. exchange time"},
+                         "note": "whole evaluation (pair-run algorithmic bytes per GPU) incl. the layout switches"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 16 * out["num_thetas"],
                     "d2h_bytes_per_step": 16 * (n + 1) + 16 * out["num_thetas"]},
             "kernel_ms": {"compute": out["compute_ms"], "barrier_wait": out.get("barrier_wait_ms", 0.0)},

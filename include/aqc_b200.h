@@ -223,7 +223,7 @@ int aqc_sv_begin(aqc_sv* sv, const double* thetas, int mode);
  * the pushed slots.  -1: the result stays in dst0 / dst1 in the epoch's own layout. */
 int aqc_sv_run_epoch(aqc_sv* sv, int mode, int epoch, int src0, int64_t basis_local, int src1,
                      int dst0, int dst1, int push0, int push1);
-/* 1 if aqc_sv_run_epoch can fuse the layout switch (sharded workspace, persistent sweep kernel). */
+/* 1 if aqc_sv_run_epoch can fuse the layout switch (sharded workspace on the dense engine). */
 int aqc_sv_can_push(const aqc_sv* sv);
 /* This rank's partial complex gradient (already scaled like grad_of_dot_product). */
 int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out);

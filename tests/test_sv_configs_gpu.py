@@ -1,7 +1,7 @@
 """
 GPU parity of EVERY engine / tile configuration against the CPU oracle:
 the configuration a workspace picks depends on the state size (nbits > 22: 4 / 3 forced low bits,
-larger tiles for the pass-per-launch kernel), so the production settings of n >= 23 are forced here
+2^11 / 2^12 tiles), so the production settings of n >= 23 are forced here
 at sizes the oracle finishes in seconds, and n = 24 is compared directly with the C oracle.
 Tolerance 1e-10 relative, norm-wise (north star).
 """
@@ -21,15 +21,10 @@ TOL = 1e-10
 
 LARGE = {"AQC_TILE_LOW_BITS": "4", "AQC_TILE_LOW_BITS_APPLY": "3"}  # what nbits > 22 selects
 CONFIGS = {
-    # persistent sweep kernel: two 32 KiB buffers per group, 2^10 / 2^11 tiles (the choice for nbits <= 22)
-    "stream": {"AQC_STREAM": "1", "AQC_STREAM_NBUF": "2"},
-    # ... one 64 KiB buffer per group, 2^11 / 2^12 tiles, 256-byte runs (the choice for nbits > 22)
-    "stream-large-state-tiles": dict(LARGE, AQC_STREAM="1", AQC_STREAM_NBUF="1", AQC_TILE_BITS_GRAD="11",
-                                     AQC_TILE_BITS_APPLY="12"),
-    "stream-pass-per-launch": {"AQC_STREAM": "1", "AQC_STREAM_COOP": "0"},
-    # one launch per tile pass, one tile per CTA
-    "perpass": {"AQC_STREAM": "0"},
-    "perpass-large-state-tiles": dict(LARGE, AQC_STREAM="0", AQC_TILE_BITS_GRAD="11", AQC_TILE_BITS_APPLY="12"),
+    "default": {},  # what the workspace picks for the state size (nbits <= 22: 2^10 / 2^11 tiles, 2 / 1 low bits)
+    "large-state-tiles": dict(LARGE, AQC_TILE_BITS_GRAD="11", AQC_TILE_BITS_APPLY="12"),
+    "small-tiles": {"AQC_TILE_BITS_GRAD": "8", "AQC_TILE_BITS_APPLY": "9"},  # generic (not unrolled) tile copies
+    "no-fused-steps": {"AQC_DENSE_PAIRS": "0"},
     "legacy": {"AQC_ENGINE": "legacy"},
 }
 
@@ -78,11 +73,8 @@ def test_every_configuration_vs_oracle(cfg, n, monkeypatch):
             _check(ParametricCircuit(n, ent, utils.rand_circuit(n, 14)), n, 200 + len(ent))
 
 
-@pytest.mark.parametrize("cfg", ["stream", "perpass"])
-def test_n24_production_configuration_vs_c_oracle(cfg, monkeypatch):
+def test_n24_production_configuration_vs_c_oracle():
     """n = 24 (> 2^22 amplitudes: the large-state tile configuration chosen by the workspace itself)."""
-    for k, v in CONFIGS[cfg].items():
-        monkeypatch.setenv(k, v)
     C.use_all_cores()
     n = 24
     circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 1), True)
