@@ -362,10 +362,13 @@ class ShardedStateVector:
         """
         rank, off = locate(int(x_basis), self.n, self.g)
         self.be.begin(thetas, MODE_GRAD)
-        # z takes over the slot of z0; z0 gets the old slot of z (content undefined until the next objective)
-        self.slot["z"], self.slot["z0"] = self.slot["z0"], self.slot["z"]
+        # z takes over the slot of z0 and sweeps it in place; the old slot of z joins the free slots, so that
+        # two landing slots exist for the fused layout switches (5 slots in all: n = 34 on 8 GPUs)
+        self.free.append(self.slot["z"])
+        self.slot["z"] = self.slot.pop("z0")
         self._run(MODE_GRAD, (-1, off if rank == self.comm.rank else -1, self.slot["z"]), ["w", "z"],
                   rest_in_layout_a=keep_states)
+        self.slot["z0"] = self.free.pop(0)  # content undefined until the next objective()
         return self.comm.allreduce_sum(self.be.grad_finish(), device=self._dev())
 
     def vdot(self, a: str, b: str) -> complex:

@@ -7,7 +7,6 @@ nvidia-smi -L | tee -a $S
 timeout -k 5 90 python scripts/gpu_smoke.py 6 10 13 > gpurun_out/c5_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $S; tail -2 gpurun_out/c5_smoke.log | tee -a $S
 if ! grep -q "smoke ok" gpurun_out/c5_smoke.log; then echo "smoke failed: stop" | tee -a $S; exit 1; fi
 timeout -k 10 400 python -m pytest tests/test_sharded_gpu.py -x -q -k "two_gpus" > gpurun_out/c5_shard_tests.log 2>&1; echo "sharded tests (push) rc=$?" | tee -a $S; tail -15 gpurun_out/c5_shard_tests.log | tee -a $S
-AQC_SHARD_PUSH=0 timeout -k 10 300 python -m pytest tests/test_sharded_gpu.py -x -q -k "two_gpus and not no-p2p" > gpurun_out/c5_shard_tests_pull.log 2>&1; echo "sharded tests (pull kernel) rc=$?" | tee -a $S; tail -3 gpurun_out/c5_shard_tests_pull.log | tee -a $S
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 timeout -k 10 400 $TR --master-port 29611 bench.py --gpus 2 --steps 10 --warmup 3 --shard-qubits 28 > gpurun_out/c5_bench_2gpu.json 2> gpurun_out/c5_bench_2gpu.err; echo "bench --gpus 2 rc=$?" | tee -a $S
 python - <<'PY' | tee -a $S
@@ -32,4 +31,4 @@ except Exception as ex:
     print("no line", ex)
 PY
 done
-tail -5 gpurun_out/c5_*.err | tail -30
+for f in gpurun_out/c5_*.err; do echo "== $f"; tail -4 $f; done | tail -40

@@ -91,8 +91,38 @@ class SimShardBackend:
         if mode == 0:
             self.gacc = np.zeros(self.num_thetas, dtype=np.complex128)
 
+    # -- emulation of the peer-memory path (enabled by the worker's --sim-push): IPC mapping is a no-op and
+    #    a fused push is the epoch followed by the block transpose into the landing slots, so the slot
+    #    pool / landing-slot logic of the driver runs on the CPU exactly as it does with the CUDA backend
+    transpose = None  # set to DistComm.transpose_chunks
+
+    def ipc_export(self, slot):
+        if self.transpose is None:
+            raise RuntimeError("no peer memory in the NumPy stand-in")
+        return bytes(64)
+
+    def ipc_import(self, peer_rank, slot, handle):
+        pass
+
+    def can_push(self):
+        return self.transpose is not None
+
+    def exchange_p2p(self, src, dst):
+        self.transpose(self.slot_tensor(src), self.slot_tensor(dst))
+
     def run_epoch(self, mode, epoch, src0, basis_local, src1, dst0, dst1, push0=-1, push1=-1):
-        assert push0 < 0 and push1 < 0, "the NumPy stand-in has no fused layout switch"
+        if push0 >= 0:
+            assert self.transpose is not None and push0 not in (src0, dst0) and (mode != 0 or push1 not in (src1, dst1, push0))
+            self.run_epoch(mode, epoch, src0, basis_local, src1, dst0, dst1)
+            self.slots[push0][:] = np.nan  # a landing slot holds nothing before the delivery
+            self.transpose(self.slot_tensor(dst0), self.slot_tensor(push0))
+            if mode == 0:
+                self.slots[push1][:] = np.nan
+                self.transpose(self.slot_tensor(dst1), self.slot_tensor(push1))
+            self.slots[dst0][:] = np.nan  # the in-place result is scratch once pushed
+            if mode == 0:
+                self.slots[dst1][:] = np.nan
+            return
         passes = self.progs[mode][epoch][1]
         if src0 >= 0:
             v0 = self.slots[src0].copy()

@@ -22,6 +22,7 @@ for p in (ROOT, HERE):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sim", action="store_true")
+    ap.add_argument("--sim-push", action="store_true", help="--sim with the fused-push protocol emulated")
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--qubits", type=int, default=8)
@@ -63,7 +64,10 @@ def main():
             be = GpuShardBackend(circ, g, rank, local_rank, num_slots=5)
         else:
             be = SimShardBackend(circ, g, rank, num_slots=5)
+            if args.sim_push:
+                be.transpose = comm.transpose_chunks
         sv = ShardedStateVector(circ, comm, be, use_p2p=not args.no_p2p)
+        assert sv.push == (args.sim_push or (args.gpu and not args.no_p2p and os.environ.get("AQC_SHARD_PUSH", "1") != "0"))
         be.upload(sv.slot["target"], shard_of(y, n, g, rank))
         idx = O.basis_state_indices(n, init_index=(1 << (n - 1)) | 1)
         hs = sv.objective(th, idx)

@@ -29,6 +29,18 @@ def test_sharded_driver_gloo(world, qubits):
     assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world,qubits", [(2, 7), (4, 8)])
+def test_sharded_driver_fused_push_protocol_gloo(world, qubits):
+    """
+    The slot pool and the landing slots of the FUSED layout switch (sharded.py ``_run`` with push) with
+    the NumPy backend emulating the delivery: five slots must suffice for the gradient sweep, pushed
+    slots must never alias the slots an epoch works on, results equal the oracle's.
+    """
+    res = _launch(world, ["--sim", "--sim-push", "--qubits", str(qubits)], 29520 + world)
+    assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "p2p=True" in res.stdout
+
+
 def test_locate_is_a_bijection():
     import numpy as np
     from aqc_research_b200.sharded import locate
