@@ -164,12 +164,12 @@ static int ensure_idx(aqc_sv* sv, size_t count) {
 template <int NVEC, int ENT, bool DAG>
 static int launch_pass_t(aqc_sv* sv, const PassArgs& args) {
   const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
-  static bool configured[8] = {false};  // per device
-  if (!configured[sv->device & 7]) {
+  static bool configured[64] = {false};  // per device; setting the attribute twice is harmless  // per device
+  if (!configured[sv->device & 63]) {
     CU(cudaFuncSetAttribute(pass_kernel<NVEC, ENT, DAG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)NVEC * sizeof(double2) << kMaxTileBits)));
-    configured[sv->device & 7] = true;
+    configured[sv->device & 63] = true;
   }
   dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
   pass_kernel<NVEC, ENT, DAG><<<grid, kThreads, smem, sv->stream>>>(args);
@@ -249,11 +249,11 @@ static int env_int(const char* name, int dflt);
 template <int NVEC>
 static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
   const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
-  static bool configured[8] = {false};
-  if (!configured[sv->device & 7]) {
+  static bool configured[64] = {false};  // per device; setting the attribute twice is harmless
+  if (!configured[sv->device & 63]) {
     CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)((size_t)NVEC * sizeof(double2) << (NVEC == 2 ? kMaxTileBits - 1 : kMaxTileBits))));
-    configured[sv->device & 7] = true;
+                            (int)((size_t)NVEC * sizeof(double2) << kMaxTileBits)));
+    configured[sv->device & 63] = true;
   }
   dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
   dense_pass_kernel<NVEC><<<grid, kDThreads, smem, sv->stream>>>(args);
@@ -536,7 +536,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   // SMs, so they use smaller gradient tiles and spend the low bits on gate qubits instead
   // (measured at n = 20: 0.42 -> 0.36 ms per evaluation).
   const bool l2_resident = sv->nbits <= 22;
-  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), kMaxTileBits - 1);
+  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), kMaxTileBits);
   // single-vector sweeps of large states: 2^12-amplitude tiles (64 KiB) with 128-byte runs need fewer
   // passes (n = 28: 16 -> 13, 47.2 -> 45.5 ms)
   const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", l2_resident ? 11 : 12), kMaxTileBits);
