@@ -386,6 +386,10 @@ struct DensePassArgs {
   // (chunk xchg_rank, offset o) of rank c -- straight into the peers' HBM (NVLink peer stores;
   // xdst[v][c] = destination vector v of rank c, mapped with CUDA IPC; c = xchg_rank is local).
   int xchg_world, xchg_rank, xchg_shift;  // chunk = local index >> xchg_shift
+  // XORed into the tile number: rank r visits the tiles of chunk (t ^ r) while the grid works through
+  // tile group t, so at any moment every rank stores to a DIFFERENT peer (a permutation instead of
+  // all ranks hitting the same destination's NVLink ingress at once)
+  unsigned tile_xor;
   double2* xdst[2][16];
 };
 
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
 
   long long base = 0;
   {
-    const unsigned long long tile = blockIdx.x;
+    const unsigned long long tile = blockIdx.x ^ A.tile_xor;
     for (int k = 0; k < A.pd.nouter; ++k)
       base |= (long long)((tile >> k) & 1ull) << A.pd.outerpos[k];
   }

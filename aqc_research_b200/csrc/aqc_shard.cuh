@@ -209,7 +209,7 @@ struct ExchangeArgs {
 // dst[chunk r] = (rank r).src[chunk my_rank]: every rank pulls its column of the block matrix
 // over NVLink with plain peer loads (coalesced 16-byte accesses) and stores locally.
 __global__ void exchange_kernel(const ExchangeArgs A) {
-  const int r = blockIdx.y;
+  const int r = (blockIdx.y + A.rank) % A.world;  // every rank starts with another peer (no hot spot)
   const double2* __restrict__ s = A.src[r] + (long long)A.rank * A.chunk;
   double2* __restrict__ d = A.dst + (long long)r * A.chunk;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -231,7 +231,7 @@ struct PushArgs {
 // The same block transpose as remote STORES: (rank r).dst[chunk my_rank] = src[chunk r].  Stores over
 // NVLink are fire-and-forget, so the link is not throttled by outstanding read requests.
 __global__ void exchange_push_kernel(const PushArgs A) {
-  const int r = blockIdx.y;
+  const int r = (blockIdx.y + A.rank) % A.world;
   const double2* __restrict__ s = A.src + (long long)r * A.chunk;
   double2* __restrict__ d = A.dst[r] + (long long)A.rank * A.chunk;
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -351,10 +351,14 @@ static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long lon
     a.dst[1] = dst1;
     a.basis_index = (i == pass_begin) ? basis : -1;
     a.xchg_world = 0;
+    a.tile_xor = 0;
     if (push0 >= 0 && i + 1 == pass_end) {  // the last pass of the range delivers its result to the peers
       a.xchg_world = 1 << sv->g;
       a.xchg_rank = sv->rank;
       a.xchg_shift = sv->nbits - sv->g;
+      for (int b = 0; b < sv->g; ++b)  // chunk bit b of the local index, if it numbers tiles (outer bit k)
+        for (int k = 0; k < a.pd.nouter; ++k)
+          if (a.pd.outerpos[k] == a.xchg_shift + b && ((sv->rank >> b) & 1)) a.tile_xor |= 1u << k;
       for (int r = 0; r < a.xchg_world; ++r) {
         a.xdst[0][r] = r == sv->rank ? sv->slots[push0] : const_cast<double2*>(sv->peer[push0][r]);
         a.xdst[1][r] = mode != 0 ? nullptr

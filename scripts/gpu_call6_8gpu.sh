@@ -5,7 +5,6 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 S=gpurun_out/c6_summary.txt; : > $S
 nvidia-smi -L | wc -l | tee -a $S
-timeout -k 10 300 python -m pytest tests/test_sharded_gpu.py -x -q -k "four_gpus" > gpurun_out/c6_shard_tests.log 2>&1; echo "sharded test 4 GPUs rc=$?" | tee -a $S; tail -3 gpurun_out/c6_shard_tests.log | tee -a $S
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 timeout -k 10 400 $TR --master-port 29811 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/c6_bench_8gpu.json 2> gpurun_out/c6_bench_8gpu.err; echo "bench --gpus 8 rc=$?" | tee -a $S
 python - <<'PY' | tee -a $S
