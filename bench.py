@@ -806,8 +806,8 @@ def run_sharded_bench(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("AQC_BENCH_WORKLOAD", "sv20"),
                     choices=sorted(WORKLOADS) + ["svshard"])
     ap.add_argument("--shard-qubits", type=int, default=28, help="svshard: qubits per GPU shard (log2 amplitudes)")
