@@ -251,24 +251,39 @@ struct PrologueArgs {
   long long nzero0;
   double* zero1;
   long long nzero1;
+  int smem_thetas;  // 1: the launch provides nthetas doubles of dynamic shared memory
 };
+
+// The angles live in pinned HOST memory: every access is a PCIe round trip, so a block first fetches all
+// angles of its batch element with one coalesced burst into shared memory (the per-unit reads of the gate
+// recipes are serially dependent: unstaged, the prologue took 14 us and the epilogue 30 us).
+__device__ __forceinline__ const double* stage_thetas_smem(const double* __restrict__ host_thetas, int nthetas,
+                                                           int use_smem, double* smem_thetas) {
+  if (!use_smem) return host_thetas;
+  for (int i = threadIdx.x; i < nthetas; i += blockDim.x) smem_thetas[i] = host_thetas[i];
+  __syncthreads();
+  return smem_thetas;
+}
 
 template <int ENT, bool DAG>
 __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  extern __shared__ double s_thetas[];
+  const int b = blockIdx.y;
+  const double* th = stage_thetas_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.smem_thetas, s_thetas);
+  const long long gt = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gsz = (long long)gridDim.x * gridDim.y * blockDim.x;
   for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
   for (long long i = gt; i < A.nzero1; i += gsz) A.zero1[i] = 0.0;
-  for (long long t = gt; t < (long long)A.batch * A.nstages * 4; t += gsz) {
-    const int k = (int)(t & 3), s = (int)((t >> 2) % A.nstages), b = (int)((t >> 2) / A.nstages);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < A.nstages * 4; t += gridDim.x * blockDim.x) {
+    const int k = t & 3, s = t >> 2;
     const StageDesc sd = A.stages[s];
-    const double* th = A.thetas + (size_t)b * A.nthetas;
     cd a[1][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
     for (int u = 0; u < sd.nunits; ++u) unit_from_theta<ENT, DAG, 1>(sd.u[u], th, a, nullptr);
     double* um = A.umat + ((size_t)b * A.nstages + s) * 64;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]; DMMA A-fragment order (see dense_umat_kernel)
+    for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]; DMMA A-fragment order: lane = c * 4 + k, c = reim | amp << 1
       um[(2 * i) * 4 + k] = a[0][i].x;
       um[32 + (2 * i) * 4 + k] = -a[0][i].y;
       um[(2 * i + 1) * 4 + k] = a[0][i].y;
@@ -285,16 +300,19 @@ struct EpilogueArgs {
   double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
   double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
   unsigned* ticket;        // completion counter (left at zero)
+  int smem_thetas;         // 1: the launch provides nthetas doubles of dynamic shared memory
 };
 
 template <int ENT>
 __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
+  extern __shared__ double s_thetas[];
   __shared__ int s_last;
+  const int b = blockIdx.y;
+  const double* th = stage_thetas_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.smem_thetas, s_thetas);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.batch * A.nstages * 4) {
-    const int r = t & 3, s = (t >> 2) % A.nstages, b = (t >> 2) / A.nstages;
+  if (t < A.nstages * 4) {
+    const int r = t & 3, s = t >> 2;
     const StageDesc sd = A.stages[s];
-    const double* th = A.thetas + (size_t)b * A.nthetas;
     const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
     // virtual quadruple r: w' = e_r, z' = M_out[:, r]; pull both back through the stage, then run it
     // forward with the reference's gate-by-gate accumulation (dense_grad_kernel)
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A
   // the CTA that finishes last converts the raw sums and hands the gradient to the host
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();

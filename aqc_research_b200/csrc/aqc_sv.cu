@@ -104,6 +104,10 @@ struct aqc_sv {
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_hs = nullptr;   // aqc_sv_eval_begin: the gathered amplitudes have reached pinned memory
+  cudaEvent_t ev_obj = nullptr;  // ... and the end of its V^H sweep (kernel-time split for bench.py)
+  float last_obj_ms = 0.f, last_grad_ms = 0.f;
+  size_t eval_hs_off = 0, eval_hs_count = 0;  // where aqc_sv_eval_hs finds its result in h_pinned
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // user timer (aqc_sv_timer_*)
   float last_ms = 0.f;
   int last_launches = 0;
@@ -279,16 +283,18 @@ static int dense_prepare(aqc_sv* sv, int mode) {
     a.zero1 = sv->d_gacc;
     a.nzero1 = (long long)sv->batch * sv->circ.nthetas * 2;
   }
-  const long long work = std::max<long long>((long long)sv->batch * a.nstages * 4, std::max(a.nzero0, a.nzero1) / 8);
-  if (work == 0) return AQC_OK;
-  const unsigned grid = (unsigned)std::min<long long>((work + 127) / 128, 4 * sv->num_sms);
+  if (a.nstages == 0 && a.nzero0 == 0 && a.nzero1 == 0) return AQC_OK;
+  const size_t smem = (size_t)sv->circ.nthetas * sizeof(double);
+  a.smem_thetas = smem <= 48 * 1024 ? 1 : 0;
+  const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
+  const size_t dyn = a.smem_thetas ? smem : 0;
   const bool dag = mode == 2;
-#define AQC_PRO(E)                                                         \
-  do {                                                                     \
-    if (dag)                                                               \
-      sweep_prologue_kernel<E, true><<<grid, 128, 0, sv->stream>>>(a);     \
-    else                                                                   \
-      sweep_prologue_kernel<E, false><<<grid, 128, 0, sv->stream>>>(a);    \
+#define AQC_PRO(E)                                                           \
+  do {                                                                       \
+    if (dag)                                                                 \
+      sweep_prologue_kernel<E, true><<<grid, 128, dyn, sv->stream>>>(a);     \
+    else                                                                     \
+      sweep_prologue_kernel<E, false><<<grid, 128, dyn, sv->stream>>>(a);    \
   } while (0)
   switch (sv->circ.ent) {
     case AQC_ENT_CX: AQC_PRO(AQC_ENT_CX); break;
@@ -318,11 +324,14 @@ static int dense_collect(aqc_sv* sv) {
   a.gacc = sv->d_gacc;
   a.out = sv->h_pinned;
   a.ticket = sv->d_ticket;
-  const unsigned grid = (unsigned)std::max<long long>(1, ((long long)sv->batch * a.nstages * 4 + 127) / 128);
+  const size_t smem = (size_t)sv->circ.nthetas * sizeof(double);
+  a.smem_thetas = smem <= 48 * 1024 ? 1 : 0;
+  const size_t dyn = a.smem_thetas ? smem : 0;
+  const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
   switch (sv->circ.ent) {
-    case AQC_ENT_CX: grad_epilogue_kernel<AQC_ENT_CX><<<grid, 128, 0, sv->stream>>>(a); break;
-    case AQC_ENT_CZ: grad_epilogue_kernel<AQC_ENT_CZ><<<grid, 128, 0, sv->stream>>>(a); break;
-    default: grad_epilogue_kernel<AQC_ENT_CP><<<grid, 128, 0, sv->stream>>>(a);
+    case AQC_ENT_CX: grad_epilogue_kernel<AQC_ENT_CX><<<grid, 128, dyn, sv->stream>>>(a); break;
+    case AQC_ENT_CZ: grad_epilogue_kernel<AQC_ENT_CZ><<<grid, 128, dyn, sv->stream>>>(a); break;
+    default: grad_epilogue_kernel<AQC_ENT_CP><<<grid, 128, dyn, sv->stream>>>(a);
   }
   CU(cudaGetLastError());
   sv->last_launches += 1;
@@ -462,6 +471,8 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   if (sv->d_ticket) cudaFree(sv->d_ticket);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages), cudaFree(p->d_passes);
+  if (sv->ev_hs) cudaEventDestroy(sv->ev_hs);
+  if (sv->ev_obj) cudaEventDestroy(sv->ev_obj);
   if (sv->ev0) cudaEventDestroy(sv->ev0);
   if (sv->ev1) cudaEventDestroy(sv->ev1);
   if (sv->tm0) cudaEventDestroy(sv->tm0);
@@ -521,6 +532,8 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   } while (0)
   CUB(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
+  CUB(cudaEventCreate(&sv->ev_hs));
+  CUB(cudaEventCreate(&sv->ev_obj));
   CUB(cudaEventCreate(&sv->ev0));
   CUB(cudaEventCreate(&sv->ev1));
   CUB(cudaEventCreate(&sv->tm0));
@@ -540,10 +553,13 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   // SMs, so they use smaller gradient tiles and spend the low bits on gate qubits instead
   // (measured at n = 20: 0.42 -> 0.36 ms per evaluation).
   const bool l2_resident = sv->nbits <= 22;
-  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", l2_resident ? 10 : 11), kMaxTileBits);
+  // tiny states (one vector <= 128 KiB) are latency bound: smaller tiles spread the few amplitudes over
+  // more SMs (n = 12: 5 797 -> 6 328 evals/s with 2^8 / 2^9 tiles)
+  const bool tiny = sv->nbits <= 13 && batch == 1;
+  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", tiny ? 8 : (l2_resident ? 10 : 11)), kMaxTileBits);
   // single-vector sweeps of large states: 2^12-amplitude tiles (64 KiB) with 128-byte runs need fewer
   // passes (n = 28: 16 -> 13, 47.2 -> 45.5 ms)
-  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", l2_resident ? 11 : 12), kMaxTileBits);
+  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", tiny ? 9 : (l2_resident ? 11 : 12)), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 4);
   const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)
@@ -1169,6 +1185,81 @@ extern "C" int aqc_sv_grad(aqc_sv* sv, const double* thetas, int x_slot, int64_t
   return aqc_sv_grad_end(sv, grad_out);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// One evaluation = objective + gradient at the same angles, enqueued in ONE go (dense engine).
+// scipy's L-BFGS-B asks for fun(theta) and then jac(theta) (optimizer.py:585-590): instead of
+// sweeping, waiting, returning to Python and only then enqueueing the gradient sweep, everything --
+// V^H sweep, gather of hs, gradient sweep from the basis state |x_basis>, epilogue -- goes to the
+// stream at once.  aqc_sv_eval_hs waits for an EVENT recorded behind the gather (the gradient sweep
+// keeps running on the device while the host forms the objective value); aqc_sv_grad_end collects the
+// gradient.  A gradient the caller turns out not to need (another leading state, other angles) is
+// simply dropped by the next call.
+// ------------------------------------------------------------------------------------------
+extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
+                                 const int64_t* idx, int count, int64_t x_basis, int w_slot, int z_slot) {
+  int rc = check_slot(sv, target_slot);
+  if (!rc) rc = check_slot(sv, z0_slot);
+  if (!rc) rc = check_slot(sv, w_slot);
+  if (!rc) rc = check_slot(sv, z_slot);
+  if (rc) return rc;
+  if (!thetas || !idx || count <= 0) return fail(AQC_EINVAL, "bad arguments");
+  if (!sv->dense) return fail(AQC_EINVAL, "aqc_sv_eval_begin needs the dense engine");
+  if (x_basis < 0 || x_basis >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
+  if (w_slot == z_slot || w_slot == z0_slot || w_slot == target_slot || z_slot == target_slot || z0_slot == target_slot)
+    return fail(AQC_EINVAL, "slot aliasing");
+  CU(cudaSetDevice(sv->device));
+  sv->last_launches = 0;
+  const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
+  const size_t nout = (size_t)2 * count * sv->batch;
+  rc = ensure_pinned(sv, 2 * tot + nout + 64);
+  if (rc) return rc;
+  rc = gather_indices(sv, idx, count);
+  if (rc) return rc;
+  rc = upload_thetas(sv, thetas, false);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev0, sv->stream));
+  rc = dense_prepare(sv, 2);
+  if (!rc) rc = run_dense_program(sv, 2, sv->slots[target_slot], -1, nullptr, sv->slots[z0_slot], nullptr, 0, -1);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev_obj, sv->stream));
+  sv->eval_hs_off = 2 * tot;  // behind the gradient's region: the two results never share bytes
+  sv->eval_hs_count = nout;
+  gather_out_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
+      sv->slots[z0_slot], sv->size, sv->d_idx, count, reinterpret_cast<double2*>(sv->h_pinned + sv->eval_hs_off));
+  CU(cudaGetLastError());
+  sv->last_launches += 1;
+  CU(cudaEventRecord(sv->ev_hs, sv->stream));
+  rc = dense_prepare(sv, 0);
+  if (!rc)
+    rc = run_dense_program(sv, 0, nullptr, x_basis, sv->slots[z0_slot], sv->slots[w_slot], sv->slots[z_slot], 0, -1);
+  if (!rc) rc = dense_collect(sv);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  sv->grad_pending = true;
+  return AQC_OK;
+}
+
+// hs of the evaluation in flight (the gradient sweep may still be running).
+extern "C" int aqc_sv_eval_hs(aqc_sv* sv, double* hs_out) {
+  if (!sv || !hs_out) return fail(AQC_EINVAL, "null pointer argument");
+  if (!sv->grad_pending || sv->eval_hs_count == 0) return fail(AQC_EINVAL, "no evaluation in flight (aqc_sv_eval_begin)");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaEventSynchronize(sv->ev_hs));
+  memcpy(hs_out, sv->h_pinned + sv->eval_hs_off, sv->eval_hs_count * sizeof(double));
+  sv->eval_hs_count = 0;
+  return AQC_OK;
+}
+
+// Kernel-time split of the last COMPLETED aqc_sv_eval_begin .. aqc_sv_grad_end pair (ms): V^H sweep
+// (prologue + passes) and gradient sweep (prologue + passes + epilogue).
+extern "C" int aqc_sv_eval_times(aqc_sv* sv, float* obj_ms, float* grad_ms) {
+  if (!sv || !obj_ms || !grad_ms) return fail(AQC_EINVAL, "null pointer argument");
+  CU(cudaSetDevice(sv->device));
+  CU(cudaEventElapsedTime(obj_ms, sv->ev0, sv->ev_obj));
+  CU(cudaEventElapsedTime(grad_ms, sv->ev_hs, sv->ev1));
+  return AQC_OK;
+}
 
 // Host-only scheduler introspection (no device needed): serialises the compiled program as
 // int32 words so that the CPU test-suite can replay it gate by gate against the oracle.

@@ -223,6 +223,29 @@ class SvWorkspace:
         _lib.check(self._lib.aqc_sv_grad_end(self.handle, _dptr(out)))
         return out
 
+    def eval_begin(self, thetas: np.ndarray, target: int, z0: int, indices, *, x_basis: int, w: int, z: int) -> np.ndarray:
+        """
+        Enqueues one whole evaluation -- V^H sweep, gather, gradient sweep from ``|x_basis>`` -- and
+        returns hs = z0[indices] (batch, len(indices)) as soon as the gather has finished; the gradient
+        sweep keeps running and is collected with ``grad_end`` (or dropped by the next call).
+        """
+        _, ptr = _thetas_ptr(thetas, self.batch * self.num_thetas)
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        _lib.check(
+            self._lib.aqc_sv_eval_begin(
+                self.handle, ptr, target, z0, idx.ctypes.data_as(_lib.c_int64_p), idx.size, int(x_basis), w, z
+            )
+        )
+        out = np.empty((self.batch, idx.size), dtype=np.complex128)
+        _lib.check(self._lib.aqc_sv_eval_hs(self.handle, _dptr(out)))
+        return out
+
+    def eval_times(self):
+        """(V^H sweep ms, gradient sweep ms) of the last completed eval_begin .. grad_end pair."""
+        a, b = ct.c_float(0), ct.c_float(0)
+        _lib.check(self._lib.aqc_sv_eval_times(self.handle, ct.byref(a), ct.byref(b)))
+        return float(a.value), float(b.value)
+
     def coord_descent(self, thetas: np.ndarray, *, target: int, w: int, z: int, num_sweeps: int = 1):
         """
         ``num_sweeps`` coordinate-descent sweeps (coord_descent_single_sweep,

@@ -278,6 +278,10 @@ class SpLHSObjectiveBase(ABC):
         self._early_thetas = None
         return True
 
+    def _structure_stale(self) -> bool:
+        """Cheap test (object identity of ``blocks``) whether a structure change may have happened."""
+        return self._circuit.blocks is not self._blocks_seen
+
     def _refresh_workspace(self):
         """Re-creates the GPU workspace if the circuit structure changed (insert_unit_blocks)."""
         if self._structure_changed():

@@ -15,7 +15,7 @@ import numpy as np
 from .. import checking as chk
 from ..core_operations import mask_gradient
 from ..parametric_circuit import ParametricCircuit
-from .objective_base import SLOT_STATE, SLOT_VH_TARGET, SLOT_W, SLOT_Z, SpLHSObjectiveBase
+from .objective_base import SLOT_STATE, SLOT_TARGET, SLOT_VH_TARGET, SLOT_W, SLOT_Z, SpLHSObjectiveBase
 
 
 class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
@@ -57,21 +57,39 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
 
     def objective(self, thetas: np.ndarray) -> float:
         self._store_latest_thetas(thetas)
-        self._hs[:] = self._hs_products(thetas)
+        if self._early_thetas is not None:  # the previous early sweep was never collected
+            self._early_thetas, self._early_on, self._early_hits = None, False, 0
+        early = self._early_on and not self._dense
+        # Leading state |s_0> (the rule near convergence): the WHOLE evaluation -- V^H sweep, hs gather and
+        # the gradient sweep from |s_0> -- is enqueued at once; hs comes back as soon as the gather is
+        # done while the gradient sweep keeps the GPU busy (aqc_sv_eval_begin).  If the hysteresis below
+        # then picks another leader, that sweep is simply not collected.
+        speculative = early and self._max_no == 0
+        if speculative:
+            if self._target is None:
+                raise RuntimeError("set_target() must be called before objective()")
+            self._refresh_workspace()
+            idx = self._state_handler.state_indices
+            self._hs[:] = self._ws.eval_begin(thetas, SLOT_TARGET, SLOT_VH_TARGET, idx, x_basis=int(idx[0]),
+                                              w=SLOT_W, z=SLOT_Z)[0]
+            self._sweep_key = (0, self._weight)
+        else:
+            self._hs[:] = self._hs_products(thetas)
         np.copyto(self._hs2, np.abs(self._hs) ** 2)
-        # hysteresis: the leader changes only if a state is better by 10% (:110-117)
+        # hysteresis: the leader changes only if a state is better by 10% (:110-117); the scan runs only
+        # when some state qualifies at all (it is sequential: the bar rises with every change)
         best = self._hs2[self._max_no]
-        for i in range(self._num_states):
-            if 1.1 * best < self._hs2[i]:
-                best = self._hs2[i]
-                self._max_no = i
+        if (self._hs2 > 1.1 * best).any():
+            for i in range(self._num_states):
+                if 1.1 * best < self._hs2[i]:
+                    best = self._hs2[i]
+                    self._max_no = i
         w = self._weight
         self._fobj = float(1.0 - (1.0 - w) * self._hs2[0] - w * self._hs2[self._max_no])
         self._fidelity = float(self._hs2[0])
-        if self._early_thetas is not None:  # the previous early sweep was never collected
-            self._early_thetas, self._early_on, self._early_hits = None, False, 0
-        if self._early_on and not self._dense:
-            self._begin_sweep(thetas)
+        if early:
+            if not speculative or self._max_no != 0:
+                self._begin_sweep(thetas)  # (drops a speculative sweep that assumed the wrong leader)
             self._early_thetas = self._last_thetas
         self._service.on_end_objective()
         return self._fobj
@@ -95,10 +113,13 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
             self._ws.grad_begin(thetas, x_slot=SLOT_W, z0=SLOT_VH_TARGET, w=SLOT_W, z=SLOT_Z)
         self._sweep_key = (self._max_no, self._weight)
 
-    def _sweep(self, thetas: np.ndarray) -> np.ndarray:
-        """Raw result of ``_begin_sweep``: collected from the early sweep if one is in flight."""
+    def _sweep(self, thetas: np.ndarray, at_last_thetas: bool) -> np.ndarray:
+        """
+        Raw result of ``_begin_sweep``: collected from the early sweep if one is in flight.  An early
+        sweep was started at ``_last_thetas``; ``at_last_thetas`` says that those are exactly ``thetas``.
+        """
         early, self._early_thetas = self._early_thetas, None
-        if (early is None or early.shape != thetas.shape or not np.array_equal(early, thetas)
+        if (early is None or early is not self._last_thetas or not at_last_thetas
                 or self._sweep_key != (self._max_no, self._weight)):
             # (a stale early sweep is dropped by the next workspace call)
             self._begin_sweep(thetas)
@@ -115,17 +136,21 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
 
     def gradient(self, thetas: np.ndarray) -> np.ndarray:
         self._service.on_begin_gradient(self._fobj, thetas, self._fidelity)  # may raise: early stop
-        same = self._last_thetas.shape == np.shape(thetas) and np.array_equal(self._last_thetas, thetas)
+        last = self._last_thetas
+        same = last.size == np.size(thetas) and np.array_equal(last, thetas)
         self._early_hits = self._early_hits + 1 if same else 0
         self._early_on = self._early_hits >= 2
-        self._calc_objective_before_gradient(thetas)
+        if not same or self._structure_stale():
+            self._calc_objective_before_gradient(thetas)  # may recompute the objective (and restart the sweep)
+            last = self._last_thetas
+            same = last.size == np.size(thetas) and np.array_equal(last, thetas)  # False: within sqrt(eps) only
         circ = self._circuit
         front = bool(self._front_layer or self._block_range == (0, circ.num_blocks))
 
         if self._dense:
             raw = self._dense_terms(thetas)
         else:
-            raw = self._sweep(thetas)
+            raw = self._sweep(thetas, same)
             if self._max_no == 0:
                 raw = -2.0 * np.conj(self._hs[0]) * raw
         full = np.ascontiguousarray(np.real(mask_gradient(circ, raw, self._block_range, front)), dtype=np.float64)

@@ -139,6 +139,18 @@ int aqc_sv_grad_end(aqc_sv* sv, double* grad_out);
 int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
                      const int64_t* idx, int count, double* hs_out);
 
+/* One evaluation (objective + gradient at the same angles) enqueued in one go -- scipy asks for
+ * fun(theta) and then jac(theta) (optimizer.py:585-590): V^H sweep of target_slot into z0_slot, gather of
+ * hs (objective_lhs_sur_max.py:98-106), gradient sweep of <V e_x | target> from the basis state x_basis
+ * (core_operations.py:823) and its epilogue.  aqc_sv_eval_hs returns hs as soon as the gather has
+ * finished (the gradient sweep keeps running); aqc_sv_grad_end collects the gradient.  A gradient that
+ * is not collected is dropped by the next call on the workspace. */
+int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
+                      const int64_t* idx, int count, int64_t x_basis, int w_slot, int z_slot);
+int aqc_sv_eval_hs(aqc_sv* sv, double* hs_out);
+/* kernel-time split (ms) of the last completed aqc_sv_eval_begin .. aqc_sv_grad_end pair */
+int aqc_sv_eval_times(aqc_sv* sv, float* obj_ms, float* grad_ms);
+
 /* Device time (ms, CUDA events on the workspace stream) of the kernels launched by the
  * most recent aqc_sv_apply / aqc_sv_grad / aqc_sv_objective call, and how many
  * kernels that call launched.  Used by bench.py for the roofline figure. */

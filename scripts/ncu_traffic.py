@@ -38,7 +38,7 @@ rec = {
     if "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active" in col else None,
     "dram_throughput_pct": sum(float(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]) for r in picked) / n,
     "capture": os.path.basename(rep),
-    "git": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
+    "git": sys.argv[4] if len(sys.argv) > 4 else subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
 }
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 path = os.path.join(root, "profiles", "ncu_traffic.json")

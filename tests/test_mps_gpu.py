@@ -291,7 +291,9 @@ def test_truncated_results_within_the_discarded_weight_bound(n, evol_time):
     bound_o = np.sqrt(2.0 * K * st_o["discarded_weight"]) + 1e-12
     assert st_o["cap_hits"] == 0 and st_o["max_discarded"] < 1e-6  # the trunc_thr rule alone was at work
     assert np.max(np.abs(hs - z0[idx])) <= bound_o, (np.max(np.abs(hs - z0[idx])), bound_o, st_o)
-    assert abs(ws.dot(1, 1) - 1) < 1e-9  # every split renormalises
+    # every split renormalises; simultaneous truncations of a half-layer leave the Vidal form canonical only
+    # up to the discarded weight, so the norm is 1 to that order, not to rounding
+    assert abs(ws.dot(1, 1) - 1) < 10 * st_o["discarded_weight"] + 1e-9
     g = ws.grad(th, x_basis=neel, z0=1, w=2, z=3)
     st_g = ws.truncation_stats()
     g_ref = O.grad_sweep(circ, th, e, z0)

@@ -60,6 +60,12 @@ class OracleWorkspace:
         self.pending = O.grad_sweep(self.circ, np.asarray(thetas), x, self.slots[z0])
         OracleWorkspace.calls.append("sweep")
 
+    def eval_begin(self, thetas, target, z0, indices, *, x_basis, w, z):
+        hs = self.objective(thetas, target, z0, indices)
+        self.grad_begin(thetas, z0=z0, w=w, z=z, x_basis=x_basis)
+        OracleWorkspace.calls.append("fused")
+        return hs
+
     def grad_end(self):
         assert self.pending is not None, "no gradient sweep in flight"
         out, self.pending = self.pending, None
@@ -162,6 +168,52 @@ def test_early_start_follows_the_fun_jac_pattern(fake_gpu):
     _, _, ref_b, _ = O.sur_max_value_and_grad(circ, th_b, g[p + "target"], w_before, objv.max_no)
     assert rel(grad_b, ref_b) < TOL
     assert not objv._early_on
+
+
+def test_fused_evaluation_when_the_leader_is_state_zero(fake_gpu):
+    """
+    Leading state |s_0> and the fun / jac pattern learnt: objective() enqueues the WHOLE evaluation
+    (aqc_sv_eval_begin: V^H sweep, gather, gradient sweep) and gradient() only collects it -- one sweep per
+    evaluation, results equal the oracle's; a leader change drops the speculative sweep and takes the
+    two-term sweep instead.
+    """
+    from aqc_research_b200 import circuit_structures as cs
+
+    rng = np.random.RandomState(12)
+    n = 5
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    th_star = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    e0 = np.zeros(2**n, dtype=np.complex128)
+    e0[0] = 1
+    target = O.apply_v(circ, th_star, e0)  # near target: the leader is |0>
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    objv.set_target(target)
+    fused_seen = 0
+    for step in range(6):
+        th = th_star + 0.02 * (2 * rng.rand(circ.num_thetas) - 1)
+        w_before = objv.weight
+        fake_gpu.calls.clear()
+        f = objv.objective(th)
+        fused = "fused" in fake_gpu.calls
+        g = objv.gradient(th)
+        f_ref, _, g_ref, _ = O.sur_max_value_and_grad(circ, th, target, w_before, 0)
+        assert objv.max_no == 0 and abs(f - f_ref) < TOL and rel(g, g_ref) < TOL
+        assert fake_gpu.calls.count("sweep") == 1 and fused == (step >= 2)
+        fused_seen += fused
+    assert fused_seen == 4
+    # another target: the leader changes inside a fused objective() -> the speculative sweep is not used
+    y = rng.rand(2**n) + 1j * rng.rand(2**n)
+    y /= np.linalg.norm(y)
+    objv.set_target(y)
+    objv._early_on, objv._early_hits = True, 2
+    th = np.pi * (2 * rng.rand(circ.num_thetas) - 1)
+    w_before = objv.weight
+    fake_gpu.calls.clear()
+    f = objv.objective(th)
+    g = objv.gradient(th)
+    assert objv.max_no != 0 and "fused" in fake_gpu.calls and "set_sparse" in fake_gpu.calls
+    f_ref, _, g_ref, _ = O.sur_max_value_and_grad(circ, th, y, w_before, objv.max_no)
+    assert abs(f - f_ref) < TOL and rel(g, g_ref) < TOL
 
 
 class OracleMpsWorkspace:

@@ -129,6 +129,41 @@ def test_objective_gather_basis_and_vdot():
     ws.close()
 
 
+@pytest.mark.parametrize("n", [6, 12, 15])
+def test_fused_evaluation_vs_oracle(n):
+    """
+    aqc_sv_eval_begin / aqc_sv_eval_hs / aqc_sv_grad_end: the whole evaluation enqueued at once equals the
+    two separate calls and the oracle; an evaluation whose gradient is never collected is dropped cleanly.
+    """
+    np.random.seed(600 + n)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    ws = SvWorkspace(circ, num_slots=4)
+    y = utils.rand_state(n)
+    ws.upload(0, y)
+    idx = O.basis_state_indices(n, init_index=5 % 2**n)
+    for rep in range(3):
+        th = utils.rand_thetas(circ.num_thetas)
+        hs = ws.eval_begin(th, 0, 1, idx, x_basis=int(idx[0]), w=2, z=3)[0]
+        if rep == 1:
+            continue  # not collected: the next call drops the sweep in flight
+        g = ws.grad_end()[0]
+        z0 = O.apply_v(circ, th, y, dagger=True)
+        e = np.zeros(2**n, dtype=np.complex128)
+        e[idx[0]] = 1
+        assert _rel(hs, z0[idx]) < TOL and _rel(g, O.grad_sweep(circ, th, e, z0)) < TOL
+        o_ms, g_ms = ws.eval_times()
+        assert o_ms > 0 and g_ms > 0
+    # and the plain calls still agree afterwards
+    th = utils.rand_thetas(circ.num_thetas)
+    hs = ws.objective(th, 0, 1, idx)[0]
+    g = ws.grad(th, x_basis=int(idx[0]), z0=1, w=2, z=3)[0]
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    e = np.zeros(2**n, dtype=np.complex128)
+    e[idx[0]] = 1
+    assert _rel(hs, z0[idx]) < TOL and _rel(g, O.grad_sweep(circ, th, e, z0)) < TOL
+    ws.close()
+
+
 @pytest.mark.parametrize("n", [16, 20])
 def test_mid_size_vs_oracle(n):
     """Multi-pass programs with many tiles (sizes the NumPy oracle finishes in seconds)."""
