@@ -218,58 +218,55 @@ static bool build_dense_tables(const Program& prog, DenseTables& T, int fuse_pai
 //                           (core_operations.py:317-351, 972-975) and the write of the finished complex
 //                           gradient into pinned host memory by the last CTA that completes.
 // ------------------------------------------------------------------------------------------------
+// One gate unit applied to NVEC amplitude quadruples with the (cos, sin) pairs of its angles taken from
+// `tr` (indexed like thetas; half angles, full angle for the CPhase parameter).
 template <int ENT, bool DAG, int NVEC>
-__device__ __forceinline__ void unit_from_theta(const UnitDesc& u, const double* __restrict__ th, cd (&a)[NVEC][4],
-                                                double* acc) {
-  const bool front = u.kind == U_FRONT_LO || u.kind == U_FRONT_HI;
-  const int np = front ? 3 : (ENT == AQC_ENT_CP ? 5 : 4);
-  double2 tr[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    if (k < np) {
-      const double t = th[u.theta + k];
-      double s, c;
-      sincos(k == 4 ? t : 0.5 * t, &s, &c);  // full angle for the CPhase parameter
-      tr[k] = make_double2(c, s);
-    }
-  }
+__device__ __forceinline__ void unit_from_trig(const UnitDesc& u, const double2* __restrict__ tr, cd (&a)[NVEC][4],
+                                               double* acc) {
+  const double2* t = tr + u.theta;
   switch (u.kind) {
-    case U_FRONT_LO: front_unit<NVEC, false, DAG>(a, tr, acc); break;
-    case U_FRONT_HI: front_unit<NVEC, true, DAG>(a, tr, acc); break;
-    case U_BLOCK_CHI: block_unit<NVEC, ENT, true, DAG>(a, tr, u.flags, acc); break;
-    case U_BLOCK_CLO: block_unit<NVEC, ENT, false, DAG>(a, tr, u.flags, acc); break;
+    case U_FRONT_LO: front_unit<NVEC, false, DAG>(a, t, acc); break;
+    case U_FRONT_HI: front_unit<NVEC, true, DAG>(a, t, acc); break;
+    case U_BLOCK_CHI: block_unit<NVEC, ENT, true, DAG>(a, t, u.flags, acc); break;
+    case U_BLOCK_CLO: block_unit<NVEC, ENT, false, DAG>(a, t, u.flags, acc); break;
     default: break;
   }
 }
 
 struct PrologueArgs {
   const StageDesc* stages;
-  int nstages, nthetas, batch;
+  int nstages, nthetas, batch, n3, tpb;
+  const double2* gtrig;  // != nullptr: (cos, sin) table in device memory (circuits with > 12 800 angles)
   const double* thetas;  // [batch][nthetas], pinned host memory mapped into the device address space
   double* umat;          // [batch][nstages][64]
   double* zero0;         // two arrays to clear (stage-matrix sums, per-angle sums); may be null
   long long nzero0;
   double* zero1;
   long long nzero1;
-  int smem_thetas;  // 1: the launch provides nthetas doubles of dynamic shared memory
 };
 
-// The angles live in pinned HOST memory: every access is a PCIe round trip, so a block first fetches all
-// angles of its batch element with one coalesced burst into shared memory (the per-unit reads of the gate
-// recipes are serially dependent: unstaged, the prologue took 14 us and the epilogue 30 us).
-__device__ __forceinline__ const double* stage_thetas_smem(const double* __restrict__ host_thetas, int nthetas,
-                                                           int use_smem, double* smem_thetas) {
-  if (!use_smem) return host_thetas;
-  for (int i = threadIdx.x; i < nthetas; i += blockDim.x) smem_thetas[i] = host_thetas[i];
+// (cos, sin) of every angle of the block's batch element, built cooperatively in shared memory: the angles
+// live in pinned HOST memory (every access is a PCIe round trip) and a sincos costs far more than the gate
+// arithmetic it feeds, so neither is left to the serial per-unit recipes (a first version that did took
+// 14 us per prologue and 28 us per epilogue launch).
+__device__ __forceinline__ void build_trig_smem(const double* __restrict__ host_thetas, int nthetas, int n3, int tpb,
+                                                double2* s_trig) {
+  for (int k = threadIdx.x; k < nthetas; k += blockDim.x) {
+    const bool full = (tpb == 5) && k >= n3 && ((k - n3) % 5 == 4);  // CPhase parameter
+    const double t = host_thetas[k];
+    double sn, cs;
+    sincos(full ? t : 0.5 * t, &sn, &cs);
+    s_trig[k] = make_double2(cs, sn);
+  }
   __syncthreads();
-  return smem_thetas;
 }
 
 template <int ENT, bool DAG>
 __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
-  extern __shared__ double s_thetas[];
+  extern __shared__ double2 s_trig_buf[];
   const int b = blockIdx.y;
-  const double* th = stage_thetas_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.smem_thetas, s_thetas);
+  const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
+  if (!A.gtrig) build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf);
   const long long gt = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
   const long long gsz = (long long)gridDim.x * gridDim.y * blockDim.x;
   for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
@@ -280,7 +277,7 @@ __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs 
     cd a[1][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[0][i].x = (i == k) ? 1.0 : 0.0, a[0][i].y = 0.0;
-    for (int u = 0; u < sd.nunits; ++u) unit_from_theta<ENT, DAG, 1>(sd.u[u], th, a, nullptr);
+    for (int u = 0; u < sd.nunits; ++u) unit_from_trig<ENT, DAG, 1>(sd.u[u], s_trig, a, nullptr);
     double* um = A.umat + ((size_t)b * A.nstages + s) * 64;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // U[i][k] = a[0][i]; DMMA A-fragment order: lane = c * 4 + k, c = reim | amp << 1
@@ -295,20 +292,21 @@ __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs 
 struct EpilogueArgs {
   const StageDesc* stages;
   int nstages, nthetas, batch, n3, tpb;
+  const double2* gtrig;    // != nullptr: (cos, sin) table in device memory instead of the shared-memory one
   const double* thetas;
   const double* gm;        // [batch][nstages][64] accumulated stage matrices
   double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
   double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
   unsigned* ticket;        // completion counter (left at zero)
-  int smem_thetas;         // 1: the launch provides nthetas doubles of dynamic shared memory
 };
 
 template <int ENT>
 __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
-  extern __shared__ double s_thetas[];
+  extern __shared__ double2 s_trig_buf[];
   __shared__ int s_last;
   const int b = blockIdx.y;
-  const double* th = stage_thetas_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.smem_thetas, s_thetas);
+  const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
+  if (!A.gtrig) build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < A.nstages * 4) {
     const int r = t & 3, s = t >> 2;
@@ -327,12 +325,12 @@ __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    for (int u = sd.nunits - 1; u >= 0; --u) unit_from_theta<ENT, true, 2>(sd.u[u], th, a, acc);
+    for (int u = sd.nunits - 1; u >= 0; --u) unit_from_trig<ENT, true, 2>(sd.u[u], s_trig, a, acc);
     double* g = A.gacc + (size_t)b * A.nthetas * 2;
     for (int u = 0; u < sd.nunits; ++u) {
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      unit_from_theta<ENT, false, 2>(sd.u[u], th, a, acc);
+      unit_from_trig<ENT, false, 2>(sd.u[u], s_trig, a, acc);
       const int kind = sd.u[u].kind;
       const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
       double* gu = g + 2 * (size_t)sd.u[u].theta;

@@ -1103,8 +1103,9 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   if (tid == 0) {
     int total = 0;
     for (int i = 0; i < Cc; ++i) total += (s_sig[s_order[i]] > kChop) ? 1 : 0;
+    // the reference's rule (qiskit-aer run WITHOUT a bond cap, mps_operations.py:248-265): drop the smallest
+    // Schmidt values while the sum of their squares stays below trunc_thr ...
     int keep = total < 1 ? 1 : total;
-    if (keep > A.chi_max) keep = A.chi_max;
     double dropped = 0.0;
     while (keep > 1) {
       const double v = s_sig[s_order[keep - 1]];
@@ -1115,22 +1116,25 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
         break;
       }
     }
+    // ... and only then this engine's bond capacity: the cap cuts a split only if the rule alone would have
+    // kept more than chi_max values
+    const int keep_rule = keep;
+    if (keep > A.chi_max) keep = A.chi_max;
     double scale = 1.0;
     if (keep < total) {
       double nrm = 0.0;
       for (int i = 0; i < keep; ++i) nrm += s_sig[s_order[i]] * s_sig[s_order[i]];
       scale = 1.0 / sqrt(nrm);
-      // what was cut: everything beyond `keep`; the cap's share is what lies beyond chi_max
       double cut = 0.0, capcut = 0.0;
       for (int i = keep; i < total; ++i) cut += s_sig[s_order[i]] * s_sig[s_order[i]];
-      for (int i = A.chi_max; i < total; ++i) capcut += s_sig[s_order[i]] * s_sig[s_order[i]];
+      for (int i = keep; i < keep_rule; ++i) capcut += s_sig[s_order[i]] * s_sig[s_order[i]];
       const double all = nrm + cut;
       if (A.trunc_stats && all > 0.0) {
         atomicAdd(A.trunc_stats + 0, cut / all);
         // (non-negative doubles order like their bit patterns)
         atomicMax(reinterpret_cast<unsigned long long*>(A.trunc_stats + 1),
                   (unsigned long long)__double_as_longlong(cut / all));
-        if (total > A.chi_max) {
+        if (keep_rule > keep) {
           atomicAdd(A.trunc_stats + 2, capcut / all);
           atomicAdd(A.trunc_stats + 3, 1.0);
         }

@@ -101,6 +101,7 @@ struct aqc_sv {
   double* h_pinned = nullptr;  // pinned staging for small results (the device writes them directly)
   double* h_thetas = nullptr;  // pinned, device-readable copy of the angles of the call in flight
   unsigned* d_ticket = nullptr;  // completion counter of grad_epilogue_kernel
+  bool trig_in_global = false;   // > 12 800 angles: the (cos, sin) table does not fit shared memory
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -200,7 +201,7 @@ static int upload_thetas(aqc_sv* sv, const double* thetas, bool to_device) {
     sv->grad_pending = false;
   }
   memcpy(sv->h_thetas, thetas, tot * sizeof(double));
-  if (!to_device) return AQC_OK;
+  if (!to_device && !sv->trig_in_global) return AQC_OK;
   CU(cudaMemcpyAsync(sv->d_thetas, sv->h_thetas, tot * sizeof(double), cudaMemcpyHostToDevice, sv->stream));
   const int thr = 128;
   trig_kernel<<<(unsigned)((tot + thr - 1) / thr), thr, 0, sv->stream>>>(
@@ -284,17 +285,24 @@ static int dense_prepare(aqc_sv* sv, int mode) {
     a.nzero1 = (long long)sv->batch * sv->circ.nthetas * 2;
   }
   if (a.nstages == 0 && a.nzero0 == 0 && a.nzero1 == 0) return AQC_OK;
-  const size_t smem = (size_t)sv->circ.nthetas * sizeof(double);
-  a.smem_thetas = smem <= 48 * 1024 ? 1 : 0;
+  a.n3 = 3 * sv->circ.n;
+  a.tpb = sv->circ.tpb;
+  a.gtrig = sv->trig_in_global ? sv->d_trig : nullptr;
+  // (cos, sin) table of one batch element in shared memory (or in d_trig for very long circuits)
+  const size_t dyn = sv->trig_in_global ? 0 : (size_t)sv->circ.nthetas * sizeof(double2);
   const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
-  const size_t dyn = a.smem_thetas ? smem : 0;
   const bool dag = mode == 2;
-#define AQC_PRO(E)                                                           \
-  do {                                                                       \
-    if (dag)                                                                 \
-      sweep_prologue_kernel<E, true><<<grid, 128, dyn, sv->stream>>>(a);     \
-    else                                                                     \
-      sweep_prologue_kernel<E, false><<<grid, 128, dyn, sv->stream>>>(a);    \
+#define AQC_PRO(E)                                                                                        \
+  do {                                                                                                    \
+    if (dag) {                                                                                            \
+      if (dyn > 48 * 1024)                                                                                \
+        CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+      sweep_prologue_kernel<E, true><<<grid, 128, dyn, sv->stream>>>(a);                                  \
+    } else {                                                                                              \
+      if (dyn > 48 * 1024)                                                                                \
+        CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+      sweep_prologue_kernel<E, false><<<grid, 128, dyn, sv->stream>>>(a);                                 \
+    }                                                                                                     \
   } while (0)
   switch (sv->circ.ent) {
     case AQC_ENT_CX: AQC_PRO(AQC_ENT_CX); break;
@@ -324,15 +332,21 @@ static int dense_collect(aqc_sv* sv) {
   a.gacc = sv->d_gacc;
   a.out = sv->h_pinned;
   a.ticket = sv->d_ticket;
-  const size_t smem = (size_t)sv->circ.nthetas * sizeof(double);
-  a.smem_thetas = smem <= 48 * 1024 ? 1 : 0;
-  const size_t dyn = a.smem_thetas ? smem : 0;
+  a.gtrig = sv->trig_in_global ? sv->d_trig : nullptr;
+  const size_t dyn = sv->trig_in_global ? 0 : (size_t)sv->circ.nthetas * sizeof(double2);
   const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
+#define AQC_EPI(E)                                                                                                  \
+  do {                                                                                                              \
+    if (dyn > 48 * 1024)                                                                                            \
+      CU(cudaFuncSetAttribute(grad_epilogue_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));     \
+    grad_epilogue_kernel<E><<<grid, 128, dyn, sv->stream>>>(a);                                                     \
+  } while (0)
   switch (sv->circ.ent) {
-    case AQC_ENT_CX: grad_epilogue_kernel<AQC_ENT_CX><<<grid, 128, dyn, sv->stream>>>(a); break;
-    case AQC_ENT_CZ: grad_epilogue_kernel<AQC_ENT_CZ><<<grid, 128, dyn, sv->stream>>>(a); break;
-    default: grad_epilogue_kernel<AQC_ENT_CP><<<grid, 128, dyn, sv->stream>>>(a);
+    case AQC_ENT_CX: AQC_EPI(AQC_ENT_CX); break;
+    case AQC_ENT_CZ: AQC_EPI(AQC_ENT_CZ); break;
+    default: AQC_EPI(AQC_ENT_CP);
   }
+#undef AQC_EPI
   CU(cudaGetLastError());
   sv->last_launches += 1;
   return AQC_OK;
@@ -545,6 +559,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMalloc(&sv->d_trig, tot * sizeof(double2)));
   CUB(cudaMalloc(&sv->d_gacc, tot * 2 * sizeof(double)));
   CUB(cudaMallocHost(&sv->h_thetas, std::max<size_t>(tot, 1) * sizeof(double)));
+  sv->trig_in_global = (size_t)circ->nthetas * sizeof(double2) > 200 * 1024;
   CUB(cudaMalloc(&sv->d_ticket, sizeof(unsigned)));
   CUB(cudaMemset(sv->d_ticket, 0, sizeof(unsigned)));
 #undef CUB
@@ -556,10 +571,13 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   // tiny states (one vector <= 128 KiB) are latency bound: smaller tiles spread the few amplitudes over
   // more SMs (n = 12: 5 797 -> 6 328 evals/s with 2^8 / 2^9 tiles)
   const bool tiny = sv->nbits <= 13 && batch == 1;
-  const int tb_grad = std::min(env_int("AQC_TILE_BITS_GRAD", tiny ? 8 : (l2_resident ? 10 : 11)), kMaxTileBits);
+  const bool small = sv->nbits <= 17 && batch == 1;  // n = 16: 6 046 -> 6 326 evals/s with 2^9 / 2^10 tiles
+  const int tb_grad =
+      std::min(env_int("AQC_TILE_BITS_GRAD", tiny ? 8 : (small ? 9 : (l2_resident ? 10 : 11))), kMaxTileBits);
   // single-vector sweeps of large states: 2^12-amplitude tiles (64 KiB) with 128-byte runs need fewer
   // passes (n = 28: 16 -> 13, 47.2 -> 45.5 ms)
-  const int tb_apply = std::min(env_int("AQC_TILE_BITS_APPLY", tiny ? 9 : (l2_resident ? 11 : 12)), kMaxTileBits);
+  const int tb_apply =
+      std::min(env_int("AQC_TILE_BITS_APPLY", tiny ? 9 : (small ? 10 : (l2_resident ? 11 : 12))), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 4);
   const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)

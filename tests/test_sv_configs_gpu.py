@@ -79,3 +79,17 @@ def test_n24_production_configuration_vs_c_oracle():
     n = 24
     circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 1), True)
     _check(circ, n, 24, oracle=C)
+
+
+@pytest.mark.parametrize("nblocks", [1000, 3300])
+def test_very_long_circuits(nblocks):
+    """
+    The prologue / epilogue kernels keep the (cos, sin) table of all angles in shared memory: more than
+    3 072 angles need the opt-in size (> 48 KiB), more than 12 800 fall back to a table in device memory.
+    (SURVEY C3 stress case: 7 qubits, 2 870 blocks, 11 501 angles.)
+    """
+    n = 5
+    np.random.seed(nblocks)
+    circ = ParametricCircuit(n, "cx", utils.rand_circuit(n, nblocks))
+    assert circ.num_thetas * 16 > (48 * 1024 if nblocks == 1000 else 200 * 1024)
+    _check(circ, n, 300 + nblocks)
