@@ -237,6 +237,7 @@ struct PrologueArgs {
   const StageDesc* stages;
   int nstages, nthetas, batch, n3, tpb;
   const double2* gtrig;  // != nullptr: (cos, sin) table in device memory (circuits with > 12 800 angles)
+  double2* trig_out;     // != nullptr: the table is also written here (gradient sweep: read by the epilogue)
   const double* thetas;  // [batch][nthetas], pinned host memory mapped into the device address space
   double* umat;          // [batch][nstages][64]
   double* zero0;         // two arrays to clear (stage-matrix sums, per-angle sums); may be null
@@ -250,13 +251,28 @@ struct PrologueArgs {
 // arithmetic it feeds, so neither is left to the serial per-unit recipes (a first version that did took
 // 14 us per prologue and 28 us per epilogue launch).
 __device__ __forceinline__ void build_trig_smem(const double* __restrict__ host_thetas, int nthetas, int n3, int tpb,
-                                                double2* s_trig) {
-  for (int k = threadIdx.x; k < nthetas; k += blockDim.x) {
-    const bool full = (tpb == 5) && k >= n3 && ((k - n3) % 5 == 4);  // CPhase parameter
-    const double t = host_thetas[k];
-    double sn, cs;
-    sincos(full ? t : 0.5 * t, &sn, &cs);
-    s_trig[k] = make_double2(cs, sn);
+                                                double2* s_trig, double2* gtrig_out) {
+  // eight loads per thread in flight before the first sincos: one PCIe latency per 1024 angles, not one
+  // per angle (a plain loop cost ~9 us for 468 angles)
+  for (int k0 = 0; k0 < nthetas; k0 += 8 * blockDim.x) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * blockDim.x + threadIdx.x;
+      v[u] = k < nthetas ? host_thetas[k] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * blockDim.x + threadIdx.x;
+      if (k < nthetas) {
+        const bool full = (tpb == 5) && k >= n3 && ((k - n3) % 5 == 4);  // CPhase parameter
+        double sn, cs;
+        sincos(full ? v[u] : 0.5 * v[u], &sn, &cs);
+        const double2 t = make_double2(cs, sn);
+        s_trig[k] = t;
+        if (gtrig_out) gtrig_out[k] = t;  // kept for the epilogue of the same sweep
+      }
+    }
   }
   __syncthreads();
 }
@@ -266,7 +282,9 @@ __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs 
   extern __shared__ double2 s_trig_buf[];
   const int b = blockIdx.y;
   const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
-  if (!A.gtrig) build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf);
+  if (!A.gtrig)
+    build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf,
+                    (A.trig_out && blockIdx.x == 0) ? A.trig_out + (size_t)b * A.nthetas : nullptr);
   const long long gt = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
   const long long gsz = (long long)gridDim.x * gridDim.y * blockDim.x;
   for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
@@ -292,8 +310,7 @@ __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs 
 struct EpilogueArgs {
   const StageDesc* stages;
   int nstages, nthetas, batch, n3, tpb;
-  const double2* gtrig;    // != nullptr: (cos, sin) table in device memory instead of the shared-memory one
-  const double* thetas;
+  const double2* gtrig;    // [batch][nthetas] (cos, sin) table in device memory, left by the sweep's prologue
   const double* gm;        // [batch][nstages][64] accumulated stage matrices
   double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
   double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
@@ -302,11 +319,9 @@ struct EpilogueArgs {
 
 template <int ENT>
 __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
-  extern __shared__ double2 s_trig_buf[];
   __shared__ int s_last;
   const int b = blockIdx.y;
-  const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
-  if (!A.gtrig) build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf);
+  const double2* s_trig = A.gtrig + (size_t)b * A.nthetas;  // written by the prologue of this sweep
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < A.nstages * 4) {
     const int r = t & 3, s = t >> 2;
@@ -452,8 +467,12 @@ __device__ __forceinline__ void tile_copy(unsigned sbase, unsigned s0x16, const 
   }
 }
 
-template <int NVEC>
-__global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_kernel(const DensePassArgs A) {
+// MINB = CTAs per SM the register allocation aims at: 3 for the gradient sweep of large states (80
+// registers, 2^11 tiles of 64 KiB), 4 for tiles of <= 2^10 amplitudes (64 registers, 24 bytes of spill):
+// L2-resident states have few tiles (n = 20: 1 024), and 592 instead of 444 resident CTAs turn 3 ragged
+// waves into 2.
+template <int NVEC, int MINB>
+__global__ void __launch_bounds__(kDThreads, MINB) dense_pass_kernel(const DensePassArgs A) {
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]
