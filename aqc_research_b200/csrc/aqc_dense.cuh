@@ -467,12 +467,10 @@ __device__ __forceinline__ void tile_copy(unsigned sbase, unsigned s0x16, const 
   }
 }
 
-// MINB = CTAs per SM the register allocation aims at: 3 for the gradient sweep of large states (80
-// registers, 2^11 tiles of 64 KiB), 4 for tiles of <= 2^10 amplitudes (64 registers, 24 bytes of spill):
-// L2-resident states have few tiles (n = 20: 1 024), and 592 instead of 444 resident CTAs turn 3 ragged
-// waves into 2.
-template <int NVEC, int MINB>
-__global__ void __launch_bounds__(kDThreads, MINB) dense_pass_kernel(const DensePassArgs A) {
+// (A 64-register instantiation with 4 CTAs per SM for tiles of <= 2^10 amplitudes was measured in r02: no
+// difference at n = 12 ... 22 -- occupancy is not what limits the small-tile passes.)
+template <int NVEC>
+__global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_kernel(const DensePassArgs A) {
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]

@@ -101,7 +101,6 @@ struct aqc_sv {
   double* h_pinned = nullptr;  // pinned staging for small results (the device writes them directly)
   double* h_thetas = nullptr;  // pinned, device-readable copy of the angles of the call in flight
   unsigned* d_ticket = nullptr;  // completion counter of grad_epilogue_kernel
-  int grad_ctas = 4;             // AQC_GRAD_CTAS: CTAs per SM of the gradient kernel on small tiles (3 or 4)
   bool trig_in_global = false;   // > 12 800 angles: the (cos, sin) table does not fit shared memory
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
@@ -252,27 +251,19 @@ static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, con
 
 static int env_int(const char* name, int dflt);
 // ---- dense-stage engine: host side ----------------------------------------------------------------
-template <int NVEC, int MINB>
-static int launch_dense_pass_t(aqc_sv* sv, const DensePassArgs& args) {
+template <int NVEC>
+static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
   const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
   static bool configured[64] = {false};  // per device; setting the attribute twice is harmless
   if (!configured[sv->device & 63]) {
-    CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)NVEC * sizeof(double2) << kMaxTileBits)));
     configured[sv->device & 63] = true;
   }
   dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
-  dense_pass_kernel<NVEC, MINB><<<grid, kDThreads, smem, sv->stream>>>(args);
+  dense_pass_kernel<NVEC><<<grid, kDThreads, smem, sv->stream>>>(args);
   CU(cudaGetLastError());
   return AQC_OK;
-}
-
-template <int NVEC>
-static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
-  if (NVEC == 1) return launch_dense_pass_t<1, 5>(sv, args);
-  // gradient tiles of <= 2^10 amplitudes (40 KiB with the partial sums): four CTAs per SM
-  if (args.pd.tb <= 10 && sv->grad_ctas >= 4) return launch_dense_pass_t<2, 4>(sv, args);
-  return launch_dense_pass_t<2, 3>(sv, args);
 }
 
 // Prologue of a sweep: stage matrices of one program from the staged angles (mode 0 gradient, 1 V,
@@ -569,7 +560,6 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMalloc(&sv->d_gacc, tot * 2 * sizeof(double)));
   CUB(cudaMallocHost(&sv->h_thetas, std::max<size_t>(tot, 1) * sizeof(double)));
   sv->trig_in_global = (size_t)circ->nthetas * sizeof(double2) > 200 * 1024;
-  sv->grad_ctas = env_int("AQC_GRAD_CTAS", 4);
   CUB(cudaMalloc(&sv->d_ticket, sizeof(unsigned)));
   CUB(cudaMemset(sv->d_ticket, 0, sizeof(unsigned)));
 #undef CUB

@@ -25,7 +25,6 @@ CONFIGS = {
     "large-state-tiles": dict(LARGE, AQC_TILE_BITS_GRAD="11", AQC_TILE_BITS_APPLY="12"),
     "small-tiles": {"AQC_TILE_BITS_GRAD": "8", "AQC_TILE_BITS_APPLY": "9"},  # generic (not unrolled) tile copies
     "no-fused-steps": {"AQC_DENSE_PAIRS": "0"},
-    "grad-3-ctas": {"AQC_GRAD_CTAS": "3"},  # the 80-register instantiation also on small tiles
     "legacy": {"AQC_ENGINE": "legacy"},
 }
 
