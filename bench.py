@@ -884,10 +884,15 @@ def main():
     shard_extra = None
     if dist is not None and not args.no_extra:
         g = world.bit_length() - 1
+        smp = ClockSampler(local_rank) if rank == 0 else None
+        if smp:
+            smp.start()
         shard_extra = {
             "svshard": measure_sharded(args.shard_qubits, 4, 2, 1, local_rank, world),
             "svshard_parity": sharded_parity(24 + g, 2, local_rank, world),
         }
+        if smp:
+            shard_extra["svshard"]["clocks"] = smp.stop()
         dist.barrier()
     if rank != 0:
         if dist is not None:
@@ -932,8 +937,21 @@ def main():
         line["cpu_baseline"] = cpu_baseline(n, layers)
     if world == 1 and not args.no_extra and args.workload == "sv20":
         # the HBM-meaningful size of BASELINE.json configs[4] (vectors >> L2), same step definition
+        def clocked(fn, **kw):
+            """Runs one extra workload with its own clock / throttle-reason record."""
+            smp = ClockSampler(local_rank)
+            smp.start()
+            try:
+                out = fn(**kw)
+            finally:
+                clk = smp.stop()
+            out["clocks"] = clk
+            return out
+
         n2, l2 = WORKLOADS["sv28"]
-        r2 = measure_gpu(n2, l2, 3, 3, local_rank, False, None)
+        smp = ClockSampler(local_rank)
+        r2 = measure_gpu(n2, l2, 3, 3, local_rank, False, smp)
+        clk2 = smp.stop()
         p2 = pair_runs(n2, l2)
         t2 = float(np.mean(r2["step_ms"])) * 1e-3
         g2 = float(np.mean(r2["grad_ms"])) * 1e-3
@@ -948,16 +966,19 @@ def main():
             "stages": {"gradient": r2["stages_grad"], "vh_apply": r2["stages_dag"]},
             "roofline": roofline_block("sv28", n2, p2, r2["stages_grad"], r2["stages_dag"], g2, o2, t2,
                                        r2["passes_grad"]),
+            "clocks": clk2,
         }}
-        try:
-            line["extra_workloads"]["mps50"] = measure_mps(device=local_rank, with_cpu=not args.no_cpu_baseline)
-            line["extra_workloads"]["mps50_physical"] = measure_mps(device=local_rank, with_cpu=False, physical=True)
-            line["extra_workloads"]["mat7"] = measure_mat7(device=local_rank, with_cpu=not args.no_cpu_baseline)
-            line["extra_workloads"]["cd7"] = measure_cd7(device=local_rank, with_cpu=not args.no_cpu_baseline)
-            line["extra_workloads"]["sketch12"] = measure_sketch(device=local_rank, with_cpu=not args.no_cpu_baseline)
-            line["extra_workloads"]["lbfgs12"] = measure_lbfgs(device=local_rank, with_cpu=not args.no_cpu_baseline)
-        except Exception as ex:  # extras must never break the headline line
-            line["extra_workloads"]["error"] = repr(ex)
+        cpu = not args.no_cpu_baseline
+        for key, fn, kw in (("mps50", measure_mps, dict(device=local_rank, with_cpu=cpu)),
+                            ("mps50_physical", measure_mps, dict(device=local_rank, with_cpu=False, physical=True)),
+                            ("mat7", measure_mat7, dict(device=local_rank, with_cpu=cpu)),
+                            ("cd7", measure_cd7, dict(device=local_rank, with_cpu=cpu)),
+                            ("sketch12", measure_sketch, dict(device=local_rank, with_cpu=cpu)),
+                            ("lbfgs12", measure_lbfgs, dict(device=local_rank, with_cpu=cpu))):
+            try:
+                line["extra_workloads"][key] = clocked(fn, **kw)
+            except Exception as ex:  # an extra must never break the headline line (nor the other extras)
+                line["extra_workloads"][key] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
