@@ -127,6 +127,7 @@ struct aqc_mps {
   int num_sms = 148;
   bool svd_precond = true;    // AQC_MPS_SVD=plain: Jacobi directly on the working matrix
   bool svd_fence = false;     // AQC_MPS_FENCE=1
+  bool svd_relaxed = true;    // AQC_MPS_SVD_TOL=strict: rounding-level Jacobi convergence also when truncating
   bool theta_scalar = false;  // AQC_MPS_THETA=scalar: thread-per-column contraction instead of the DMMA GEMM
   double* h_pinned = nullptr;
   size_t pinned_cap = 0;
@@ -749,7 +750,7 @@ __device__ __forceinline__ void jacobi_inner(double2 (&x)[8][NE], double (&nrm)[
 // itself is bound by FP64 issue: 2 cycles per instruction).
 template <int NE>
 __device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int Cc, bool solo, int crank,
-                                              int csize, int* conv, int* sweeps_out, bool fence) {
+                                              int csize, int* conv, int* sweeps_out, bool fence, double tol_floor) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -764,7 +765,9 @@ __device__ __forceinline__ void jacobi_sweeps(double2* Bw, int ldw, int Rj, int 
   const int npairs = ne / 2;
   // convergence: |<p, q>| <= tol |p| |q| with tol ~ 2 sqrt(R) eps (LAPACK xGESVJ uses sqrt(m) eps);
   // a tighter value sits below the rounding noise of the inner product and never converges
-  const double tol = 2.0 * sqrt((double)Rj) * 2.220446049250313e-16;
+  // When the split that follows discards weight up to trunc_thr anyway, orthogonality far below that is
+  // wasted sweeps: tol_floor (0 for untruncated runs) relaxes the test (section 6 of DESIGN.md).
+  const double tol = fmax(2.0 * sqrt((double)Rj) * 2.220446049250313e-16, tol_floor);
   const double tol2 = tol * tol;
   for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
@@ -904,6 +907,9 @@ struct SvdArgs {
   // values relative to the split's total), [1] largest single discard, [2] part of [0] that only the
   // chi_max cap removed (beyond the trunc_thr rule), [3] number of splits the cap cut
   double* trunc_stats;
+  // relaxed Jacobi convergence for truncated runs: columns count as orthogonal once |<p, q>| <= tol_floor
+  // |p| |q| (1e-3 trunc_thr, at most 1e-9; 0 keeps the rounding-level test of untruncated runs)
+  double tol_floor;
 };
 
 __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
@@ -1068,11 +1074,11 @@ __global__ void __launch_bounds__(256) mps_svd_kernel(const SvdArgs A) {
   }
   int* sweeps_out = A.sweeps ? A.sweeps + s * A.maxtasks + t : nullptr;
   if (Rj <= 32)
-    jacobi_sweeps<1>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
+    jacobi_sweeps<1>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0, A.tol_floor);
   else if (Rj <= 64)
-    jacobi_sweeps<2>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
+    jacobi_sweeps<2>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0, A.tol_floor);
   else
-    jacobi_sweeps<4>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0);
+    jacobi_sweeps<4>(Bw, ldw, Rj, Cc, solo, crank, csize, conv, sweeps_out, A.fence != 0, A.tol_floor);
   if (crank != 0) return;
   if (Bw != B) {  // back to global memory for the split below
     __syncthreads();
@@ -1757,6 +1763,8 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
     m->svd_precond = !(sv && std::string(sv) == "plain");
     const char* fe = getenv("AQC_MPS_FENCE");
     m->svd_fence = fe && std::string(fe) == "1";
+    const char* st = getenv("AQC_MPS_SVD_TOL");
+    m->svd_relaxed = !(st && std::string(st) == "strict");
   }
   for (MpsProgram* p : {&m->fwd, &m->dag}) {
     alloc((void**)&p->d_tasks, p->tasks.size() * sizeof(MpsTask));
@@ -1937,6 +1945,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   sa.chi_max = m->chi_max;
   sa.trunc_thr = m->trunc_thr;
   sa.trunc_stats = m->d_trunc;
+  sa.tol_floor = m->svd_relaxed && m->trunc_thr >= 1e-10 ? fmin(1e-9, 1e-3 * m->trunc_thr) : 0.0;
   sa.sweeps = m->d_sweeps;
   sa.conv = m->d_conv;
   sa.precond = m->svd_precond ? 1 : 0;
