@@ -322,33 +322,35 @@ __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A
   __shared__ int s_last;
   const int b = blockIdx.y;
   const double2* s_trig = A.gtrig + (size_t)b * A.nthetas;  // written by the prologue of this sweep
+  // one thread per (stage, unit, virtual quadruple r): w' = e_r, z' = M_out[:, r]; pull both back through
+  // the units behind unit u0 and through u0 itself, then run u0 forward with the reference's gate-by-gate
+  // accumulation (a chain of at most nunits + 1 recipes per thread instead of 2 nunits)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nstages * 4) {
-    const int r = t & 3, s = t >> 2;
-    const StageDesc sd = A.stages[s];
-    const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
-    // virtual quadruple r: w' = e_r, z' = M_out[:, r]; pull both back through the stage, then run it
-    // forward with the reference's gate-by-gate accumulation (dense_grad_kernel)
-    cd a[2][4];
+  if (t < A.nstages * kStageUnits * 4) {
+    const int r = t & 3, s = (t >> 2) / kStageUnits, u0 = (t >> 2) % kStageUnits;
+    const StageDesc& sd = A.stages[s];
+    const int nunits = sd.nunits;
+    if (u0 < nunits) {
+      const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
+      cd a[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
-      a[1][i].x = Mq[(i << 3) | r];
-      a[1][i].y = Mq[(i << 3) | 4 | r];
-    }
-    constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
-    double acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    for (int u = sd.nunits - 1; u >= 0; --u) unit_from_trig<ENT, true, 2>(sd.u[u], s_trig, a, acc);
-    double* g = A.gacc + (size_t)b * A.nthetas * 2;
-    for (int u = 0; u < sd.nunits; ++u) {
+      for (int i = 0; i < 4; ++i) {
+        a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
+        a[1][i].x = Mq[(i << 3) | r];
+        a[1][i].y = Mq[(i << 3) | 4 | r];
+      }
+      constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
+      double acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      unit_from_trig<ENT, false, 2>(sd.u[u], s_trig, a, acc);
-      const int kind = sd.u[u].kind;
+      for (int u = nunits - 1; u >= u0; --u) unit_from_trig<ENT, true, 2>(sd.u[u], s_trig, a, acc);
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      const UnitDesc ud = sd.u[u0];
+      unit_from_trig<ENT, false, 2>(ud, s_trig, a, acc);
+      const int kind = ud.kind;
       const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
-      double* gu = g + 2 * (size_t)sd.u[u].theta;
+      double* gu = A.gacc + (size_t)b * A.nthetas * 2 + 2 * (size_t)ud.theta;
 #pragma unroll
       for (int k = 0; k < NACC; ++k)
         if (k < nval) atomicAdd(gu + k, acc[k]);

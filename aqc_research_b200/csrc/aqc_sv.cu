@@ -119,6 +119,10 @@ struct aqc_sv {
   int num_sms = 148;
   DenseTables dt_grad, dt_fwd, dt_dag;
   double *d_umat = nullptr, *d_gm = nullptr;
+  double* d_umat_grad = nullptr;        // stage matrices of the gradient program (own buffer: its prologue may
+                                        // run on stream_aux while the V^H sweep still uses d_umat)
+  cudaStream_t stream_aux = nullptr;    // aqc_sv_eval_begin: gradient prologue next to the V^H sweep
+  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
   // coordinate descent (aqc_cd.cuh)
   CdUnit* d_cd_units = nullptr;
   int cd_nunits = 0;
@@ -268,7 +272,8 @@ static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
 
 // Prologue of a sweep: stage matrices of one program from the staged angles (mode 0 gradient, 1 V,
 // 2 V^H); the gradient prologue also clears the stage-matrix sums and the per-angle sums.
-static int dense_prepare(aqc_sv* sv, int mode) {
+static int dense_prepare(aqc_sv* sv, int mode, cudaStream_t stream = nullptr) {
+  if (!stream) stream = sv->stream;
   const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
   PrologueArgs a;
   memset(&a, 0, sizeof(a));
@@ -277,7 +282,7 @@ static int dense_prepare(aqc_sv* sv, int mode) {
   a.nthetas = sv->circ.nthetas;
   a.batch = sv->batch;
   a.thetas = sv->h_thetas;
-  a.umat = sv->d_umat;
+  a.umat = mode == 0 ? sv->d_umat_grad : sv->d_umat;
   if (mode == 0) {
     a.zero0 = sv->d_gm;
     a.nzero0 = (long long)sv->batch * a.nstages * 64;
@@ -298,11 +303,11 @@ static int dense_prepare(aqc_sv* sv, int mode) {
     if (dag) {                                                                                            \
       if (dyn > 48 * 1024)                                                                                \
         CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-      sweep_prologue_kernel<E, true><<<grid, 128, dyn, sv->stream>>>(a);                                  \
+      sweep_prologue_kernel<E, true><<<grid, 128, dyn, stream>>>(a);                                  \
     } else {                                                                                              \
       if (dyn > 48 * 1024)                                                                                \
         CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-      sweep_prologue_kernel<E, false><<<grid, 128, dyn, sv->stream>>>(a);                                 \
+      sweep_prologue_kernel<E, false><<<grid, 128, dyn, stream>>>(a);                                 \
     }                                                                                                     \
   } while (0)
   switch (sv->circ.ent) {
@@ -334,7 +339,7 @@ static int dense_collect(aqc_sv* sv) {
   a.ticket = sv->d_ticket;
   a.gtrig = sv->d_trig;
   const size_t dyn = 0;
-  const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
+  const dim3 grid((unsigned)std::max(1, (a.nstages * kStageUnits * 4 + 127) / 128), (unsigned)sv->batch);
 #define AQC_EPI(E)                                                                                                  \
   do {                                                                                                              \
     if (dyn > 48 * 1024)                                                                                            \
@@ -362,7 +367,7 @@ static int run_dense_program(aqc_sv* sv, int mode, const double2* src0, long lon
   memset(&a, 0, sizeof(a));
   a.vec_stride = sv->size;
   a.lanes = dt.d_lanes;
-  a.umat = sv->d_umat;
+  a.umat = mode == 0 ? sv->d_umat_grad : sv->d_umat;
   a.gm = sv->d_gm;
   a.nstages_total = (int)prog.stages.size();
   if (pass_end < 0) pass_end = (int)prog.passes.size();
@@ -477,7 +482,7 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   for (void* q : {(void*)sv->d_cd_units, (void*)sv->d_cd_fobj, (void*)sv->d_target, (void*)sv->d_gram,
                   (void*)sv->d_rinv, (void*)sv->d_info})
     if (q) cudaFree(q);
-  for (void* q : {(void*)sv->d_umat, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
+  for (void* q : {(void*)sv->d_umat, (void*)sv->d_umat_grad, (void*)sv->d_gm, (void*)sv->dt_grad.d_lanes, (void*)sv->dt_fwd.d_lanes,
                   (void*)sv->dt_dag.d_lanes})
     if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
@@ -485,6 +490,9 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   if (sv->d_ticket) cudaFree(sv->d_ticket);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages), cudaFree(p->d_passes);
+  if (sv->ev_aux0) cudaEventDestroy(sv->ev_aux0);
+  if (sv->ev_aux1) cudaEventDestroy(sv->ev_aux1);
+  if (sv->stream_aux) cudaStreamDestroy(sv->stream_aux);
   if (sv->ev_hs) cudaEventDestroy(sv->ev_hs);
   if (sv->ev_obj) cudaEventDestroy(sv->ev_obj);
   if (sv->ev0) cudaEventDestroy(sv->ev0);
@@ -546,6 +554,9 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   } while (0)
   CUB(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
+  CUB(cudaStreamCreateWithFlags(&sv->stream_aux, cudaStreamNonBlocking));
+  CUB(cudaEventCreateWithFlags(&sv->ev_aux0, cudaEventDisableTiming));
+  CUB(cudaEventCreateWithFlags(&sv->ev_aux1, cudaEventDisableTiming));
   CUB(cudaEventCreate(&sv->ev_hs));
   CUB(cudaEventCreate(&sv->ev_obj));
   CUB(cudaEventCreate(&sv->ev0));
@@ -627,6 +638,8 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     }
     const size_t B = batch;
     cudaError_t e = cudaMalloc(&sv->d_umat, B * smax * 64 * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&sv->d_umat_grad, B * std::max<size_t>(1, sv->prog_grad.stages.size()) * 64 * sizeof(double));
     if (e == cudaSuccess)
       e = cudaMalloc(&sv->d_gm, B * std::max<size_t>(1, sv->prog_grad.stages.size()) * 64 * sizeof(double));
     if (e != cudaSuccess) {
@@ -1237,6 +1250,13 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   rc = upload_thetas(sv, thetas, false);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev0, sv->stream));
+  // the gradient program's prologue (stage matrices, cleared sums, trig table) does not depend on the V^H
+  // sweep: it runs next to it on the auxiliary stream, behind everything enqueued so far
+  CU(cudaEventRecord(sv->ev_aux0, sv->stream));
+  CU(cudaStreamWaitEvent(sv->stream_aux, sv->ev_aux0, 0));
+  rc = dense_prepare(sv, 0, sv->stream_aux);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev_aux1, sv->stream_aux));
   rc = dense_prepare(sv, 2);
   if (!rc) rc = run_dense_program(sv, 2, sv->slots[target_slot], -1, nullptr, sv->slots[z0_slot], nullptr, 0, -1);
   if (rc) return rc;
@@ -1248,7 +1268,7 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   CU(cudaGetLastError());
   sv->last_launches += 1;
   CU(cudaEventRecord(sv->ev_hs, sv->stream));
-  rc = dense_prepare(sv, 0);
+  CU(cudaStreamWaitEvent(sv->stream, sv->ev_aux1, 0));
   if (!rc)
     rc = run_dense_program(sv, 0, nullptr, x_basis, sv->slots[z0_slot], sv->slots[w_slot], sv->slots[z_slot], 0, -1);
   if (!rc) rc = dense_collect(sv);
