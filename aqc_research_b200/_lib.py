@@ -66,6 +66,7 @@ SIGNATURES = {
         [ct.c_void_p, c_double_p, ct.c_int, ct.c_int, c_int64_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_int],
     ),
     "aqc_sv_eval_hs": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+    "aqc_sv_can_eval": (ct.c_int, [ct.c_void_p]),
     "aqc_sv_eval_times": (ct.c_int, [ct.c_void_p, ct.POINTER(ct.c_float), ct.POINTER(ct.c_float)]),
     "aqc_sv_last_kernel_ms": (ct.c_float, [ct.c_void_p]),
     "aqc_sv_last_num_launches": (ct.c_int, [ct.c_void_p]),

@@ -1236,6 +1236,7 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   if (rc) return rc;
   if (!thetas || !idx || count <= 0) return fail(AQC_EINVAL, "bad arguments");
   if (!sv->dense) return fail(AQC_EINVAL, "aqc_sv_eval_begin needs the dense engine");
+  if (sv->g != 0) return fail(AQC_EINVAL, "aqc_sv_eval_begin is for unsharded workspaces (sharded states run epoch by epoch)");
   if (x_basis < 0 || x_basis >= sv->size) return fail(AQC_EINVAL, "basis index out of range");
   if (w_slot == z_slot || w_slot == z0_slot || w_slot == target_slot || z_slot == target_slot || z0_slot == target_slot)
     return fail(AQC_EINVAL, "slot aliasing");
@@ -1277,6 +1278,9 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   sv->grad_pending = true;
   return AQC_OK;
 }
+
+// 1 if aqc_sv_eval_begin is available on this workspace (dense engine, unsharded), else 0.
+extern "C" int aqc_sv_can_eval(const aqc_sv* sv) { return (sv && sv->dense && sv->g == 0) ? 1 : 0; }
 
 // hs of the evaluation in flight (the gradient sweep may still be running).
 extern "C" int aqc_sv_eval_hs(aqc_sv* sv, double* hs_out) {

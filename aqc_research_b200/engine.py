@@ -127,6 +127,7 @@ class SvWorkspace:
         )
         self.handle = handle
         self.size = int(self._lib.aqc_sv_state_size(handle))
+        self.can_eval = bool(self._lib.aqc_sv_can_eval(handle))  # one-submission evaluations (eval_begin)
 
     # -- data movement ---------------------------------------------------------------------
     def upload(self, slot: int, data: np.ndarray, batch_index: int = -1):

@@ -64,7 +64,7 @@ class SpSurrogateObjectiveMax(SpLHSObjectiveBase):
         # the gradient sweep from |s_0> -- is enqueued at once; hs comes back as soon as the gather is
         # done while the gradient sweep keeps the GPU busy (aqc_sv_eval_begin).  If the hysteresis below
         # then picks another leader, that sweep is simply not collected.
-        speculative = early and self._max_no == 0
+        speculative = early and self._max_no == 0 and getattr(self._ws, "can_eval", True)
         if speculative:
             if self._target is None:
                 raise RuntimeError("set_target() must be called before objective()")

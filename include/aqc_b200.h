@@ -148,6 +148,9 @@ int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slot, int z0_s
 int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_slot, int z0_slot,
                       const int64_t* idx, int count, int64_t x_basis, int w_slot, int z_slot);
 int aqc_sv_eval_hs(aqc_sv* sv, double* hs_out);
+/* 1 if aqc_sv_eval_begin is available (dense engine, unsharded workspace; states of fewer than 32
+ * amplitudes run on the legacy engine), else 0: callers then use aqc_sv_objective + aqc_sv_grad. */
+int aqc_sv_can_eval(const aqc_sv* sv);
 /* kernel-time split (ms) of the last completed aqc_sv_eval_begin .. aqc_sv_grad_end pair */
 int aqc_sv_eval_times(aqc_sv* sv, float* obj_ms, float* grad_ms);
 

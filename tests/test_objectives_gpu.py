@@ -215,6 +215,34 @@ def test_early_gradient_start_and_its_fallbacks():
     check(ths[3])
 
 
+@pytest.mark.parametrize("n", [3, 6, 11])
+def test_one_submission_evaluation_with_leader_zero(n):
+    """
+    Near target (the leading state stays |s_0>): once the fun / jac pattern is learnt objective() enqueues the
+    whole evaluation (aqc_sv_eval_begin) and gradient() collects it; values and gradients equal the oracle's.
+    n = 3 runs on the legacy engine, which has no such call (the class falls back to the two-step path).
+    """
+    from aqc_research_b200 import circuit_structures as cs, utils
+
+    np.random.seed(1300 + n)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, 2), True)
+    th_star = utils.rand_thetas(circ.num_thetas)
+    e0 = np.zeros(2**n, dtype=np.complex128)
+    e0[0] = 1
+    target = O.apply_v(circ, th_star, e0)
+    objv = SpSurrogateObjectiveMax(user_parameters=_params(n), circ=circ, front_layer=True)
+    objv.set_target(target)
+    assert objv.workspace.can_eval == (n >= 5)
+    for step in range(6):
+        th = th_star + 0.02 * (2 * np.random.rand(circ.num_thetas) - 1)
+        w_before = objv.weight
+        f = objv.objective(th)
+        g = objv.gradient(th)
+        f_ref, _, g_ref, _ = O.sur_max_value_and_grad(circ, th, target, w_before, 0)
+        assert objv.max_no == 0 and abs(f - f_ref) < TOL and rel(g, g_ref) < TOL, step
+    assert objv._early_on
+
+
 def test_set_sparse_and_fused_two_term_sweep():
     """
     aqc_sv_set_sparse writes a few basis amplitudes; one sweep started from the weighted combination
