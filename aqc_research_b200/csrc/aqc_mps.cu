@@ -127,6 +127,7 @@ struct aqc_mps {
   int num_sms = 148;
   bool svd_precond = true;    // AQC_MPS_SVD=plain: Jacobi directly on the working matrix
   bool svd_fence = false;     // AQC_MPS_FENCE=1
+  int svd_cluster = 0;        // AQC_MPS_CLUSTER=1|2|4: CTAs per SVD instead of "as many as fit one wave"
   bool svd_relaxed = true;    // AQC_MPS_SVD_TOL=strict: rounding-level Jacobi convergence also when truncating
   bool theta_scalar = false;  // AQC_MPS_THETA=scalar: thread-per-column contraction instead of the DMMA GEMM
   double* h_pinned = nullptr;
@@ -1763,6 +1764,8 @@ extern "C" int aqc_mps_create(const aqc_circuit* circ, int device, int chi_max, 
     m->svd_precond = !(sv && std::string(sv) == "plain");
     const char* fe = getenv("AQC_MPS_FENCE");
     m->svd_fence = fe && std::string(fe) == "1";
+    const char* cl = getenv("AQC_MPS_CLUSTER");
+    m->svd_cluster = (cl && (*cl == '1' || *cl == '2' || *cl == '4') && !cl[1]) ? (*cl - '0') : 0;
     const char* st = getenv("AQC_MPS_SVD_TOL");
     m->svd_relaxed = !(st && std::string(st) == "strict");
   }
@@ -1955,6 +1958,7 @@ static int run_step_svd(aqc_mps* m, const MpsProgram& prog, const MpsStep& st, c
   const int nsvd = st.ntasks * nstates;
   if (nsvd * 4 <= m->num_sms) csize = 4;
   else if (nsvd * 2 <= m->num_sms) csize = 2;
+  if (m->svd_cluster > 0) csize = m->svd_cluster;  // AQC_MPS_CLUSTER (development switch)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(st.ntasks * csize, nstates);
