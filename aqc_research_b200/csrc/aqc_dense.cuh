@@ -213,10 +213,9 @@ static bool build_dense_tables(const Program& prog, DenseTables& T, int fuse_pai
 //   sweep_prologue_kernel : stage matrices U_s(theta) of one program straight from the angles (the host
 //                           writes them into pinned, device-mapped memory -- no H2D copy, no (cos, sin)
 //                           table), and the zeroing of the gradient accumulators;
-//   grad_epilogue_kernel  : per-rotation inner products from the accumulated stage matrices
-//                           (see dense_grad_kernel), the 0.5 / 0.5j / -i factors of the reference
-//                           (core_operations.py:317-351, 972-975) and the write of the finished complex
-//                           gradient into pinned host memory by the last CTA that completes.
+//   grad_epilogue_kernel  : per-rotation inner products from the accumulated stage matrices, the
+//                           0.5 / 0.5j / -i factors of the reference (core_operations.py:317-351, 972-975)
+//                           and the write of the finished complex gradient into pinned host memory.
 // ------------------------------------------------------------------------------------------------
 // One gate unit applied to NVEC amplitude quadruples with the (cos, sin) pairs of its angles taken from
 // `tr` (indexed like thetas; half angles, full angle for the CPhase parameter).
@@ -232,6 +231,13 @@ __device__ __forceinline__ void unit_from_trig(const UnitDesc& u, const double2*
     default: break;
   }
 }
+
+// Programmatic dependent launch (the kernels of one evaluation are a chain in one stream): a kernel lets its
+// successor be scheduled at once, and waits for its predecessor's memory before it touches anything a
+// kernel wrote or still reads -- the successor's launch latency and index arithmetic hide behind the
+// predecessor's tail.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 struct PrologueArgs {
   const StageDesc* stages;
@@ -278,13 +284,17 @@ __device__ __forceinline__ void build_trig_smem(const double* __restrict__ host_
 }
 
 template <int ENT, bool DAG>
-__global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
+__device__ __forceinline__ void sweep_prologue_body(const PrologueArgs& A, const double* thetas) {
   extern __shared__ double2 s_trig_buf[];
   const int b = blockIdx.y;
   const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
-  if (!A.gtrig)
-    build_trig_smem(A.thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf,
-                    (A.trig_out && blockIdx.x == 0) ? A.trig_out + (size_t)b * A.nthetas : nullptr);
+  pdl_launch_dependents();
+  // (the angles come from the host -- launch parameters or pinned memory -- so the table is built BEFORE the
+  // wait; everything below writes memory the previous evaluation's kernels read)
+  if (!A.gtrig) build_trig_smem(thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf, nullptr);
+  pdl_wait();
+  if (!A.gtrig && A.trig_out && blockIdx.x == 0)  // kept for the epilogue of the same sweep
+    for (int k = threadIdx.x; k < A.nthetas; k += blockDim.x) A.trig_out[(size_t)b * A.nthetas + k] = s_trig_buf[k];
   const long long gt = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
   const long long gsz = (long long)gridDim.x * gridDim.y * blockDim.x;
   for (long long i = gt; i < A.nzero0; i += gsz) A.zero0[i] = 0.0;
@@ -307,66 +317,102 @@ __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs 
   }
 }
 
+template <int ENT, bool DAG>
+__global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
+  sweep_prologue_body<ENT, DAG>(A, A.thetas);
+}
+
+// The same with the angles INSIDE the launch parameters (one state, <= kArgThetas angles -- every
+// BASELINE configuration): they arrive with the launch instead of through PCIe reads of pinned memory
+// from inside the kernel (~2 us of the 6-7 us a prologue took at n = 12 ... 20).
+constexpr int kArgThetas = 480;
+struct PrologueArgsT {
+  PrologueArgs a;
+  double th[kArgThetas];
+};
+static_assert(sizeof(PrologueArgsT) <= 4096, "launch parameters");
+template <int ENT, bool DAG>
+__global__ void __launch_bounds__(128) sweep_prologue_args_kernel(const __grid_constant__ PrologueArgsT P) {
+  sweep_prologue_body<ENT, DAG>(P.a, P.th);
+}
+
 struct EpilogueArgs {
   const StageDesc* stages;
   int nstages, nthetas, batch, n3, tpb;
+  int trig_smem;           // 1: the (cos, sin) table is staged in shared memory first (it fits the launch's window)
   const double2* gtrig;    // [batch][nthetas] (cos, sin) table in device memory, left by the sweep's prologue
   const double* gm;        // [batch][nstages][64] accumulated stage matrices
-  double* gacc;            // [batch][nthetas] complex raw sums (zeroed by the prologue)
   double* out;             // [batch][nthetas] complex gradient 0.5j <P w|z>, pinned host memory
-  unsigned* ticket;        // completion counter (left at zero)
+  // Second-order Trotter circuits end with a half layer that REUSES the angles of the first one
+  // (parametric_circuit.py:326-336): units of that trailing layer (occurrence number >= extra_seq) store
+  // into out2, a second [batch][nthetas] array, and the host adds the two
+  double* out2;
+  int extra_seq;
 };
 
 template <int ENT>
 __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A) {
-  __shared__ int s_last;
+  extern __shared__ double2 s_trig_e[];
   const int b = blockIdx.y;
-  const double2* s_trig = A.gtrig + (size_t)b * A.nthetas;  // written by the prologue of this sweep
+  const double2* gt = A.gtrig + (size_t)b * A.nthetas;  // written by the prologue of this sweep
   // one thread per (stage, unit, virtual quadruple r): w' = e_r, z' = M_out[:, r]; pull both back through
   // the units behind unit u0 and through u0 itself, then run u0 forward with the reference's gate-by-gate
   // accumulation (a chain of at most nunits + 1 recipes per thread instead of 2 nunits)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nstages * kStageUnits * 4) {
-    const int r = t & 3, s = (t >> 2) / kStageUnits, u0 = (t >> 2) % kStageUnits;
-    const StageDesc& sd = A.stages[s];
-    const int nunits = sd.nunits;
-    if (u0 < nunits) {
-      const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
-      cd a[2][4];
+  const int r = t & 3, s = (t >> 2) / kStageUnits, u0 = (t >> 2) % kStageUnits;
+  pdl_launch_dependents();
+  const bool live = s < A.nstages && u0 < A.stages[s].nunits;
+  pdl_wait();
+  // the stage matrix and the table are requested together: one L2 round trip in front of the chain
+  cd a[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0;
-        a[1][i].x = Mq[(i << 3) | r];
-        a[1][i].y = Mq[(i << 3) | 4 | r];
-      }
-      constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
-      double acc[NACC];
+  for (int i = 0; i < 4; ++i) a[0][i].x = (i == r) ? 1.0 : 0.0, a[0][i].y = 0.0, a[1][i].x = a[1][i].y = 0.0;
+  if (live) {
+    const double* Mq = A.gm + ((size_t)b * A.nstages + s) * 64;
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      for (int u = nunits - 1; u >= u0; --u) unit_from_trig<ENT, true, 2>(sd.u[u], s_trig, a, acc);
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      const UnitDesc ud = sd.u[u0];
-      unit_from_trig<ENT, false, 2>(ud, s_trig, a, acc);
-      const int kind = ud.kind;
-      const int nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
-      double* gu = A.gacc + (size_t)b * A.nthetas * 2 + 2 * (size_t)ud.theta;
-#pragma unroll
-      for (int k = 0; k < NACC; ++k)
-        if (k < nval) atomicAdd(gu + k, acc[k]);
+    for (int i = 0; i < 4; ++i) {
+      a[1][i].x = __ldcg(Mq + ((i << 3) | r));
+      a[1][i].y = __ldcg(Mq + ((i << 3) | 4 | r));
     }
   }
-  // the CTA that finishes last converts the raw sums and hands the gradient to the host
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int total = A.batch * A.nthetas;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int k = i % A.nthetas;
-    const double re = __ldcg(A.gacc + 2 * (size_t)i), im = __ldcg(A.gacc + 2 * (size_t)i + 1);
+  const double2* s_trig = gt;
+  if (A.trig_smem) {
+    for (int k = threadIdx.x; k < A.nthetas; k += blockDim.x) s_trig_e[k] = gt[k];
+    __syncthreads();
+    s_trig = s_trig_e;
+  }
+  constexpr int NACC = (ENT == AQC_ENT_CP) ? 16 : 8;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  int theta0 = 0, nval = 0;
+  double* out = A.out;
+  if (live) {
+    const StageDesc& sd = A.stages[s];
+    for (int u = sd.nunits - 1; u >= u0; --u) unit_from_trig<ENT, true, 2>(sd.u[u], s_trig, a, acc);
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    const UnitDesc ud = sd.u[u0];
+    unit_from_trig<ENT, false, 2>(ud, s_trig, a, acc);
+    const int kind = ud.kind;
+    nval = (kind == U_FRONT_LO || kind == U_FRONT_HI) ? 6 : ((kind == U_NONE) ? 0 : (ENT == AQC_ENT_CP ? 10 : 8));
+    theta0 = ud.theta;
+    if (ud.slot >= 5 * A.extra_seq) out = A.out2;
+  }
+  // Every angle belongs to exactly ONE unit occurrence per output array (checked when the program is built),
+  // so its inner product is the sum over the unit's four r lanes -- adjacent lanes of one warp: two
+  // shuffles, no atomics, no second phase.  Lane r converts and stores angles r and r + 4 of the unit with the
+  // reference's 0.5 / 0.5j / -i factors (core_operations.py:317-351, 972-975), straight into pinned memory.
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+  }
+#pragma unroll
+  for (int j = 0; j < NACC / 2; ++j) {
+    if ((j & 3) != r || 2 * j >= nval) continue;
+    const int k = theta0 + j;
+    const double re = acc[2 * j], im = acc[2 * j + 1];
     int kind;  // 0: Ry (0.5), 1: Rz / Rx (0.5j), 2: CPhase (-i)
     if (k < A.n3)
       kind = (k % 3 == 1) ? 0 : 1;
@@ -381,14 +427,15 @@ __global__ void __launch_bounds__(128) grad_epilogue_kernel(const EpilogueArgs A
       v = make_double2(-0.5 * im, 0.5 * re);
     else
       v = make_double2(im, -re);
-    reinterpret_cast<double2*>(A.out)[i] = v;
+    reinterpret_cast<double2*>(out)[(size_t)b * A.nthetas + k] = v;
   }
-  if (threadIdx.x == 0) *A.ticket = 0u;
 }
 
 // hs[b][i] = v[b][idx[i]] written straight into pinned host memory
 __global__ void gather_out_kernel(const double2* __restrict__ v, long long stride, const long long* __restrict__ idx,
                                   int count, double2* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   out[(size_t)blockIdx.y * count + i] = v[(long long)blockIdx.y * stride + idx[i]];
@@ -478,6 +525,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]
   __shared__ double2* s_xdst[32];                                       // [vector][rank] push destinations
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
   if (A.xchg_world > 0 && tid < 32) s_xdst[tid] = A.xdst[tid >> 4][tid & 15];  // (read after the stage barriers)
   const int lane = tid & 31, warp = tid >> 5;
   const int tb = A.pd.tb;
@@ -520,6 +568,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
   // kPairSwap flag once it has arrived, so no load waits for another one
   double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // stage matrices of stages s and s + 1
   uint2 dl = make_uint2(0u, 0u);
+  pdl_wait();  // everything above is index arithmetic; from here on the pass reads what its predecessors wrote
   if (nstages > 0) {
     dl = lt[0];
     c0 = um[0];

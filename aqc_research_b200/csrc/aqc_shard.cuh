@@ -100,12 +100,12 @@ extern "C" int aqc_sv_grad_finish(aqc_sv* sv, double* grad_out) {
   if (!sv || !grad_out) return fail(AQC_EINVAL, "bad arguments");
   CU(cudaSetDevice(sv->device));
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
-  int rc = ensure_pinned(sv, tot * 2 + 64);
+  int rc = ensure_pinned(sv, tot * 4 + 64);
   if (rc) return rc;
   if (sv->dense) {  // the epilogue kernel converts and writes the (partial) gradient into h_pinned
     if ((rc = dense_collect(sv))) return rc;
     CU(cudaStreamSynchronize(sv->stream));
-    memcpy(grad_out, sv->h_pinned, tot * 2 * sizeof(double));
+    dense_gradient_from_pinned(sv, grad_out);
     return AQC_OK;
   }
   CU(cudaMemcpyAsync(sv->h_pinned, sv->d_gacc, tot * 2 * sizeof(double), cudaMemcpyDeviceToHost,

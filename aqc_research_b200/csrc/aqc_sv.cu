@@ -100,7 +100,6 @@ struct aqc_sv {
   size_t idx_cap = 0, scratch_cap = 0;
   double* h_pinned = nullptr;  // pinned staging for small results (the device writes them directly)
   double* h_thetas = nullptr;  // pinned, device-readable copy of the angles of the call in flight
-  unsigned* d_ticket = nullptr;  // completion counter of grad_epilogue_kernel
   bool trig_in_global = false;   // > 12 800 angles: the (cos, sin) table does not fit shared memory
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;
@@ -255,6 +254,26 @@ static int run_program(aqc_sv* sv, const Program& prog, bool grad, bool dag, con
 
 static int env_int(const char* name, int dflt);
 // ---- dense-stage engine: host side ----------------------------------------------------------------
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in aqc_dense.cuh): the kernel
+// may be scheduled while its predecessor in the stream drains.  AQC_PDL=0 launches plainly.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  static const bool pdl = env_int("AQC_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int NVEC>
 static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
   const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
@@ -265,13 +284,12 @@ static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
     configured[sv->device & 63] = true;
   }
   dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
-  dense_pass_kernel<NVEC><<<grid, kDThreads, smem, sv->stream>>>(args);
-  CU(cudaGetLastError());
+  CU(launch_chained(dense_pass_kernel<NVEC>, grid, dim3(kDThreads), smem, sv->stream, args));
   return AQC_OK;
 }
 
 // Prologue of a sweep: stage matrices of one program from the staged angles (mode 0 gradient, 1 V,
-// 2 V^H); the gradient prologue also clears the stage-matrix sums and the per-angle sums.
+// 2 V^H); the gradient prologue also clears the stage-matrix sums.
 static int dense_prepare(aqc_sv* sv, int mode, cudaStream_t stream = nullptr) {
   if (!stream) stream = sv->stream;
   const Program& p = mode == 0 ? sv->prog_grad : (mode == 1 ? sv->prog_fwd : sv->prog_dag);
@@ -286,8 +304,6 @@ static int dense_prepare(aqc_sv* sv, int mode, cudaStream_t stream = nullptr) {
   if (mode == 0) {
     a.zero0 = sv->d_gm;
     a.nzero0 = (long long)sv->batch * a.nstages * 64;
-    a.zero1 = sv->d_gacc;
-    a.nzero1 = (long long)sv->batch * sv->circ.nthetas * 2;
   }
   if (a.nstages == 0 && a.nzero0 == 0 && a.nzero1 == 0) return AQC_OK;
   a.n3 = 3 * sv->circ.n;
@@ -298,16 +314,39 @@ static int dense_prepare(aqc_sv* sv, int mode, cudaStream_t stream = nullptr) {
   const size_t dyn = sv->trig_in_global ? 0 : (size_t)sv->circ.nthetas * sizeof(double2);
   const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
   const bool dag = mode == 2;
+  if (sv->batch == 1 && sv->circ.nthetas <= kArgThetas && !sv->trig_in_global) {
+    // the angles travel inside the launch parameters
+    PrologueArgsT pa;
+    pa.a = a;
+    pa.a.thetas = nullptr;
+    memcpy(pa.th, sv->h_thetas, (size_t)sv->circ.nthetas * sizeof(double));
+#define AQC_PROA(E)                                                              \
+  do {                                                                           \
+    if (dag)                                                                     \
+      CU(launch_chained(sweep_prologue_args_kernel<E, true>, grid, dim3(128), dyn, stream, pa));  \
+    else                                                                         \
+      CU(launch_chained(sweep_prologue_args_kernel<E, false>, grid, dim3(128), dyn, stream, pa)); \
+  } while (0)
+    switch (sv->circ.ent) {
+      case AQC_ENT_CX: AQC_PROA(AQC_ENT_CX); break;
+      case AQC_ENT_CZ: AQC_PROA(AQC_ENT_CZ); break;
+      default: AQC_PROA(AQC_ENT_CP);
+    }
+#undef AQC_PROA
+    CU(cudaGetLastError());
+    sv->last_launches += 1;
+    return AQC_OK;
+  }
 #define AQC_PRO(E)                                                                                        \
   do {                                                                                                    \
     if (dag) {                                                                                            \
       if (dyn > 48 * 1024)                                                                                \
         CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-      sweep_prologue_kernel<E, true><<<grid, 128, dyn, stream>>>(a);                                  \
+      CU(launch_chained(sweep_prologue_kernel<E, true>, grid, dim3(128), dyn, stream, a));            \
     } else {                                                                                              \
       if (dyn > 48 * 1024)                                                                                \
         CU(cudaFuncSetAttribute(sweep_prologue_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-      sweep_prologue_kernel<E, false><<<grid, 128, dyn, stream>>>(a);                                 \
+      CU(launch_chained(sweep_prologue_kernel<E, false>, grid, dim3(128), dyn, stream, a));           \
     }                                                                                                     \
   } while (0)
   switch (sv->circ.ent) {
@@ -334,17 +373,20 @@ static int dense_collect(aqc_sv* sv) {
   a.n3 = 3 * sv->circ.n;
   a.tpb = sv->circ.tpb;
   a.gm = sv->d_gm;
-  a.gacc = sv->d_gacc;
   a.out = sv->h_pinned;
-  a.ticket = sv->d_ticket;
+  a.out2 = sv->h_pinned + 2 * (size_t)sv->batch * sv->circ.nthetas;
+  a.extra_seq = sv->circ.n + sv->circ.nb;
   a.gtrig = sv->d_trig;
-  const size_t dyn = 0;
+  // the (cos, sin) table of one batch element is staged in shared memory when it fits the default window
+  const size_t table = (size_t)sv->circ.nthetas * sizeof(double2);
+  a.trig_smem = table <= 40 * 1024 ? 1 : 0;
+  const size_t dyn = a.trig_smem ? table : 0;
   const dim3 grid((unsigned)std::max(1, (a.nstages * kStageUnits * 4 + 127) / 128), (unsigned)sv->batch);
 #define AQC_EPI(E)                                                                                                  \
   do {                                                                                                              \
     if (dyn > 48 * 1024)                                                                                            \
       CU(cudaFuncSetAttribute(grad_epilogue_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));     \
-    grad_epilogue_kernel<E><<<grid, 128, dyn, sv->stream>>>(a);                                                     \
+    CU(launch_chained(grad_epilogue_kernel<E>, grid, dim3(128), dyn, sv->stream, a));                               \
   } while (0)
   switch (sv->circ.ent) {
     case AQC_ENT_CX: AQC_EPI(AQC_ENT_CX); break;
@@ -355,6 +397,20 @@ static int dense_collect(aqc_sv* sv) {
   CU(cudaGetLastError());
   sv->last_launches += 1;
   return AQC_OK;
+}
+
+// The finished gradient of the dense engine from the pinned buffer the epilogue wrote (after a synchronize):
+// the first array plus, for the angles a trailing half layer shares with the first layer, the second one.
+static void dense_gradient_from_pinned(const aqc_sv* sv, double* grad_out) {
+  const size_t T = (size_t)sv->circ.nthetas, tot = (size_t)sv->batch * T;
+  memcpy(grad_out, sv->h_pinned, tot * 2 * sizeof(double));
+  if (sv->circ.half <= 0) return;
+  const size_t k0 = 2 * (size_t)(3 * sv->circ.n), k1 = k0 + 2 * (size_t)sv->circ.half * sv->circ.tpb;
+  for (int b = 0; b < sv->batch; ++b) {
+    const double* second = sv->h_pinned + 2 * tot + (size_t)b * T * 2;
+    double* g = grad_out + (size_t)b * T * 2;
+    for (size_t k = k0; k < k1; ++k) g[k] += second[k];
+  }
 }
 
 // passes [pass_begin, pass_end) of a program on the dense engine; mode 0: (w, z), else one vector
@@ -487,7 +543,6 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
     if (q) cudaFree(q);
   if (sv->h_pinned) cudaFreeHost(sv->h_pinned);
   if (sv->h_thetas) cudaFreeHost(sv->h_thetas);
-  if (sv->d_ticket) cudaFree(sv->d_ticket);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages), cudaFree(p->d_passes);
   if (sv->ev_aux0) cudaEventDestroy(sv->ev_aux0);
@@ -571,8 +626,6 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMalloc(&sv->d_gacc, tot * 2 * sizeof(double)));
   CUB(cudaMallocHost(&sv->h_thetas, std::max<size_t>(tot, 1) * sizeof(double)));
   sv->trig_in_global = (size_t)circ->nthetas * sizeof(double2) > 200 * 1024;
-  CUB(cudaMalloc(&sv->d_ticket, sizeof(unsigned)));
-  CUB(cudaMemset(sv->d_ticket, 0, sizeof(unsigned)));
 #undef CUB
   // Tile shape.  States beyond the L2 (> 64 MiB) want 256-byte contiguous runs (4 low bits) and the
   // largest tile; L2-resident states (nbits <= 22) have too few tiles to fill 3 CTAs on each of the
@@ -617,6 +670,34 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
     if (rc) return bail(rc);
   }
   if (sv->dense) {
+    // grad_epilogue_kernel stores every angle's inner product from the ONE unit that owns it: each angle
+    // must be covered exactly once by the gradient program
+    // (the trailing half layer of a second-order circuit repeats the first one's angles: those occurrences
+    // go to a second array, see EpilogueArgs::out2)
+    std::vector<int> cover((size_t)sv->circ.nthetas, 0), cover2((size_t)sv->circ.nthetas, 0);
+    const int extra_seq = sv->circ.n + sv->circ.nb;
+    for (const StageDesc& sd : sv->prog_grad.stages)
+      for (int u = 0; u < sd.nunits; ++u) {
+        const int k = sd.u[u].kind;
+        const int na = (k == U_FRONT_LO || k == U_FRONT_HI) ? 3 : (k == U_NONE ? 0 : sv->circ.tpb);
+        for (int j = 0; j < na; ++j) {
+          const int th = sd.u[u].theta + j;
+          if (th < 0 || th >= sv->circ.nthetas) {
+            fail(AQC_EINVAL, "internal: unit angle %d outside the circuit's %d angles", th, sv->circ.nthetas);
+            return bail(AQC_EINVAL);
+          }
+          (sd.u[u].slot >= 5 * extra_seq ? cover2 : cover)[(size_t)th] += 1;
+        }
+      }
+    const int n3 = 3 * sv->circ.n, shared_end = n3 + sv->circ.half * sv->circ.tpb;
+    for (int th = 0; th < sv->circ.nthetas; ++th) {
+      const int want2 = (th >= n3 && th < shared_end) ? 1 : 0;
+      if (cover[(size_t)th] != 1 || cover2[(size_t)th] != want2) {
+        fail(AQC_EINVAL, "internal: angle %d is covered by %d + %d units of the gradient program", th,
+             cover[(size_t)th], cover2[(size_t)th]);
+        return bail(AQC_EINVAL);
+      }
+    }
     size_t smax = 1;
     Program* progs[3] = {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag};
     DenseTables* tabs[3] = {&sv->dt_grad, &sv->dt_fwd, &sv->dt_dag};
@@ -1112,9 +1193,9 @@ extern "C" int aqc_sv_objective(aqc_sv* sv, const double* thetas, int target_slo
   rc = apply_async(sv, thetas, 1, target_slot, z0_slot);
   if (rc) return rc;
   // the gathered amplitudes go straight into the pinned result buffer
-  gather_out_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
-      sv->slots[z0_slot], sv->size, sv->d_idx, count, reinterpret_cast<double2*>(sv->h_pinned));
-  CU(cudaGetLastError());
+  CU(launch_chained(gather_out_kernel, dim3((count + 127) / 128, sv->batch), dim3(128), 0, sv->stream,
+                    (const double2*)sv->slots[z0_slot], (long long)sv->size, (const long long*)sv->d_idx, count,
+                    reinterpret_cast<double2*>(sv->h_pinned)));
   sv->last_launches += 1;
   CU(cudaStreamSynchronize(sv->stream));
   memcpy(hs_out, sv->h_pinned, nout * sizeof(double));
@@ -1142,7 +1223,7 @@ extern "C" int aqc_sv_grad_begin(aqc_sv* sv, const double* thetas, int x_slot, i
   CU(cudaSetDevice(sv->device));
   sv->last_launches = 0;
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
-  rc = ensure_pinned(sv, tot * 2 + 64);
+  rc = ensure_pinned(sv, tot * 4 + 64);  // (two arrays: see EpilogueArgs::out2)
   if (rc) return rc;
   rc = upload_thetas(sv, thetas, !sv->dense);
   if (rc) return rc;
@@ -1176,7 +1257,7 @@ extern "C" int aqc_sv_grad_end(aqc_sv* sv, double* grad_out) {
   CU(cudaStreamSynchronize(sv->stream));
   CU(cudaEventElapsedTime(&sv->last_ms, sv->ev0, sv->ev1));
   if (sv->dense) {
-    memcpy(grad_out, sv->h_pinned, tot * 2 * sizeof(double));
+    dense_gradient_from_pinned(sv, grad_out);
     return AQC_OK;
   }
   // legacy engine: raw sums -> 0.5j <P w|z>: Ry 0.5, Rz/Rx 0.5j, CPhase -i
@@ -1244,7 +1325,7 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   sv->last_launches = 0;
   const size_t tot = (size_t)sv->batch * sv->circ.nthetas;
   const size_t nout = (size_t)2 * count * sv->batch;
-  rc = ensure_pinned(sv, 2 * tot + nout + 64);
+  rc = ensure_pinned(sv, 4 * tot + nout + 64);
   if (rc) return rc;
   rc = gather_indices(sv, idx, count);
   if (rc) return rc;
@@ -1262,18 +1343,23 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   if (!rc) rc = run_dense_program(sv, 2, sv->slots[target_slot], -1, nullptr, sv->slots[z0_slot], nullptr, 0, -1);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev_obj, sv->stream));
-  sv->eval_hs_off = 2 * tot;  // behind the gradient's region: the two results never share bytes
+  sv->eval_hs_off = 4 * tot;  // behind the gradient's two arrays: the results never share bytes
   sv->eval_hs_count = nout;
-  gather_out_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream>>>(
+  // hs leaves on the auxiliary stream, next to the gradient sweep (which only reads z0): the gather is
+  // not on the critical path of the evaluation
+  CU(cudaStreamWaitEvent(sv->stream_aux, sv->ev_obj, 0));
+  gather_out_kernel<<<dim3((count + 127) / 128, sv->batch), 128, 0, sv->stream_aux>>>(
       sv->slots[z0_slot], sv->size, sv->d_idx, count, reinterpret_cast<double2*>(sv->h_pinned + sv->eval_hs_off));
   CU(cudaGetLastError());
   sv->last_launches += 1;
-  CU(cudaEventRecord(sv->ev_hs, sv->stream));
+  CU(cudaEventRecord(sv->ev_hs, sv->stream_aux));
   CU(cudaStreamWaitEvent(sv->stream, sv->ev_aux1, 0));
   if (!rc)
     rc = run_dense_program(sv, 0, nullptr, x_basis, sv->slots[z0_slot], sv->slots[w_slot], sv->slots[z_slot], 0, -1);
   if (!rc) rc = dense_collect(sv);
   if (rc) return rc;
+  // (the main stream ends behind the gather as well: a synchronize on it covers the whole evaluation)
+  CU(cudaStreamWaitEvent(sv->stream, sv->ev_hs, 0));
   CU(cudaEventRecord(sv->ev1, sv->stream));
   sv->grad_pending = true;
   return AQC_OK;
@@ -1299,7 +1385,7 @@ extern "C" int aqc_sv_eval_times(aqc_sv* sv, float* obj_ms, float* grad_ms) {
   if (!sv || !obj_ms || !grad_ms) return fail(AQC_EINVAL, "null pointer argument");
   CU(cudaSetDevice(sv->device));
   CU(cudaEventElapsedTime(obj_ms, sv->ev0, sv->ev_obj));
-  CU(cudaEventElapsedTime(grad_ms, sv->ev_hs, sv->ev1));
+  CU(cudaEventElapsedTime(grad_ms, sv->ev_obj, sv->ev1));
   return AQC_OK;
 }
 
