@@ -289,8 +289,9 @@ __device__ __forceinline__ void sweep_prologue_body(const PrologueArgs& A, const
   const int b = blockIdx.y;
   const double2* s_trig = A.gtrig ? A.gtrig + (size_t)b * A.nthetas : s_trig_buf;
   pdl_launch_dependents();
-  // (the angles come from the host -- launch parameters or pinned memory -- so the table is built BEFORE the
-  // wait; everything below writes memory the previous evaluation's kernels read)
+  // (the angles come from the host -- pinned memory -- so the table is built BEFORE the wait; everything
+  // below writes memory the previous evaluation's kernels read.  Angles inside the launch parameters were
+  // measured too: a 4 KiB parameter block costs more at launch than the PCIe reads it saves.)
   if (!A.gtrig) build_trig_smem(thetas + (size_t)b * A.nthetas, A.nthetas, A.n3, A.tpb, s_trig_buf, nullptr);
   pdl_wait();
   if (!A.gtrig && A.trig_out && blockIdx.x == 0)  // kept for the epilogue of the same sweep
@@ -320,20 +321,6 @@ __device__ __forceinline__ void sweep_prologue_body(const PrologueArgs& A, const
 template <int ENT, bool DAG>
 __global__ void __launch_bounds__(128) sweep_prologue_kernel(const PrologueArgs A) {
   sweep_prologue_body<ENT, DAG>(A, A.thetas);
-}
-
-// The same with the angles INSIDE the launch parameters (one state, <= kArgThetas angles -- every
-// BASELINE configuration): they arrive with the launch instead of through PCIe reads of pinned memory
-// from inside the kernel (~2 us of the 6-7 us a prologue took at n = 12 ... 20).
-constexpr int kArgThetas = 480;
-struct PrologueArgsT {
-  PrologueArgs a;
-  double th[kArgThetas];
-};
-static_assert(sizeof(PrologueArgsT) <= 4096, "launch parameters");
-template <int ENT, bool DAG>
-__global__ void __launch_bounds__(128) sweep_prologue_args_kernel(const __grid_constant__ PrologueArgsT P) {
-  sweep_prologue_body<ENT, DAG>(P.a, P.th);
 }
 
 struct EpilogueArgs {

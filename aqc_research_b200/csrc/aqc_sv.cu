@@ -121,7 +121,7 @@ struct aqc_sv {
   double* d_umat_grad = nullptr;        // stage matrices of the gradient program (own buffer: its prologue may
                                         // run on stream_aux while the V^H sweep still uses d_umat)
   cudaStream_t stream_aux = nullptr;    // aqc_sv_eval_begin: gradient prologue next to the V^H sweep
-  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
+  cudaEvent_t ev_aux1 = nullptr;
   // coordinate descent (aqc_cd.cuh)
   CdUnit* d_cd_units = nullptr;
   int cd_nunits = 0;
@@ -314,29 +314,6 @@ static int dense_prepare(aqc_sv* sv, int mode, cudaStream_t stream = nullptr) {
   const size_t dyn = sv->trig_in_global ? 0 : (size_t)sv->circ.nthetas * sizeof(double2);
   const dim3 grid((unsigned)std::max(1, (a.nstages * 4 + 127) / 128), (unsigned)sv->batch);
   const bool dag = mode == 2;
-  if (sv->batch == 1 && sv->circ.nthetas <= kArgThetas && !sv->trig_in_global) {
-    // the angles travel inside the launch parameters
-    PrologueArgsT pa;
-    pa.a = a;
-    pa.a.thetas = nullptr;
-    memcpy(pa.th, sv->h_thetas, (size_t)sv->circ.nthetas * sizeof(double));
-#define AQC_PROA(E)                                                              \
-  do {                                                                           \
-    if (dag)                                                                     \
-      CU(launch_chained(sweep_prologue_args_kernel<E, true>, grid, dim3(128), dyn, stream, pa));  \
-    else                                                                         \
-      CU(launch_chained(sweep_prologue_args_kernel<E, false>, grid, dim3(128), dyn, stream, pa)); \
-  } while (0)
-    switch (sv->circ.ent) {
-      case AQC_ENT_CX: AQC_PROA(AQC_ENT_CX); break;
-      case AQC_ENT_CZ: AQC_PROA(AQC_ENT_CZ); break;
-      default: AQC_PROA(AQC_ENT_CP);
-    }
-#undef AQC_PROA
-    CU(cudaGetLastError());
-    sv->last_launches += 1;
-    return AQC_OK;
-  }
 #define AQC_PRO(E)                                                                                        \
   do {                                                                                                    \
     if (dag) {                                                                                            \
@@ -545,7 +522,6 @@ extern "C" void aqc_sv_destroy(aqc_sv* sv) {
   if (sv->h_thetas) cudaFreeHost(sv->h_thetas);
   for (Program* p : {&sv->prog_grad, &sv->prog_fwd, &sv->prog_dag})
     if (p->d_stages) cudaFree(p->d_stages), cudaFree(p->d_passes);
-  if (sv->ev_aux0) cudaEventDestroy(sv->ev_aux0);
   if (sv->ev_aux1) cudaEventDestroy(sv->ev_aux1);
   if (sv->stream_aux) cudaStreamDestroy(sv->stream_aux);
   if (sv->ev_hs) cudaEventDestroy(sv->ev_hs);
@@ -610,7 +586,6 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUB(cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking));
   CUB(cudaStreamCreateWithFlags(&sv->stream_aux, cudaStreamNonBlocking));
-  CUB(cudaEventCreateWithFlags(&sv->ev_aux0, cudaEventDisableTiming));
   CUB(cudaEventCreateWithFlags(&sv->ev_aux1, cudaEventDisableTiming));
   CUB(cudaEventCreate(&sv->ev_hs));
   CUB(cudaEventCreate(&sv->ev_obj));
@@ -1332,17 +1307,17 @@ extern "C" int aqc_sv_eval_begin(aqc_sv* sv, const double* thetas, int target_sl
   rc = upload_thetas(sv, thetas, false);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev0, sv->stream));
-  // the gradient program's prologue (stage matrices, cleared sums, trig table) does not depend on the V^H
-  // sweep: it runs next to it on the auxiliary stream, behind everything enqueued so far
-  CU(cudaEventRecord(sv->ev_aux0, sv->stream));
-  CU(cudaStreamWaitEvent(sv->stream_aux, sv->ev_aux0, 0));
-  rc = dense_prepare(sv, 0, sv->stream_aux);
-  if (rc) return rc;
-  CU(cudaEventRecord(sv->ev_aux1, sv->stream_aux));
+  // The V^H sweep is enqueued first (it is the critical path); the gradient program's prologue (stage
+  // matrices, cleared sums, trig table) does not depend on it and runs next to it on the auxiliary stream,
+  // behind everything that was in the main stream when the evaluation began (ev0).
   rc = dense_prepare(sv, 2);
   if (!rc) rc = run_dense_program(sv, 2, sv->slots[target_slot], -1, nullptr, sv->slots[z0_slot], nullptr, 0, -1);
   if (rc) return rc;
   CU(cudaEventRecord(sv->ev_obj, sv->stream));
+  CU(cudaStreamWaitEvent(sv->stream_aux, sv->ev0, 0));
+  rc = dense_prepare(sv, 0, sv->stream_aux);
+  if (rc) return rc;
+  CU(cudaEventRecord(sv->ev_aux1, sv->stream_aux));
   sv->eval_hs_off = 4 * tot;  // behind the gradient's two arrays: the results never share bytes
   sv->eval_hs_count = nout;
   // hs leaves on the auxiliary stream, next to the gradient sweep (which only reads z0): the gather is
