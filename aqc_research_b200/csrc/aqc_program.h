@@ -94,9 +94,10 @@ static void build_units(const aqc_circuit& c, bool reversed, std::vector<HostUni
 // `units` carry PHYSICAL bit positions in qa / qb.  Passes are appended to `prog`.
 // `max_units` caps the units of a stage; `merge_fronts` (dense-stage programs) lets a block unit
 // join the front-gate stage that holds its qubits, so the front layer costs no stages of its own.
-static void build_program_units(const std::vector<HostUnit>& units, int nbits, int tb_max,
-                                int lowbits, Program& prog, int max_units = kMaxUnits,
-                                bool merge_fronts = false) {
+// `plan` (optional): the tile of pass i is the bit set plan[i] (see plan_tiles) instead of the greedy choice.
+static void build_program_units_impl(const std::vector<HostUnit>& units, int nbits, int tb_max,
+                                     int lowbits, Program& prog, int max_units, bool merge_fronts,
+                                     const std::vector<unsigned long long>* plan) {
   const int qoff = 0;
   const size_t pass_begin = prog.passes.size();
   const int tb = std::min(nbits, tb_max);
@@ -107,7 +108,13 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
   while (ndone < units.size() || prog.passes.size() == pass_begin) {
     std::vector<char> intile(nbits, 0), blocked(nbits, 0);
     int ntile = 0;
-    for (int b = 0; b < low; ++b) intile[b] = 1, ++ntile;
+    const size_t pass_no = prog.passes.size() - pass_begin;
+    if (plan && pass_no < plan->size()) {
+      for (int b = 0; b < nbits; ++b)
+        if (((*plan)[pass_no] >> b) & 1ull) intile[b] = 1, ++ntile;
+    } else {
+      for (int b = 0; b < low; ++b) intile[b] = 1, ++ntile;
+    }
     std::vector<int> picked;
     for (size_t k = 0; k < units.size(); ++k) {
       if (done[k]) continue;
@@ -256,6 +263,123 @@ static void build_program_units(const std::vector<HostUnit>& units, int nbits, i
     ndone += picked.size();
     if (picked.empty() && ndone < units.size()) break;  // cannot happen (tb >= 2)
   }
+}
+
+// Tile planner.  The greedy scheduler above grows each tile along the unit order, which follows the
+// layers of the circuit: on a brick-wall circuit it sweeps one window after the other across the qubits
+// and pays a pass per window and layer group.  Which units a pass can run depends only on its bit SET
+// (light cones inside the set), so the sets are searched instead: candidates are the fixed low bits plus
+// up to two contiguous runs of the other bits, a beam search over passes maximises the units done, and
+// the plan is used when it needs FEWER passes than the greedy schedule (n = 20, L = 2 gradient program:
+// 4 instead of 5 passes; n = 22: 4 instead of 6).  Fewer passes = fewer trips of the state through the
+// memory system and fewer launches.  AQC_TILE_PLAN=0 keeps the greedy schedule.
+static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, int low, int greedy_passes,
+                       std::vector<unsigned long long>& plan) {
+  const int U = (int)units.size();
+  if (greedy_passes < 2 || U == 0 || nbits > 62 || tb >= nbits) return false;
+  const int k = tb - low;
+  if (k < 2) return false;
+  // candidate sets
+  std::vector<unsigned long long> cands;
+  {
+    std::set<unsigned long long> seen;
+    const unsigned long long lowmask = (1ull << low) - 1ull;
+    for (int a = low; a < nbits; ++a)
+      for (int la = (k + 1) / 2; la <= k; ++la)
+        for (int b = low; b < nbits; ++b) {
+          unsigned long long m = lowmask;
+          for (int q = a; q < a + la && q < nbits; ++q) m |= 1ull << q;
+          for (int q = b; q < b + (k - la) && q < nbits; ++q) m |= 1ull << q;
+          int cnt = __builtin_popcountll(m);
+          for (int q = 0; q < nbits && cnt < tb; ++q)  // pad with the lowest free bits
+            if (!((m >> q) & 1ull)) m |= 1ull << q, ++cnt;
+          if (cnt == tb && seen.insert(m).second) cands.push_back(m);
+        }
+  }
+  struct State {
+    std::vector<char> done;
+    int ndone, first;  // first: index of the first unit not yet done
+    int parent;        // index in the previous level
+    unsigned long long tile;
+  };
+  const int beam = U > 600 ? 8 : (U > 250 ? 16 : 48);
+  std::vector<std::vector<State>> levels;
+  levels.push_back({State{std::vector<char>((size_t)U, 0), 0, 0, -1, 0ull}});
+  std::vector<unsigned long long> bits((size_t)U);
+  for (int i = 0; i < U; ++i)
+    bits[(size_t)i] = (1ull << units[(size_t)i].qa) | (units[(size_t)i].kind ? (1ull << units[(size_t)i].qb) : 0ull);
+  for (int level = 1; level < greedy_passes; ++level) {
+    const std::vector<State>& prev = levels.back();
+    std::vector<State> next;
+    std::set<std::vector<char>> seen;
+    for (int pi = 0; pi < (int)prev.size(); ++pi) {
+      const State& st = prev[(size_t)pi];
+      // bits any remaining unit could use right now: a candidate that holds none of the frontier's pairs is
+      // skipped cheaply by the simulation itself
+      for (unsigned long long S : cands) {
+        unsigned long long blocked = 0ull;
+        int nd = st.ndone;
+        std::vector<char> d;
+        for (int i = st.first; i < U; ++i) {
+          if (st.done[(size_t)i]) continue;
+          const unsigned long long b = bits[(size_t)i];
+          if ((b & ~S) == 0ull && (b & blocked) == 0ull) {
+            if (d.empty()) d = st.done;
+            d[(size_t)i] = 1;
+            ++nd;
+          } else {
+            blocked |= b;
+            if ((~blocked & S) == 0ull) break;  // every tile bit is blocked: nothing else can run
+          }
+        }
+        if (nd == st.ndone) continue;
+        if (!seen.insert(d).second) continue;
+        int first = st.first;
+        while (first < U && d[(size_t)first]) ++first;
+        next.push_back(State{std::move(d), nd, first, pi, S});
+      }
+    }
+    if (next.empty()) return false;
+    std::sort(next.begin(), next.end(), [](const State& a, const State& b) { return a.ndone > b.ndone; });
+    if ((int)next.size() > beam) next.resize((size_t)beam);
+    // parents are indices into `prev`; keep the level
+    levels.push_back(std::move(next));
+    if (levels.back()[0].ndone == U) {
+      plan.clear();
+      int idx = 0;
+      for (int l = (int)levels.size() - 1; l >= 1; --l) {
+        plan.push_back(levels[(size_t)l][(size_t)idx].tile);
+        idx = levels[(size_t)l][(size_t)idx].parent;
+      }
+      std::reverse(plan.begin(), plan.end());
+      return true;
+    }
+  }
+  return false;
+}
+
+static int env_int(const char* name, int dflt);
+static void build_program_units(const std::vector<HostUnit>& units, int nbits, int tb_max,
+                                int lowbits, Program& prog, int max_units = kMaxUnits,
+                                bool merge_fronts = false) {
+  static const bool planner = env_int("AQC_TILE_PLAN", 1) != 0;
+  Program greedy, planned;
+  build_program_units_impl(units, nbits, tb_max, lowbits, greedy, max_units, merge_fronts, nullptr);
+  const Program* best = &greedy;
+  if (planner) {
+    const int tb = std::min(nbits, tb_max);
+    std::vector<unsigned long long> plan;
+    if (plan_tiles(units, nbits, tb, std::min(lowbits, tb), (int)greedy.passes.size(), plan)) {
+      build_program_units_impl(units, nbits, tb_max, lowbits, planned, max_units, merge_fronts, &plan);
+      if (planned.passes.size() < greedy.passes.size()) best = &planned;
+    }
+  }
+  const int stage_off = (int)prog.stages.size();
+  for (PassDesc pd : best->passes) {
+    pd.stage0 += stage_off;
+    prog.passes.push_back(pd);
+  }
+  prog.stages.insert(prog.stages.end(), best->stages.begin(), best->stages.end());
 }
 
 static void build_program(const aqc_circuit& c, int qoff, int nbits, int tb_max, int lowbits,
