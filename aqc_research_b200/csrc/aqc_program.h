@@ -273,6 +273,7 @@ static void build_program_units_impl(const std::vector<HostUnit>& units, int nbi
 // the plan is used when it needs FEWER passes than the greedy schedule (n = 20, L = 2 gradient program:
 // 4 instead of 5 passes; n = 22: 4 instead of 6).  Fewer passes = fewer trips of the state through the
 // memory system and fewer launches.  AQC_TILE_PLAN=0 keeps the greedy schedule.
+static int env_int(const char* name, int dflt);
 static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, int low, int greedy_passes,
                        std::vector<unsigned long long>& plan) {
   const int U = (int)units.size();
@@ -302,7 +303,7 @@ static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, in
     int parent;        // index in the previous level
     unsigned long long tile;
   };
-  const int beam = U > 600 ? 8 : (U > 250 ? 16 : 48);
+  const int beam = env_int("AQC_TILE_PLAN_BEAM", U > 250 ? 8 : 16);
   std::vector<std::vector<State>> levels;
   levels.push_back({State{std::vector<char>((size_t)U, 0), 0, 0, -1, 0ull}});
   std::vector<unsigned long long> bits((size_t)U);
@@ -358,11 +359,10 @@ static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, in
   return false;
 }
 
-static int env_int(const char* name, int dflt);
 static void build_program_units(const std::vector<HostUnit>& units, int nbits, int tb_max,
                                 int lowbits, Program& prog, int max_units = kMaxUnits,
                                 bool merge_fronts = false) {
-  static const bool planner = env_int("AQC_TILE_PLAN", 1) != 0;
+  const bool planner = env_int("AQC_TILE_PLAN", 1) != 0;  // (read per program: the tests switch it)
   Program greedy, planned;
   build_program_units_impl(units, nbits, tb_max, lowbits, greedy, max_units, merge_fronts, nullptr);
   const Program* best = &greedy;

@@ -257,10 +257,11 @@ static int env_int(const char* name, int dflt);
 // ---- dense-stage engine: host side ----------------------------------------------------------------
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in aqc_dense.cuh): the kernel
 // may be scheduled while its predecessor in the stream drains.  AQC_PDL=0 launches plainly.
+static bool g_pdl = true;  // AQC_PDL, read whenever a workspace is created
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                   Args&&... args) {
-  static const bool pdl = env_int("AQC_PDL", 1) != 0;
+  const bool pdl = g_pdl;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -603,10 +604,12 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   CUB(cudaMallocHost(&sv->h_thetas, std::max<size_t>(tot, 1) * sizeof(double)));
   sv->trig_in_global = (size_t)circ->nthetas * sizeof(double2) > 200 * 1024;
 #undef CUB
-  // Tile shape.  States beyond the L2 (> 64 MiB) want 256-byte contiguous runs (4 low bits) and the
-  // largest tile; L2-resident states (nbits <= 22) have too few tiles to fill 3 CTAs on each of the
+  // Tile shape.  States beyond the L2 (> 64 MiB) want long contiguous runs and the largest tile (with the
+  // tile planner 128-byte runs, 3 low bits, beat 256-byte ones: one more free tile bit saves two of eleven
+  // passes at n = 28, 114.3 -> 109.7 ms per gradient sweep); L2-resident states (nbits <= 22) have too few tiles to fill 3 CTAs on each of the
   // SMs, so they use smaller gradient tiles and spend the low bits on gate qubits instead
   // (measured at n = 20: 0.42 -> 0.36 ms per evaluation).
+  g_pdl = env_int("AQC_PDL", 1) != 0;
   const bool l2_resident = sv->nbits <= 22;
   // tiny states (one vector <= 128 KiB) are latency bound: smaller tiles spread the few amplitudes over
   // more SMs (n = 12: 5 797 -> 6 328 evals/s with 2^8 / 2^9 tiles)
@@ -618,7 +621,7 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   // passes (n = 28: 16 -> 13, 47.2 -> 45.5 ms)
   const int tb_apply =
       std::min(env_int("AQC_TILE_BITS_APPLY", tiny ? 9 : (small ? 10 : (l2_resident ? 11 : 12))), kMaxTileBits);
-  const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 4);
+  const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 3);
   const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)
   {
