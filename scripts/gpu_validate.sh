@@ -28,8 +28,9 @@ try:
 except Exception as ex:
     print("no line", repr(ex))
 PY
-for wl in sv12 sv16 sv22 sv24; do
-  timeout -k 10 120 python bench.py --workload $wl --steps 100 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/val_bench_$wl.json 2> gpurun_out/val_bench_$wl.err
+for spec in sv12:200 sv16:200 sv22:100 sv24:30 sv28:5; do
+  wl=${spec%%:*}; st=${spec##*:}
+  timeout -k 10 200 python bench.py --workload $wl --steps $st --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/val_bench_$wl.json 2> gpurun_out/val_bench_$wl.err
   python - <<PY | tee -a $S
 import json
 try:
