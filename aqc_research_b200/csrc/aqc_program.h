@@ -304,6 +304,9 @@ static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, in
     unsigned long long tile;
   };
   const int beam = env_int("AQC_TILE_PLAN_BEAM", U > 250 ? 8 : 16);
+  // the search visits beam x candidates x units per level: deep circuits (thousands of blocks, hundreds of
+  // passes) keep the greedy schedule instead of spending seconds here
+  if ((double)beam * (double)cands.size() * (double)U * (double)greedy_passes > 4e8) return false;
   std::vector<std::vector<State>> levels;
   levels.push_back({State{std::vector<char>((size_t)U, 0), 0, 0, -1, 0ull}});
   std::vector<unsigned long long> bits((size_t)U);
