@@ -111,3 +111,53 @@ def test_fused_steps_at_benchmark_size():
     stages = sum(len(ps["stages"]) for ps in prog)
     steps = sum(len(dense_steps(ps["stages"])) for ps in prog)
     assert steps < 0.7 * stages, (steps, stages)
+
+
+@pytest.mark.parametrize("n,layers,tb,low", [(12, 2, 6, 2), (13, 3, 7, 2), (14, 2, 8, 3)])
+def test_tile_planner_needs_fewer_passes_and_replays_exactly(n, layers, tb, low, monkeypatch):
+    """
+    The planned tile sets (csrc/aqc_program.h plan_tiles) replace the greedy schedule only when they need fewer
+    passes; the planned program is replayed gate by gate against the oracle, forward, reversed and with the
+    gradient, like the greedy one above.  (n = 20 / 22 / 24 / 28 at the production tile sizes: 4 / 4 / 8 / 9
+    instead of 5 / 6 / 13 / 20 gradient passes -- checked below without the replay.)
+    """
+    np.random.seed(6000 + n)
+    circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+    h = CircuitHandle(circ)
+    th = utils.rand_thetas(circ.num_thetas)
+    x, y = utils.rand_state(n), utils.rand_state(n)
+    for rev in (False, True):
+        monkeypatch.setenv("AQC_TILE_PLAN", "0")
+        greedy = parse_program(h.debug_program(0, tb, low, rev, dense=True, fused=True), dense=True)
+        monkeypatch.setenv("AQC_TILE_PLAN", "1")
+        planned = parse_program(h.debug_program(0, tb, low, rev, dense=True, fused=True), dense=True)
+        assert len(planned) <= len(greedy)
+        if not rev:
+            assert len(planned) < len(greedy), "the planner is expected to win on a brick-wall circuit"
+        check_structure(planned, n)
+        dense_check_tables(planned)
+        units = sum(len(st[2]) for ps in planned for st in ps["stages"])
+        assert units == n + circ.num_blocks + circ.half_layer_num_blocks
+        ref = O.apply_v(circ, th, y, dagger=rev)
+        (v,), _ = dense_emulate(planned, circ.entangler, th, [y], dagger=rev, grad=False)
+        assert _rel(v, ref) < TOL
+    z0 = O.apply_v(circ, th, y, dagger=True)
+    planned = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
+    (w, z), g = dense_emulate(planned, circ.entangler, th, [x, z0], dagger=False, grad=True)
+    assert _rel(g, O.grad_sweep(circ, th, x, z0)) < TOL
+    assert _rel(w, O.apply_v(circ, th, x)) < TOL and _rel(z, y) < 1e-10
+
+
+def test_tile_planner_pass_counts_at_benchmark_sizes(monkeypatch):
+    """Pass counts of the BASELINE configurations (host-side scheduling only, no state is touched)."""
+    want = {(20, 2, 10, 2): (5, 4), (22, 2, 10, 2): (6, 4), (24, 4, 11, 3): (None, 8), (28, 4, 11, 3): (None, 9)}
+    for (n, layers, tb, low), (greedy_want, planned_want) in want.items():
+        circ = TrotterAnsatz(n, cs.make_trotter_like_circuit(n, layers), True)
+        h = CircuitHandle(circ)
+        monkeypatch.setenv("AQC_TILE_PLAN", "1")
+        planned = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
+        assert len(planned) <= planned_want, (n, len(planned))
+        if greedy_want is not None:
+            monkeypatch.setenv("AQC_TILE_PLAN", "0")
+            greedy = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
+            assert len(greedy) == greedy_want
