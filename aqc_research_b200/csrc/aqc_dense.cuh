@@ -505,8 +505,12 @@ __device__ __forceinline__ void tile_copy(unsigned sbase, unsigned s0x16, const 
 
 // (A 64-register instantiation with 4 CTAs per SM for tiles of <= 2^10 amplitudes was measured in r02: no
 // difference at n = 12 ... 22 -- occupancy is not what limits the small-tile passes.)
-template <int NVEC>
-__global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_kernel(const DensePassArgs A) {
+// MINB = CTAs per SM the register budget is sized for.  Single-vector passes on 2^12 tiles are limited to
+// three CTAs per SM by shared memory anyway: that instantiation (MINB = 3) spends the registers on four
+// iterations in flight per warp instead of two (its top stall is the LDS -> DMMA latency, short_scoreboard).
+template <int NVEC, int MINB>
+__global__ void __launch_bounds__(kDThreads, MINB) dense_pass_kernel(const DensePassArgs A) {
+  constexpr int UNR = (NVEC == 1 && MINB <= 3) ? 4 : 2;
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
     double m0 = 0.0, m1 = 0.0, n0 = 0.0, n1 = 0.0;
     int j = 0;
     if (!paired) {
-#pragma unroll 2
+#pragma unroll UNR
       for (int it = warp; it < nit; it += kDWarps, ++j) {
         const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
         const unsigned la = sm_u32 + (b16 ^ sl16);
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(kDThreads, (NVEC == 1 ? 5 : 3)) dense_pass_ker
       }
     } else {
       // fused step: stage A, lane ^ 4 exchange (re/im lane bit <-> r0 register bit), stage B
-#pragma unroll 2
+#pragma unroll UNR
       for (int it = warp; it < nit; it += kDWarps, ++j) {
         const unsigned b16 = __shfl_sync(0xffffffffu, sb16, j);
         const unsigned la = sm_u32 + (b16 ^ sl16);

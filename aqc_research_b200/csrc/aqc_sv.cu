@@ -276,18 +276,28 @@ static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block,
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-template <int NVEC>
-static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
+template <int NVEC, int MINB>
+static int launch_dense_pass_inst(aqc_sv* sv, const DensePassArgs& args) {
   const size_t smem = (size_t)NVEC * sizeof(double2) << args.pd.tb;
   static bool configured[64] = {false};  // per device; setting the attribute twice is harmless
   if (!configured[sv->device & 63]) {
-    CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(dense_pass_kernel<NVEC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)NVEC * sizeof(double2) << kMaxTileBits)));
     configured[sv->device & 63] = true;
   }
   dim3 grid((unsigned)(1ull << args.pd.nouter), (unsigned)sv->batch);
-  CU(launch_chained(dense_pass_kernel<NVEC>, grid, dim3(kDThreads), smem, sv->stream, args));
+  CU(launch_chained(dense_pass_kernel<NVEC, MINB>, grid, dim3(kDThreads), smem, sv->stream, args));
   return AQC_OK;
+}
+template <int NVEC>
+static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
+  if (NVEC == 1) {
+    // 2^12-amplitude tiles: three CTAs per SM fit (shared memory), so the deeper-unrolled instantiation runs
+    static const bool deep = env_int("AQC_DENSE_UNROLL4", 1) != 0;
+    if (args.pd.tb == 12 && deep) return launch_dense_pass_inst<1, 3>(sv, args);
+    return launch_dense_pass_inst<1, 5>(sv, args);
+  }
+  return launch_dense_pass_inst<2, 3>(sv, args);
 }
 
 // Prologue of a sweep: stage matrices of one program from the staged angles (mode 0 gradient, 1 V,
