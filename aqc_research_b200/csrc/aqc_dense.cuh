@@ -505,12 +505,13 @@ __device__ __forceinline__ void tile_copy(unsigned sbase, unsigned s0x16, const 
 
 // (A 64-register instantiation with 4 CTAs per SM for tiles of <= 2^10 amplitudes was measured in r02: no
 // difference at n = 12 ... 22 -- occupancy is not what limits the small-tile passes.)
-// MINB = CTAs per SM the register budget is sized for.  Single-vector passes on 2^12 tiles are limited to
-// three CTAs per SM by shared memory anyway: that instantiation (MINB = 3) spends the registers on four
-// iterations in flight per warp instead of two (its top stall is the LDS -> DMMA latency, short_scoreboard).
+// MINB = CTAs per SM the register budget is sized for.  The single-vector passes keep four iterations in
+// flight per warp (their top stall is the LDS -> DMMA latency, short_scoreboard): 2^12 tiles are limited to
+// three CTAs per SM by shared memory anyway (MINB = 3), smaller tiles run with four (64 registers; a fifth
+// resident CTA with two iterations in flight was slower: n = 20 V^H sweep 0.115 -> 0.104 ms).
 template <int NVEC, int MINB>
 __global__ void __launch_bounds__(kDThreads, MINB) dense_pass_kernel(const DensePassArgs A) {
-  constexpr int UNR = (NVEC == 1 && MINB <= 3) ? 4 : 2;
+  constexpr int UNR = (NVEC == 1) ? 4 : 2;
   extern __shared__ double2 smem[];
   __shared__ long long s_hioff[16];
   __shared__ double s_mpart[(NVEC == 2) ? 2 * 2 * kDWarps * 32 : 2];  // [parity][set][warp][32]

@@ -292,11 +292,11 @@ static int launch_dense_pass_inst(aqc_sv* sv, const DensePassArgs& args) {
 template <int NVEC>
 static int launch_dense_pass(aqc_sv* sv, const DensePassArgs& args) {
   if (NVEC == 1) {
-    // 2^12-amplitude tiles: three CTAs per SM fit (shared memory), so the deeper-unrolled instantiation runs
-    static const bool deep = env_int("AQC_DENSE_UNROLL4", 1) != 0;
-    if (args.pd.tb == 12 && deep) return launch_dense_pass_inst<1, 3>(sv, args);
-    return launch_dense_pass_inst<1, 5>(sv, args);
+    if (args.pd.tb == 12) return launch_dense_pass_inst<1, 3>(sv, args);
+    return launch_dense_pass_inst<1, 4>(sv, args);
   }
+  // (a two-CTA, four-iterations-in-flight instantiation of the gradient pass, 110 registers, was measured:
+  // n = 20 gradient sweep 0.223 -> 0.264 ms, n = 24 6.13 -> 6.31 ms -- the third resident CTA is worth more)
   return launch_dense_pass_inst<2, 3>(sv, args);
 }
 
