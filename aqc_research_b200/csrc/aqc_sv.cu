@@ -616,11 +616,13 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
 #undef CUB
   // Tile shape.  States beyond the L2 (> 64 MiB) want long contiguous runs and the largest tile (with the
   // tile planner 128-byte runs, 3 low bits, beat 256-byte ones: one more free tile bit saves two of eleven
-  // passes at n = 28, 114.3 -> 109.7 ms per gradient sweep); L2-resident states (nbits <= 22) have too few tiles to fill 3 CTAs on each of the
+  // passes at n = 28, 114.3 -> 109.7 ms per gradient sweep); L2-resident states (nbits <= 21) have too few tiles to fill 3 CTAs on each of the
   // SMs, so they use smaller gradient tiles and spend the low bits on gate qubits instead
   // (measured at n = 20: 0.42 -> 0.36 ms per evaluation).
   g_pdl = env_int("AQC_PDL", 1) != 0;
-  const bool l2_resident = sv->nbits <= 22;
+  // (n = 22: w and z together are 128 MiB, more than the L2 holds; with the planner the large-state tiles
+  // win there too: 836 -> 869 evals/s)
+  const bool l2_resident = sv->nbits <= 21;
   // tiny states (one vector <= 128 KiB) are latency bound: smaller tiles spread the few amplitudes over
   // more SMs (n = 12: 5 797 -> 6 328 evals/s with 2^8 / 2^9 tiles)
   const bool tiny = sv->nbits <= 13 && batch == 1;
@@ -632,7 +634,8 @@ static int sv_create_impl(const aqc_circuit* circ, int device, int log2_cols, in
   const int tb_apply =
       std::min(env_int("AQC_TILE_BITS_APPLY", tiny ? 9 : (small ? 10 : (l2_resident ? 11 : 12))), kMaxTileBits);
   const int low = env_int("AQC_TILE_LOW_BITS", l2_resident ? 2 : 3);
-  const int low_apply = env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : 3));
+  const int low_apply =
+      env_int("AQC_TILE_LOW_BITS_APPLY", env_int("AQC_TILE_LOW_BITS", l2_resident ? 1 : (sv->nbits <= 22 ? 2 : 3)));
   // engine: dense-stage DMMA sweeps (default) or "legacy" (gate-by-gate register kernel)
   {
     const char* eng = getenv("AQC_ENGINE");

@@ -1,6 +1,6 @@
 """
 GPU parity of EVERY engine / tile configuration against the CPU oracle:
-the configuration a workspace picks depends on the state size (nbits > 22: 3 / 3 forced low bits,
+the configuration a workspace picks depends on the state size (nbits > 21: 3 / 3 forced low bits (3 / 2 at 22),
 2^11 / 2^12 tiles), so the production settings of n >= 23 are forced here
 at sizes the oracle finishes in seconds, and n = 24 is compared directly with the C oracle.
 Tolerance 1e-10 relative, norm-wise (north star).
@@ -19,12 +19,14 @@ from oracle import sv_oracle as O
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-LARGE = {"AQC_TILE_LOW_BITS": "3", "AQC_TILE_LOW_BITS_APPLY": "3"}  # what nbits > 22 selects
+LARGE = {"AQC_TILE_LOW_BITS": "3", "AQC_TILE_LOW_BITS_APPLY": "3"}  # what nbits > 22 selects (nbits = 22: 3 / 2)
 CONFIGS = {
-    "default": {},  # what the workspace picks for the state size (nbits <= 22: 2^10 / 2^11 tiles, 2 / 1 low bits)
+    "default": {},  # what the workspace picks for the state size (nbits <= 21: 2^10 / 2^11 tiles, 2 / 1 low bits)
     "large-state-tiles": dict(LARGE, AQC_TILE_BITS_GRAD="11", AQC_TILE_BITS_APPLY="12"),
     "256-byte-runs": dict(AQC_TILE_LOW_BITS="4", AQC_TILE_LOW_BITS_APPLY="3", AQC_TILE_BITS_GRAD="11",
                           AQC_TILE_BITS_APPLY="12"),
+    "n22-tiles": dict(AQC_TILE_LOW_BITS="3", AQC_TILE_LOW_BITS_APPLY="2", AQC_TILE_BITS_GRAD="11",
+                      AQC_TILE_BITS_APPLY="12"),  # what nbits = 22 selects
     "greedy-schedule": {"AQC_TILE_PLAN": "0"},  # the tile planner off
     "plain-launches": {"AQC_PDL": "0"},  # no programmatic dependent launch
     "small-tiles": {"AQC_TILE_BITS_GRAD": "8", "AQC_TILE_BITS_APPLY": "9"},  # generic (not unrolled) tile copies
