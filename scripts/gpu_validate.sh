@@ -40,6 +40,7 @@ except Exception as ex:
     print("$wl: no line", ex)
 PY
 done
+if [ -n "$VAL_SKIP_NCU" ]; then echo "ncu passes skipped (VAL_SKIP_NCU)" | tee -a $S; exit 0; fi
 timeout -k 10 120 python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/val_plain_sv20.json 2> gpurun_out/val_plain_sv20.err &&
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/val_launches_sv20.csv python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/val_ncu_launches.log 2>&1
 echo "ncu launch list rc=$?" | tee -a $S
