@@ -303,10 +303,14 @@ static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, in
     int parent;        // index in the previous level
     unsigned long long tile;
   };
-  const int beam = env_int("AQC_TILE_PLAN_BEAM", U > 250 ? 8 : 16);
-  // the search visits beam x candidates x units per level: deep circuits (thousands of blocks, hundreds of
-  // passes) keep the greedy schedule instead of spending seconds here
-  if ((double)beam * (double)cands.size() * (double)U * (double)greedy_passes > 4e8) return false;
+  // the search visits beam x candidates x units per level (a few ns each, spread over up to 8 host threads):
+  // the beam narrows for long unit lists, and deep circuits (thousands of blocks, hundreds of passes) keep the
+  // greedy schedule instead of spending seconds here
+  int beam = env_int("AQC_TILE_PLAN_BEAM", 24);
+  auto effort = [&](int bm) { return (double)bm * (double)cands.size() * (double)U * (double)greedy_passes; };
+  while (beam > 6 && effort(beam) > 6e8) beam /= 2;
+  if (effort(beam) > 6e8) return false;
+  const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
   std::vector<std::vector<State>> levels;
   levels.push_back({State{std::vector<char>((size_t)U, 0), 0, 0, -1, 0ull}});
   std::vector<unsigned long long> bits((size_t)U);
@@ -314,39 +318,62 @@ static bool plan_tiles(const std::vector<HostUnit>& units, int nbits, int tb, in
     bits[(size_t)i] = (1ull << units[(size_t)i].qa) | (units[(size_t)i].kind ? (1ull << units[(size_t)i].qb) : 0ull);
   for (int level = 1; level < greedy_passes; ++level) {
     const std::vector<State>& prev = levels.back();
+    // every (state, candidate) pair is simulated independently: candidates are dealt out to the threads
+    std::vector<std::vector<State>> part((size_t)nthreads);
+    auto work = [&](int t) {
+      std::vector<State>& out = part[(size_t)t];
+      for (size_t ci = (size_t)t; ci < cands.size(); ci += (size_t)nthreads) {
+        const unsigned long long S = cands[ci];
+        for (int pi = 0; pi < (int)prev.size(); ++pi) {
+          const State& st = prev[(size_t)pi];
+          unsigned long long blocked = 0ull;
+          int nd = st.ndone;
+          std::vector<char> d;
+          for (int i = st.first; i < U; ++i) {
+            if (st.done[(size_t)i]) continue;
+            const unsigned long long b = bits[(size_t)i];
+            if ((b & ~S) == 0ull && (b & blocked) == 0ull) {
+              if (d.empty()) d = st.done;
+              d[(size_t)i] = 1;
+              ++nd;
+            } else {
+              blocked |= b;
+              if ((~blocked & S) == 0ull) break;  // every tile bit is blocked: nothing else can run
+            }
+          }
+          if (nd == st.ndone) continue;
+          int first = st.first;
+          while (first < U && d[(size_t)first]) ++first;
+          out.push_back(State{std::move(d), nd, first, pi, S});
+        }
+      }
+    };
+    if (nthreads > 1 && (double)prev.size() * (double)cands.size() * (double)U > 2e6) {
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+      work(0);
+      for (std::thread& th : pool) th.join();
+    } else {
+      for (int t = 0; t < nthreads; ++t) work(t);
+    }
+    std::vector<State> all;
+    for (std::vector<State>& v : part) {
+      for (State& st : v) all.push_back(std::move(st));
+      v.clear();
+    }
+    if (all.empty()) return false;
+    // deterministic order whatever the thread count: most units done first, then parent, then tile set
+    std::sort(all.begin(), all.end(), [](const State& x, const State& y) {
+      if (x.ndone != y.ndone) return x.ndone > y.ndone;
+      if (x.parent != y.parent) return x.parent < y.parent;
+      return x.tile < y.tile;
+    });
     std::vector<State> next;
     std::set<std::vector<char>> seen;
-    for (int pi = 0; pi < (int)prev.size(); ++pi) {
-      const State& st = prev[(size_t)pi];
-      // bits any remaining unit could use right now: a candidate that holds none of the frontier's pairs is
-      // skipped cheaply by the simulation itself
-      for (unsigned long long S : cands) {
-        unsigned long long blocked = 0ull;
-        int nd = st.ndone;
-        std::vector<char> d;
-        for (int i = st.first; i < U; ++i) {
-          if (st.done[(size_t)i]) continue;
-          const unsigned long long b = bits[(size_t)i];
-          if ((b & ~S) == 0ull && (b & blocked) == 0ull) {
-            if (d.empty()) d = st.done;
-            d[(size_t)i] = 1;
-            ++nd;
-          } else {
-            blocked |= b;
-            if ((~blocked & S) == 0ull) break;  // every tile bit is blocked: nothing else can run
-          }
-        }
-        if (nd == st.ndone) continue;
-        if (!seen.insert(d).second) continue;
-        int first = st.first;
-        while (first < U && d[(size_t)first]) ++first;
-        next.push_back(State{std::move(d), nd, first, pi, S});
-      }
+    for (State& st : all) {
+      if ((int)next.size() >= beam) break;
+      if (seen.insert(st.done).second) next.push_back(std::move(st));
     }
-    if (next.empty()) return false;
-    std::sort(next.begin(), next.end(), [](const State& a, const State& b) { return a.ndone > b.ndone; });
-    if ((int)next.size() > beam) next.resize((size_t)beam);
-    // parents are indices into `prev`; keep the level
     levels.push_back(std::move(next));
     if (levels.back()[0].ndone == U) {
       plan.clear();

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/aqc_b200.h"
