@@ -161,3 +161,28 @@ def test_tile_planner_pass_counts_at_benchmark_sizes(monkeypatch):
             monkeypatch.setenv("AQC_TILE_PLAN", "0")
             greedy = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
             assert len(greedy) == greedy_want
+
+
+def test_tile_planner_on_generic_layouts(monkeypatch):
+    """Random / spin layouts (units on arbitrary qubit pairs): planned programs stay exact, never need more passes."""
+    n, tb, low = 10, 6, 2
+    np.random.seed(6100)
+    wins = 0
+    for name, circ in _circuits(n):
+        h = CircuitHandle(circ)
+        th = utils.rand_thetas(circ.num_thetas)
+        x, y = utils.rand_state(n), utils.rand_state(n)
+        z0 = O.apply_v(circ, th, y, dagger=True)
+        gref = O.grad_sweep(circ, th, x, z0)
+        monkeypatch.setenv("AQC_TILE_PLAN", "0")
+        greedy = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
+        monkeypatch.setenv("AQC_TILE_PLAN", "1")
+        planned = parse_program(h.debug_program(0, tb, low, False, dense=True, fused=True), dense=True)
+        assert len(planned) <= len(greedy), name
+        wins += len(planned) < len(greedy)
+        check_structure(planned, n)
+        dense_check_tables(planned)
+        (w, z), g = dense_emulate(planned, circ.entangler, th, [x, z0], dagger=False, grad=True)
+        assert _rel(g, gref) < TOL, name
+        assert _rel(w, O.apply_v(circ, th, x)) < TOL and _rel(z, y) < 1e-10, name
+    assert wins >= 1
