@@ -23,9 +23,10 @@ def _launch(world, extra, port):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, check=False)
 
 
-@pytest.mark.parametrize("world,qubits", [(2, 7), (4, 8)])
+# (2, 11): 10 local bits against 6-bit tiles -- the per-epoch programs go through the tile planner
+@pytest.mark.parametrize("world,qubits", [(2, 7), (4, 8), (2, 11)])
 def test_sharded_driver_gloo(world, qubits):
-    res = _launch(world, ["--sim", "--qubits", str(qubits)], 29500 + world)
+    res = _launch(world, ["--sim", "--qubits", str(qubits)], 29500 + world + qubits)
     assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
